@@ -1,0 +1,3 @@
+// shim: see oracle/shim/msgs_common.hpp
+#pragma once
+#include "msgs_common.hpp"
