@@ -1,0 +1,151 @@
+/*
+ * include/mcl_b200.h -- C ABI of the B200-native MCL update (libmcl_b200.so).
+ *
+ * This is the drop-in boundary for ONE path of AE-HYU/monte_carlo_localization
+ * (package particle_filter_cpp): ParticleFilter::MCL + expected_pose and the setup
+ * state they read.  The reference has no FFI of its own -- the path is reached through
+ * private members of particle_filter_cpp::ParticleFilter
+ * (include/particle_filter_cpp/particle_filter.hpp:37-75) -- so every entry point below
+ * names the member function or statement range it replaces.  Host code (the C++
+ * ParticleFilter mirror in monte_carlo_localization_b200/host/, a ROS 2 node, ctypes)
+ * binds exactly these symbols; there are no torch or C++ types in the signatures.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative mcl_status; nothing throws.
+ *   - a context is used from one host thread at a time (the reference serialises the path
+ *     with state_lock_, src/particle_filter.cpp:756).
+ *   - all pointers are HOST pointers unless the name ends in _dev.
+ *   - particles are column-major N x 3 doubles (x[N], y[N], theta[N]) -- the layout of the
+ *     reference's Eigen::MatrixXd particles_ (particle_filter.hpp:102).
+ *   - there is no CPU fallback: without a CUDA device mcl_create fails with
+ *     MCL_ERR_NO_DEVICE.
+ */
+#ifndef MCL_B200_H_
+#define MCL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCL_B200_ABI_VERSION 1
+
+typedef enum mcl_status {
+    MCL_OK = 0,
+    MCL_ERR_INVALID = -1,      /* bad argument / call order */
+    MCL_ERR_NO_DEVICE = -2,    /* no usable CUDA device (no CPU fallback exists) */
+    MCL_ERR_CUDA = -3,         /* CUDA runtime error; see mcl_last_error */
+    MCL_ERR_NO_MAP = -4,       /* reference: cast_ray returns MAX_RANGE when !map_initialized_ (:613) */
+    MCL_ERR_UNSUPPORTED = -5,  /* e.g. MAX_RANGE_PX > 254 or more than 128 beams */
+    MCL_ERR_NO_FREE_SPACE = -6 /* reference: "No free space found in map!" (:423-427) */
+} mcl_status;
+
+/* The ROS parameters that reach the path, same names and defaults as
+ * src/particle_filter.cpp:23-47 (config/mcl_config.yaml overrides some). */
+typedef struct mcl_params {
+    int32_t max_particles;            /* :24   2000 */
+    int32_t max_viz_particles;        /* :25   60   */
+    int32_t angle_step;               /* :23   18   (host-side scan downsampling) */
+    double squash_factor;             /* :26   2.2  */
+    double max_range;                 /* :27   12.0 */
+    double z_short, z_max, z_rand, z_hit, sigma_hit;                 /* :30-34 */
+    double motion_dispersion_x, motion_dispersion_y, motion_dispersion_theta; /* :35-37 */
+    uint64_t seed;                    /* device RNG seed (reference: std::random_device, :20) */
+    int32_t num_filters;              /* batch of independent filters sharing map/params; 1 = the reference */
+} mcl_params;
+
+/* Injected noise for ONE update of ONE filter, in the reference's draw order:
+ * u[N]  = the uniforms std::discrete_distribution would draw (:661-665),
+ * z[3N] = the standard normals motion_model would draw, x,y,theta per particle (:496-498).
+ * Either pointer may be NULL (device Philox stream used for that part). */
+typedef struct mcl_noise {
+    const double* u_resample;
+    const double* z_motion;
+} mcl_noise;
+
+/* Per-stage device time of the last update in milliseconds (CUDA events; filled only
+ * when profiling is enabled with mcl_set_profiling). */
+typedef struct mcl_stage_ms {
+    float cdf, resample_motion, raycast_weight, normalize_pose, total;
+} mcl_stage_ms;
+
+typedef struct mcl_ctx mcl_ctx;
+
+void mcl_default_params(mcl_params* p);
+const char* mcl_last_error(void);
+const char* mcl_status_str(int status);
+int mcl_abi_version(void);
+int mcl_device_count(void);
+
+/* ParticleFilter ctor :19-112 (parameter read-out and buffer allocation). */
+int mcl_create(const mcl_params* p, int device, mcl_ctx** out);
+int mcl_destroy(mcl_ctx* ctx);
+
+/* get_omap :190-213 + precompute_sensor_model :233-292.  data: int8 row-major, row 0 =
+ * bottom, as nav_msgs/OccupancyGrid; resolution is the message's float32. */
+int mcl_set_map(mcl_ctx* ctx, const int8_t* data, int width, int height, float resolution,
+                double origin_x, double origin_y, double origin_yaw);
+int mcl_max_range_px(const mcl_ctx* ctx);                 /* MAX_RANGE_PX :195 */
+int mcl_get_sensor_table(const mcl_ctx* ctx, double* table_colmajor); /* (M+1)^2 */
+/* Override the internally built table (e.g. with the reference's own bytes). */
+int mcl_set_sensor_table(mcl_ctx* ctx, const double* table_colmajor, int table_width);
+/* lidarCB :297-313: the downsampled beam angles (float32). */
+int mcl_set_beam_angles(mcl_ctx* ctx, const float* angles, int num_beams);
+
+/* initialize_particles_pose :382-399 (sigma 0.5/0.5/0.4, uniform weights).
+ * normals_3n NULL => device RNG.  filter = -1 applies to every filter of a batch. */
+int mcl_init_pose(mcl_ctx* ctx, int filter, const double pose[3], const double* normals_3n);
+/* initialize_global :401-446.  cell_ordinal/theta NULL => device RNG;
+ * otherwise the injected draws (index into the row-major list of free cells, heading). */
+int mcl_init_global(mcl_ctx* ctx, int filter, const int32_t* cell_ordinal, const double* theta);
+int mcl_num_free_cells(const mcl_ctx* ctx);
+/* Upload / download state (parity harness, visualize() :944-963). */
+int mcl_set_particles(mcl_ctx* ctx, int filter, const double* particles_colmajor, const double* weights);
+int mcl_get_particles(mcl_ctx* ctx, int filter, double* particles_colmajor);
+int mcl_get_weights(mcl_ctx* ctx, int filter, double* weights);
+
+/* MCL(action, observation) :652-694 followed by expected_pose() :696-716, as
+ * timer_update calls them (:777-778).  action = [forward, (ignored), angular] (:456-457).
+ * obs = downsampled ranges (float32 metres), num_beams of them.  pose_out = [x, y, theta].
+ * For a batch, action/obs/pose_out hold num_filters consecutive records and noise (if not
+ * NULL) points at num_filters mcl_noise records. */
+int mcl_update(mcl_ctx* ctx, const double* action, const float* obs, int num_beams,
+               const mcl_noise* noise, double* pose_out);
+/* Same update with inputs already resident on the device (action_dev: 3 doubles per
+ * filter, obs_dev: num_beams floats per filter) and no host synchronisation: the pose is
+ * left in device memory (mcl_pose_dev) and copied out by mcl_read_pose. */
+int mcl_update_dev(mcl_ctx* ctx, const double* action_dev, const float* obs_dev, int num_beams);
+int mcl_read_pose(mcl_ctx* ctx, double* pose_out);
+int mcl_synchronize(mcl_ctx* ctx);
+
+/* expected_pose() alone :696-716 over the current state. */
+int mcl_expected_pose(mcl_ctx* ctx, int filter, double pose_out[3]);
+
+/* calc_range_many :586-609 / cast_ray :611-650: queries column-major n x 3
+ * (x[n], y[n], angle[n]); ranges in metres as float32. */
+int mcl_calc_range_many(mcl_ctx* ctx, const double* queries_colmajor, int64_t n, float* ranges_out);
+int mcl_cast_ray(mcl_ctx* ctx, double x, double y, double angle, float* range_out);
+
+/* Stage read-backs of the last update (parity tests). */
+int mcl_get_resample_indices(mcl_ctx* ctx, int filter, int32_t* idx_out);      /* N */
+int mcl_get_ranges(mcl_ctx* ctx, int filter, float* ranges_out);               /* N*R particle-major, metres */
+int mcl_get_range_steps(mcl_ctx* ctx, int filter, uint8_t* steps_out);         /* N*R step index, M = no hit */
+int mcl_get_raw_weights(mcl_ctx* ctx, int filter, double* weights_out);        /* before :679-686 */
+int mcl_get_cdf(mcl_ctx* ctx, int filter, double* cdf_out);                    /* discrete_distribution _M_cp */
+/* visualize() :946-958: k weighted samples of the particle set (k x 3 column-major). */
+int mcl_sample_particles(mcl_ctx* ctx, int filter, int k, double* particles_out);
+
+/* Options / introspection. */
+int mcl_set_profiling(mcl_ctx* ctx, int enabled);
+int mcl_get_stage_ms(mcl_ctx* ctx, mcl_stage_ms* out);
+int mcl_set_keep_ranges(mcl_ctx* ctx, int enabled);   /* store per-ray steps for read-back */
+int mcl_kernel_launches(mcl_ctx* ctx, int64_t* count); /* kernels launched so far by this ctx */
+/* Use the caller's CUDA stream (cudaStream_t passed as void*) instead of the ctx's own. */
+int mcl_set_stream(mcl_ctx* ctx, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCL_B200_H_ */

@@ -1,0 +1,814 @@
+// csrc/kernels.cuh -- the sm_100a kernels of the MCL update.
+//
+// One update of the reference (src/particle_filter.cpp:652-716) becomes, per filter:
+//   exact sums / CDF   k_tile_sums, k_exact_chunks, k_exact_walk, k_exact_emit   (:658, :679)
+//   resample + motion  k_resample_motion                                         (:661-665, :449-503)
+//   ray cast + weight  k_prepare_obs, k_raycast_weight                           (:506-650)
+//   normalise + pose   k_normalize_pose, k_pose_final                            (:679-686, :696-716)
+// blockIdx.y is the filter of a batch; every per-filter array is [F][...] contiguous.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "device_utils.cuh"
+#include "exact_sum.cuh"
+#include "map_prep.h"
+#include "march.cuh"
+
+namespace mclb200 {
+
+constexpr int kMaxBeams = 128;
+
+// Everything the ray/weight kernels need to know about the map and the beams.  Passed by
+// value: kernel parameters live in the constant bank, so the beam tables below are read
+// through the constant cache with warp-uniform indices.
+struct MapDev {
+    const int8_t* grid;    // reference occupancy, W*H
+    const uint8_t* v8;     // skip map, PH*PW
+    const uint8_t* v4;     // nibble skip map, PH*PW/2
+    int W, H, PW, PH;
+    double res, ox, oy;
+    int M;                 // MAX_RANGE_PX
+    // shared-memory window geometry (cells); ww == 0 disables the window path
+    int ww, wh;
+};
+
+struct BeamDev {
+    int R;
+    float angle[kMaxBeams];     // downsampled_angles_ (float32)
+    double cosa[kMaxBeams];     // cos((double)angle)
+    double sina[kMaxBeams];
+};
+
+// ------------------------------------------------------------------------------------------
+// exact sequential sums
+// ------------------------------------------------------------------------------------------
+struct ExactArgs {
+    const double* src;       // [F][N] addends (before the optional division)
+    const double* div;       // [F] divisor or nullptr
+    int64_t N;
+    int T;                   // tiles per filter
+    int C;                   // chunks per filter = T * kTileChunks
+    double* tile_sum;        // [F][T] approximate tile sums of src
+    StepFn* chunk_fn;        // [F][C]
+    StepFn* chunk_pre;       // [F][C]  (opaque chunks: step map since the previous anchor in the tile)
+    uint8_t* chunk_flag;     // [F][C]  bit0 opaque, bit1 first opaque of its tile
+    int* tile_opq;           // [F][T]  opaque chunks per tile
+    int64_t* tile_elem;      // [F][T][3]  (a0, a1, reset)
+    int* list_chunk;         // [F][C]  opaque chunks in order
+    StepFn* list_fn;         // [F][C]
+    double* anchors;         // [F][C]  exact running sum after each opaque chunk, by rank
+    double* anchor_val;      // [F][C]  same, by chunk index
+    double* tile_start;      // [F][T]  exact running sum before each tile
+    double* total;           // [F]     exact sequential sum
+    double* out;             // [F][N]  prefix sums (emit) or nullptr
+    int force_last_one;      // discrete_distribution sets _M_cp.back() = 1.0 (random.tcc:2677)
+};
+
+struct RFn {
+    StepFn f;
+    int64_t reset;
+};
+struct RFnOp {
+    __device__ __forceinline__ RFn operator()(const RFn& l, const RFn& r) const {
+        if (r.reset) return r;
+        return RFn{fn_compose(l.f, r.f), l.reset};
+    }
+};
+struct SEOp {
+    __device__ __forceinline__ ScanElem operator()(const ScanElem& l, const ScanElem& r) const { return se_combine(l, r); }
+};
+struct AddOp {
+    __device__ __forceinline__ double operator()(double a, double b) const { return a + b; }
+};
+
+__device__ __forceinline__ void load_chunk(double (&v)[kChunk], const double* __restrict__ src, int64_t base,
+                                           int64_t N, bool use_div, double div) {
+    if (base + kChunk <= N) {
+        const double2* p = reinterpret_cast<const double2*>(src + base);
+#pragma unroll
+        for (int i = 0; i < kChunk / 2; ++i) {
+            const double2 t = __ldg(p + i);
+            v[2 * i] = t.x;
+            v[2 * i + 1] = t.y;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < kChunk; ++i) v[i] = (base + i < N) ? __ldg(src + base + i) : 0.0;
+    }
+    if (use_div) {
+#pragma unroll
+        for (int i = 0; i < kChunk; ++i) v[i] = __ddiv_rn(v[i], div);
+    }
+}
+
+// approximate per-tile sums of src (no division)
+__global__ void __launch_bounds__(kTileChunks) k_tile_sums(ExactArgs a) {
+    __shared__ double sm[kTileChunks / 32];
+    const int f = blockIdx.y, t = blockIdx.x;
+    const double* src = a.src + static_cast<int64_t>(f) * a.N;
+    const int64_t base = (static_cast<int64_t>(t) * kTileChunks + threadIdx.x) * kChunk;
+    double v[kChunk];
+    load_chunk(v, src, base, a.N, false, 1.0);
+    double c = 0.0;
+#pragma unroll
+    for (int i = 0; i < kChunk; ++i) c += v[i];
+    const double s = block_sum<kTileChunks>(c, sm);
+    if (threadIdx.x == 0) a.tile_sum[static_cast<int64_t>(f) * a.T + t] = s;
+}
+
+__global__ void __launch_bounds__(kTileChunks) k_exact_chunks(ExactArgs a) {
+    __shared__ double smd[kTileChunks / 32];
+    __shared__ RFn smr[kTileChunks / 32];
+    __shared__ RFn sm_inc[kTileChunks];
+    const int f = blockIdx.y, t = blockIdx.x, tid = threadIdx.x;
+    const double* src = a.src + static_cast<int64_t>(f) * a.N;
+    const bool use_div = a.div != nullptr;
+    const double div = use_div ? a.div[f] : 1.0;
+
+    // approximate running sum before this tile
+    double pre = 0.0;
+    for (int tt = tid; tt < t; tt += kTileChunks) pre += a.tile_sum[static_cast<int64_t>(f) * a.T + tt];
+    pre = block_sum<kTileChunks>(pre, smd);
+    if (use_div) pre = pre / div;
+
+    const int64_t base = (static_cast<int64_t>(t) * kTileChunks + tid) * kChunk;
+    double v[kChunk];
+    load_chunk(v, src, base, a.N, use_div, div);
+    double c = 0.0;
+#pragma unroll
+    for (int i = 0; i < kChunk; ++i) c += v[i];
+    const double incl = block_scan_inclusive<kTileChunks>(c, AddOp(), smd, 0.0);
+    const double s_in = pre + (incl - c);
+    const double s_out = s_in + c;
+
+    StepFn fn = fn_identity();
+    int opaque = 0;
+    if (base < a.N) {
+        const int64_t cnt = (base + kChunk < a.N) ? base + kChunk : a.N;
+        const int e = chunk_safe_binade(s_in, s_out, cnt);
+        if (e < 0) {
+            fn = fn_opaque();
+            opaque = 1;
+        } else {
+            fn = chunk_step_fn(v, kChunk, e);
+        }
+    }
+    const int64_t cidx = static_cast<int64_t>(f) * a.C + static_cast<int64_t>(t) * kTileChunks + tid;
+    a.chunk_fn[cidx] = fn;
+
+    const RFn ident{fn_identity(), 0};
+    RFn el = opaque ? RFn{fn_identity(), 1} : RFn{fn, 0};
+    const RFn inc = block_scan_inclusive<kTileChunks>(el, RFnOp(), smr, ident);
+    sm_inc[tid] = inc;
+    __syncthreads();
+    const RFn exc = tid ? sm_inc[tid - 1] : ident;
+    uint8_t flag = 0;
+    if (opaque) {
+        a.chunk_pre[cidx] = exc.f;
+        flag = exc.reset ? 1 : 3;
+    }
+    a.chunk_flag[cidx] = flag;
+    const int nopq = __syncthreads_count(opaque);
+    if (tid == kTileChunks - 1) {
+        int64_t* te = a.tile_elem + (static_cast<int64_t>(f) * a.T + t) * 3;
+        te[0] = inc.f.a0;
+        te[1] = inc.f.a1;
+        te[2] = inc.reset;
+        a.tile_opq[static_cast<int64_t>(f) * a.T + t] = nopq;
+    }
+}
+
+constexpr int kWalkThreads = 512;
+constexpr int kWalkBatch = 128;
+
+__global__ void __launch_bounds__(kWalkThreads) k_exact_walk(ExactArgs a) {
+    __shared__ RFn smr[kWalkThreads / 32];
+    __shared__ RFn sm_inc[kWalkThreads];
+    __shared__ int smi[kWalkThreads / 32];
+    __shared__ int sm_cinc[kWalkThreads];
+    __shared__ double sm_add[kWalkBatch][kChunk];
+    __shared__ StepFn sm_fn[kWalkBatch];
+    __shared__ double sm_v;
+
+    const int f = blockIdx.y, tid = threadIdx.x;
+    const int T = a.T;
+    const int tpt = (T + kWalkThreads - 1) / kWalkThreads;
+    const int t0 = min(T, tid * tpt), t1 = min(T, t0 + tpt);
+    const int64_t* tile_elem = a.tile_elem + static_cast<int64_t>(f) * T * 3;
+    const int* tile_opq = a.tile_opq + static_cast<int64_t>(f) * T;
+    const uint8_t* chunk_flag = a.chunk_flag + static_cast<int64_t>(f) * a.C;
+    const StepFn* chunk_pre = a.chunk_pre + static_cast<int64_t>(f) * a.C;
+    int* list_chunk = a.list_chunk + static_cast<int64_t>(f) * a.C;
+    StepFn* list_fn = a.list_fn + static_cast<int64_t>(f) * a.C;
+    double* anchors = a.anchors + static_cast<int64_t>(f) * a.C;
+    double* anchor_val = a.anchor_val + static_cast<int64_t>(f) * a.C;
+    const double* src = a.src + static_cast<int64_t>(f) * a.N;
+    const bool use_div = a.div != nullptr;
+    const double div = use_div ? a.div[f] : 1.0;
+
+    const RFn ident{fn_identity(), 0};
+    RFn loc = ident;
+    int cnt = 0;
+    for (int t = t0; t < t1; ++t) {
+        loc = RFnOp()(loc, RFn{StepFn{tile_elem[3 * t], tile_elem[3 * t + 1]}, tile_elem[3 * t + 2]});
+        cnt += tile_opq[t];
+    }
+    const RFn inc = block_scan_inclusive<kWalkThreads>(loc, RFnOp(), smr, ident);
+    sm_inc[tid] = inc;
+    // integer inclusive scan of the counts
+    {
+        int v = cnt;
+        const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(kFullMask, v, d);
+            if (lane >= d) v += o;
+        }
+        if (lane == 31) smi[warp] = v;
+        __syncthreads();
+        if (warp == 0) {
+            int w = lane < kWalkThreads / 32 ? smi[lane] : 0;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(kFullMask, w, d);
+                if (lane >= d) w += o;
+            }
+            if (lane < kWalkThreads / 32) smi[lane] = w;
+        }
+        __syncthreads();
+        if (warp > 0) v += smi[warp - 1];
+        sm_cinc[tid] = v;
+    }
+    __syncthreads();
+    const RFn exc = tid ? sm_inc[tid - 1] : ident;
+    const int cexc = tid ? sm_cinc[tid - 1] : 0;
+    const int K = sm_cinc[kWalkThreads - 1];
+
+    // emit the ordered list of opaque chunks with their incoming step maps
+    {
+        RFn run = exc;
+        int rank = cexc;
+        for (int t = t0; t < t1; ++t) {
+            if (tile_opq[t] > 0) {
+                for (int c = t * kTileChunks; c < (t + 1) * kTileChunks; ++c) {
+                    const uint8_t fl = chunk_flag[c];
+                    if (fl & 1) {
+                        const StepFn pre = chunk_pre[c];
+                        list_chunk[rank] = c;
+                        list_fn[rank] = (fl & 2) ? fn_compose(run.f, pre) : pre;
+                        ++rank;
+                    }
+                }
+            }
+            run = RFnOp()(run, RFn{StepFn{tile_elem[3 * t], tile_elem[3 * t + 1]}, tile_elem[3 * t + 2]});
+        }
+    }
+    if (tid == 0) sm_v = 0.0;
+    __syncthreads();
+
+    // serial pass over the opaque chunks, batches staged through shared memory
+    for (int b0 = 0; b0 < K; b0 += kWalkBatch) {
+        const int nb = min(kWalkBatch, K - b0);
+        for (int i = tid; i < nb * kChunk; i += kWalkThreads) {
+            const int r = i / kChunk, e = i % kChunk;
+            const int64_t k = static_cast<int64_t>(list_chunk[b0 + r]) * kChunk + e;
+            double x = (k < a.N) ? src[k] : 0.0;
+            if (use_div) x = __ddiv_rn(x, div);
+            sm_add[r][e] = x;
+        }
+        for (int i = tid; i < nb; i += kWalkThreads) sm_fn[i] = list_fn[b0 + i];
+        __syncthreads();
+        if (tid == 0) {
+            double V = sm_v;
+            for (int r = 0; r < nb; ++r) {
+                const double vin = fn_apply(sm_fn[r], V);
+                V = chunk_seq_eval(sm_add[r], kChunk, vin);
+                anchors[b0 + r] = V;
+                anchor_val[list_chunk[b0 + r]] = V;
+            }
+            sm_v = V;
+        }
+        __syncthreads();
+    }
+
+    // exact running sum at every tile start, and the total
+    {
+        RFn run = exc;
+        int rank = cexc;
+        for (int t = t0; t < t1; ++t) {
+            a.tile_start[static_cast<int64_t>(f) * T + t] = fn_apply(run.f, run.reset ? anchors[rank - 1] : 0.0);
+            rank += tile_opq[t];
+            run = RFnOp()(run, RFn{StepFn{tile_elem[3 * t], tile_elem[3 * t + 1]}, tile_elem[3 * t + 2]});
+        }
+        if (t1 == T && t0 < t1) a.total[f] = fn_apply(run.f, run.reset ? anchors[rank - 1] : 0.0);
+    }
+}
+
+__global__ void __launch_bounds__(kTileChunks) k_exact_emit(ExactArgs a) {
+    __shared__ ScanElem sms[kTileChunks / 32];
+    __shared__ ScanElem sm_inc[kTileChunks];
+    const int f = blockIdx.y, t = blockIdx.x, tid = threadIdx.x;
+    const double* src = a.src + static_cast<int64_t>(f) * a.N;
+    const bool use_div = a.div != nullptr;
+    const double div = use_div ? a.div[f] : 1.0;
+    const int64_t cidx = static_cast<int64_t>(f) * a.C + static_cast<int64_t>(t) * kTileChunks + tid;
+    const double tstart = a.tile_start[static_cast<int64_t>(f) * a.T + t];
+
+    const uint8_t fl = a.chunk_flag[cidx];
+    ScanElem el = (fl & 1) ? se_abs(a.anchor_val[cidx]) : se_fn(a.chunk_fn[cidx]);
+    if (tid == 0) el = se_combine(se_abs(tstart), el);
+    const ScanElem ident = se_fn(fn_identity());
+    const ScanElem inc = block_scan_inclusive<kTileChunks>(el, SEOp(), sms, ident);
+    sm_inc[tid] = inc;
+    __syncthreads();
+    double s = tid ? bits_dbl(sm_inc[tid - 1].a0) : tstart;
+
+    const int64_t base = (static_cast<int64_t>(t) * kTileChunks + tid) * kChunk;
+    if (base >= a.N) return;
+    double v[kChunk];
+    load_chunk(v, src, base, a.N, use_div, div);
+    double* out = a.out + static_cast<int64_t>(f) * a.N;
+#pragma unroll
+    for (int i = 0; i < kChunk; ++i) {
+        s = __dadd_rn(s, v[i]);
+        v[i] = s;
+    }
+    if (a.force_last_one && a.N - 1 >= base && a.N - 1 < base + kChunk) v[a.N - 1 - base] = 1.0;
+    if (base + kChunk <= a.N) {
+        double2* p = reinterpret_cast<double2*>(out + base);
+#pragma unroll
+        for (int i = 0; i < kChunk / 2; ++i) p[i] = make_double2(v[2 * i], v[2 * i + 1]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < kChunk; ++i)
+            if (base + i < a.N) out[base + i] = v[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// resample (:658-665) + motion model (:449-503)
+// ------------------------------------------------------------------------------------------
+struct MotionArgs {
+    int64_t N;
+    const double* cdf;        // [F][N]
+    const double* sx;         // source state [F][N] each
+    const double* sy;
+    const double* st;
+    double* dx;               // destination state
+    double* dy;
+    double* dt;
+    int32_t* idx_out;         // [F][N]
+    const double* u;          // [F][N] injected or nullptr
+    const double* z;          // [F][3N] injected or nullptr
+    const double* action;     // [F][3] device
+    double disp_x, disp_y, disp_t;
+    uint64_t seed;
+    uint64_t update_no;
+    double* centre;           // [F][2] accumulators (sum x, sum y)
+};
+
+struct MotionScalars {
+    double dt, vel, omega, radius, dtheta, vdt;
+    int straight;
+};
+
+// the scalar preamble of motion_model (:452-471, :487-488), same operations in the same order
+__device__ __forceinline__ MotionScalars motion_scalars(double fwd, double ang) {
+    MotionScalars m;
+    m.dt = 0.01;
+    m.vel = 0.0;
+    m.omega = 0.0;
+    if (fabs(fwd) > 0.001) {
+        if (fabs(fwd) < 0.1)
+            m.dt = __ddiv_rn(fabs(fwd), 1.0);
+        else
+            m.dt = __ddiv_rn(fabs(fwd), 5.0);
+        m.dt = fmax(0.001, fmin(m.dt, 0.1));
+        m.vel = __ddiv_rn(fwd, m.dt);
+    }
+    if (fabs(ang) > 0.001) m.omega = __ddiv_rn(ang, m.dt);
+    m.straight = fabs(m.omega) < 1e-6;
+    m.vdt = __dmul_rn(m.vel, m.dt);
+    m.radius = m.straight ? 0.0 : __ddiv_rn(m.vel, m.omega);
+    m.dtheta = __dmul_rn(m.omega, m.dt);
+    return m;
+}
+
+__device__ __forceinline__ double wrap_angle_dev(double a) {  // src/utils.cpp:43-48
+    const double pi = 3.14159265358979323846, two_pi = 2.0 * 3.14159265358979323846;
+    while (a > pi) a = __dsub_rn(a, two_pi);
+    while (a < -pi) a = __dadd_rn(a, two_pi);
+    return a;
+}
+
+constexpr int kMotionThreads = 256;
+
+__global__ void __launch_bounds__(kMotionThreads) k_resample_motion(MotionArgs a) {
+    __shared__ double sm[kMotionThreads / 32];
+    const int f = blockIdx.y;
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * kMotionThreads + threadIdx.x;
+    const int64_t N = a.N;
+    const int64_t fo = static_cast<int64_t>(f) * N;
+    const MotionScalars m = motion_scalars(a.action[3 * f + 0], a.action[3 * f + 2]);
+    double nx = 0.0, ny = 0.0;
+    if (i < N) {
+        // noise: injected arrays in the reference's draw order, else Philox keyed by
+        // (seed, update) and counted by (filter, particle)
+        double u, z0, z1, z2;
+        Philox4 r0{}, r1{};
+        const bool need_rng = (a.u == nullptr) || (a.z == nullptr);
+        if (need_rng) {
+            r0 = philox4x32_10(static_cast<uint32_t>(i), static_cast<uint32_t>(i >> 32), static_cast<uint32_t>(f), 0u,
+                               static_cast<uint32_t>(a.seed) ^ static_cast<uint32_t>(a.update_no),
+                               static_cast<uint32_t>(a.seed >> 32) ^ static_cast<uint32_t>(a.update_no >> 32) ^ 0x5bd1e995u);
+            r1 = philox4x32_10(static_cast<uint32_t>(i), static_cast<uint32_t>(i >> 32), static_cast<uint32_t>(f), 1u,
+                               static_cast<uint32_t>(a.seed) ^ static_cast<uint32_t>(a.update_no),
+                               static_cast<uint32_t>(a.seed >> 32) ^ static_cast<uint32_t>(a.update_no >> 32) ^ 0x5bd1e995u);
+        }
+        u = a.u ? a.u[fo + i] : canonical_from_words(r0.v[0], r0.v[1]);
+        if (a.z) {
+            z0 = a.z[3 * (fo + i) + 0];
+            z1 = a.z[3 * (fo + i) + 1];
+            z2 = a.z[3 * (fo + i) + 2];
+        } else {
+            double t;
+            normal_pair(r0.v[2], r0.v[3], &z0, &z1);
+            normal_pair(r1.v[0], r1.v[1], &z2, &t);
+        }
+        // lower_bound(cp.begin(), cp.end(), u)  (random.tcc:2709-2713)
+        const double* cp = a.cdf + fo;
+        int64_t lo = 0, hi = N;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (__ldg(cp + mid) < u)
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        if (lo >= N) lo = N - 1;  // unreachable for u < 1 == cp[N-1]; keeps reads in range
+        if (N < 2) lo = 0;        // libstdc++ clears the table for fewer than 2 weights
+        a.idx_out[fo + i] = static_cast<int32_t>(lo);
+        const double x = a.sx[fo + lo], y = a.sy[fo + lo], th = a.st[fo + lo];
+        double nt;
+        if (m.straight) {
+            double s, c;
+            sincos(th, &s, &c);
+            nx = __dadd_rn(x, __dmul_rn(m.vdt, c));
+            ny = __dadd_rn(y, __dmul_rn(m.vdt, s));
+            nt = th;
+        } else {
+            double s0, c0, s1, c1;
+            sincos(th, &s0, &c0);
+            sincos(__dadd_rn(th, m.dtheta), &s1, &c1);
+            nx = __dadd_rn(x, __dmul_rn(m.radius, __dsub_rn(s1, s0)));
+            ny = __dsub_rn(y, __dmul_rn(m.radius, __dsub_rn(c1, c0)));
+            nt = __dadd_rn(th, m.dtheta);
+        }
+        nx = __dadd_rn(nx, __dmul_rn(z0, a.disp_x));
+        ny = __dadd_rn(ny, __dmul_rn(z1, a.disp_y));
+        nt = __dadd_rn(nt, __dmul_rn(z2, a.disp_t));
+        nt = wrap_angle_dev(nt);
+        a.dx[fo + i] = nx;
+        a.dy[fo + i] = ny;
+        a.dt[fo + i] = nt;
+        if (!(fabs(nx) < 1e12) || !(fabs(ny) < 1e12)) nx = ny = 0.0;  // keep the window centre finite
+    }
+    // cloud centre for the shared-memory window of the ray kernel
+    const double bx = block_sum<kMotionThreads>(nx, sm);
+    const double by = block_sum<kMotionThreads>(ny, sm);
+    if (threadIdx.x == 0) {
+        atomicAdd(a.centre + 2 * f + 0, bx);
+        atomicAdd(a.centre + 2 * f + 1, by);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// sensor model (:506-583): observation -> table rows, ray march, weight product
+// ------------------------------------------------------------------------------------------
+struct ObsArgs {
+    const float* obs;          // [F][R]
+    const double* tabT;        // [(M+1)][(M+1)] transposed table: tabT[obs_idx*(M+1) + range_idx]
+    const int32_t* step2idx;   // [M+1] range_idx the reference derives from step r (M = no hit)
+    double* slice;             // [F][R][M+1]  slice[j][r] = table(obs_idx_j, range_idx(r))
+    int R, M;
+    double res;
+};
+
+__global__ void k_prepare_obs(ObsArgs a) {
+    const int j = blockIdx.x, f = blockIdx.y;
+    // obs_px = obs / res, clamp, round (:549-554, :570, :573)
+    float opx = static_cast<float>(static_cast<double>(a.obs[f * a.R + j]) / a.res);
+    if (opx > static_cast<float>(a.M)) opx = static_cast<float>(a.M);
+    int oi = isnan(opx) ? 0 : static_cast<int>(roundf(opx));  // x86 cvttss2si(NaN) = INT_MIN -> clamps to 0
+    oi = max(0, min(oi, a.M));
+    const double* row = a.tabT + static_cast<int64_t>(oi) * (a.M + 1);
+    double* dst = a.slice + (static_cast<int64_t>(f) * a.R + j) * (a.M + 1);
+    for (int r = threadIdx.x; r <= a.M; r += blockDim.x) dst[r] = row[a.step2idx[r]];
+}
+
+struct RayArgs {
+    MapDev map;
+    BeamDev beams;
+    int64_t N;
+    const double* px;          // [F][N] proposal particles
+    const double* py;
+    const double* pt;
+    const double* slice;       // [F][R][M+1]
+    double* w_raw;             // [F][N]
+    uint8_t* steps;            // [F][N*R] or nullptr
+    const double* centre;      // [F][2] sums of x and y over the filter's particles
+    double inv_squash;
+    int64_t* replay_count;     // diagnostics (nullable)
+};
+
+constexpr int kRayThreads = 512;
+
+// One lane = one particle; the lane walks its R beams in order and folds the table
+// entries into the weight product in the reference's multiplication order (:564-579).
+__global__ void __launch_bounds__(kRayThreads, 1) k_raycast_weight(RayArgs a) {
+    extern __shared__ __align__(16) uint8_t smem_win[];
+    const int f = blockIdx.y;
+    const MapDev& mp = a.map;
+    const int64_t N = a.N;
+    const int64_t fo = static_cast<int64_t>(f) * N;
+    const int M = mp.M;
+    const int R = a.beams.R;
+
+    // ---- stage the window of the nibble skip map around the cloud centre -------------------
+    int wx0 = 0, wy0 = 0, vx0 = 0, vx1 = 0, vy0 = 0, vy1 = 0;
+    const int pitch = mp.ww >> 1;
+    if (mp.ww > 0) {
+        const double mx = a.centre[2 * f + 0] / static_cast<double>(N);
+        const double my = a.centre[2 * f + 1] / static_cast<double>(N);
+        const double qx = (mx - mp.ox) / mp.res + kPadL, qy = (my - mp.oy) / mp.res + kPadL;
+        int cx = (qx > -1e9 && qx < 1e9) ? static_cast<int>(floor(qx)) : 0;
+        int cy = (qy > -1e9 && qy < 1e9) ? static_cast<int>(floor(qy)) : 0;
+        wx0 = cx - mp.ww / 2;
+        wy0 = cy - mp.wh / 2;
+        wx0 = max(0, min(wx0, mp.PW - mp.ww)) & ~31;
+        wy0 = max(0, min(wy0, mp.PH - mp.wh));
+        // particles whose rays provably stay inside the window
+        vx0 = (wx0 == 0) ? 2 : wx0 + M + 2;
+        vx1 = (wx0 + mp.ww >= mp.PW) ? mp.PW - 2 : wx0 + mp.ww - M - 2;
+        vy0 = (wy0 == 0) ? 2 : wy0 + M + 2;
+        vy1 = (wy0 + mp.wh >= mp.PH) ? mp.PH - 2 : wy0 + mp.wh - M - 2;
+        const int vec_per_row = pitch >> 4;  // 16-byte vectors per window row
+        const int total = vec_per_row * mp.wh;
+        const int gpitch = mp.PW >> 1;
+        for (int i = threadIdx.x; i < total; i += kRayThreads) {
+            const int row = i / vec_per_row, col = i - row * vec_per_row;
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(mp.v4 + static_cast<int64_t>(wy0 + row) * gpitch + (wx0 >> 1)) + col);
+            reinterpret_cast<uint4*>(smem_win + row * pitch)[col] = v;
+        }
+        __syncthreads();
+    }
+    const WindowV4 wacc{smem_win, wx0, wy0, pitch};
+    const GlobalV8 gacc{mp.v8, mp.PW};
+    const RefGrid rg{mp.grid, mp.W, mp.H, mp.res, mp.ox, mp.oy};
+    const double* slice = a.slice + static_cast<int64_t>(f) * R * (M + 1);
+    int replays = 0;
+
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * kRayThreads + threadIdx.x; i < N;
+         i += static_cast<int64_t>(gridDim.x) * kRayThreads) {
+        const double x = a.px[fo + i], y = a.py[fo + i], th = a.pt[fo + i];
+        double sth, cth;
+        sincos(th, &sth, &cth);
+        const double qx = p_coord(x, mp.ox, mp.res, kPadL);
+        const double qy = p_coord(y, mp.oy, mp.res, kPadL);
+        const bool inside = p_inside(qx, qy, mp.PW, mp.PH);
+        double acc = 1.0;
+        uint8_t* steps = a.steps ? a.steps + (fo + i) * R : nullptr;
+        if (!inside) {
+            // first sample is already out of bounds for every beam (:632-636): step 0
+            for (int j = 0; j < R; ++j) {
+                acc = __dmul_rn(acc, __ldg(slice + j * (M + 1)));
+                if (steps) steps[j] = 0;
+            }
+        } else {
+            const int fqx = static_cast<int>(floor(qx)), fqy = static_cast<int>(floor(qy));
+            const RayStart st = make_ray_start(qx, qy, fqx, fqy);
+            const bool in_win = (mp.ww > 0) && fqx >= vx0 && fqx < vx1 && fqy >= vy0 && fqy < vy1;
+            for (int j = 0; j < R; ++j) {
+                int dxf, dyf;
+                beam_direction_fixed(cth, sth, a.beams.cosa[j], a.beams.sina[j], &dxf, &dyf);
+                const ReplayArgs ra{x, y, __dadd_rn(th, static_cast<double>(a.beams.angle[j]))};
+                int r;
+                if (in_win)
+                    r = march_ray(wacc, st, dxf, dyf, M, rg, ra, &replays);
+                else
+                    r = march_ray(gacc, st, dxf, dyf, M, rg, ra, &replays);
+                acc = __dmul_rn(acc, __ldg(slice + j * (M + 1) + r));
+                if (steps) steps[j] = static_cast<uint8_t>(r);
+            }
+        }
+        a.w_raw[fo + i] = pow(acc, a.inv_squash);
+    }
+    if (a.replay_count && replays) atomicAdd(reinterpret_cast<unsigned long long*>(a.replay_count), static_cast<unsigned long long>(replays));
+}
+
+// ------------------------------------------------------------------------------------------
+// normalisation (:679-686) + expected pose (:696-716)
+// ------------------------------------------------------------------------------------------
+struct NormArgs {
+    int64_t N;
+    const double* w_raw;      // [F][N]
+    const double* total;      // [F] exact sequential sum of w_raw (nullptr: weights already normalised)
+    double* wn;               // [F][N]
+    const double* px;
+    const double* py;
+    const double* pt;
+    double* partial;          // [F][nblk][4]
+    int nblk;
+};
+constexpr int kNormThreads = 256;
+
+__global__ void __launch_bounds__(kNormThreads) k_normalize_pose(NormArgs a) {
+    __shared__ double sm[kNormThreads / 32];
+    const int f = blockIdx.y;
+    const int64_t fo = static_cast<int64_t>(f) * a.N;
+    const double tot = a.total ? a.total[f] : 0.0;
+    const bool do_div = a.total && tot > 0.0;   // `if (sum_weights > 0)` (:680)
+    double ax = 0.0, ay = 0.0, as = 0.0, ac = 0.0;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * kNormThreads + threadIdx.x; i < a.N;
+         i += static_cast<int64_t>(gridDim.x) * kNormThreads) {
+        double w = a.w_raw[fo + i];
+        if (do_div) w = __ddiv_rn(w, tot);
+        if (a.wn) a.wn[fo + i] = w;
+        double s, c;
+        sincos(a.pt[fo + i], &s, &c);
+        ax += w * a.px[fo + i];
+        ay += w * a.py[fo + i];
+        as += w * s;
+        ac += w * c;
+    }
+    ax = block_sum<kNormThreads>(ax, sm);
+    ay = block_sum<kNormThreads>(ay, sm);
+    as = block_sum<kNormThreads>(as, sm);
+    ac = block_sum<kNormThreads>(ac, sm);
+    if (threadIdx.x == 0) {
+        double* p = a.partial + (static_cast<int64_t>(f) * a.nblk + blockIdx.x) * 4;
+        p[0] = ax;
+        p[1] = ay;
+        p[2] = as;
+        p[3] = ac;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_pose_final(const double* partial, int nblk, double* pose_out) {
+    __shared__ double sm[8];
+    const int f = blockIdx.x;
+    double v[4] = {0, 0, 0, 0};
+    for (int b = threadIdx.x; b < nblk; b += 256) {
+        const double* p = partial + (static_cast<int64_t>(f) * nblk + b) * 4;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] += p[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = block_sum<256>(v[k], sm);
+    if (threadIdx.x == 0) {
+        pose_out[3 * f + 0] = v[0];
+        pose_out[3 * f + 1] = v[1];
+        pose_out[3 * f + 2] = atan2(v[2], v[3]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// initialisers (:382-446), batch ray queries (:586-609), weighted sub-sampling (:946-958)
+// ------------------------------------------------------------------------------------------
+struct InitArgs {
+    int64_t N;
+    double* px;
+    double* py;
+    double* pt;
+    double* wn;
+    const double* pose;        // [F][3] (init_pose)
+    const double* normals;     // [F][3N] or nullptr
+    const int32_t* cell;       // [F][N] or nullptr (init_global)
+    const double* theta;       // [F][N] or nullptr
+    const int32_t* free_cells;
+    int n_free, W;
+    double res, ox, oy;
+    uint64_t seed, stream_no;
+    int filter0;               // first filter this launch applies to
+};
+
+__global__ void k_init_pose(InitArgs a) {
+    const int f = a.filter0 + blockIdx.y;
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= a.N) return;
+    const int64_t fo = static_cast<int64_t>(f) * a.N;
+    double z0, z1, z2;
+    if (a.normals) {
+        const double* z = a.normals + 3 * (static_cast<int64_t>(blockIdx.y) * a.N + i);
+        z0 = z[0];
+        z1 = z[1];
+        z2 = z[2];
+    } else {
+        const Philox4 r = philox4x32_10(static_cast<uint32_t>(i), static_cast<uint32_t>(i >> 32), static_cast<uint32_t>(f), 7u,
+                                        static_cast<uint32_t>(a.seed) ^ static_cast<uint32_t>(a.stream_no),
+                                        static_cast<uint32_t>(a.seed >> 32) ^ 0x9e3779b9u);
+        double t;
+        normal_pair(r.v[0], r.v[1], &z0, &z1);
+        normal_pair(r.v[2], r.v[3], &z2, &t);
+    }
+    const double* pose = a.pose + 3 * blockIdx.y;
+    a.px[fo + i] = __dadd_rn(pose[0], __dmul_rn(z0, 0.5));
+    a.py[fo + i] = __dadd_rn(pose[1], __dmul_rn(z1, 0.5));
+    a.pt[fo + i] = wrap_angle_dev(__dadd_rn(pose[2], __dmul_rn(z2, 0.4)));
+    a.wn[fo + i] = 1.0 / static_cast<double>(a.N);
+}
+
+__global__ void k_init_global(InitArgs a) {
+    const int f = a.filter0 + blockIdx.y;
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= a.N) return;
+    const int64_t fo = static_cast<int64_t>(f) * a.N;
+    int32_t ord;
+    double th;
+    if (a.cell) {
+        ord = a.cell[static_cast<int64_t>(blockIdx.y) * a.N + i];
+        th = a.theta[static_cast<int64_t>(blockIdx.y) * a.N + i];
+    } else {
+        const Philox4 r = philox4x32_10(static_cast<uint32_t>(i), static_cast<uint32_t>(i >> 32), static_cast<uint32_t>(f), 11u,
+                                        static_cast<uint32_t>(a.seed) ^ static_cast<uint32_t>(a.stream_no),
+                                        static_cast<uint32_t>(a.seed >> 32) ^ 0x85ebca6bu);
+        ord = static_cast<int32_t>(__umulhi(r.v[0], static_cast<uint32_t>(a.n_free)));
+        th = canonical_from_words(r.v[1], r.v[2]) * (2.0 * 3.14159265358979323846);
+    }
+    ord = max(0, min(ord, a.n_free - 1));
+    const int32_t lin = a.free_cells[ord];
+    const int row = lin / a.W, col = lin - row * a.W;
+    a.px[fo + i] = __dadd_rn(__dmul_rn(static_cast<double>(col), a.res), a.ox);   // :438
+    a.py[fo + i] = __dadd_rn(__dmul_rn(static_cast<double>(row), a.res), a.oy);   // :439
+    a.pt[fo + i] = th;
+    a.wn[fo + i] = 1.0 / static_cast<double>(a.N);
+}
+
+struct QueryArgs {
+    MapDev map;
+    const double* q;     // column-major n x 3 on the device
+    int64_t n;
+    float* out;
+    double max_range;
+};
+
+__global__ void __launch_bounds__(256) k_range_queries(QueryArgs a) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+    if (i >= a.n) return;
+    const MapDev& mp = a.map;
+    const double x = a.q[i], y = a.q[a.n + i], ang = a.q[2 * a.n + i];
+    const double qx = p_coord(x, mp.ox, mp.res, kPadL);
+    const double qy = p_coord(y, mp.oy, mp.res, kPadL);
+    const bool inside = p_inside(qx, qy, mp.PW, mp.PH);
+    int r = 0;
+    if (inside) {
+        double s, c;
+        sincos(ang, &s, &c);
+        const RayStart st = make_ray_start(qx, qy, static_cast<int>(floor(qx)), static_cast<int>(floor(qy)));
+        const GlobalV8 gacc{mp.v8, mp.PW};
+        const RefGrid rg{mp.grid, mp.W, mp.H, mp.res, mp.ox, mp.oy};
+        const ReplayArgs ra{x, y, ang};
+        int dxf, dyf;
+        beam_direction_fixed(c, s, 1.0, 0.0, &dxf, &dyf);
+        r = march_ray(gacc, st, dxf, dyf, mp.M, rg, ra, nullptr);
+    }
+    // `return step * map_resolution_` / `return MAX_RANGE_METERS` as float (:635, :644, :649)
+    a.out[i] = (r >= mp.M) ? static_cast<float>(a.max_range) : static_cast<float>(__dmul_rn(static_cast<double>(r), mp.res));
+}
+
+__global__ void k_steps_to_ranges(const uint8_t* steps, int64_t n, int M, double res, double max_range, float* out) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int r = steps[i];
+    out[i] = (r >= M) ? static_cast<float>(max_range) : static_cast<float>(__dmul_rn(static_cast<double>(r), res));
+}
+
+// weighted sub-sample for visualisation: k draws from the CDF of the current weights
+__global__ void k_sample_particles(const double* cdf, int64_t N, const double* px, const double* py, const double* pt,
+                                   int k, uint64_t seed, uint64_t stream_no, double* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= k) return;
+    const Philox4 r = philox4x32_10(static_cast<uint32_t>(i), 0u, 0u, 13u, static_cast<uint32_t>(seed) ^ static_cast<uint32_t>(stream_no),
+                                    static_cast<uint32_t>(seed >> 32) ^ 0xc2b2ae35u);
+    const double u = canonical_from_words(r.v[0], r.v[1]);
+    int64_t lo = 0, hi = N;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (cdf[mid] < u)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    if (lo >= N) lo = N - 1;
+    out[i] = px[lo];
+    out[k + i] = py[lo];
+    out[2 * k + i] = pt[lo];
+}
+
+__global__ void k_fill(double* p, int64_t n, double v) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+}  // namespace mclb200

@@ -1,0 +1,203 @@
+// csrc/march.cuh -- the ray march on the reference's sample lattice, with skipping.
+//
+// Replaces ParticleFilter::cast_ray (src/particle_filter.cpp:611-650).  The reference visits
+// lattice samples k = 1..M at c_k = c_{k-1} + (cos a, sin a)*res (accumulated in double) and
+// returns at the first sample whose cell is out of bounds or occupied (> 50).  Here the
+// same lattice is walked in 9.23 fixed point relative to the ray's start cell; the skip map
+// (map_prep.h) says how many following samples cannot be hits, so most samples are never
+// touched.  The answer is the reference's step index r (hit at sample r+1) or M (no hit).
+//
+// Exactness.  The fixed-point position of sample k differs from the reference's computed
+// quotient by less than kEta cells (kEtaFix units): 2^-24 for the start, k*2^-24 for the
+// rounded direction, ~1e-10 for the reference's own accumulated rounding.  A sample is only
+// ever *classified* (hit / not hit) in a cell of code 0 or 1; if it then lies within kEta of
+// a cell edge and the cell across that edge has the other class, the reference's arithmetic
+// is replayed operation for operation in FP64 (replay_sample_is_hit) and decides.  Skips are
+// conservative by construction (map_prep.h), so every classification equals the reference's.
+//
+// All functions are MCL_HD so the same code is exercised on the CPU by tests/emu (test
+// harness only -- the product has no CPU path).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define MCL_HD __host__ __device__ __forceinline__
+#define MCL_D __device__ __forceinline__
+#else
+#define MCL_HD inline
+#define MCL_D inline
+#endif
+
+namespace mclb200 {
+
+constexpr int kFrac = 23;                         // fraction bits of the ray-local position
+constexpr uint32_t kOne = 1u << kFrac;
+constexpr uint32_t kFracMask = kOne - 1u;
+constexpr int kLocalOrigin = 256;                 // ray-local coordinate of the start cell
+constexpr uint32_t kEtaFix = 160;                 // > (M+2) * 2^-24 in 2^-23 units, M <= 254
+constexpr int kMaxRangePxSupported = 254;
+
+// Geometry of the reference grid, needed by the exact replay.
+struct RefGrid {
+    const int8_t* data;   // row-major int8 occupancy (device or host pointer)
+    int W, H;
+    double res, ox, oy;
+};
+
+// FP64 helpers that must not be contracted into FMAs: the reference is built without FMA
+// (CMakeLists.txt:5-11, no -march), see SURVEY F11.
+#if defined(__CUDA_ARCH__)
+MCL_D double nf_add(double a, double b) { return __dadd_rn(a, b); }
+MCL_D double nf_sub(double a, double b) { return __dsub_rn(a, b); }
+MCL_D double nf_mul(double a, double b) { return __dmul_rn(a, b); }
+MCL_D double nf_div(double a, double b) { return __ddiv_rn(a, b); }
+MCL_D int d2i_trunc(double a) { return __double2int_rz(a); }
+#else
+inline double nf_add(double a, double b) { volatile double r = a + b; return r; }
+inline double nf_sub(double a, double b) { volatile double r = a - b; return r; }
+inline double nf_mul(double a, double b) { volatile double r = a * b; return r; }
+inline double nf_div(double a, double b) { volatile double r = a / b; return r; }
+inline int d2i_trunc(double a) { return static_cast<int>(a); }
+#endif
+
+// The reference's arithmetic for sample k (1-based) of the ray from (x, y) with step
+// (dx, dy) = (cos a * res, sin a * res): :619-646.  O(k); only called on ambiguous samples.
+MCL_HD bool replay_sample_is_hit(const RefGrid& g, double x, double y, double dx, double dy, int k) {
+    double cx = x, cy = y;
+    for (int s = 0; s < k; ++s) {
+        cx = nf_add(cx, dx);
+        cy = nf_add(cy, dy);
+    }
+    const int gx = d2i_trunc(nf_div(nf_sub(cx, g.ox), g.res));
+    const int gy = d2i_trunc(nf_div(nf_sub(cy, g.oy), g.res));
+    if (gx < 0 || gx >= g.W || gy < 0 || gy >= g.H) return true;
+    return g.data[static_cast<int64_t>(gy) * g.W + gx] > 50;
+}
+
+// Fixed-point start of a ray inside P-cell coordinates.  q = (x - origin)/res + kPadL.
+struct RayStart {
+    uint32_t p0x, p0y;   // ray-local 9.23 position of the start (integer part == kLocalOrigin)
+    int bx, by;          // P-cell of local coordinate 0:  cell = b + (p >> kFrac)
+};
+
+MCL_HD RayStart make_ray_start(double qx, double qy, int fqx, int fqy) {
+    // fqx = floor(qx) as int; frac in [0,1)
+    RayStart s;
+    const double fx = qx - static_cast<double>(fqx);
+    const double fy = qy - static_cast<double>(fqy);
+    uint32_t ux = static_cast<uint32_t>(fx * static_cast<double>(kOne) + 0.5);
+    uint32_t uy = static_cast<uint32_t>(fy * static_cast<double>(kOne) + 0.5);
+    s.p0x = (static_cast<uint32_t>(kLocalOrigin) << kFrac) + ux;   // ux may equal kOne: carries into the cell
+    s.p0y = (static_cast<uint32_t>(kLocalOrigin) << kFrac) + uy;
+    s.bx = fqx - kLocalOrigin;
+    s.by = fqy - kLocalOrigin;
+    return s;
+}
+
+// Skip-map accessors.  get(cx, cy) returns the skip code of P-cell (cx, cy); both are
+// guaranteed in range by the callers' validity tests.
+struct GlobalV8 {
+    const uint8_t* v8;
+    int PW;
+    MCL_HD int get(int cx, int cy) const {
+#if defined(__CUDA_ARCH__)
+        return __ldg(v8 + static_cast<int64_t>(cy) * PW + cx);
+#else
+        return v8[static_cast<int64_t>(cy) * PW + cx];
+#endif
+    }
+};
+
+// 4-bit window in shared memory: P-cells [wx0, wx0+ww) x [wy0, wy0+wh), wx0 even.
+struct WindowV4 {
+    const uint8_t* w4;   // wh rows of pitch bytes
+    int wx0, wy0, pitch;
+    MCL_HD int get(int cx, int cy) const {
+        const int lx = cx - wx0, ly = cy - wy0;
+        const int b = w4[ly * pitch + (lx >> 1)];
+        return (b >> ((lx & 1) << 2)) & 15;
+    }
+};
+
+struct ReplayArgs {
+    double x, y;        // particle position (metres)
+    double ang;         // theta + (double)beam_angle, as the reference forms it (:533)
+};
+
+#if defined(__CUDA_ARCH__)
+MCL_D void sincos_ref(double a, double* s, double* c) { sincos(a, s, c); }
+#else
+}  // namespace mclb200
+#include <cmath>
+namespace mclb200 {
+inline void sincos_ref(double a, double* s, double* c) { *s = std::sin(a); *c = std::cos(a); }
+#endif
+
+
+// P-lattice coordinate of a world coordinate: the reference's quotient (:628-629) + kPadL.
+MCL_HD double p_coord(double c, double origin, double res, int pad_l) {
+    return nf_div(nf_sub(c, origin), res) + static_cast<double>(pad_l);
+}
+
+// Fixed-point direction of beam (ca, sa) = (cos, sin)(beam angle) for a particle with heading
+// (cth, sth): cos/sin(theta + alpha) by angle addition, rounded to 2^-23.
+MCL_HD void beam_direction_fixed(double cth, double sth, double ca, double sa, int* dxf, int* dyf) {
+    const double c = cth * ca - sth * sa;
+    const double s = sth * ca + cth * sa;
+#if defined(__CUDA_ARCH__)
+    *dxf = __double2int_rn(c * static_cast<double>(kOne));
+    *dyf = __double2int_rn(s * static_cast<double>(kOne));
+#else
+    *dxf = static_cast<int>(__builtin_lrint(c * static_cast<double>(kOne)));
+    *dyf = static_cast<int>(__builtin_lrint(s * static_cast<double>(kOne)));
+#endif
+}
+
+// Can a particle at P-coordinates (qx, qy) be marched at all?  Outside, its first sample is
+// already out of bounds for every beam (:632-636) and the step index is 0.
+MCL_HD bool p_inside(double qx, double qy, int PW, int PH) {
+    return (qx >= 2.0) && (qx < static_cast<double>(PW - 2)) && (qy >= 2.0) && (qy < static_cast<double>(PH - 2));
+}
+
+// March one ray.  (dxf, dyf) = round(cos a * 2^23), round(sin a * 2^23).  Returns the step
+// index r in [0, M] (M == no hit).  `replays` (nullable) counts exact replays for diagnostics.
+template <class Acc>
+MCL_HD int march_ray(const Acc& acc, const RayStart& st, int dxf, int dyf, int M, const RefGrid& g,
+                     const ReplayArgs& ra, int* replays) {
+    int k = 1;
+    while (k <= M) {
+        const uint32_t px = st.p0x + static_cast<uint32_t>(k * dxf);
+        const uint32_t py = st.p0y + static_cast<uint32_t>(k * dyf);
+        const int cx = st.bx + static_cast<int>(px >> kFrac);
+        const int cy = st.by + static_cast<int>(py >> kFrac);
+        const int v = acc.get(cx, cy);
+        if (v >= 2) {
+            k += v - 1;
+            continue;
+        }
+        // code 0 or 1: the class of this very sample matters
+        bool hit = (v == 0);
+        const uint32_t fx = px & kFracMask, fy = py & kFracMask;
+        const bool ux = ((fx + kEtaFix) & kFracMask) < 2u * kEtaFix;
+        const bool uy = ((fy + kEtaFix) & kFracMask) < 2u * kEtaFix;
+        if (ux || uy) {
+            const int nx = cx + (fx < kEtaFix ? -1 : 1);
+            const int ny = cy + (fy < kEtaFix ? -1 : 1);
+            bool differs = false;
+            if (ux) differs |= ((acc.get(nx, cy) == 0) != hit);
+            if (uy) differs |= ((acc.get(cx, ny) == 0) != hit);
+            if (ux && uy) differs |= ((acc.get(nx, ny) == 0) != hit);
+            if (differs) {
+                double sn, cs;
+                sincos_ref(ra.ang, &sn, &cs);
+                hit = replay_sample_is_hit(g, ra.x, ra.y, nf_mul(cs, g.res), nf_mul(sn, g.res), k);
+                if (replays) ++*replays;
+            }
+        }
+        if (hit) return k - 1;
+        k += 1;
+    }
+    return M;
+}
+
+}  // namespace mclb200

@@ -1,0 +1,955 @@
+// csrc/mcl_b200.cu -- C ABI (include/mcl_b200.h) over the sm_100a kernels in kernels.cuh.
+//
+// Host side of the drop-in boundary: owns the device buffers of one ParticleFilter (or a
+// batch of independent ones), uploads map / table / beams, and sequences the kernels of one
+// MCL update on a CUDA stream.  There is deliberately no CPU implementation behind these
+// entry points: without a CUDA device mcl_create fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mcl_b200.h"
+#include "kernels.cuh"
+
+using namespace mclb200;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(MCL_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+template <class T>
+cudaError_t dalloc(T** p, size_t n) {
+    return cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(n, 1) * sizeof(T));
+}
+
+constexpr size_t kWindowBudget = 200 * 1024;   // bytes of shared memory for the skip-map window
+
+}  // namespace
+
+struct mcl_ctx {
+    mcl_params prm{};
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
+    int F = 1;
+    int64_t N = 0;
+    int R = 0, M = 0;
+    bool have_map = false, have_beams = false;
+    double res = 0, ox = 0, oy = 0, oyaw = 0;
+    SkipMap skip;
+    std::vector<double> table;       // (M+1)^2 column-major, host copy
+    MapDev map{};
+    BeamDev beams{};
+    int8_t* d_grid = nullptr;
+    uint8_t* d_v8 = nullptr;
+    uint8_t* d_v4 = nullptr;
+    int32_t* d_free = nullptr;
+    double* d_tabT = nullptr;
+    int32_t* d_step2idx = nullptr;
+    // state
+    double* d_px[2] = {nullptr, nullptr};
+    double* d_py[2] = {nullptr, nullptr};
+    double* d_pt[2] = {nullptr, nullptr};
+    int cur = 0;
+    double* d_wraw = nullptr;
+    double* d_wn = nullptr;
+    double* d_cdf = nullptr;
+    int32_t* d_idx = nullptr;
+    uint8_t* d_steps = nullptr;
+    bool keep_ranges = false;
+    double* d_u = nullptr;
+    double* d_z = nullptr;
+    double* d_action = nullptr;
+    float* d_obs = nullptr;
+    double* d_slice = nullptr;
+    size_t slice_elems = 0;
+    // exact-sum workspaces
+    int T = 0, C = 0;
+    double* d_tile_sum = nullptr;
+    StepFn* d_chunk_fn = nullptr;
+    StepFn* d_chunk_pre = nullptr;
+    uint8_t* d_chunk_flag = nullptr;
+    int* d_tile_opq = nullptr;
+    int64_t* d_tile_elem = nullptr;
+    int* d_list_chunk = nullptr;
+    StepFn* d_list_fn = nullptr;
+    double* d_anchors = nullptr;
+    double* d_anchor_val = nullptr;
+    double* d_tile_start = nullptr;
+    double* d_S1 = nullptr;
+    double* d_S2 = nullptr;
+    double* d_scratch_total = nullptr;
+    // pose
+    int norm_blocks = 1;
+    double* d_partial = nullptr;
+    double* d_pose = nullptr;
+    double* d_centre = nullptr;
+    int64_t* d_replays = nullptr;
+    // pinned staging for the host-facing update
+    double* h_action = nullptr;
+    float* h_obs = nullptr;
+    double* h_pose = nullptr;
+    uint64_t update_no = 0, init_no = 0;
+    int64_t launches = 0;
+    bool profiling = false;
+    cudaEvent_t ev[6] = {};
+    mcl_stage_ms last_ms{};
+    bool cdf_valid = false;
+};
+
+namespace {
+
+ExactArgs exact_args(mcl_ctx* c, const double* src, const double* div, double* total, double* out, int force_one) {
+    ExactArgs a{};
+    a.src = src;
+    a.div = div;
+    a.N = c->N;
+    a.T = c->T;
+    a.C = c->C;
+    a.tile_sum = c->d_tile_sum;
+    a.chunk_fn = c->d_chunk_fn;
+    a.chunk_pre = c->d_chunk_pre;
+    a.chunk_flag = c->d_chunk_flag;
+    a.tile_opq = c->d_tile_opq;
+    a.tile_elem = c->d_tile_elem;
+    a.list_chunk = c->d_list_chunk;
+    a.list_fn = c->d_list_fn;
+    a.anchors = c->d_anchors;
+    a.anchor_val = c->d_anchor_val;
+    a.tile_start = c->d_tile_start;
+    a.total = total;
+    a.out = out;
+    a.force_last_one = force_one;
+    return a;
+}
+
+// sequential-order sum (and optionally prefix sums) of src[k] (/ div), see exact_sum.cuh
+int run_exact(mcl_ctx* c, const double* src, const double* div, double* total, double* out, int force_one,
+              bool need_tile_sums) {
+    ExactArgs a = exact_args(c, src, div, total, out, force_one);
+    const dim3 gt(c->T, c->F);
+    if (need_tile_sums) {
+        k_tile_sums<<<gt, kTileChunks, 0, c->stream>>>(a);
+        c->launches++;
+    }
+    k_exact_chunks<<<gt, kTileChunks, 0, c->stream>>>(a);
+    k_exact_walk<<<dim3(1, c->F), kWalkThreads, 0, c->stream>>>(a);
+    c->launches += 2;
+    if (out) {
+        k_exact_emit<<<gt, kTileChunks, 0, c->stream>>>(a);
+        c->launches++;
+    }
+    CK(cudaGetLastError());
+    return MCL_OK;
+}
+
+// the reference's conversion of a returned range back to a table index (:556-561, :571-574)
+void build_step2idx(const mcl_ctx* c, std::vector<int32_t>& out) {
+    const int M = c->M;
+    out.resize(M + 1);
+    for (int r = 0; r <= M; ++r) {
+        const double rd = (r >= M) ? c->prm.max_range : static_cast<double>(r) * c->res;
+        const float range_f = static_cast<float>(rd);                 // cast_ray returns float
+        float px = static_cast<float>(static_cast<double>(range_f) / c->res);   // ranges_px[i] = ranges_[i] / res
+        if (px > static_cast<float>(M)) px = static_cast<float>(M);
+        int idx = static_cast<int>(std::round(px));
+        out[r] = std::max(0, std::min(idx, M));
+    }
+}
+
+// precompute_sensor_model (:233-292), column-major (r + d*(M+1)).  Host code is compiled
+// with -ffp-contract=off so the expression below rounds like the reference's build.
+void build_sensor_table(const mcl_ctx* c, std::vector<double>& tab) {
+    const int M = c->M, tw = M + 1;
+    const double zs = c->prm.z_short, zm = c->prm.z_max, zr = c->prm.z_rand, zh = c->prm.z_hit, sg = c->prm.sigma_hit;
+    tab.assign(static_cast<size_t>(tw) * tw, 0.0);
+    for (int d = 0; d < tw; ++d) {
+        double* col = &tab[static_cast<size_t>(d) * tw];
+        double norm = 0.0;
+        for (int r = 0; r < tw; ++r) {
+            const double z = static_cast<double>(r - d);
+            double prob = 0.0;
+            prob += zh * std::exp(-(z * z) / (2.0 * sg * sg)) / (sg * std::sqrt(2.0 * M_PI));
+            if (r < d) prob += 2.0 * zs * (d - r) / static_cast<double>(d);
+            if (r == M) prob += zm;
+            if (r < M) prob += zr * 1.0 / static_cast<double>(M);
+            norm += prob;
+            col[r] = prob;
+        }
+        if (norm > 0)
+            for (int r = 0; r < tw; ++r) col[r] /= norm;
+    }
+}
+
+int upload_table(mcl_ctx* c) {
+    const int tw = c->M + 1;
+    std::vector<double> tabT(static_cast<size_t>(tw) * tw);
+    for (int d = 0; d < tw; ++d)
+        for (int r = 0; r < tw; ++r) tabT[static_cast<size_t>(r) * tw + d] = c->table[static_cast<size_t>(d) * tw + r];
+    // table(obs=r, range=d) lives at r + d*tw; tabT[obs*tw + range]
+    if (c->d_tabT) cudaFree(c->d_tabT);
+    c->d_tabT = nullptr;
+    CK(dalloc(&c->d_tabT, tabT.size()));
+    CK(cudaMemcpy(c->d_tabT, tabT.data(), tabT.size() * sizeof(double), cudaMemcpyHostToDevice));
+    return MCL_OK;
+}
+
+int ensure_slice(mcl_ctx* c) {
+    if (!c->have_map || !c->have_beams) return MCL_OK;
+    const size_t need = static_cast<size_t>(c->F) * c->R * (c->M + 1);
+    if (need > c->slice_elems) {
+        if (c->d_slice) cudaFree(c->d_slice);
+        c->d_slice = nullptr;
+        CK(dalloc(&c->d_slice, need));
+        c->slice_elems = need;
+    }
+    if (!c->d_obs) CK(dalloc(&c->d_obs, static_cast<size_t>(c->F) * kMaxBeams));
+    return MCL_OK;
+}
+
+int check_filter(const mcl_ctx* c, int filter, bool allow_all) {
+    if (!c) return fail(MCL_ERR_INVALID, "null context");
+    if (filter == -1 && allow_all) return MCL_OK;
+    if (filter < 0 || filter >= c->F) return fail(MCL_ERR_INVALID, "filter %d out of range [0,%d)", filter, c->F);
+    return MCL_OK;
+}
+
+int launch_pose(mcl_ctx* c, const double* w, const double* total, double* wn_out, int buf) {
+    NormArgs na{};
+    na.N = c->N;
+    na.w_raw = w;
+    na.total = total;
+    na.wn = wn_out;
+    na.px = c->d_px[buf];
+    na.py = c->d_py[buf];
+    na.pt = c->d_pt[buf];
+    na.partial = c->d_partial;
+    na.nblk = c->norm_blocks;
+    k_normalize_pose<<<dim3(c->norm_blocks, c->F), kNormThreads, 0, c->stream>>>(na);
+    k_pose_final<<<c->F, 256, 0, c->stream>>>(c->d_partial, c->norm_blocks, c->d_pose);
+    c->launches += 2;
+    CK(cudaGetLastError());
+    return MCL_OK;
+}
+
+// one MCL() + expected_pose() for every filter, inputs already in d_action / d_obs
+int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, const double* u_dev, const double* z_dev) {
+    if (!c->have_map) return fail(MCL_ERR_NO_MAP, "mcl_set_map has not been called");
+    if (!c->have_beams) return fail(MCL_ERR_INVALID, "mcl_set_beam_angles has not been called");
+    const int src = c->cur, dst = c->cur ^ 1;
+    cudaStream_t s = c->stream;
+    if (c->profiling) CK(cudaEventRecord(c->ev[0], s));
+
+    CK(cudaMemsetAsync(c->d_centre, 0, sizeof(double) * 2 * c->F, s));
+    ObsArgs oa{};
+    oa.obs = obs_dev;
+    oa.tabT = c->d_tabT;
+    oa.step2idx = c->d_step2idx;
+    oa.slice = c->d_slice;
+    oa.R = c->R;
+    oa.M = c->M;
+    oa.res = c->res;
+    k_prepare_obs<<<dim3(c->R, c->F), 256, 0, s>>>(oa);
+    c->launches++;
+
+    // discrete_distribution(weights_): sum, normalise, partial_sum (random.tcc:2657-2678)
+    int rc = run_exact(c, c->d_wn, nullptr, c->d_S2, nullptr, 0, true);
+    if (rc) return rc;
+    rc = run_exact(c, c->d_wn, c->d_S2, c->d_scratch_total, c->d_cdf, 1, false);
+    if (rc) return rc;
+    c->cdf_valid = true;
+    if (c->profiling) CK(cudaEventRecord(c->ev[1], s));
+
+    MotionArgs ma{};
+    ma.N = c->N;
+    ma.cdf = c->d_cdf;
+    ma.sx = c->d_px[src];
+    ma.sy = c->d_py[src];
+    ma.st = c->d_pt[src];
+    ma.dx = c->d_px[dst];
+    ma.dy = c->d_py[dst];
+    ma.dt = c->d_pt[dst];
+    ma.idx_out = c->d_idx;
+    ma.u = u_dev;
+    ma.z = z_dev;
+    ma.action = action_dev;
+    ma.disp_x = c->prm.motion_dispersion_x;
+    ma.disp_y = c->prm.motion_dispersion_y;
+    ma.disp_t = c->prm.motion_dispersion_theta;
+    ma.seed = c->prm.seed;
+    ma.update_no = c->update_no;
+    ma.centre = c->d_centre;
+    const int mblocks = static_cast<int>((c->N + kMotionThreads - 1) / kMotionThreads);
+    k_resample_motion<<<dim3(mblocks, c->F), kMotionThreads, 0, s>>>(ma);
+    c->launches++;
+    if (c->profiling) CK(cudaEventRecord(c->ev[2], s));
+
+    RayArgs ra{};
+    ra.map = c->map;
+    ra.beams = c->beams;
+    ra.N = c->N;
+    ra.px = c->d_px[dst];
+    ra.py = c->d_py[dst];
+    ra.pt = c->d_pt[dst];
+    ra.slice = c->d_slice;
+    ra.w_raw = c->d_wraw;
+    ra.steps = c->keep_ranges ? c->d_steps : nullptr;
+    ra.centre = c->d_centre;
+    ra.inv_squash = 1.0 / c->prm.squash_factor;
+    ra.replay_count = c->d_replays;
+    const size_t smem = static_cast<size_t>(c->map.ww / 2) * c->map.wh;
+    // persistent blocks: one per SM when the window fills shared memory, a few otherwise
+    const int per_sm = smem > 100 * 1024 ? 1 : (smem > 48 * 1024 ? 2 : 4);
+    const int budget = std::max(1, (c->num_sms * per_sm) / std::min(c->F, c->num_sms * per_sm));
+    const int rblocks = static_cast<int>(std::min<int64_t>((c->N + kRayThreads - 1) / kRayThreads, budget));
+    k_raycast_weight<<<dim3(rblocks, c->F), kRayThreads, smem, s>>>(ra);
+    c->launches++;
+    if (c->profiling) CK(cudaEventRecord(c->ev[3], s));
+
+    // sum_weights = accumulate(weights_) ; w /= sum (:679-686) ; expected_pose (:696-716)
+    rc = run_exact(c, c->d_wraw, nullptr, c->d_S1, nullptr, 0, true);
+    if (rc) return rc;
+    rc = launch_pose(c, c->d_wraw, c->d_S1, c->d_wn, dst);
+    if (rc) return rc;
+    if (c->profiling) CK(cudaEventRecord(c->ev[4], s));
+    CK(cudaGetLastError());
+    c->cur = dst;
+    c->update_no++;
+    return MCL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void mcl_default_params(mcl_params* p) {
+    if (!p) return;
+    std::memset(p, 0, sizeof *p);
+    p->max_particles = 2000;
+    p->max_viz_particles = 60;
+    p->angle_step = 18;
+    p->squash_factor = 2.2;
+    p->max_range = 12.0;
+    p->z_short = 0.01;
+    p->z_max = 0.07;
+    p->z_rand = 0.12;
+    p->z_hit = 0.80;
+    p->sigma_hit = 8.0;
+    p->motion_dispersion_x = 0.05;
+    p->motion_dispersion_y = 0.025;
+    p->motion_dispersion_theta = 0.25;
+    p->seed = 0x9E3779B97F4A7C15ull;
+    p->num_filters = 1;
+}
+
+const char* mcl_last_error(void) { return g_err.c_str(); }
+
+const char* mcl_status_str(int s) {
+    switch (s) {
+        case MCL_OK: return "ok";
+        case MCL_ERR_INVALID: return "invalid argument";
+        case MCL_ERR_NO_DEVICE: return "no CUDA device (this library has no CPU fallback)";
+        case MCL_ERR_CUDA: return "CUDA error";
+        case MCL_ERR_NO_MAP: return "map not set";
+        case MCL_ERR_UNSUPPORTED: return "unsupported configuration";
+        case MCL_ERR_NO_FREE_SPACE: return "no free space in map";
+        default: return "unknown";
+    }
+}
+
+int mcl_abi_version(void) { return MCL_B200_ABI_VERSION; }
+
+int mcl_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int mcl_create(const mcl_params* p, int device, mcl_ctx** out) {
+    if (!p || !out) return fail(MCL_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (p->max_particles < 1) return fail(MCL_ERR_INVALID, "max_particles must be >= 1");
+    if (p->num_filters < 1) return fail(MCL_ERR_INVALID, "num_filters must be >= 1");
+    if (!(p->squash_factor > 0) || !(p->max_range > 0)) return fail(MCL_ERR_INVALID, "squash_factor / max_range must be positive");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(MCL_ERR_NO_DEVICE, "no CUDA device visible; the MCL update has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return fail(MCL_ERR_INVALID, "device %d not in [0,%d)", device, ndev);
+    CK(cudaSetDevice(device));
+    auto* c = new mcl_ctx();
+    c->prm = *p;
+    c->device = device;
+    c->F = p->num_filters;
+    c->N = p->max_particles;
+    cudaDeviceProp prop{};
+    CK(cudaGetDeviceProperties(&prop, device));
+    c->num_sms = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    for (auto& e : c->ev) CK(cudaEventCreate(&e));
+
+    const size_t FN = static_cast<size_t>(c->F) * c->N;
+    for (int b = 0; b < 2; ++b) {
+        CK(dalloc(&c->d_px[b], FN));
+        CK(dalloc(&c->d_py[b], FN));
+        CK(dalloc(&c->d_pt[b], FN));
+        CK(cudaMemset(c->d_px[b], 0, FN * sizeof(double)));   // particles_ = Zero (:106)
+        CK(cudaMemset(c->d_py[b], 0, FN * sizeof(double)));
+        CK(cudaMemset(c->d_pt[b], 0, FN * sizeof(double)));
+    }
+    CK(dalloc(&c->d_wraw, FN));
+    CK(dalloc(&c->d_wn, FN));
+    CK(dalloc(&c->d_cdf, FN));
+    CK(dalloc(&c->d_idx, FN));
+    CK(cudaMemset(c->d_idx, 0, FN * sizeof(int32_t)));
+    {   // weights_ = 1/N (:107)
+        const int64_t n = static_cast<int64_t>(FN);
+        k_fill<<<static_cast<unsigned>((n + 255) / 256), 256>>>(c->d_wn, n, 1.0 / static_cast<double>(c->N));
+        k_fill<<<static_cast<unsigned>((n + 255) / 256), 256>>>(c->d_wraw, n, 1.0 / static_cast<double>(c->N));
+        c->launches += 2;
+    }
+    c->T = static_cast<int>((c->N + kTile - 1) / kTile);
+    c->C = c->T * kTileChunks;
+    const size_t FT = static_cast<size_t>(c->F) * c->T, FC = static_cast<size_t>(c->F) * c->C;
+    CK(dalloc(&c->d_tile_sum, FT));
+    CK(dalloc(&c->d_chunk_fn, FC));
+    CK(dalloc(&c->d_chunk_pre, FC));
+    CK(dalloc(&c->d_chunk_flag, FC));
+    CK(dalloc(&c->d_tile_opq, FT));
+    CK(dalloc(&c->d_tile_elem, FT * 3));
+    CK(dalloc(&c->d_list_chunk, FC));
+    CK(dalloc(&c->d_list_fn, FC));
+    CK(dalloc(&c->d_anchors, FC));
+    CK(dalloc(&c->d_anchor_val, FC));
+    CK(dalloc(&c->d_tile_start, FT));
+    CK(dalloc(&c->d_S1, static_cast<size_t>(c->F)));
+    CK(dalloc(&c->d_S2, static_cast<size_t>(c->F)));
+    CK(dalloc(&c->d_scratch_total, static_cast<size_t>(c->F)));
+    c->norm_blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((c->N + kNormThreads * 4 - 1) / (kNormThreads * 4),
+                                                                               std::max(1, 4 * c->num_sms / std::min(c->F, 4 * c->num_sms)))));
+    CK(dalloc(&c->d_partial, static_cast<size_t>(c->F) * c->norm_blocks * 4));
+    CK(dalloc(&c->d_pose, static_cast<size_t>(c->F) * 3));
+    CK(cudaMemset(c->d_pose, 0, sizeof(double) * 3 * c->F));
+    CK(dalloc(&c->d_centre, static_cast<size_t>(c->F) * 2));
+    CK(dalloc(&c->d_replays, size_t{1}));
+    CK(cudaMemset(c->d_replays, 0, sizeof(int64_t)));
+    CK(dalloc(&c->d_action, static_cast<size_t>(c->F) * 3));
+    CK(cudaMallocHost(reinterpret_cast<void**>(&c->h_action), sizeof(double) * 3 * c->F));
+    CK(cudaMallocHost(reinterpret_cast<void**>(&c->h_obs), sizeof(float) * kMaxBeams * c->F));
+    CK(cudaMallocHost(reinterpret_cast<void**>(&c->h_pose), sizeof(double) * 3 * c->F));
+    CK(cudaFuncSetAttribute(k_raycast_weight, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kWindowBudget)));
+    CK(cudaDeviceSynchronize());
+    *out = c;
+    return MCL_OK;
+}
+
+int mcl_destroy(mcl_ctx* c) {
+    if (!c) return MCL_OK;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    void* ptrs[] = {c->d_grid, c->d_v8, c->d_v4, c->d_free, c->d_tabT, c->d_step2idx, c->d_px[0], c->d_px[1], c->d_py[0],
+                    c->d_py[1], c->d_pt[0], c->d_pt[1], c->d_wraw, c->d_wn, c->d_cdf, c->d_idx, c->d_steps, c->d_u, c->d_z,
+                    c->d_action, c->d_obs, c->d_slice, c->d_tile_sum, c->d_chunk_fn, c->d_chunk_pre, c->d_chunk_flag,
+                    c->d_tile_opq, c->d_tile_elem, c->d_list_chunk, c->d_list_fn, c->d_anchors, c->d_anchor_val,
+                    c->d_tile_start, c->d_S1, c->d_S2, c->d_scratch_total, c->d_partial, c->d_pose, c->d_centre, c->d_replays};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    if (c->h_action) cudaFreeHost(c->h_action);
+    if (c->h_obs) cudaFreeHost(c->h_obs);
+    if (c->h_pose) cudaFreeHost(c->h_pose);
+    for (auto& e : c->ev)
+        if (e) cudaEventDestroy(e);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+    return MCL_OK;
+}
+
+int mcl_set_map(mcl_ctx* c, const int8_t* data, int width, int height, float resolution, double ox, double oy,
+                double oyaw) {
+    if (!c || !data) return fail(MCL_ERR_INVALID, "null argument");
+    if (width <= 0 || height <= 0) return fail(MCL_ERR_INVALID, "bad grid size %dx%d", width, height);
+    CK(cudaSetDevice(c->device));
+    const double res = static_cast<double>(resolution);   // map_resolution_ = info.resolution (:191)
+    if (!(res > 0.0)) return fail(MCL_ERR_INVALID, "Invalid map resolution: %.6f", res);   // :236-240
+    const int M = static_cast<int>(c->prm.max_range / res);   // :195
+    if (M < 1 || M > kMaxRangePxSupported)
+        return fail(MCL_ERR_UNSUPPORTED, "MAX_RANGE_PX = %d outside [1,%d] (max_range %.3f / resolution %.6f)", M,
+                    kMaxRangePxSupported, c->prm.max_range, res);
+    if (!build_skip_map(data, width, height, c->skip)) return fail(MCL_ERR_UNSUPPORTED, "grid %dx%d too large", width, height);
+    CK(cudaStreamSynchronize(c->stream));
+    c->res = res;
+    c->ox = ox;
+    c->oy = oy;
+    c->oyaw = oyaw;   // read by the reference (:192-193) but never used by the march (:628-629)
+    c->M = M;
+    for (void* p : {static_cast<void*>(c->d_grid), static_cast<void*>(c->d_v8), static_cast<void*>(c->d_v4),
+                    static_cast<void*>(c->d_free), static_cast<void*>(c->d_step2idx)})
+        if (p) cudaFree(p);
+    c->d_grid = nullptr;
+    c->d_v8 = c->d_v4 = nullptr;
+    c->d_free = nullptr;
+    c->d_step2idx = nullptr;
+    const size_t cells = static_cast<size_t>(width) * height;
+    CK(dalloc(&c->d_grid, cells));
+    CK(cudaMemcpy(c->d_grid, data, cells, cudaMemcpyHostToDevice));
+    CK(dalloc(&c->d_v8, c->skip.v8.size()));
+    CK(cudaMemcpy(c->d_v8, c->skip.v8.data(), c->skip.v8.size(), cudaMemcpyHostToDevice));
+    CK(dalloc(&c->d_v4, c->skip.v4.size()));
+    CK(cudaMemcpy(c->d_v4, c->skip.v4.data(), c->skip.v4.size(), cudaMemcpyHostToDevice));
+    CK(dalloc(&c->d_free, c->skip.free_cells.size()));
+    if (!c->skip.free_cells.empty())
+        CK(cudaMemcpy(c->d_free, c->skip.free_cells.data(), c->skip.free_cells.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    std::vector<int32_t> s2i;
+    build_step2idx(c, s2i);
+    CK(dalloc(&c->d_step2idx, s2i.size()));
+    CK(cudaMemcpy(c->d_step2idx, s2i.data(), s2i.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+
+    MapDev& m = c->map;
+    m.grid = c->d_grid;
+    m.v8 = c->d_v8;
+    m.v4 = c->d_v4;
+    m.W = width;
+    m.H = height;
+    m.PW = c->skip.PW;
+    m.PH = c->skip.PH;
+    m.res = res;
+    m.ox = ox;
+    m.oy = oy;
+    m.M = M;
+    // shared-memory window: the whole P-grid if it fits, else the largest box within budget
+    const size_t whole = static_cast<size_t>(m.PW / 2) * m.PH;
+    if (whole <= kWindowBudget) {
+        m.ww = m.PW;
+        m.wh = m.PH;
+    } else {
+        int side = static_cast<int>(std::sqrt(2.0 * kWindowBudget));
+        side &= ~31;
+        m.ww = std::min(m.PW, side);
+        m.wh = std::min(m.PH, static_cast<int>(2 * kWindowBudget / m.ww));
+        if (m.wh < m.PH && m.ww == side) m.wh = std::min(m.wh, side);
+        if (m.wh == m.PH) m.ww = std::min(m.PW, static_cast<int>(2 * kWindowBudget / m.wh) & ~31);
+        // a window narrower than two ray lengths can hold no particle safely
+        if (m.ww < 2 * (M + 2) + 32 && m.ww < m.PW) m.ww = m.wh = 0;
+        if (m.ww && m.wh < 2 * (M + 2) + 32 && m.wh < m.PH) m.ww = m.wh = 0;
+    }
+    c->have_map = true;
+    build_sensor_table(c, c->table);
+    int rc = upload_table(c);
+    if (rc) return rc;
+    return ensure_slice(c);
+}
+
+int mcl_max_range_px(const mcl_ctx* c) { return c ? c->M : 0; }
+
+int mcl_get_sensor_table(const mcl_ctx* c, double* out) {
+    if (!c || !out) return fail(MCL_ERR_INVALID, "null argument");
+    if (!c->have_map) return fail(MCL_ERR_NO_MAP, "map not set");
+    std::memcpy(out, c->table.data(), c->table.size() * sizeof(double));
+    return MCL_OK;
+}
+
+int mcl_set_sensor_table(mcl_ctx* c, const double* tab, int tw) {
+    if (!c || !tab) return fail(MCL_ERR_INVALID, "null argument");
+    if (!c->have_map) return fail(MCL_ERR_NO_MAP, "map not set");
+    if (tw != c->M + 1) return fail(MCL_ERR_INVALID, "table width %d != MAX_RANGE_PX+1 = %d", tw, c->M + 1);
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    c->table.assign(tab, tab + static_cast<size_t>(tw) * tw);
+    return upload_table(c);
+}
+
+int mcl_set_beam_angles(mcl_ctx* c, const float* angles, int n) {
+    if (!c || !angles) return fail(MCL_ERR_INVALID, "null argument");
+    if (n < 1 || n > kMaxBeams) return fail(MCL_ERR_UNSUPPORTED, "%d beams outside [1,%d]", n, kMaxBeams);
+    CK(cudaSetDevice(c->device));
+    c->R = n;
+    c->beams.R = n;
+    for (int j = 0; j < n; ++j) {
+        c->beams.angle[j] = angles[j];
+        c->beams.cosa[j] = std::cos(static_cast<double>(angles[j]));
+        c->beams.sina[j] = std::sin(static_cast<double>(angles[j]));
+    }
+    c->have_beams = true;
+    if (c->d_steps) {
+        cudaFree(c->d_steps);
+        c->d_steps = nullptr;
+    }
+    if (c->keep_ranges) CK(dalloc(&c->d_steps, static_cast<size_t>(c->F) * c->N * c->R));
+    return ensure_slice(c);
+}
+
+int mcl_num_free_cells(const mcl_ctx* c) { return c ? static_cast<int>(c->skip.free_cells.size()) : 0; }
+
+int mcl_init_pose(mcl_ctx* c, int filter, const double pose[3], const double* normals) {
+    int rc = check_filter(c, filter, true);
+    if (rc) return rc;
+    if (!pose) return fail(MCL_ERR_INVALID, "null pose");
+    CK(cudaSetDevice(c->device));
+    const int f0 = filter < 0 ? 0 : filter, nf = filter < 0 ? c->F : 1;
+    double* d_pose = nullptr;
+    double* d_norm = nullptr;
+    std::vector<double> hp(static_cast<size_t>(3) * nf);
+    for (int k = 0; k < nf; ++k) std::memcpy(&hp[3 * k], pose, 3 * sizeof(double));
+    CK(dalloc(&d_pose, hp.size()));
+    CK(cudaMemcpyAsync(d_pose, hp.data(), hp.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (normals) {
+        CK(dalloc(&d_norm, static_cast<size_t>(3) * c->N * nf));
+        for (int k = 0; k < nf; ++k)   // the same injected stream for every addressed filter
+            CK(cudaMemcpyAsync(d_norm + static_cast<size_t>(3) * c->N * k, normals, sizeof(double) * 3 * c->N,
+                               cudaMemcpyHostToDevice, c->stream));
+    }
+    InitArgs a{};
+    a.N = c->N;
+    a.px = c->d_px[c->cur];
+    a.py = c->d_py[c->cur];
+    a.pt = c->d_pt[c->cur];
+    a.wn = c->d_wn;
+    a.pose = d_pose;
+    a.normals = d_norm;
+    a.seed = c->prm.seed;
+    a.stream_no = ++c->init_no;
+    a.filter0 = f0;
+    k_init_pose<<<dim3(static_cast<unsigned>((c->N + 255) / 256), nf), 256, 0, c->stream>>>(a);
+    c->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFree(d_pose);
+    if (d_norm) cudaFree(d_norm);
+    c->cdf_valid = false;
+    return MCL_OK;
+}
+
+int mcl_init_global(mcl_ctx* c, int filter, const int32_t* cell, const double* theta) {
+    int rc = check_filter(c, filter, true);
+    if (rc) return rc;
+    if (!c->have_map) return fail(MCL_ERR_NO_MAP, "map not set");   // :403-404
+    if (c->skip.free_cells.empty()) return fail(MCL_ERR_NO_FREE_SPACE, "No free space found in map!");
+    if ((cell == nullptr) != (theta == nullptr)) return fail(MCL_ERR_INVALID, "cell_ordinal and theta must both be given or both NULL");
+    CK(cudaSetDevice(c->device));
+    const int f0 = filter < 0 ? 0 : filter, nf = filter < 0 ? c->F : 1;
+    int32_t* d_cell = nullptr;
+    double* d_theta = nullptr;
+    if (cell) {
+        CK(dalloc(&d_cell, static_cast<size_t>(c->N) * nf));
+        CK(dalloc(&d_theta, static_cast<size_t>(c->N) * nf));
+        for (int k = 0; k < nf; ++k) {
+            CK(cudaMemcpyAsync(d_cell + static_cast<size_t>(c->N) * k, cell, sizeof(int32_t) * c->N, cudaMemcpyHostToDevice, c->stream));
+            CK(cudaMemcpyAsync(d_theta + static_cast<size_t>(c->N) * k, theta, sizeof(double) * c->N, cudaMemcpyHostToDevice, c->stream));
+        }
+    }
+    InitArgs a{};
+    a.N = c->N;
+    a.px = c->d_px[c->cur];
+    a.py = c->d_py[c->cur];
+    a.pt = c->d_pt[c->cur];
+    a.wn = c->d_wn;
+    a.cell = d_cell;
+    a.theta = d_theta;
+    a.free_cells = c->d_free;
+    a.n_free = static_cast<int>(c->skip.free_cells.size());
+    a.W = c->map.W;
+    a.res = c->res;
+    a.ox = c->ox;
+    a.oy = c->oy;
+    a.seed = c->prm.seed;
+    a.stream_no = ++c->init_no;
+    a.filter0 = f0;
+    k_init_global<<<dim3(static_cast<unsigned>((c->N + 255) / 256), nf), 256, 0, c->stream>>>(a);
+    c->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+    if (d_cell) cudaFree(d_cell);
+    if (d_theta) cudaFree(d_theta);
+    c->cdf_valid = false;
+    return MCL_OK;
+}
+
+int mcl_set_particles(mcl_ctx* c, int filter, const double* P, const double* w) {
+    int rc = check_filter(c, filter, false);
+    if (rc) return rc;
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    const size_t N = static_cast<size_t>(c->N), fo = N * filter;
+    if (P) {
+        CK(cudaMemcpy(c->d_px[c->cur] + fo, P, N * sizeof(double), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->d_py[c->cur] + fo, P + N, N * sizeof(double), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->d_pt[c->cur] + fo, P + 2 * N, N * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    if (w) CK(cudaMemcpy(c->d_wn + fo, w, N * sizeof(double), cudaMemcpyHostToDevice));
+    c->cdf_valid = false;
+    return MCL_OK;
+}
+
+int mcl_get_particles(mcl_ctx* c, int filter, double* P) {
+    int rc = check_filter(c, filter, false);
+    if (rc) return rc;
+    if (!P) return fail(MCL_ERR_INVALID, "null output");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    const size_t N = static_cast<size_t>(c->N), fo = N * filter;
+    CK(cudaMemcpy(P, c->d_px[c->cur] + fo, N * sizeof(double), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(P + N, c->d_py[c->cur] + fo, N * sizeof(double), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(P + 2 * N, c->d_pt[c->cur] + fo, N * sizeof(double), cudaMemcpyDeviceToHost));
+    return MCL_OK;
+}
+
+static int get_array(mcl_ctx* c, int filter, const void* dev, size_t elem, size_t per_filter, void* out) {
+    int rc = check_filter(c, filter, false);
+    if (rc) return rc;
+    if (!out) return fail(MCL_ERR_INVALID, "null output");
+    if (!dev) return fail(MCL_ERR_INVALID, "array not available (option disabled or no update yet)");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(out, static_cast<const char*>(dev) + elem * per_filter * filter, elem * per_filter, cudaMemcpyDeviceToHost));
+    return MCL_OK;
+}
+
+int mcl_get_weights(mcl_ctx* c, int filter, double* w) {
+    return get_array(c, filter, c ? c->d_wn : nullptr, sizeof(double), c ? c->N : 0, w);
+}
+int mcl_get_raw_weights(mcl_ctx* c, int filter, double* w) {
+    return get_array(c, filter, c ? c->d_wraw : nullptr, sizeof(double), c ? c->N : 0, w);
+}
+int mcl_get_cdf(mcl_ctx* c, int filter, double* out) {
+    if (c && !c->cdf_valid) return fail(MCL_ERR_INVALID, "no CDF yet: call mcl_update first");
+    return get_array(c, filter, c ? c->d_cdf : nullptr, sizeof(double), c ? c->N : 0, out);
+}
+int mcl_get_resample_indices(mcl_ctx* c, int filter, int32_t* out) {
+    return get_array(c, filter, c ? c->d_idx : nullptr, sizeof(int32_t), c ? c->N : 0, out);
+}
+int mcl_get_range_steps(mcl_ctx* c, int filter, uint8_t* out) {
+    return get_array(c, filter, c ? c->d_steps : nullptr, 1, c ? static_cast<size_t>(c->N) * c->R : 0, out);
+}
+
+int mcl_get_ranges(mcl_ctx* c, int filter, float* out) {
+    int rc = check_filter(c, filter, false);
+    if (rc) return rc;
+    if (!out) return fail(MCL_ERR_INVALID, "null output");
+    if (!c->d_steps) return fail(MCL_ERR_INVALID, "ranges are not kept: call mcl_set_keep_ranges(ctx, 1) before the update");
+    CK(cudaSetDevice(c->device));
+    const int64_t n = c->N * c->R;
+    float* d_out = nullptr;
+    CK(dalloc(&d_out, static_cast<size_t>(n)));
+    k_steps_to_ranges<<<static_cast<unsigned>((n + 255) / 256), 256, 0, c->stream>>>(c->d_steps + n * filter, n, c->M, c->res,
+                                                                                       c->prm.max_range, d_out);
+    c->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(out, d_out, sizeof(float) * n, cudaMemcpyDeviceToHost));
+    cudaFree(d_out);
+    return MCL_OK;
+}
+
+int mcl_update_dev(mcl_ctx* c, const double* action_dev, const float* obs_dev, int num_beams) {
+    if (!c || !action_dev || !obs_dev) return fail(MCL_ERR_INVALID, "null argument");
+    if (num_beams != c->R) return fail(MCL_ERR_INVALID, "num_beams %d != configured %d", num_beams, c->R);
+    CK(cudaSetDevice(c->device));
+    return update_device(c, action_dev, obs_dev, nullptr, nullptr);
+}
+
+int mcl_read_pose(mcl_ctx* c, double* pose_out) {
+    if (!c || !pose_out) return fail(MCL_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(c->h_pose, c->d_pose, sizeof(double) * 3 * c->F, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    std::memcpy(pose_out, c->h_pose, sizeof(double) * 3 * c->F);
+    return MCL_OK;
+}
+
+int mcl_synchronize(mcl_ctx* c) {
+    if (!c) return fail(MCL_ERR_INVALID, "null context");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    return MCL_OK;
+}
+
+int mcl_update(mcl_ctx* c, const double* action, const float* obs, int num_beams, const mcl_noise* noise, double* pose_out) {
+    if (!c || !action || !obs) return fail(MCL_ERR_INVALID, "null argument");
+    if (!c->have_map) return fail(MCL_ERR_NO_MAP, "mcl_set_map has not been called");
+    if (!c->have_beams) return fail(MCL_ERR_INVALID, "mcl_set_beam_angles has not been called");
+    if (num_beams != c->R) return fail(MCL_ERR_INVALID, "num_beams %d != configured %d", num_beams, c->R);
+    CK(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    std::memcpy(c->h_action, action, sizeof(double) * 3 * c->F);
+    std::memcpy(c->h_obs, obs, sizeof(float) * c->R * c->F);
+    CK(cudaMemcpyAsync(c->d_action, c->h_action, sizeof(double) * 3 * c->F, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(c->d_obs, c->h_obs, sizeof(float) * c->R * c->F, cudaMemcpyHostToDevice, s));
+    const double* u_dev = nullptr;
+    const double* z_dev = nullptr;
+    if (noise) {
+        bool any_u = false, any_z = false, all_u = true, all_z = true;
+        for (int f = 0; f < c->F; ++f) {
+            any_u |= noise[f].u_resample != nullptr;
+            all_u &= noise[f].u_resample != nullptr;
+            any_z |= noise[f].z_motion != nullptr;
+            all_z &= noise[f].z_motion != nullptr;
+        }
+        if (any_u != all_u || any_z != all_z) return fail(MCL_ERR_INVALID, "noise must be injected for all filters of a batch or none");
+        const size_t N = static_cast<size_t>(c->N);
+        if (any_u) {
+            if (!c->d_u) CK(dalloc(&c->d_u, N * c->F));
+            for (int f = 0; f < c->F; ++f)
+                CK(cudaMemcpyAsync(c->d_u + N * f, noise[f].u_resample, N * sizeof(double), cudaMemcpyHostToDevice, s));
+            u_dev = c->d_u;
+        }
+        if (any_z) {
+            if (!c->d_z) CK(dalloc(&c->d_z, 3 * N * c->F));
+            for (int f = 0; f < c->F; ++f)
+                CK(cudaMemcpyAsync(c->d_z + 3 * N * f, noise[f].z_motion, 3 * N * sizeof(double), cudaMemcpyHostToDevice, s));
+            z_dev = c->d_z;
+        }
+    }
+    int rc = update_device(c, c->d_action, c->d_obs, u_dev, z_dev);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(c->h_pose, c->d_pose, sizeof(double) * 3 * c->F, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (pose_out) std::memcpy(pose_out, c->h_pose, sizeof(double) * 3 * c->F);
+    if (c->profiling) {
+        float t = 0;
+        cudaEventElapsedTime(&t, c->ev[0], c->ev[1]);
+        c->last_ms.cdf = t;
+        cudaEventElapsedTime(&t, c->ev[1], c->ev[2]);
+        c->last_ms.resample_motion = t;
+        cudaEventElapsedTime(&t, c->ev[2], c->ev[3]);
+        c->last_ms.raycast_weight = t;
+        cudaEventElapsedTime(&t, c->ev[3], c->ev[4]);
+        c->last_ms.normalize_pose = t;
+        cudaEventElapsedTime(&t, c->ev[0], c->ev[4]);
+        c->last_ms.total = t;
+    }
+    return MCL_OK;
+}
+
+int mcl_expected_pose(mcl_ctx* c, int filter, double pose_out[3]) {
+    int rc = check_filter(c, filter, false);
+    if (rc) return rc;
+    if (!pose_out) return fail(MCL_ERR_INVALID, "null output");
+    CK(cudaSetDevice(c->device));
+    rc = launch_pose(c, c->d_wn, nullptr, nullptr, c->cur);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(c->h_pose, c->d_pose, sizeof(double) * 3 * c->F, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    std::memcpy(pose_out, c->h_pose + 3 * filter, sizeof(double) * 3);
+    return MCL_OK;
+}
+
+int mcl_calc_range_many(mcl_ctx* c, const double* q, int64_t n, float* out) {
+    if (!c || !q || !out) return fail(MCL_ERR_INVALID, "null argument");
+    if (n < 0) return fail(MCL_ERR_INVALID, "negative query count");
+    if (!c->have_map) return fail(MCL_ERR_NO_MAP, "map not set");   // reference returns MAX_RANGE here (:613)
+    if (n == 0) return MCL_OK;
+    CK(cudaSetDevice(c->device));
+    double* d_q = nullptr;
+    float* d_o = nullptr;
+    CK(dalloc(&d_q, static_cast<size_t>(3 * n)));
+    CK(dalloc(&d_o, static_cast<size_t>(n)));
+    CK(cudaMemcpyAsync(d_q, q, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+    QueryArgs a{};
+    a.map = c->map;
+    a.q = d_q;
+    a.n = n;
+    a.out = d_o;
+    a.max_range = c->prm.max_range;
+    k_range_queries<<<static_cast<unsigned>((n + 255) / 256), 256, 0, c->stream>>>(a);
+    c->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, d_o, sizeof(float) * n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFree(d_q);
+    cudaFree(d_o);
+    return MCL_OK;
+}
+
+int mcl_cast_ray(mcl_ctx* c, double x, double y, double angle, float* out) {
+    const double q[3] = {x, y, angle};
+    return mcl_calc_range_many(c, q, 1, out);
+}
+
+int mcl_sample_particles(mcl_ctx* c, int filter, int k, double* out) {
+    int rc = check_filter(c, filter, false);
+    if (rc) return rc;
+    if (!out || k < 1) return fail(MCL_ERR_INVALID, "bad arguments");
+    CK(cudaSetDevice(c->device));
+    // CDF of the current weights, as visualize() builds it (:949)
+    rc = run_exact(c, c->d_wn, nullptr, c->d_S2, nullptr, 0, true);
+    if (rc) return rc;
+    rc = run_exact(c, c->d_wn, c->d_S2, c->d_scratch_total, c->d_cdf, 1, false);
+    if (rc) return rc;
+    c->cdf_valid = true;
+    double* d_o = nullptr;
+    CK(dalloc(&d_o, static_cast<size_t>(3) * k));
+    const size_t fo = static_cast<size_t>(c->N) * filter;
+    k_sample_particles<<<(k + 127) / 128, 128, 0, c->stream>>>(c->d_cdf + fo, c->N, c->d_px[c->cur] + fo, c->d_py[c->cur] + fo,
+                                                               c->d_pt[c->cur] + fo, k, c->prm.seed, ++c->init_no, d_o);
+    c->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(out, d_o, sizeof(double) * 3 * k, cudaMemcpyDeviceToHost));
+    cudaFree(d_o);
+    return MCL_OK;
+}
+
+int mcl_set_profiling(mcl_ctx* c, int enabled) {
+    if (!c) return fail(MCL_ERR_INVALID, "null context");
+    c->profiling = enabled != 0;
+    return MCL_OK;
+}
+
+int mcl_get_stage_ms(mcl_ctx* c, mcl_stage_ms* out) {
+    if (!c || !out) return fail(MCL_ERR_INVALID, "null argument");
+    *out = c->last_ms;
+    return MCL_OK;
+}
+
+int mcl_set_keep_ranges(mcl_ctx* c, int enabled) {
+    if (!c) return fail(MCL_ERR_INVALID, "null context");
+    CK(cudaSetDevice(c->device));
+    c->keep_ranges = enabled != 0;
+    if (c->keep_ranges && !c->d_steps && c->R > 0) CK(dalloc(&c->d_steps, static_cast<size_t>(c->F) * c->N * c->R));
+    return MCL_OK;
+}
+
+int mcl_kernel_launches(mcl_ctx* c, int64_t* count) {
+    if (!c || !count) return fail(MCL_ERR_INVALID, "null argument");
+    *count = c->launches;
+    return MCL_OK;
+}
+
+int mcl_set_stream(mcl_ctx* c, void* stream) {
+    if (!c) return fail(MCL_ERR_INVALID, "null context");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    c->stream = stream ? static_cast<cudaStream_t>(stream) : c->own_stream;
+    return MCL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,213 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the CPU oracle and the
+committed golden vectors (which were produced by the unmodified reference).
+
+Tolerances are the north_star's: resample indices bit-exact, range step indices equal
+(<= 1 cell allowed), normalised weights <= 1e-5 relative, pose <= 1 mm / 1e-4 rad.
+"""
+import numpy as np
+import pytest
+
+from helpers import assert_pose_close, assert_weights_close, load_golden, steps_from_ranges
+
+pytestmark = pytest.mark.gpu
+
+
+def _ctx(grid, angles, N, **kw):
+    from monte_carlo_localization_b200 import MclContext
+    c = MclContext(max_particles=N, **kw)
+    c.set_map(grid)
+    c.set_beam_angles(angles)
+    c.set_keep_ranges(True)
+    return c
+
+
+@pytest.mark.parametrize("fixture", ["update_sibal1_4000.npz", "update_Spielberg_map_2000.npz",
+                                     "update_basement_fixed_1000.npz"])
+def test_golden_updates_teacher_forced(fixture):
+    """Every update starts from the reference's own state, so each stage is compared on
+    identical inputs: indices and ranges must match exactly."""
+    from monte_carlo_localization_b200 import maps
+    z = load_golden(fixture)
+    g = maps.load_named_map(str(z["map"]))
+    N = int(z["N"])
+    c = _ctx(g, z["angles"], N)
+    prev_p, prev_w = z["init_particles"], z["init_weights"]
+    for t in range(len(z["u"])):
+        c.set_particles(prev_p, prev_w)
+        pose = c.update(z["actions"][t], z["obs"][t], z["u"][t], z["z"][t])
+        assert np.array_equal(c.resample_indices(), z["idx"][t]), "resample indices differ at update %d" % t
+        steps = c.range_steps()
+        assert np.array_equal(steps, z["steps"][t]), "range steps differ at update %d: %d rays" % (
+            t, int((steps != z["steps"][t]).sum()))
+        assert_weights_close(c.raw_weights(), z["raw_weights"][t])
+        assert_weights_close(c.get_weights(), z["weights"][t])
+        p = c.get_particles()
+        assert np.abs(p[:2] - z["particles"][t][:2]).max() < 1e-9
+        assert np.abs(p[2] - z["particles"][t][2]).max() < 1e-9
+        assert_pose_close(pose, z["pose"][t])
+        prev_p, prev_w = z["particles"][t], z["weights"][t]
+    c.close()
+
+
+def test_golden_updates_free_running():
+    """No teacher forcing: the GPU filter runs on its own state for all updates."""
+    from monte_carlo_localization_b200 import maps
+    z = load_golden("update_sibal1_4000.npz")
+    g = maps.load_named_map("sibal1")
+    c = _ctx(g, z["angles"], int(z["N"]))
+    c.init_pose(z["gt"][0], z["z_init"])
+    p0 = c.get_particles()
+    assert np.abs(p0 - z["init_particles"]).max() < 1e-12
+    for t in range(len(z["u"])):
+        pose = c.update(z["actions"][t], z["obs"][t], z["u"][t], z["z"][t])
+        assert np.array_equal(c.resample_indices(), z["idx"][t])
+        assert_pose_close(pose, z["pose"][t])
+    c.close()
+
+
+def test_sensor_table_matches_oracle():
+    from monte_carlo_localization_b200 import maps
+    from oracle import bindings as ob
+    for name in ("sibal1", "Spielberg_map"):
+        g = maps.load_named_map(name)
+        z = load_golden("update_sibal1_4000.npz")
+        c = _ctx(g, z["angles"], 16)
+        orc = ob.Oracle(g, z["angles"], max_particles=16)
+        assert c.M == orc.M
+        assert np.array_equal(c.sensor_table(), orc.sensor_table())
+        c.close()
+
+
+@pytest.mark.parametrize("name,n", [("sibal1", 200000), ("Spielberg_map", 200000), ("first_map", 100000)])
+def test_calc_range_many_matches_oracle(name, n):
+    """cast_ray parity on random and adversarial queries (cell corners, axis-aligned rays,
+    poses outside the map): float ranges must be identical."""
+    from monte_carlo_localization_b200 import maps
+    from oracle import bindings as ob
+    g = maps.load_named_map(name)
+    angles = load_golden("update_sibal1_4000.npz")["angles"]
+    rng = np.random.default_rng(5)
+    res = g.resolution_f64
+    x = rng.uniform(g.origin[0] - 1.0, g.origin[0] + g.width * res + 1.0, n)
+    y = rng.uniform(g.origin[1] - 1.0, g.origin[1] + g.height * res + 1.0, n)
+    th = rng.uniform(-np.pi, np.pi, n)
+    k = n // 2
+    x[:k] = rng.integers(0, g.width, k) * res + g.origin[0]
+    y[:k] = rng.integers(0, g.height, k) * res + g.origin[1]
+    th[:k // 2] = rng.integers(-2, 3, k // 2) * np.pi / 2
+    q = np.stack([x, y, th])
+    c = _ctx(g, angles, 16)
+    orc = ob.Oracle(g, angles, max_particles=16)
+    got = c.calc_range_many(q)
+    want = orc.calc_range_many(q)
+    bad = got != want
+    assert not bad.any(), "%d / %d ranges differ, first %s" % (bad.sum(), n, np.argwhere(bad)[:3].ravel())
+    c.close()
+
+
+@pytest.mark.parametrize("N", [1, 2, 17, 4096, 4097, 100000, 1000000])
+def test_resample_indices_exact(N):
+    """discrete_distribution parity at sizes up to BASELINE's 1M: CDF bits and indices."""
+    from monte_carlo_localization_b200 import maps
+    from oracle import bindings as ob
+    g = maps.load_named_map("sibal1")
+    angles = load_golden("update_sibal1_4000.npz")["angles"]
+    rng = np.random.default_rng(N)
+    w = rng.random(N) ** 6 + 1e-12
+    w /= w.sum()
+    ns = ob.NoiseStream(99 + N)
+    u, z = ns.update_noise(N)
+    c = _ctx(g, angles, N)
+    c.set_keep_ranges(False)
+    p = np.zeros((3, N))
+    p[0] = -3.3
+    p[1] = 1.6
+    p[2] = np.linspace(-3, 3, N)
+    c.set_particles(p, w)
+    obs = np.full(len(angles), 2.0, dtype=np.float32)
+    c.update([0.05, 0, 0.01], obs, u, z)
+    idx_ref, cdf_ref = ob.resample_indices(w, u, want_cdf=True)
+    if N >= 2:
+        assert np.array_equal(c.cdf(), cdf_ref), "CDF bits differ in %d places" % int((c.cdf() != cdf_ref).sum())
+    assert np.array_equal(c.resample_indices(), idx_ref)
+    # replication counts follow from the indices
+    assert np.array_equal(np.bincount(c.resample_indices(), minlength=N), np.bincount(idx_ref, minlength=N))
+    c.close()
+
+
+def test_full_update_vs_oracle_100k():
+    """One update at 100k particles (BASELINE config 2 size) against the oracle."""
+    from monte_carlo_localization_b200 import maps, synth
+    from oracle import bindings as ob
+    g = maps.load_named_map("basement_fixed")
+    angles_full = synth.laser_angles()
+    angles = synth.downsample(angles_full)
+    N = 100000
+    orc = ob.Oracle(g, angles, max_particles=N)
+    gt, actions = synth.trajectory(g, 2, 3.0)
+    ns = ob.NoiseStream(4242)
+    orc.init_pose(gt[0], ns.normal(3 * N))
+    c = _ctx(g, angles, N)
+    for t in range(2):
+        p, w = orc.get_state()
+        c.set_particles(p, w)
+        scan = synth.scan_from_pose(orc.calc_range_many, gt[t + 1], angles_full, np.random.default_rng(t))
+        obs = scan[::18]
+        u, z = ns.update_noise(N)
+        idx = orc.update(actions[t], obs, u, z)
+        pose_ref = orc.expected_pose()
+        pose = c.update(actions[t], obs, u, z)
+        assert np.array_equal(c.resample_indices(), idx)
+        want = steps_from_ranges(orc.ranges(), g.resolution_f64, orc.M)
+        got = c.range_steps()
+        assert np.abs(got.astype(np.int64) - want).max() <= 1
+        assert (got != want).sum() == 0
+        assert_weights_close(c.get_weights(), orc.get_state()[1])
+        assert_pose_close(pose, pose_ref)
+    c.close()
+
+
+def test_batch_of_filters_matches_single():
+    """A batch of independent filters equals the same filters run one by one (config 4 shape)."""
+    from monte_carlo_localization_b200 import maps
+    z = load_golden("update_sibal1_4000.npz")
+    g = maps.load_named_map("sibal1")
+    N, F = int(z["N"]), 3
+    single = _ctx(g, z["angles"], N)
+    batch = _ctx(g, z["angles"], N, num_filters=F)
+    rng = np.random.default_rng(0)
+    shifts = rng.normal(0, 0.05, (F, 3))
+    poses_single = []
+    for f in range(F):
+        p = z["init_particles"].copy()
+        p += shifts[f][:, None]
+        batch.set_particles(p, z["init_weights"], filter=f)
+        single.set_particles(p, z["init_weights"])
+        poses_single.append(single.update(z["actions"][0], z["obs"][f % len(z["obs"])], z["u"][f % 3], z["z"][f % 3]))
+        if f == F - 1:
+            idx_last = single.resample_indices()
+    acts = np.stack([z["actions"][0]] * F)
+    obs = np.stack([z["obs"][f % len(z["obs"])] for f in range(F)])
+    u = np.stack([z["u"][f % 3] for f in range(F)])
+    zz = np.stack([z["z"][f % 3] for f in range(F)])
+    poses = batch.update(acts, obs, u, zz)
+    for f in range(F):
+        assert np.array_equal(poses[f], poses_single[f])
+    assert np.array_equal(batch.resample_indices(filter=F - 1), idx_last)
+    single.close()
+    batch.close()
+
+
+def test_device_rng_update_runs_and_tracks():
+    """Production mode (no injected noise): the filter tracks the ground truth."""
+    from monte_carlo_localization_b200 import maps
+    z = load_golden("update_sibal1_4000.npz")
+    g = maps.load_named_map("sibal1")
+    c = _ctx(g, z["angles"], 4000, seed=1234)
+    c.init_pose(z["gt"][0])
+    for t in range(len(z["obs"])):
+        pose = c.update(z["actions"][t], z["obs"][t])
+    assert np.hypot(*(pose[:2] - z["gt"][-1][:2])) < 0.3
+    w = c.get_weights()
+    assert abs(w.sum() - 1.0) < 1e-9 and (w > 0).all()
+    c.close()
