@@ -33,6 +33,19 @@ struct MapDev {
     int ww, wh;
 };
 
+// Shared-memory form of the 4-bit window: a 32-bit shared-space address, so the march issues
+// plain LDS.U8 without generic-address conversion.
+struct WindowV4S {
+    uint32_t saddr;          // shared address of the window's first byte
+    int offx, offy, pitch;
+    __device__ __forceinline__ int get(int lx, int ly) const {
+        const int x = lx + offx, y = ly + offy;
+        uint32_t b;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b) : "r"(saddr + static_cast<uint32_t>(y * pitch + (x >> 1))));
+        return (b >> ((x & 1) << 2)) & 15;
+    }
+};
+
 struct BeamDev {
     int R;
     float angle[kMaxBeams];     // downsampled_angles_ (float32)
@@ -368,6 +381,13 @@ struct MotionArgs {
     double* centre;           // [F][2] accumulators (sum x, sum y)
 };
 
+// heading bucket of the coherence sort: particles with nearly equal headings cast nearly
+// identical rays, so a warp of bucket-neighbours marches in lock step
+__device__ __forceinline__ int theta_bucket(double th, int B) {
+    const int b = static_cast<int>((th + 3.14159265358979323846) * (static_cast<double>(B) * 0.15915494309189535));
+    return max(0, min(b, B - 1));
+}
+
 struct MotionScalars {
     double dt, vel, omega, radius, dtheta, vdt;
     int straight;
@@ -483,6 +503,106 @@ __global__ void __launch_bounds__(kMotionThreads) k_resample_motion(MotionArgs a
     }
 }
 
+// Counting sort of the particles by heading bucket, in two kernels of fat blocks so that the
+// only global atomics are one per (block, non-empty bucket):
+//   k_sort_hist     block-private shared-memory histogram of a contiguous chunk, flushed once
+//   k_sort_scatter  bucket bases (scan of the global histogram), a block-private count to
+//                   reserve the block's range in each bucket, then shared-memory ranks
+// perm[f][pos] = particle index.  The order inside a bucket is arbitrary; it only decides
+// which warp marches which particle, never a result.
+struct SortArgs {
+    int64_t N;
+    const double* pt;     // [F][N]
+    int* hist;            // [F][B] zeroed before k_sort_hist
+    int* cursor;          // [F][B] zeroed
+    int32_t* perm;        // [F][N]
+    int B;
+    int64_t chunk;        // particles per block (multiple of kSortThreads)
+};
+constexpr int kSortThreads = 1024;
+constexpr int kMaxBuckets = 4096;
+
+__global__ void __launch_bounds__(kSortThreads) k_sort_hist(SortArgs a) {
+    __shared__ int cnt[kMaxBuckets];
+    const int f = blockIdx.y, tid = threadIdx.x;
+    for (int b = tid; b < a.B; b += kSortThreads) cnt[b] = 0;
+    __syncthreads();
+    const int64_t fo = static_cast<int64_t>(f) * a.N;
+    const int64_t lo = static_cast<int64_t>(blockIdx.x) * a.chunk;
+    const int64_t hi = min(a.N, lo + a.chunk);
+    for (int64_t i = lo + tid; i < hi; i += kSortThreads) atomicAdd(&cnt[theta_bucket(a.pt[fo + i], a.B)], 1);
+    __syncthreads();
+    int* hist = a.hist + static_cast<int64_t>(f) * a.B;
+    for (int b = tid; b < a.B; b += kSortThreads) {
+        const int c = cnt[b];
+        if (c) atomicAdd(hist + b, c);
+    }
+}
+
+__global__ void __launch_bounds__(kSortThreads) k_sort_scatter(SortArgs a) {
+    __shared__ int base[kMaxBuckets];
+    __shared__ int cnt[kMaxBuckets];
+    __shared__ int wsum[kSortThreads / 32];
+    const int f = blockIdx.y, tid = threadIdx.x;
+    const int* hist = a.hist + static_cast<int64_t>(f) * a.B;
+    // exclusive scan of the global histogram, kMaxBuckets / kSortThreads entries per thread
+    constexpr int kPer = kMaxBuckets / kSortThreads;
+    int h[kPer];
+    int loc = 0;
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+        const int b = tid * kPer + q;
+        h[q] = b < a.B ? hist[b] : 0;
+        loc += h[q];
+        cnt[b] = 0;
+    }
+    int v = loc;
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(kFullMask, v, d);
+        if (lane >= d) v += o;
+    }
+    if (lane == 31) wsum[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        int w = wsum[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(kFullMask, w, d);
+            if (lane >= d) w += o;
+        }
+        wsum[lane] = w;
+    }
+    __syncthreads();
+    int excl = v - loc + (warp ? wsum[warp - 1] : 0);
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+        base[tid * kPer + q] = excl;
+        excl += h[q];
+    }
+    __syncthreads();
+    const int64_t fo = static_cast<int64_t>(f) * a.N;
+    const int64_t lo = static_cast<int64_t>(blockIdx.x) * a.chunk;
+    const int64_t hi = min(a.N, lo + a.chunk);
+    // this block's population of every bucket
+    for (int64_t i = lo + tid; i < hi; i += kSortThreads) atomicAdd(&cnt[theta_bucket(a.pt[fo + i], a.B)], 1);
+    __syncthreads();
+    // reserve the block's range inside each bucket; cnt[] becomes the running cursor
+    int* cursor = a.cursor + static_cast<int64_t>(f) * a.B;
+    for (int b = tid; b < a.B; b += kSortThreads) {
+        const int c = cnt[b];
+        if (c) base[b] += atomicAdd(cursor + b, c);
+        cnt[b] = 0;
+    }
+    __syncthreads();
+    for (int64_t i = lo + tid; i < hi; i += kSortThreads) {
+        const int b = theta_bucket(a.pt[fo + i], a.B);
+        const int pos = base[b] + atomicAdd(&cnt[b], 1);
+        a.perm[fo + pos] = static_cast<int32_t>(i);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // sensor model (:506-583): observation -> table rows, ray march, weight product
 // ------------------------------------------------------------------------------------------
@@ -514,6 +634,7 @@ struct RayArgs {
     const double* px;          // [F][N] proposal particles
     const double* py;
     const double* pt;
+    const int32_t* perm;       // [F][N] processing order (heading-sorted) or nullptr
     const double* slice;       // [F][R][M+1]
     double* w_raw;             // [F][N]
     uint8_t* steps;            // [F][N*R] or nullptr
@@ -522,10 +643,11 @@ struct RayArgs {
     int64_t* replay_count;     // diagnostics (nullable)
 };
 
-constexpr int kRayThreads = 512;
+constexpr int kRayThreads = 1024;
 
 // One lane = one particle; the lane walks its R beams in order and folds the table
 // entries into the weight product in the reference's multiplication order (:564-579).
+// Lanes of a warp hold heading-neighbours (perm), so their rays and trip counts agree.
 __global__ void __launch_bounds__(kRayThreads, 1) k_raycast_weight(RayArgs a) {
     extern __shared__ __align__(16) uint8_t smem_win[];
     const int f = blockIdx.y;
@@ -563,14 +685,18 @@ __global__ void __launch_bounds__(kRayThreads, 1) k_raycast_weight(RayArgs a) {
         }
         __syncthreads();
     }
-    const WindowV4 wacc{smem_win, wx0, wy0, pitch};
-    const GlobalV8 gacc{mp.v8, mp.PW};
+    // shared-space address of the window; the volatile asm keeps it in a register instead of
+    // being rematerialised (S2R + LEA) inside the march loop
+    uint32_t win_saddr;
+    asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(win_saddr) : "l"(smem_win));
     const RefGrid rg{mp.grid, mp.W, mp.H, mp.res, mp.ox, mp.oy};
     const double* slice = a.slice + static_cast<int64_t>(f) * R * (M + 1);
+    const int32_t* perm = a.perm ? a.perm + fo : nullptr;
     int replays = 0;
 
-    for (int64_t i = static_cast<int64_t>(blockIdx.x) * kRayThreads + threadIdx.x; i < N;
-         i += static_cast<int64_t>(gridDim.x) * kRayThreads) {
+    for (int64_t s = static_cast<int64_t>(blockIdx.x) * kRayThreads + threadIdx.x; s < N;
+         s += static_cast<int64_t>(gridDim.x) * kRayThreads) {
+        const int64_t i = perm ? perm[s] : s;
         const double x = a.px[fo + i], y = a.py[fo + i], th = a.pt[fo + i];
         double sth, cth;
         sincos(th, &sth, &cth);
@@ -589,6 +715,8 @@ __global__ void __launch_bounds__(kRayThreads, 1) k_raycast_weight(RayArgs a) {
             const int fqx = static_cast<int>(floor(qx)), fqy = static_cast<int>(floor(qy));
             const RayStart st = make_ray_start(qx, qy, fqx, fqy);
             const bool in_win = (mp.ww > 0) && fqx >= vx0 && fqx < vx1 && fqy >= vy0 && fqy < vy1;
+            const WindowV4S wacc{win_saddr, st.bx - wx0, st.by - wy0, pitch};
+            const GlobalV8 gacc = make_global_v8(mp.v8, mp.PW, st.bx, st.by);
             for (int j = 0; j < R; ++j) {
                 int dxf, dyf;
                 beam_direction_fixed(cth, sth, a.beams.cosa[j], a.beams.sina[j], &dxf, &dyf);
@@ -766,7 +894,7 @@ __global__ void __launch_bounds__(256) k_range_queries(QueryArgs a) {
         double s, c;
         sincos(ang, &s, &c);
         const RayStart st = make_ray_start(qx, qy, static_cast<int>(floor(qx)), static_cast<int>(floor(qy)));
-        const GlobalV8 gacc{mp.v8, mp.PW};
+        const GlobalV8 gacc = make_global_v8(mp.v8, mp.PW, st.bx, st.by);
         const RefGrid rg{mp.grid, mp.W, mp.H, mp.res, mp.ox, mp.oy};
         const ReplayArgs ra{x, y, ang};
         int dxf, dyf;

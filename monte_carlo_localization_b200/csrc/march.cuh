@@ -94,30 +94,39 @@ MCL_HD RayStart make_ray_start(double qx, double qy, int fqx, int fqy) {
     return s;
 }
 
-// Skip-map accessors.  get(cx, cy) returns the skip code of P-cell (cx, cy); both are
-// guaranteed in range by the callers' validity tests.
+// Skip-map accessors.  get(lx, ly) returns the skip code of the cell at ray-local integer
+// coordinates (lx, ly) = (p >> kFrac); the particle's base cell is folded into the accessor
+// when it is built (make_*), so the march spends no instructions on it.  Callers guarantee
+// that every cell a ray can reach is in range.
 struct GlobalV8 {
-    const uint8_t* v8;
+    const uint8_t* base;   // &v8[by * PW + bx]
     int PW;
-    MCL_HD int get(int cx, int cy) const {
+    MCL_HD int get(int lx, int ly) const {
 #if defined(__CUDA_ARCH__)
-        return __ldg(v8 + static_cast<int64_t>(cy) * PW + cx);
+        return __ldg(base + static_cast<int64_t>(ly) * PW + lx);
 #else
-        return v8[static_cast<int64_t>(cy) * PW + cx];
+        return base[static_cast<int64_t>(ly) * PW + lx];
 #endif
     }
 };
+MCL_HD GlobalV8 make_global_v8(const uint8_t* v8, int PW, int bx, int by) {
+    return GlobalV8{v8 + static_cast<int64_t>(by) * PW + bx, PW};
+}
 
-// 4-bit window in shared memory: P-cells [wx0, wx0+ww) x [wy0, wy0+wh), wx0 even.
+// 4-bit window (host pointer form, used by the CPU emulation harness): P-cells
+// [wx0, wx0+ww) x [wy0, wy0+wh), wx0 even, two cells per byte.
 struct WindowV4 {
     const uint8_t* w4;   // wh rows of pitch bytes
-    int wx0, wy0, pitch;
-    MCL_HD int get(int cx, int cy) const {
-        const int lx = cx - wx0, ly = cy - wy0;
-        const int b = w4[ly * pitch + (lx >> 1)];
-        return (b >> ((lx & 1) << 2)) & 15;
+    int offx, offy, pitch;   // bx - wx0, by - wy0
+    MCL_HD int get(int lx, int ly) const {
+        const int x = lx + offx, y = ly + offy;
+        const int b = w4[y * pitch + (x >> 1)];
+        return (b >> ((x & 1) << 2)) & 15;
     }
 };
+MCL_HD WindowV4 make_window_v4(const uint8_t* w4, int wx0, int wy0, int pitch, int bx, int by) {
+    return WindowV4{w4, bx - wx0, by - wy0, pitch};
+}
 
 struct ReplayArgs {
     double x, y;        // particle position (metres)
@@ -164,40 +173,44 @@ MCL_HD bool p_inside(double qx, double qy, int PW, int PH) {
 template <class Acc>
 MCL_HD int march_ray(const Acc& acc, const RayStart& st, int dxf, int dyf, int M, const RefGrid& g,
                      const ReplayArgs& ra, int* replays) {
-    int k = 1;
-    while (k <= M) {
+    // Single back edge, no early return: lanes that finish simply drop out of the loop, which
+    // keeps the per-iteration control overhead to one predicated branch.
+    int k = 1, r = M;
+    do {
         const uint32_t px = st.p0x + static_cast<uint32_t>(k * dxf);
         const uint32_t py = st.p0y + static_cast<uint32_t>(k * dyf);
-        const int cx = st.bx + static_cast<int>(px >> kFrac);
-        const int cy = st.by + static_cast<int>(py >> kFrac);
-        const int v = acc.get(cx, cy);
-        if (v >= 2) {
-            k += v - 1;
-            continue;
-        }
-        // code 0 or 1: the class of this very sample matters
-        bool hit = (v == 0);
-        const uint32_t fx = px & kFracMask, fy = py & kFracMask;
-        const bool ux = ((fx + kEtaFix) & kFracMask) < 2u * kEtaFix;
-        const bool uy = ((fy + kEtaFix) & kFracMask) < 2u * kEtaFix;
-        if (ux || uy) {
-            const int nx = cx + (fx < kEtaFix ? -1 : 1);
-            const int ny = cy + (fy < kEtaFix ? -1 : 1);
-            bool differs = false;
-            if (ux) differs |= ((acc.get(nx, cy) == 0) != hit);
-            if (uy) differs |= ((acc.get(cx, ny) == 0) != hit);
-            if (ux && uy) differs |= ((acc.get(nx, ny) == 0) != hit);
-            if (differs) {
-                double sn, cs;
-                sincos_ref(ra.ang, &sn, &cs);
-                hit = replay_sample_is_hit(g, ra.x, ra.y, nf_mul(cs, g.res), nf_mul(sn, g.res), k);
-                if (replays) ++*replays;
+        const int cx = static_cast<int>(px >> kFrac);   // ray-local cell
+        const int cy = static_cast<int>(py >> kFrac);
+        int v = acc.get(cx, cy);
+        if (v < 2) {
+            // code 0 or 1: the class of this very sample matters
+            bool hit = (v == 0);
+            const uint32_t fx = px & kFracMask, fy = py & kFracMask;
+            const bool ux = ((fx + kEtaFix) & kFracMask) < 2u * kEtaFix;
+            const bool uy = ((fy + kEtaFix) & kFracMask) < 2u * kEtaFix;
+            if (ux || uy) {
+                const int nx = cx + (fx < kEtaFix ? -1 : 1);
+                const int ny = cy + (fy < kEtaFix ? -1 : 1);
+                bool differs = false;
+                if (ux) differs |= ((acc.get(nx, cy) == 0) != hit);
+                if (uy) differs |= ((acc.get(cx, ny) == 0) != hit);
+                if (ux && uy) differs |= ((acc.get(nx, ny) == 0) != hit);
+                if (differs) {
+                    double sn, cs;
+                    sincos_ref(ra.ang, &sn, &cs);
+                    hit = replay_sample_is_hit(g, ra.x, ra.y, nf_mul(cs, g.res), nf_mul(sn, g.res), k);
+                    if (replays) ++*replays;
+                }
             }
+            if (hit) {
+                r = k - 1;
+                k = M;      // k + 1 > M ends the loop
+            }
+            v = 2;
         }
-        if (hit) return k - 1;
-        k += 1;
-    }
-    return M;
+        k += v - 1;
+    } while (k <= M);
+    return r;
 }
 
 }  // namespace mclb200

@@ -109,6 +109,11 @@ struct mcl_ctx {
     double* d_pose = nullptr;
     double* d_centre = nullptr;
     int64_t* d_replays = nullptr;
+    // heading sort (coherent warps in the ray kernel)
+    int B = 0;
+    int* d_hist = nullptr;      // [F][2B]: histogram | scatter cursors
+    int32_t* d_perm = nullptr;
+    bool sort_enabled = true;
     // pinned staging for the host-facing update
     double* h_action = nullptr;
     float* h_obs = nullptr;
@@ -265,6 +270,7 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
     if (c->profiling) CK(cudaEventRecord(c->ev[0], s));
 
     CK(cudaMemsetAsync(c->d_centre, 0, sizeof(double) * 2 * c->F, s));
+    if (c->sort_enabled) CK(cudaMemsetAsync(c->d_hist, 0, sizeof(int) * 2 * c->B * c->F, s));
     ObsArgs oa{};
     oa.obs = obs_dev;
     oa.tabT = c->d_tabT;
@@ -306,6 +312,24 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
     const int mblocks = static_cast<int>((c->N + kMotionThreads - 1) / kMotionThreads);
     k_resample_motion<<<dim3(mblocks, c->F), kMotionThreads, 0, s>>>(ma);
     c->launches++;
+    if (c->sort_enabled) {
+        SortArgs sa{};
+        sa.N = c->N;
+        sa.pt = c->d_pt[dst];
+        sa.hist = c->d_hist;
+        sa.cursor = c->d_hist + static_cast<size_t>(c->B) * c->F;
+        sa.perm = c->d_perm;
+        sa.B = c->B;
+        // a few fat blocks per filter: ~one per SM for a single big filter
+        const int64_t per_filter = std::max<int64_t>(1, c->num_sms / std::min(c->F, c->num_sms));
+        int64_t chunk = (c->N + per_filter - 1) / per_filter;
+        chunk = std::max<int64_t>(kSortThreads, (chunk + kSortThreads - 1) / kSortThreads * kSortThreads);
+        sa.chunk = chunk;
+        const dim3 gs(static_cast<unsigned>((c->N + chunk - 1) / chunk), c->F);
+        k_sort_hist<<<gs, kSortThreads, 0, s>>>(sa);
+        k_sort_scatter<<<gs, kSortThreads, 0, s>>>(sa);
+        c->launches += 2;
+    }
     if (c->profiling) CK(cudaEventRecord(c->ev[2], s));
 
     RayArgs ra{};
@@ -315,6 +339,7 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
     ra.px = c->d_px[dst];
     ra.py = c->d_py[dst];
     ra.pt = c->d_pt[dst];
+    ra.perm = c->sort_enabled ? c->d_perm : nullptr;
     ra.slice = c->d_slice;
     ra.w_raw = c->d_wraw;
     ra.steps = c->keep_ranges ? c->d_steps : nullptr;
@@ -460,6 +485,13 @@ int mcl_create(const mcl_params* p, int device, mcl_ctx** out) {
     CK(dalloc(&c->d_pose, static_cast<size_t>(c->F) * 3));
     CK(cudaMemset(c->d_pose, 0, sizeof(double) * 3 * c->F));
     CK(dalloc(&c->d_centre, static_cast<size_t>(c->F) * 2));
+    {   // heading buckets: ~16 particles per bucket, power of two in [32, 4096]
+        int B = 32;
+        while (B < kMaxBuckets && static_cast<int64_t>(B) * 16 < c->N) B <<= 1;
+        c->B = B;
+        CK(dalloc(&c->d_hist, static_cast<size_t>(2) * B * c->F));
+        CK(dalloc(&c->d_perm, FN));
+    }
     CK(dalloc(&c->d_replays, size_t{1}));
     CK(cudaMemset(c->d_replays, 0, sizeof(int64_t)));
     CK(dalloc(&c->d_action, static_cast<size_t>(c->F) * 3));
@@ -480,7 +512,8 @@ int mcl_destroy(mcl_ctx* c) {
                     c->d_py[1], c->d_pt[0], c->d_pt[1], c->d_wraw, c->d_wn, c->d_cdf, c->d_idx, c->d_steps, c->d_u, c->d_z,
                     c->d_action, c->d_obs, c->d_slice, c->d_tile_sum, c->d_chunk_fn, c->d_chunk_pre, c->d_chunk_flag,
                     c->d_tile_opq, c->d_tile_elem, c->d_list_chunk, c->d_list_fn, c->d_anchors, c->d_anchor_val,
-                    c->d_tile_start, c->d_S1, c->d_S2, c->d_scratch_total, c->d_partial, c->d_pose, c->d_centre, c->d_replays};
+                    c->d_tile_start, c->d_S1, c->d_S2, c->d_scratch_total, c->d_partial, c->d_pose, c->d_centre, c->d_replays,
+                    c->d_hist, c->d_perm};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (c->h_action) cudaFreeHost(c->h_action);

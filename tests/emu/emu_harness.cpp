@@ -75,8 +75,6 @@ long long emu_range_steps(const emu_map* m, const double* px, const double* py, 
         vy0 = (wy0 == 0) ? 2 : wy0 + M + 2;
         vy1 = (wy0 + wh >= sk.PH) ? sk.PH - 2 : wy0 + wh - M - 2;
     }
-    const WindowV4 wacc{win.data(), wx0, wy0, pitch};
-    const GlobalV8 gacc{sk.v8.data(), sk.PW};
     const RefGrid rg{m->grid.data(), sk.W, sk.H, m->res, m->ox, m->oy};
     int replays = 0;
     long long iters = 0;
@@ -93,6 +91,8 @@ long long emu_range_steps(const emu_map* m, const double* px, const double* py, 
         const int fqx = static_cast<int>(std::floor(qx)), fqy = static_cast<int>(std::floor(qy));
         const RayStart st = make_ray_start(qx, qy, fqx, fqy);
         const bool in_win = mode == 1 && fqx >= vx0 && fqx < vx1 && fqy >= vy0 && fqy < vy1;
+        const WindowV4 wacc = make_window_v4(win.data(), wx0, wy0, pitch, st.bx, st.by);
+        const GlobalV8 gacc = make_global_v8(sk.v8.data(), sk.PW, st.bx, st.by);
         for (int j = 0; j < R; ++j) {
             int dxf, dyf;
             beam_direction_fixed(cth, sth, ca[j], sa[j], &dxf, &dyf);
