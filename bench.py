@@ -312,19 +312,22 @@ def run_gpu(args):
     ctx.set_profiling(False)
 
     # ---- e2e: host buffers through the C-ABI call -----------------------------------------
-    e2e = None
-    if flt is None:
-        Ke = max(3, min(K, 50))
-        acts_h = [np.ascontiguousarray(actions[t + i]) for i in range(Ke)]
-        obs_h = [np.ascontiguousarray(obs[t + i]) for i in range(Ke)]
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(Ke):
-            pose = ctx.update(acts_h[i], obs_h[i])       # H2D action+scan, D2H pose, sync
-        barrier()
-        e_sec = time.perf_counter() - t0
-        e2e = {"value": N * R * Ke / e_sec, "unit": UNIT, "h2d_bytes_per_step": 24 + 4 * R,
-               "d2h_bytes_per_step": 24, "steps": Ke, "ms_per_step": 1e3 * e_sec / Ke}
+    Ke = max(3, min(K, 50))
+    acts_h = [np.ascontiguousarray(actions[t + i]) for i in range(Ke)]
+    obs_h = [np.ascontiguousarray(obs[t + i]) for i in range(Ke)]
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(Ke):
+        # H2D action+scan, D2H pose, host sync -- every step
+        pose = ctx.update(acts_h[i], obs_h[i]) if flt is None else flt.update(acts_h[i], obs_h[i])
+    barrier()
+    e_sec = time.perf_counter() - t0
+    if world > 1:
+        te = torch.tensor([e_sec], dtype=torch.float64, device="cuda")
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e_sec = float(te.item())
+    e2e = {"value": N * world * R * Ke / e_sec, "unit": UNIT, "h2d_bytes_per_step": 24 + 4 * R,
+           "d2h_bytes_per_step": 24, "steps": Ke, "ms_per_step": 1e3 * e_sec / Ke}
 
     # ---- max over ranks --------------------------------------------------------------------
     if world > 1:

@@ -145,6 +145,24 @@ int mcl_kernel_launches(mcl_ctx* ctx, int64_t* count); /* kernels launched so fa
 /* Use the caller's CUDA stream (cudaStream_t passed as void*) instead of the ctx's own. */
 int mcl_set_stream(mcl_ctx* ctx, void* cuda_stream);
 
+/* ---- particle-sharded operation: one rank per GPU, ONE global filter ---------------------
+ * The reference has no multi-process path; the coupling points of its update are the weight
+ * sum (:679), the global CDF + source gather (:658-665) and the pose sums (:702-710).  Every
+ * rank keeps the whole filter state (max_particles = global count) but computes only output
+ * slots [lo, lo+count).  Per update:
+ *   mcl_update_local_dev      CDF over all particles, then resample / motion / ray cast /
+ *                             weights for the rank's slots
+ *   (caller)                  all-gather the four arrays of mcl_exchange_buffers_dev in place
+ *                             (x, y, theta, raw weight; slice [lo, lo+count) is this rank's)
+ *   mcl_update_finish_dev     global weight sum, normalisation and expected pose on every rank
+ * Resampling is the reference's exact global multinomial draw: with the same injected noise
+ * the gathered result equals the single-filter update bit for bit. */
+int mcl_set_shard(mcl_ctx* ctx, int64_t lo, int64_t count);
+int mcl_update_local_dev(mcl_ctx* ctx, const double* action_dev, const float* obs_dev, int num_beams,
+                         const double* u_dev /*nullable, N*/, const double* z_dev /*nullable, 3N*/);
+int mcl_exchange_buffers_dev(mcl_ctx* ctx, void* ptrs_out[4], int64_t* n_total, int64_t* lo, int64_t* count);
+int mcl_update_finish_dev(mcl_ctx* ctx);
+
 #ifdef __cplusplus
 }
 #endif

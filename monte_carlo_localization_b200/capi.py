@@ -85,6 +85,11 @@ SIGNATURES = {
     "mcl_set_keep_ranges": (C.c_int, [C.c_void_p, C.c_int]),
     "mcl_kernel_launches": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "mcl_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mcl_set_shard": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64]),
+    "mcl_update_local_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "mcl_exchange_buffers_dev": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
+                                           C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "mcl_update_finish_dev": (C.c_int, [C.c_void_p]),
 }
 
 _lib = None
@@ -318,6 +323,26 @@ class MclContext:
         n = C.c_int64(0)
         self._check(self._L.mcl_kernel_launches(self._h, C.byref(n)), "mcl_kernel_launches")
         return int(n.value)
+
+    # ---- particle sharding -------------------------------------------------------------
+    def set_shard(self, lo: int, count: int):
+        self._check(self._L.mcl_set_shard(self._h, lo, count), "mcl_set_shard")
+
+    def update_local_dev(self, action_dev_ptr: int, obs_dev_ptr: int, u_dev_ptr: int = 0, z_dev_ptr: int = 0):
+        self._check(self._L.mcl_update_local_dev(self._h, C.c_void_p(action_dev_ptr), C.c_void_p(obs_dev_ptr), self.R,
+                                                 C.c_void_p(u_dev_ptr or None), C.c_void_p(z_dev_ptr or None)),
+                    "mcl_update_local_dev")
+
+    def exchange_buffers_dev(self):
+        """(ptrs[4], n_total, lo, count): device addresses of x, y, theta, raw weight."""
+        ptrs = (C.c_void_p * 4)()
+        n, lo, cnt = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        self._check(self._L.mcl_exchange_buffers_dev(self._h, ptrs, C.byref(n), C.byref(lo), C.byref(cnt)),
+                    "mcl_exchange_buffers_dev")
+        return [int(p) for p in ptrs], int(n.value), int(lo.value), int(cnt.value)
+
+    def update_finish_dev(self):
+        self._check(self._L.mcl_update_finish_dev(self._h), "mcl_update_finish_dev")
 
     def set_stream(self, cuda_stream_ptr: int):
         self._check(self._L.mcl_set_stream(self._h, C.c_void_p(cuda_stream_ptr)), "mcl_set_stream")

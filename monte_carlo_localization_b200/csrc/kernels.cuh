@@ -363,7 +363,8 @@ __global__ void __launch_bounds__(kTileChunks) k_exact_emit(ExactArgs a) {
 // resample (:658-665) + motion model (:449-503)
 // ------------------------------------------------------------------------------------------
 struct MotionArgs {
-    int64_t N;
+    int64_t N;                // particles of the whole filter (CDF length)
+    int64_t lo, cnt;          // output slots [lo, lo+cnt) computed by this launch (shard)
     const double* cdf;        // [F][N]
     const double* sx;         // source state [F][N] each
     const double* sy;
@@ -427,12 +428,13 @@ constexpr int kMotionThreads = 256;
 __global__ void __launch_bounds__(kMotionThreads) k_resample_motion(MotionArgs a) {
     __shared__ double sm[kMotionThreads / 32];
     const int f = blockIdx.y;
-    const int64_t i = static_cast<int64_t>(blockIdx.x) * kMotionThreads + threadIdx.x;
+    const int64_t li = static_cast<int64_t>(blockIdx.x) * kMotionThreads + threadIdx.x;
+    const int64_t i = a.lo + li;   // global slot: noise and RNG counters do not depend on the sharding
     const int64_t N = a.N;
     const int64_t fo = static_cast<int64_t>(f) * N;
     const MotionScalars m = motion_scalars(a.action[3 * f + 0], a.action[3 * f + 2]);
     double nx = 0.0, ny = 0.0;
-    if (i < N) {
+    if (li < a.cnt) {
         // noise: injected arrays in the reference's draw order, else Philox keyed by
         // (seed, update) and counted by (filter, particle)
         double u, z0, z1, z2;
@@ -511,7 +513,8 @@ __global__ void __launch_bounds__(kMotionThreads) k_resample_motion(MotionArgs a
 // perm[f][pos] = particle index.  The order inside a bucket is arbitrary; it only decides
 // which warp marches which particle, never a result.
 struct SortArgs {
-    int64_t N;
+    int64_t N;            // particles per filter (array stride)
+    int64_t lo, cnt;      // the slots [lo, lo+cnt) being sorted; perm holds indices relative to lo
     const double* pt;     // [F][N]
     int* hist;            // [F][B] zeroed before k_sort_hist
     int* cursor;          // [F][B] zeroed
@@ -527,9 +530,9 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_hist(SortArgs a) {
     const int f = blockIdx.y, tid = threadIdx.x;
     for (int b = tid; b < a.B; b += kSortThreads) cnt[b] = 0;
     __syncthreads();
-    const int64_t fo = static_cast<int64_t>(f) * a.N;
+    const int64_t fo = static_cast<int64_t>(f) * a.N + a.lo;
     const int64_t lo = static_cast<int64_t>(blockIdx.x) * a.chunk;
-    const int64_t hi = min(a.N, lo + a.chunk);
+    const int64_t hi = min(a.cnt, lo + a.chunk);
     for (int64_t i = lo + tid; i < hi; i += kSortThreads) atomicAdd(&cnt[theta_bucket(a.pt[fo + i], a.B)], 1);
     __syncthreads();
     int* hist = a.hist + static_cast<int64_t>(f) * a.B;
@@ -582,9 +585,9 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_scatter(SortArgs a) {
         excl += h[q];
     }
     __syncthreads();
-    const int64_t fo = static_cast<int64_t>(f) * a.N;
+    const int64_t fo = static_cast<int64_t>(f) * a.N + a.lo;
     const int64_t lo = static_cast<int64_t>(blockIdx.x) * a.chunk;
-    const int64_t hi = min(a.N, lo + a.chunk);
+    const int64_t hi = min(a.cnt, lo + a.chunk);
     // this block's population of every bucket
     for (int64_t i = lo + tid; i < hi; i += kSortThreads) atomicAdd(&cnt[theta_bucket(a.pt[fo + i], a.B)], 1);
     __syncthreads();
@@ -634,7 +637,8 @@ struct RayArgs {
     const double* px;          // [F][N] proposal particles
     const double* py;
     const double* pt;
-    const int32_t* perm;       // [F][N] processing order (heading-sorted) or nullptr
+    int64_t lo, cnt;           // slots [lo, lo+cnt) computed by this launch (shard)
+    const int32_t* perm;       // [F][N] processing order (heading-sorted, shard-local) or nullptr
     const double* slice;       // [F][R][M+1]
     double* w_raw;             // [F][N]
     uint8_t* steps;            // [F][N*R] or nullptr
@@ -661,8 +665,8 @@ __global__ void __launch_bounds__(kRayThreads, 1) k_raycast_weight(RayArgs a) {
     int wx0 = 0, wy0 = 0, vx0 = 0, vx1 = 0, vy0 = 0, vy1 = 0;
     const int pitch = mp.ww >> 1;
     if (mp.ww > 0) {
-        const double mx = a.centre[2 * f + 0] / static_cast<double>(N);
-        const double my = a.centre[2 * f + 1] / static_cast<double>(N);
+        const double mx = a.centre[2 * f + 0] / static_cast<double>(a.cnt);
+        const double my = a.centre[2 * f + 1] / static_cast<double>(a.cnt);
         const double qx = (mx - mp.ox) / mp.res + kPadL, qy = (my - mp.oy) / mp.res + kPadL;
         int cx = (qx > -1e9 && qx < 1e9) ? static_cast<int>(floor(qx)) : 0;
         int cy = (qy > -1e9 && qy < 1e9) ? static_cast<int>(floor(qy)) : 0;
@@ -691,12 +695,12 @@ __global__ void __launch_bounds__(kRayThreads, 1) k_raycast_weight(RayArgs a) {
     asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(win_saddr) : "l"(smem_win));
     const RefGrid rg{mp.grid, mp.W, mp.H, mp.res, mp.ox, mp.oy};
     const double* slice = a.slice + static_cast<int64_t>(f) * R * (M + 1);
-    const int32_t* perm = a.perm ? a.perm + fo : nullptr;
+    const int32_t* perm = a.perm ? a.perm + fo + a.lo : nullptr;
     int replays = 0;
 
-    for (int64_t s = static_cast<int64_t>(blockIdx.x) * kRayThreads + threadIdx.x; s < N;
+    for (int64_t s = static_cast<int64_t>(blockIdx.x) * kRayThreads + threadIdx.x; s < a.cnt;
          s += static_cast<int64_t>(gridDim.x) * kRayThreads) {
-        const int64_t i = perm ? perm[s] : s;
+        const int64_t i = a.lo + (perm ? perm[s] : s);
         const double x = a.px[fo + i], y = a.py[fo + i], th = a.pt[fo + i];
         double sth, cth;
         sincos(th, &sth, &cth);

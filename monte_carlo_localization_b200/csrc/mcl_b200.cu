@@ -114,6 +114,9 @@ struct mcl_ctx {
     int* d_hist = nullptr;      // [F][2B]: histogram | scatter cursors
     int32_t* d_perm = nullptr;
     bool sort_enabled = true;
+    // particle shard: this context computes output slots [lo, lo+cnt) of the filter
+    int64_t lo = 0, cnt = 0;
+    bool local_pending = false;
     // pinned staging for the host-facing update
     double* h_action = nullptr;
     float* h_obs = nullptr;
@@ -261,10 +264,12 @@ int launch_pose(mcl_ctx* c, const double* w, const double* total, double* wn_out
     return MCL_OK;
 }
 
-// one MCL() + expected_pose() for every filter, inputs already in d_action / d_obs
-int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, const double* u_dev, const double* z_dev) {
+// First half of MCL(): CDF of the current weights, then resample / motion / ray cast / weight
+// for this context's slots [lo, lo+cnt) into the destination buffers.
+int update_local(mcl_ctx* c, const double* action_dev, const float* obs_dev, const double* u_dev, const double* z_dev) {
     if (!c->have_map) return fail(MCL_ERR_NO_MAP, "mcl_set_map has not been called");
     if (!c->have_beams) return fail(MCL_ERR_INVALID, "mcl_set_beam_angles has not been called");
+    if (c->local_pending) return fail(MCL_ERR_INVALID, "mcl_update_finish must follow mcl_update_local");
     const int src = c->cur, dst = c->cur ^ 1;
     cudaStream_t s = c->stream;
     if (c->profiling) CK(cudaEventRecord(c->ev[0], s));
@@ -292,6 +297,8 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
 
     MotionArgs ma{};
     ma.N = c->N;
+    ma.lo = c->lo;
+    ma.cnt = c->cnt;
     ma.cdf = c->d_cdf;
     ma.sx = c->d_px[src];
     ma.sy = c->d_py[src];
@@ -309,12 +316,14 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
     ma.seed = c->prm.seed;
     ma.update_no = c->update_no;
     ma.centre = c->d_centre;
-    const int mblocks = static_cast<int>((c->N + kMotionThreads - 1) / kMotionThreads);
+    const int mblocks = static_cast<int>((c->cnt + kMotionThreads - 1) / kMotionThreads);
     k_resample_motion<<<dim3(mblocks, c->F), kMotionThreads, 0, s>>>(ma);
     c->launches++;
     if (c->sort_enabled) {
         SortArgs sa{};
         sa.N = c->N;
+        sa.lo = c->lo;
+        sa.cnt = c->cnt;
         sa.pt = c->d_pt[dst];
         sa.hist = c->d_hist;
         sa.cursor = c->d_hist + static_cast<size_t>(c->B) * c->F;
@@ -322,10 +331,10 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
         sa.B = c->B;
         // a few fat blocks per filter: ~one per SM for a single big filter
         const int64_t per_filter = std::max<int64_t>(1, c->num_sms / std::min(c->F, c->num_sms));
-        int64_t chunk = (c->N + per_filter - 1) / per_filter;
+        int64_t chunk = (c->cnt + per_filter - 1) / per_filter;
         chunk = std::max<int64_t>(kSortThreads, (chunk + kSortThreads - 1) / kSortThreads * kSortThreads);
         sa.chunk = chunk;
-        const dim3 gs(static_cast<unsigned>((c->N + chunk - 1) / chunk), c->F);
+        const dim3 gs(static_cast<unsigned>((c->cnt + chunk - 1) / chunk), c->F);
         k_sort_hist<<<gs, kSortThreads, 0, s>>>(sa);
         k_sort_scatter<<<gs, kSortThreads, 0, s>>>(sa);
         c->launches += 2;
@@ -336,6 +345,8 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
     ra.map = c->map;
     ra.beams = c->beams;
     ra.N = c->N;
+    ra.lo = c->lo;
+    ra.cnt = c->cnt;
     ra.px = c->d_px[dst];
     ra.py = c->d_py[dst];
     ra.pt = c->d_pt[dst];
@@ -348,23 +359,38 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
     ra.replay_count = c->d_replays;
     const size_t smem = static_cast<size_t>(c->map.ww / 2) * c->map.wh;
     // persistent blocks: one per SM when the window fills shared memory, a few otherwise
-    const int per_sm = smem > 100 * 1024 ? 1 : (smem > 48 * 1024 ? 2 : 4);
+    const int per_sm = smem > 100 * 1024 ? 1 : 2;
     const int budget = std::max(1, (c->num_sms * per_sm) / std::min(c->F, c->num_sms * per_sm));
-    const int rblocks = static_cast<int>(std::min<int64_t>((c->N + kRayThreads - 1) / kRayThreads, budget));
+    const int rblocks = static_cast<int>(std::min<int64_t>((c->cnt + kRayThreads - 1) / kRayThreads, budget));
     k_raycast_weight<<<dim3(rblocks, c->F), kRayThreads, smem, s>>>(ra);
     c->launches++;
     if (c->profiling) CK(cudaEventRecord(c->ev[3], s));
+    CK(cudaGetLastError());
+    c->local_pending = true;
+    return MCL_OK;
+}
 
-    // sum_weights = accumulate(weights_) ; w /= sum (:679-686) ; expected_pose (:696-716)
-    rc = run_exact(c, c->d_wraw, nullptr, c->d_S1, nullptr, 0, true);
+// Second half: sum_weights = accumulate(weights_); w /= sum (:679-686); particles_ = proposal
+// (:689); expected_pose (:696-716) -- over ALL particles of the filter.
+int update_finish(mcl_ctx* c) {
+    if (!c->local_pending) return fail(MCL_ERR_INVALID, "mcl_update_finish without mcl_update_local");
+    const int dst = c->cur ^ 1;
+    int rc = run_exact(c, c->d_wraw, nullptr, c->d_S1, nullptr, 0, true);
     if (rc) return rc;
     rc = launch_pose(c, c->d_wraw, c->d_S1, c->d_wn, dst);
     if (rc) return rc;
-    if (c->profiling) CK(cudaEventRecord(c->ev[4], s));
+    if (c->profiling) CK(cudaEventRecord(c->ev[4], c->stream));
     CK(cudaGetLastError());
     c->cur = dst;
     c->update_no++;
+    c->local_pending = false;
     return MCL_OK;
+}
+
+int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, const double* u_dev, const double* z_dev) {
+    int rc = update_local(c, action_dev, obs_dev, u_dev, z_dev);
+    if (rc) return rc;
+    return update_finish(c);
 }
 
 }  // namespace
@@ -435,6 +461,7 @@ int mcl_create(const mcl_params* p, int device, mcl_ctx** out) {
     c->device = device;
     c->F = p->num_filters;
     c->N = p->max_particles;
+    c->cnt = c->N;
     cudaDeviceProp prop{};
     CK(cudaGetDeviceProperties(&prop, device));
     c->num_sms = prop.multiProcessorCount;
@@ -975,6 +1002,45 @@ int mcl_kernel_launches(mcl_ctx* c, int64_t* count) {
     if (!c || !count) return fail(MCL_ERR_INVALID, "null argument");
     *count = c->launches;
     return MCL_OK;
+}
+
+int mcl_set_shard(mcl_ctx* c, int64_t lo, int64_t count) {
+    if (!c) return fail(MCL_ERR_INVALID, "null context");
+    if (c->F != 1) return fail(MCL_ERR_INVALID, "particle sharding applies to a single filter, not a batch");
+    if (lo < 0 || count < 1 || lo + count > c->N) return fail(MCL_ERR_INVALID, "shard [%lld,+%lld) outside [0,%lld)",
+                                                               (long long)lo, (long long)count, (long long)c->N);
+    if (c->local_pending) return fail(MCL_ERR_INVALID, "update in flight");
+    c->lo = lo;
+    c->cnt = count;
+    return MCL_OK;
+}
+
+int mcl_update_local_dev(mcl_ctx* c, const double* action_dev, const float* obs_dev, int num_beams, const double* u_dev,
+                         const double* z_dev) {
+    if (!c || !action_dev || !obs_dev) return fail(MCL_ERR_INVALID, "null argument");
+    if (num_beams != c->R) return fail(MCL_ERR_INVALID, "num_beams %d != configured %d", num_beams, c->R);
+    CK(cudaSetDevice(c->device));
+    return update_local(c, action_dev, obs_dev, u_dev, z_dev);
+}
+
+int mcl_exchange_buffers_dev(mcl_ctx* c, void* ptrs_out[4], int64_t* n_total, int64_t* lo, int64_t* count) {
+    if (!c || !ptrs_out) return fail(MCL_ERR_INVALID, "null argument");
+    if (!c->local_pending) return fail(MCL_ERR_INVALID, "call mcl_update_local_dev first");
+    const int dst = c->cur ^ 1;
+    ptrs_out[0] = c->d_px[dst];
+    ptrs_out[1] = c->d_py[dst];
+    ptrs_out[2] = c->d_pt[dst];
+    ptrs_out[3] = c->d_wraw;
+    if (n_total) *n_total = c->N;
+    if (lo) *lo = c->lo;
+    if (count) *count = c->cnt;
+    return MCL_OK;
+}
+
+int mcl_update_finish_dev(mcl_ctx* c) {
+    if (!c) return fail(MCL_ERR_INVALID, "null context");
+    CK(cudaSetDevice(c->device));
+    return update_finish(c);
 }
 
 int mcl_set_stream(mcl_ctx* c, void* stream) {

@@ -1,0 +1,115 @@
+"""Particle-sharded operation of ONE global filter: one process per GPU.
+
+The reference has a single process and no collectives.  Its update couples particles in three
+places -- the weight sum (src/particle_filter.cpp:679), the global CDF + source gather of the
+multinomial resampling (:658-665) and the expected-pose sums (:702-710).  Sharding keeps the
+reference's semantics exactly:
+
+  * every rank holds the whole filter state, but computes only output slots
+    [rank * n_local, (rank + 1) * n_local) of the expensive per-particle stages
+    (resample search, motion, ray cast, weights);
+  * ONE exchange step per update: an in-place all-gather of the four state arrays
+    (x, y, theta, raw weight) over NCCL / NVLink;
+  * the global weight sum, normalisation, pose and the next CDF are then computed on every
+    rank from identical data with deterministic kernels, so all ranks stay bit-identical and
+    the gathered result equals the single-filter update with the same noise.
+
+`ShardPlan` and `exchange` are backend-agnostic host logic (exercised with gloo on CPU in
+tests/test_sharded_gloo.py); `ShardedFilter` binds them to the CUDA context.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+class ShardPlan:
+    """Contiguous, equal slot ranges: rank r owns [r * n_local, (r + 1) * n_local)."""
+
+    def __init__(self, n_global: int, world: int):
+        if world < 1 or n_global < world:
+            raise ValueError("bad shard plan: %d particles over %d ranks" % (n_global, world))
+        if n_global % world:
+            raise ValueError("max_particles (%d) must be a multiple of the number of ranks (%d)" % (n_global, world))
+        self.n_global = n_global
+        self.world = world
+        self.n_local = n_global // world
+
+    def slots(self, rank: int):
+        if not 0 <= rank < self.world:
+            raise ValueError("rank %d outside [0,%d)" % (rank, self.world))
+        return rank * self.n_local, self.n_local
+
+    def owner(self, slot):
+        return np.asarray(slot) // self.n_local
+
+
+def exchange(arrays, plan: ShardPlan, rank: int, group=None):
+    """All-gather, in place, the rank's slice of every array in `arrays` (1-D torch tensors of
+    length n_global living on the backend's device)."""
+    import torch.distributed as dist
+    lo, cnt = plan.slots(rank)
+    backend = dist.get_backend(group)
+    for full in arrays:
+        if full.numel() != plan.n_global:
+            raise ValueError("array of %d elements, expected %d" % (full.numel(), plan.n_global))
+        if backend == "nccl":
+            # in place: the send buffer is the rank's own slice of the receive buffer
+            dist.all_gather_into_tensor(full, full[lo:lo + cnt], group=group)
+        else:
+            mine = full[lo:lo + cnt].clone()
+            dist.all_gather([full[r * cnt:(r + 1) * cnt] for r in range(plan.world)], mine, group=group)
+
+
+class _DevArray:
+    """A device pointer dressed as a __cuda_array_interface__ object so torch can alias it."""
+
+    def __init__(self, ptr: int, n: int, typestr: str = "<f8"):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+class ShardedFilter:
+    """One rank's share of a particle-sharded global filter (needs torch.distributed + NCCL)."""
+
+    def __init__(self, grid, angles, n_local: int, rank: int, world: int, device: int = 0, seed: int = 0, **params):
+        import torch
+        from .capi import MclContext
+        self.torch = torch
+        self.rank, self.world, self.device = rank, world, device
+        self.plan = ShardPlan(n_local * world, world)
+        self.ctx = MclContext(device=device, max_particles=self.plan.n_global, seed=seed, **params)
+        self.ctx.set_map(grid)
+        self.ctx.set_beam_angles(angles)
+        lo, cnt = self.plan.slots(rank)
+        self.ctx.set_shard(lo, cnt)
+        self._alias = {}
+        self._pinned = None
+
+    def init_pose(self, pose, normals_3n=None):
+        # every rank initialises the full state; the device RNG is keyed by the global slot,
+        # so all ranks hold identical particles
+        self.ctx.init_pose(pose, normals_3n)
+
+    def _tensor(self, ptr: int, n: int):
+        t = self._alias.get(ptr)
+        if t is None:
+            t = self.torch.as_tensor(_DevArray(ptr, n), device="cuda:%d" % self.device)
+            self._alias[ptr] = t
+        return t
+
+    def update_dev(self, action_dev_ptr: int, obs_dev_ptr: int, u_dev_ptr: int = 0, z_dev_ptr: int = 0):
+        """One MCL update; inputs on the device; the ctx must launch on torch's current stream."""
+        self.ctx.update_local_dev(action_dev_ptr, obs_dev_ptr, u_dev_ptr, z_dev_ptr)
+        ptrs, n, _, _ = self.ctx.exchange_buffers_dev()
+        exchange([self._tensor(p, n) for p in ptrs], self.plan, self.rank)
+        self.ctx.update_finish_dev()
+
+    def update(self, action, obs, u=None, z3n=None):
+        """Host-facing update: action/scan (and optional injected noise for the WHOLE filter)
+        copied in, pose copied out."""
+        torch = self.torch
+        a = torch.as_tensor(np.ascontiguousarray(action, dtype=np.float64)).cuda(self.device)
+        o = torch.as_tensor(np.ascontiguousarray(obs, dtype=np.float32)).cuda(self.device)
+        ud = None if u is None else torch.as_tensor(np.ascontiguousarray(u, dtype=np.float64)).cuda(self.device)
+        zd = None if z3n is None else torch.as_tensor(np.ascontiguousarray(z3n, dtype=np.float64)).cuda(self.device)
+        self.update_dev(a.data_ptr(), o.data_ptr(), 0 if ud is None else ud.data_ptr(), 0 if zd is None else zd.data_ptr())
+        return self.ctx.read_pose()

@@ -1,0 +1,117 @@
+"""The algorithms the CUDA kernels run (csrc/march.cuh, csrc/exact_sum.cuh, csrc/map_prep.cpp),
+compiled for the CPU by tests/emu and checked against the oracle -- so the kernel LOGIC is
+verified in the GPU-less container.  The kernels themselves are checked by tests/test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+from emu_bindings import EmuMap, exact_scan
+from helpers import steps_from_ranges
+from monte_carlo_localization_b200 import maps, synth
+from oracle import bindings as ob
+
+
+def _seq_cumsum(a):
+    return np.add.accumulate(np.asarray(a, dtype=np.float64))   # strictly sequential
+
+
+CASES = {
+    "pow8": lambda rng, n: rng.random(n) ** 8 + 1e-300,
+    "uniform": lambda rng, n: np.full(n, 1.0 / n),
+    "lognormal": lambda rng, n: np.exp(rng.normal(size=n) * 20),
+    "spike": lambda rng, n: np.where(np.arange(n) == n // 2, 1e6, rng.random(n)),
+    "onehot": lambda rng, n: np.where(np.arange(n) == min(77, n - 1), 1.0, 0.0),
+    "stuck_at_binade": lambda rng, n: np.concatenate([[0.5 - 2.0 ** -40], np.full(n - 1, 2.0 ** -60)]),
+}
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+@pytest.mark.parametrize("n", [1, 2, 15, 16, 17, 4000, 4096, 4097, 65536, 300001])
+def test_exact_sum_and_cdf_equal_sequential(case, n):
+    rng = np.random.default_rng(n)
+    w = np.ascontiguousarray(CASES[case](rng, n), dtype=np.float64)
+    seq = _seq_cumsum(w)
+    total, prefix, _ = exact_scan(w)
+    assert total == seq[-1]
+    assert np.array_equal(prefix, seq)
+    if seq[-1] > 0:
+        p = w / seq[-1]
+        cp = _seq_cumsum(p)
+        cp[-1] = 1.0
+        _, cdf, _ = exact_scan(w, div=float(seq[-1]), force_last_one=True)
+        assert np.array_equal(cdf, cp)
+
+
+def test_exact_cdf_matches_libstdcpp_discrete_distribution():
+    rng = np.random.default_rng(1)
+    for n in (2, 100, 4000, 100000):
+        w = rng.random(n) ** 4 + 1e-9
+        u = rng.random(2000)
+        idx_ref, cdf_ref = ob.resample_indices(w, u, want_cdf=True)
+        s, _, _ = exact_scan(w, want_prefix=False)
+        _, cdf, _ = exact_scan(w, div=s, force_last_one=True)
+        assert np.array_equal(cdf, cdf_ref)
+        assert np.array_equal(np.searchsorted(cdf, u, side="left"), idx_ref)
+
+
+def test_plain_parallel_scan_would_not_be_exact():
+    """Why the exact machinery exists: a chunked parallel-style scan differs in the last bits."""
+    rng = np.random.default_rng(2)
+    w = rng.random(100000)
+    seq = _seq_cumsum(w)
+    chunked = np.cumsum(np.cumsum(w.reshape(-1, 16), axis=1)[:, -1])
+    assert (chunked != seq[15::16]).any()
+
+
+def _stress_poses(g, n, seed, angles):
+    rng = np.random.default_rng(seed)
+    res = g.resolution_f64
+    x = rng.uniform(g.origin[0] - 1.0, g.origin[0] + g.width * res + 1.0, n)
+    y = rng.uniform(g.origin[1] - 1.0, g.origin[1] + g.height * res + 1.0, n)
+    th = rng.uniform(-np.pi, np.pi, n)
+    k = n // 2   # cell corners (initialize_global poses) and axis-aligned rays stress the edge rule
+    x[:k] = rng.integers(0, g.width, k) * res + g.origin[0]
+    y[:k] = rng.integers(0, g.height, k) * res + g.origin[1]
+    th[:k // 2] = rng.integers(-2, 3, k // 2) * np.pi / 2 - angles[rng.integers(0, len(angles), k // 2)].astype(np.float64)
+    return x, y, th
+
+
+@pytest.mark.parametrize("name", ["sibal1", "Spielberg_map", "basement_fixed", "first_map"])
+@pytest.mark.parametrize("use_window", [False, True])
+def test_skip_map_march_equals_reference_march(name, use_window):
+    g = maps.load_named_map(name)
+    angles = synth.beam_angles()
+    em = EmuMap(g)
+    n = 6000
+    x, y, th = _stress_poses(g, n, 3, angles)
+    orc = ob.Oracle(g, angles, max_particles=n)
+    q = np.stack([np.repeat(x, len(angles)), np.repeat(y, len(angles)),
+                  (th[:, None] + angles[None, :].astype(np.float64)).reshape(-1)])
+    want = steps_from_ranges(orc.calc_range_many(q), g.resolution_f64, orc.M).reshape(n, len(angles))
+    window = None
+    if use_window:
+        ww, wh = min(em.PW, 640), min(em.PH, 640)
+        wx0 = max(0, min(em.PW - ww, em.PW // 2 - ww // 2)) & ~31
+        wy0 = max(0, min(em.PH - wh, em.PH // 2 - wh // 2))
+        window = (wx0, wy0, ww, wh)
+    got, replays = em.range_steps(x, y, th, angles, window)
+    assert em.M == orc.M
+    assert np.array_equal(got.astype(np.int64), want), "%d rays differ" % int((got != want).sum())
+    assert replays > 0   # the stress poses do exercise the exact-replay rule
+
+
+def test_skip_map_codes_are_conservative():
+    """Every code's promise holds: no blocked cell within adv cells of a cell of code 1+adv."""
+    g = maps.load_named_map("sibal1")
+    em = EmuMap(g)
+    v8 = em.v8().astype(np.int32)
+    blocked = v8 == 0
+    from scipy import ndimage
+    dil = ndimage.binary_dilation(blocked, structure=np.ones((3, 3), bool), border_value=1)
+    d = ndimage.distance_transform_edt(~dil)
+    free = v8 >= 2
+    adv = v8 - 1
+    assert (adv[free] < d[free] + 1.0 + 1e-9).all()
+    assert ((v8 == 1) == (dil & ~blocked)).all()
+    v4 = em.v4()
+    lo, hi = v4 & 15, v4 >> 4
+    assert np.array_equal(lo, np.minimum(v8[:, 0::2], 15)) and np.array_equal(hi, np.minimum(v8[:, 1::2], 15))

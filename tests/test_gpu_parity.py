@@ -211,3 +211,56 @@ def test_device_rng_update_runs_and_tracks():
     w = c.get_weights()
     assert abs(w.sum() - 1.0) < 1e-9 and (w > 0).all()
     c.close()
+
+
+def test_particle_shards_reproduce_single_filter():
+    """Two emulated ranks on one GPU (run one after the other, exchange by copying slices):
+    local slots -> exchange -> finish must equal the golden single-filter update exactly."""
+    import torch
+    from monte_carlo_localization_b200 import maps
+    from monte_carlo_localization_b200.sharded import ShardPlan, _DevArray
+    z = load_golden("update_sibal1_4000.npz")
+    g = maps.load_named_map("sibal1")
+    N, world = int(z["N"]), 2
+    plan = ShardPlan(N, world)
+    ranks = []
+    for r in range(world):
+        c = _ctx(g, z["angles"], N)
+        c.set_shard(*plan.slots(r))
+        ranks.append(c)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    for c in ranks:
+        c.set_stream(stream.cuda_stream)
+    prev_p, prev_w = z["init_particles"], z["init_weights"]
+    for t in range(len(z["u"])):
+        a = torch.from_numpy(z["actions"][t].copy()).cuda()
+        o = torch.from_numpy(z["obs"][t].copy()).cuda()
+        u = torch.from_numpy(z["u"][t].copy()).cuda()
+        zz = torch.from_numpy(z["z"][t].copy()).cuda()
+        bufs = []
+        for c in ranks:
+            c.set_particles(prev_p, prev_w)
+            c.update_local_dev(a.data_ptr(), o.data_ptr(), u.data_ptr(), zz.data_ptr())
+            ptrs, n, lo, cnt = c.exchange_buffers_dev()
+            bufs.append([torch.as_tensor(_DevArray(p, n), device="cuda") for p in ptrs])
+        for r, c in enumerate(ranks):          # the all-gather, emulated with copies
+            for q in range(world):
+                if q == r:
+                    continue
+                lo, cnt = plan.slots(q)
+                for k in range(4):
+                    bufs[r][k][lo:lo + cnt].copy_(bufs[q][k][lo:lo + cnt])
+        torch.cuda.synchronize()
+        for r, c in enumerate(ranks):
+            c.update_finish_dev()
+            pose = c.read_pose()
+            lo, cnt = plan.slots(r)
+            assert np.array_equal(c.resample_indices()[lo:lo + cnt], z["idx"][t][lo:lo + cnt])
+            assert_weights_close(c.get_weights(), z["weights"][t])
+            assert_pose_close(pose, z["pose"][t])
+        assert np.array_equal(ranks[0].get_weights(), ranks[1].get_weights())   # ranks bit-identical
+        assert np.array_equal(ranks[0].get_particles(), ranks[1].get_particles())
+        prev_p, prev_w = z["particles"][t], z["weights"][t]
+    for c in ranks:
+        c.close()
