@@ -265,6 +265,10 @@ def run_gpu(args):
         step_dev(t)
         t += 1
     barrier()
+    # snapshot of the filter at the start of the timed region, so that the e2e leg below
+    # replays exactly the same K steps from exactly the same state
+    t_start = t
+    snap_p, snap_w = ctx.get_particles(), ctx.get_weights()
 
     # ---- timed: inputs resident in HBM -----------------------------------------------------
     sampler = ClockSampler(local_rank)
@@ -276,7 +280,8 @@ def run_gpu(args):
     barrier()
     wall0 = time.perf_counter()
     for k in range(K):
-        flush.zero_()                      # L2 flush, outside the timed interval
+        if not os.environ.get('BENCH_NOFLUSH'):
+            flush.zero_()                  # L2 flush, outside the timed interval
         ev[k][0].record(stream)
         step_dev(t)
         ev[k][1].record(stream)
@@ -312,9 +317,10 @@ def run_gpu(args):
     ctx.set_profiling(False)
 
     # ---- e2e: host buffers through the C-ABI call -----------------------------------------
-    Ke = max(3, min(K, 50))
-    acts_h = [np.ascontiguousarray(actions[t + i]) for i in range(Ke)]
-    obs_h = [np.ascontiguousarray(obs[t + i]) for i in range(Ke)]
+    Ke = K
+    acts_h = [np.ascontiguousarray(actions[t_start + i]) for i in range(Ke)]
+    obs_h = [np.ascontiguousarray(obs[t_start + i]) for i in range(Ke)]
+    ctx.set_particles(snap_p, snap_w)      # same state, same steps as the device-resident leg
     barrier()
     t0 = time.perf_counter()
     for i in range(Ke):

@@ -10,6 +10,8 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
+#include <type_traits>
+
 #include "device_utils.cuh"
 #include "exact_sum.cuh"
 #include "map_prep.h"
@@ -29,8 +31,9 @@ struct MapDev {
     int W, H, PW, PH;
     double res, ox, oy;
     int M;                 // MAX_RANGE_PX
-    // shared-memory window geometry (cells); ww == 0 disables the window path
-    int ww, wh;
+    // shared-memory window geometry (cells); ww == 0 disables the window path.
+    // wbits = 8: one byte per cell (full skip code); 4: two cells per byte (code clamped to 15)
+    int ww, wh, wbits;
 };
 
 // Shared-memory form of the 4-bit window: a 32-bit shared-space address, so the march issues
@@ -45,6 +48,24 @@ struct WindowV4S {
         return (b >> ((x & 1) << 2)) & 15;
     }
 };
+
+// One byte per cell: the march reads the full 8-bit skip code with a single LDS.U8.
+struct WindowV8S {
+    uint32_t saddr;
+    int offx, offy, pitch;
+    __device__ __forceinline__ int get(int lx, int ly) const {
+        uint32_t b;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b) : "r"(saddr + static_cast<uint32_t>((ly + offy) * pitch + lx + offx)));
+        return static_cast<int>(b);
+    }
+};
+
+// keeps a value in a register: the compiler may not rematerialise it inside the march loop
+__device__ __forceinline__ int pin_reg(int v) {
+    int r;
+    asm volatile("mov.b32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
+}
 
 struct BeamDev {
     int R;
@@ -652,18 +673,19 @@ constexpr int kRayThreads = 1024;
 // One lane = one particle; the lane walks its R beams in order and folds the table
 // entries into the weight product in the reference's multiplication order (:564-579).
 // Lanes of a warp hold heading-neighbours (perm), so their rays and trip counts agree.
+template <int WBITS>
 __global__ void __launch_bounds__(kRayThreads, 1) k_raycast_weight(RayArgs a) {
     extern __shared__ __align__(16) uint8_t smem_win[];
     const int f = blockIdx.y;
     const MapDev& mp = a.map;
     const int64_t N = a.N;
     const int64_t fo = static_cast<int64_t>(f) * N;
-    const int M = mp.M;
+    const int M = pin_reg(mp.M);
     const int R = a.beams.R;
 
-    // ---- stage the window of the nibble skip map around the cloud centre -------------------
+    // ---- stage the window of the skip map around the cloud centre --------------------------
     int wx0 = 0, wy0 = 0, vx0 = 0, vx1 = 0, vy0 = 0, vy1 = 0;
-    const int pitch = mp.ww >> 1;
+    const int pitch = WBITS == 8 ? mp.ww : (mp.ww >> 1);
     if (mp.ww > 0) {
         const double mx = a.centre[2 * f + 0] / static_cast<double>(a.cnt);
         const double my = a.centre[2 * f + 1] / static_cast<double>(a.cnt);
@@ -681,10 +703,11 @@ __global__ void __launch_bounds__(kRayThreads, 1) k_raycast_weight(RayArgs a) {
         vy1 = (wy0 + mp.wh >= mp.PH) ? mp.PH - 2 : wy0 + mp.wh - M - 2;
         const int vec_per_row = pitch >> 4;  // 16-byte vectors per window row
         const int total = vec_per_row * mp.wh;
-        const int gpitch = mp.PW >> 1;
+        const int gpitch = WBITS == 8 ? mp.PW : (mp.PW >> 1);
+        const uint8_t* gsrc = WBITS == 8 ? mp.v8 + wx0 : mp.v4 + (wx0 >> 1);
         for (int i = threadIdx.x; i < total; i += kRayThreads) {
             const int row = i / vec_per_row, col = i - row * vec_per_row;
-            const uint4 v = __ldg(reinterpret_cast<const uint4*>(mp.v4 + static_cast<int64_t>(wy0 + row) * gpitch + (wx0 >> 1)) + col);
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(gsrc + static_cast<int64_t>(wy0 + row) * gpitch) + col);
             reinterpret_cast<uint4*>(smem_win + row * pitch)[col] = v;
         }
         __syncthreads();
@@ -694,7 +717,8 @@ __global__ void __launch_bounds__(kRayThreads, 1) k_raycast_weight(RayArgs a) {
     uint32_t win_saddr;
     asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(win_saddr) : "l"(smem_win));
     const RefGrid rg{mp.grid, mp.W, mp.H, mp.res, mp.ox, mp.oy};
-    const double* slice = a.slice + static_cast<int64_t>(f) * R * (M + 1);
+    const int tw = M + 1;
+    const double* slice = a.slice + static_cast<int64_t>(f) * R * tw;
     const int32_t* perm = a.perm ? a.perm + fo + a.lo : nullptr;
     int replays = 0;
 
@@ -712,25 +736,26 @@ __global__ void __launch_bounds__(kRayThreads, 1) k_raycast_weight(RayArgs a) {
         if (!inside) {
             // first sample is already out of bounds for every beam (:632-636): step 0
             for (int j = 0; j < R; ++j) {
-                acc = __dmul_rn(acc, __ldg(slice + j * (M + 1)));
+                acc = __dmul_rn(acc, __ldg(slice + static_cast<unsigned>(j * tw)));
                 if (steps) steps[j] = 0;
             }
         } else {
             const int fqx = static_cast<int>(floor(qx)), fqy = static_cast<int>(floor(qy));
             const RayStart st = make_ray_start(qx, qy, fqx, fqy);
             const bool in_win = (mp.ww > 0) && fqx >= vx0 && fqx < vx1 && fqy >= vy0 && fqy < vy1;
-            const WindowV4S wacc{win_saddr, st.bx - wx0, st.by - wy0, pitch};
+            using WinAcc = typename std::conditional<WBITS == 8, WindowV8S, WindowV4S>::type;
+            const WinAcc wacc{win_saddr, pin_reg(st.bx - wx0), pin_reg(st.by - wy0), pitch};
             const GlobalV8 gacc = make_global_v8(mp.v8, mp.PW, st.bx, st.by);
             for (int j = 0; j < R; ++j) {
                 int dxf, dyf;
                 beam_direction_fixed(cth, sth, a.beams.cosa[j], a.beams.sina[j], &dxf, &dyf);
-                const ReplayArgs ra{x, y, __dadd_rn(th, static_cast<double>(a.beams.angle[j]))};
+                const ReplayArgs ra{x, y, th, a.beams.angle[j]};
                 int r;
                 if (in_win)
                     r = march_ray(wacc, st, dxf, dyf, M, rg, ra, &replays);
                 else
                     r = march_ray(gacc, st, dxf, dyf, M, rg, ra, &replays);
-                acc = __dmul_rn(acc, __ldg(slice + j * (M + 1) + r));
+                acc = __dmul_rn(acc, __ldg(slice + static_cast<unsigned>(j * tw + r)));
                 if (steps) steps[j] = static_cast<uint8_t>(r);
             }
         }
@@ -900,7 +925,7 @@ __global__ void __launch_bounds__(256) k_range_queries(QueryArgs a) {
         const RayStart st = make_ray_start(qx, qy, static_cast<int>(floor(qx)), static_cast<int>(floor(qy)));
         const GlobalV8 gacc = make_global_v8(mp.v8, mp.PW, st.bx, st.by);
         const RefGrid rg{mp.grid, mp.W, mp.H, mp.res, mp.ox, mp.oy};
-        const ReplayArgs ra{x, y, ang};
+        const ReplayArgs ra{x, y, ang, 0.0f};
         int dxf, dyf;
         beam_direction_fixed(c, s, 1.0, 0.0, &dxf, &dyf);
         r = march_ray(gacc, st, dxf, dyf, mp.M, rg, ra, nullptr);

@@ -130,7 +130,8 @@ MCL_HD WindowV4 make_window_v4(const uint8_t* w4, int wx0, int wy0, int pitch, i
 
 struct ReplayArgs {
     double x, y;        // particle position (metres)
-    double ang;         // theta + (double)beam_angle, as the reference forms it (:533)
+    double theta;       // particle heading
+    float beam;         // beam angle (float32, as downsampled_angles_ holds it)
 };
 
 #if defined(__CUDA_ARCH__)
@@ -168,6 +169,37 @@ MCL_HD bool p_inside(double qx, double qy, int PW, int PH) {
     return (qx >= 2.0) && (qx < static_cast<double>(PW - 2)) && (qy >= 2.0) && (qy < static_cast<double>(PH - 2));
 }
 
+#if defined(__CUDA_ARCH__)
+#define MCL_NOINLINE __device__ __noinline__
+#else
+#define MCL_NOINLINE
+#endif
+
+// Rare path of the march: sample k lies within kEta of a cell edge while sitting in a cell of
+// code 0/1.  If a cell across a close edge has the other class, the reference's FP64
+// arithmetic decides.  Kept out of line so none of it (FP64 sincos, replay loop) is hoisted
+// into the per-ray or per-sample code.
+template <class Acc>
+MCL_NOINLINE int resolve_uncertain(const Acc& acc, uint32_t px, uint32_t py, int v, const RefGrid& g,
+                                   const ReplayArgs& ra, int k, int* replays) {
+    const bool hit = (v == 0);
+    const int cx = static_cast<int>(px >> kFrac), cy = static_cast<int>(py >> kFrac);
+    const uint32_t fx = px & kFracMask, fy = py & kFracMask;
+    const bool ux = ((fx + kEtaFix) & kFracMask) < 2u * kEtaFix;
+    const bool uy = ((fy + kEtaFix) & kFracMask) < 2u * kEtaFix;
+    const int nx = cx + (fx < kEtaFix ? -1 : 1);
+    const int ny = cy + (fy < kEtaFix ? -1 : 1);
+    bool differs = false;
+    if (ux) differs |= ((acc.get(nx, cy) == 0) != hit);
+    if (uy) differs |= ((acc.get(cx, ny) == 0) != hit);
+    if (ux && uy) differs |= ((acc.get(nx, ny) == 0) != hit);
+    if (!differs) return v;
+    double sn, cs;
+    sincos_ref(nf_add(ra.theta, static_cast<double>(ra.beam)), &sn, &cs);   // theta + angle (:533)
+    if (replays) ++*replays;
+    return replay_sample_is_hit(g, ra.x, ra.y, nf_mul(cs, g.res), nf_mul(sn, g.res), k) ? 0 : 1;
+}
+
 // March one ray.  (dxf, dyf) = round(cos a * 2^23), round(sin a * 2^23).  Returns the step
 // index r in [0, M] (M == no hit).  `replays` (nullable) counts exact replays for diagnostics.
 template <class Acc>
@@ -179,32 +211,14 @@ MCL_HD int march_ray(const Acc& acc, const RayStart& st, int dxf, int dyf, int M
     do {
         const uint32_t px = st.p0x + static_cast<uint32_t>(k * dxf);
         const uint32_t py = st.p0y + static_cast<uint32_t>(k * dyf);
-        const int cx = static_cast<int>(px >> kFrac);   // ray-local cell
-        const int cy = static_cast<int>(py >> kFrac);
-        int v = acc.get(cx, cy);
+        int v = acc.get(static_cast<int>(px >> kFrac), static_cast<int>(py >> kFrac));   // ray-local cell
         if (v < 2) {
-            // code 0 or 1: the class of this very sample matters
-            bool hit = (v == 0);
-            const uint32_t fx = px & kFracMask, fy = py & kFracMask;
-            const bool ux = ((fx + kEtaFix) & kFracMask) < 2u * kEtaFix;
-            const bool uy = ((fy + kEtaFix) & kFracMask) < 2u * kEtaFix;
-            if (ux || uy) {
-                const int nx = cx + (fx < kEtaFix ? -1 : 1);
-                const int ny = cy + (fy < kEtaFix ? -1 : 1);
-                bool differs = false;
-                if (ux) differs |= ((acc.get(nx, cy) == 0) != hit);
-                if (uy) differs |= ((acc.get(cx, ny) == 0) != hit);
-                if (ux && uy) differs |= ((acc.get(nx, ny) == 0) != hit);
-                if (differs) {
-                    double sn, cs;
-                    sincos_ref(ra.ang, &sn, &cs);
-                    hit = replay_sample_is_hit(g, ra.x, ra.y, nf_mul(cs, g.res), nf_mul(sn, g.res), k);
-                    if (replays) ++*replays;
-                }
-            }
-            if (hit) {
+            // code 0 (blocked) or 1 (next to blocked): the class of this very sample matters
+            const uint32_t tx = (px + kEtaFix) & kFracMask, ty = (py + kEtaFix) & kFracMask;
+            if ((tx < ty ? tx : ty) < 2u * kEtaFix) v = resolve_uncertain(acc, px, py, v, g, ra, k, replays);
+            if (v == 0) {
                 r = k - 1;
-                k = M;      // k + 1 > M ends the loop
+                k = 1 << 20;      // ends the loop
             }
             v = 2;
         }

@@ -45,7 +45,7 @@ cudaError_t dalloc(T** p, size_t n) {
     return cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(n, 1) * sizeof(T));
 }
 
-constexpr size_t kWindowBudget = 200 * 1024;   // bytes of shared memory for the skip-map window
+constexpr size_t kWindowBudget = 226 * 1024;   // shared memory for the skip-map window (227 KB/CTA - 1 KB reserved)
 
 }  // namespace
 
@@ -357,12 +357,15 @@ int update_local(mcl_ctx* c, const double* action_dev, const float* obs_dev, con
     ra.centre = c->d_centre;
     ra.inv_squash = 1.0 / c->prm.squash_factor;
     ra.replay_count = c->d_replays;
-    const size_t smem = static_cast<size_t>(c->map.ww / 2) * c->map.wh;
+    const size_t smem = static_cast<size_t>(c->map.wbits == 8 ? c->map.ww : c->map.ww / 2) * c->map.wh;
     // persistent blocks: one per SM when the window fills shared memory, a few otherwise
     const int per_sm = smem > 100 * 1024 ? 1 : 2;
     const int budget = std::max(1, (c->num_sms * per_sm) / std::min(c->F, c->num_sms * per_sm));
     const int rblocks = static_cast<int>(std::min<int64_t>((c->cnt + kRayThreads - 1) / kRayThreads, budget));
-    k_raycast_weight<<<dim3(rblocks, c->F), kRayThreads, smem, s>>>(ra);
+    if (c->map.wbits == 8)
+        k_raycast_weight<8><<<dim3(rblocks, c->F), kRayThreads, smem, s>>>(ra);
+    else
+        k_raycast_weight<4><<<dim3(rblocks, c->F), kRayThreads, smem, s>>>(ra);
     c->launches++;
     if (c->profiling) CK(cudaEventRecord(c->ev[3], s));
     CK(cudaGetLastError());
@@ -525,7 +528,8 @@ int mcl_create(const mcl_params* p, int device, mcl_ctx** out) {
     CK(cudaMallocHost(reinterpret_cast<void**>(&c->h_action), sizeof(double) * 3 * c->F));
     CK(cudaMallocHost(reinterpret_cast<void**>(&c->h_obs), sizeof(float) * kMaxBeams * c->F));
     CK(cudaMallocHost(reinterpret_cast<void**>(&c->h_pose), sizeof(double) * 3 * c->F));
-    CK(cudaFuncSetAttribute(k_raycast_weight, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kWindowBudget)));
+    CK(cudaFuncSetAttribute(k_raycast_weight<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kWindowBudget)));
+    CK(cudaFuncSetAttribute(k_raycast_weight<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kWindowBudget)));
     CK(cudaDeviceSynchronize());
     *out = c;
     return MCL_OK;
@@ -605,21 +609,32 @@ int mcl_set_map(mcl_ctx* c, const int8_t* data, int width, int height, float res
     m.ox = ox;
     m.oy = oy;
     m.M = M;
-    // shared-memory window: the whole P-grid if it fits, else the largest box within budget
-    const size_t whole = static_cast<size_t>(m.PW / 2) * m.PH;
-    if (whole <= kWindowBudget) {
-        m.ww = m.PW;
-        m.wh = m.PH;
-    } else {
-        int side = static_cast<int>(std::sqrt(2.0 * kWindowBudget));
-        side &= ~31;
-        m.ww = std::min(m.PW, side);
-        m.wh = std::min(m.PH, static_cast<int>(2 * kWindowBudget / m.ww));
-        if (m.wh < m.PH && m.ww == side) m.wh = std::min(m.wh, side);
-        if (m.wh == m.PH) m.ww = std::min(m.PW, static_cast<int>(2 * kWindowBudget / m.wh) & ~31);
-        // a window narrower than two ray lengths can hold no particle safely
-        if (m.ww < 2 * (M + 2) + 32 && m.ww < m.PW) m.ww = m.wh = 0;
-        if (m.ww && m.wh < 2 * (M + 2) + 32 && m.wh < m.PH) m.ww = m.wh = 0;
+    // Shared-memory window of the skip map.  Preference: 8-bit codes (one LDS, longest skips)
+    // if the whole P-grid fits or a window with at least kMinSpan cells of particle room
+    // around two ray lengths does; else 4-bit codes (two cells per byte).
+    constexpr int kMinSpan = 48;
+    auto plan = [&](int bits, int* ww, int* wh) {
+        const size_t cells = kWindowBudget * (bits == 8 ? 1 : 2);
+        if (static_cast<size_t>(m.PW) * m.PH <= cells) {
+            *ww = m.PW;
+            *wh = m.PH;
+            return true;
+        }
+        int w = static_cast<int>(std::sqrt(static_cast<double>(cells))) & ~31;
+        w = std::min(w, m.PW);
+        int h = std::min(m.PH, static_cast<int>(cells / w));
+        if (h == m.PH) w = std::min(m.PW, static_cast<int>(cells / h) & ~31);
+        const int need = 2 * (M + 2) + kMinSpan;
+        if ((w < need && w < m.PW) || (h < need && h < m.PH)) return false;
+        *ww = w;
+        *wh = h;
+        return true;
+    };
+    m.ww = m.wh = 0;
+    m.wbits = 8;
+    if (!plan(8, &m.ww, &m.wh)) {
+        m.wbits = 4;
+        if (!plan(4, &m.ww, &m.wh)) m.ww = m.wh = 0;   // window path disabled: global-memory march only
     }
     c->have_map = true;
     build_sensor_table(c, c->table);

@@ -96,7 +96,7 @@ long long emu_range_steps(const emu_map* m, const double* px, const double* py, 
         for (int j = 0; j < R; ++j) {
             int dxf, dyf;
             beam_direction_fixed(cth, sth, ca[j], sa[j], &dxf, &dyf);
-            const ReplayArgs ra{x, y, th + static_cast<double>(angles[j])};
+            const ReplayArgs ra{x, y, th, angles[j]};
             const int r = in_win ? march_ray(wacc, st, dxf, dyf, M, rg, ra, &replays)
                                  : march_ray(gacc, st, dxf, dyf, M, rg, ra, &replays);
             out[j] = static_cast<uint8_t>(r);
