@@ -96,15 +96,17 @@ __device__ __forceinline__ double canonical_from_words(uint32_t a, uint32_t b) {
     return r;
 }
 
-// Two standard normals from two 32-bit words (Box-Muller in FP64).
+// Two standard normals from two 32-bit words (Box-Muller).  The transcendentals run in FP32:
+// this is the production noise source (the reference draws from std::mt19937 + Marsaglia polar,
+// so no bit pattern has to be matched) and FP32 resolution is far below the noise it models.
 __device__ __forceinline__ void normal_pair(uint32_t a, uint32_t b, double* n0, double* n1) {
-    const double u1 = (static_cast<double>(a) + 0.5) * (1.0 / 4294967296.0);  // (0,1)
-    const double u2 = (static_cast<double>(b) + 0.5) * (1.0 / 4294967296.0);
-    const double r = sqrt(-2.0 * log(u1));
-    double s, c;
-    sincospi(2.0 * u2, &s, &c);
-    *n0 = r * c;
-    *n1 = r * s;
+    const float u1 = (static_cast<float>(a >> 8) + 0.5f) * (1.0f / 16777216.0f);   // (0,1), 24 bits
+    const float u2 = (static_cast<float>(b >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float r = sqrtf(-2.0f * logf(u1));
+    float s, c;
+    sincospif(2.0f * u2, &s, &c);
+    *n0 = static_cast<double>(r * c);
+    *n1 = static_cast<double>(r * s);
 }
 
 }  // namespace mclb200

@@ -85,8 +85,9 @@ struct ExactArgs {
     int C;                   // chunks per filter = T * kTileChunks
     double* tile_sum;        // [F][T] approximate tile sums of src
     StepFn* chunk_fn;        // [F][C]
-    StepFn* chunk_pre;       // [F][C]  (opaque chunks: step map since the previous anchor in the tile)
-    uint8_t* chunk_flag;     // [F][C]  bit0 opaque, bit1 first opaque of its tile
+    StepFn* opq_pre;         // [F][C]  tile-compacted: step map from the previous anchor in the tile (or the
+                             //         tile start for the tile's first opaque chunk) to each opaque chunk
+    int* opq_idx;            // [F][C]  tile-compacted: index of the opaque chunk inside its tile
     int* tile_opq;           // [F][T]  opaque chunks per tile
     int64_t* tile_elem;      // [F][T][3]  (a0, a1, reset)
     int* list_chunk;         // [F][C]  opaque chunks in order
@@ -197,13 +198,23 @@ __global__ void __launch_bounds__(kTileChunks) k_exact_chunks(ExactArgs a) {
     sm_inc[tid] = inc;
     __syncthreads();
     const RFn exc = tid ? sm_inc[tid - 1] : ident;
-    uint8_t flag = 0;
-    if (opaque) {
-        a.chunk_pre[cidx] = exc.f;
-        flag = exc.reset ? 1 : 3;
+    // compact the tile's opaque chunks (in order) so the walk kernel never scans chunk records
+    __shared__ int wcnt[kTileChunks / 32];
+    const unsigned bal = __ballot_sync(kFullMask, opaque);
+    if ((tid & 31) == 0) wcnt[tid >> 5] = __popc(bal);
+    __syncthreads();
+    int orank = __popc(bal & ((1u << (tid & 31)) - 1u));
+    int nopq = 0;
+#pragma unroll
+    for (int w = 0; w < kTileChunks / 32; ++w) {
+        if (w < (tid >> 5)) orank += wcnt[w];
+        nopq += wcnt[w];
     }
-    a.chunk_flag[cidx] = flag;
-    const int nopq = __syncthreads_count(opaque);
+    if (opaque) {
+        const int64_t slot = static_cast<int64_t>(f) * a.C + static_cast<int64_t>(t) * kTileChunks + orank;
+        a.opq_pre[slot] = exc.f;
+        a.opq_idx[slot] = tid;
+    }
     if (tid == kTileChunks - 1) {
         int64_t* te = a.tile_elem + (static_cast<int64_t>(f) * a.T + t) * 3;
         te[0] = inc.f.a0;
@@ -231,8 +242,8 @@ __global__ void __launch_bounds__(kWalkThreads) k_exact_walk(ExactArgs a) {
     const int t0 = min(T, tid * tpt), t1 = min(T, t0 + tpt);
     const int64_t* tile_elem = a.tile_elem + static_cast<int64_t>(f) * T * 3;
     const int* tile_opq = a.tile_opq + static_cast<int64_t>(f) * T;
-    const uint8_t* chunk_flag = a.chunk_flag + static_cast<int64_t>(f) * a.C;
-    const StepFn* chunk_pre = a.chunk_pre + static_cast<int64_t>(f) * a.C;
+    const int* opq_idx = a.opq_idx + static_cast<int64_t>(f) * a.C;
+    const StepFn* opq_pre = a.opq_pre + static_cast<int64_t>(f) * a.C;
     int* list_chunk = a.list_chunk + static_cast<int64_t>(f) * a.C;
     StepFn* list_fn = a.list_fn + static_cast<int64_t>(f) * a.C;
     double* anchors = a.anchors + static_cast<int64_t>(f) * a.C;
@@ -284,16 +295,13 @@ __global__ void __launch_bounds__(kWalkThreads) k_exact_walk(ExactArgs a) {
         RFn run = exc;
         int rank = cexc;
         for (int t = t0; t < t1; ++t) {
-            if (tile_opq[t] > 0) {
-                for (int c = t * kTileChunks; c < (t + 1) * kTileChunks; ++c) {
-                    const uint8_t fl = chunk_flag[c];
-                    if (fl & 1) {
-                        const StepFn pre = chunk_pre[c];
-                        list_chunk[rank] = c;
-                        list_fn[rank] = (fl & 2) ? fn_compose(run.f, pre) : pre;
-                        ++rank;
-                    }
-                }
+            const int n = tile_opq[t];
+            for (int q = 0; q < n; ++q) {
+                const StepFn pre = opq_pre[t * kTileChunks + q];
+                list_chunk[rank] = t * kTileChunks + opq_idx[t * kTileChunks + q];
+                // the tile's first opaque chunk continues the run that entered the tile
+                list_fn[rank] = q == 0 ? fn_compose(run.f, pre) : pre;
+                ++rank;
             }
             run = RFnOp()(run, RFn{StepFn{tile_elem[3 * t], tile_elem[3 * t + 1]}, tile_elem[3 * t + 2]});
         }
@@ -349,8 +357,8 @@ __global__ void __launch_bounds__(kTileChunks) k_exact_emit(ExactArgs a) {
     const int64_t cidx = static_cast<int64_t>(f) * a.C + static_cast<int64_t>(t) * kTileChunks + tid;
     const double tstart = a.tile_start[static_cast<int64_t>(f) * a.T + t];
 
-    const uint8_t fl = a.chunk_flag[cidx];
-    ScanElem el = (fl & 1) ? se_abs(a.anchor_val[cidx]) : se_fn(a.chunk_fn[cidx]);
+    const StepFn cf = a.chunk_fn[cidx];
+    ScanElem el = fn_is_opaque(cf) ? se_abs(a.anchor_val[cidx]) : se_fn(cf);
     if (tid == 0) el = se_combine(se_abs(tstart), el);
     const ScanElem ident = se_fn(fn_identity());
     const ScanElem inc = block_scan_inclusive<kTileChunks>(el, SEOp(), sms, ident);
@@ -396,6 +404,8 @@ struct MotionArgs {
     int32_t* idx_out;         // [F][N]
     const double* u;          // [F][N] injected or nullptr
     const double* z;          // [F][3N] injected or nullptr
+    const double* tile_start; // [F][T] exact CDF value before each 4096-particle tile (from the walk)
+    int T;
     const double* action;     // [F][3] device
     double disp_x, disp_y, disp_t;
     uint64_t seed;
@@ -446,9 +456,17 @@ __device__ __forceinline__ double wrap_angle_dev(double a) {  // src/utils.cpp:4
 
 constexpr int kMotionThreads = 256;
 
+constexpr int kMaxSearchTiles = 4096;   // coarse CDF level kept in shared memory (32 KB)
+
 __global__ void __launch_bounds__(kMotionThreads) k_resample_motion(MotionArgs a) {
     __shared__ double sm[kMotionThreads / 32];
+    extern __shared__ double ts[];   // a.T doubles when the coarse level is used
     const int f = blockIdx.y;
+    const bool two_level = a.T > 1 && a.T <= kMaxSearchTiles;
+    if (two_level) {
+        for (int t = threadIdx.x; t < a.T; t += kMotionThreads) ts[t] = a.tile_start[static_cast<int64_t>(f) * a.T + t];
+        __syncthreads();
+    }
     const int64_t li = static_cast<int64_t>(blockIdx.x) * kMotionThreads + threadIdx.x;
     const int64_t i = a.lo + li;   // global slot: noise and RNG counters do not depend on the sharding
     const int64_t N = a.N;
@@ -482,6 +500,21 @@ __global__ void __launch_bounds__(kMotionThreads) k_resample_motion(MotionArgs a
         // lower_bound(cp.begin(), cp.end(), u)  (random.tcc:2709-2713)
         const double* cp = a.cdf + fo;
         int64_t lo = 0, hi = N;
+        if (two_level) {
+            // coarse level: ts[t] = cp[t*kTile - 1]; every index below t*kTile has cp <= ts[t], so
+            // with t* the last tile whose ts < u the answer lies inside tile t*
+            int tl = 0, th2 = a.T;
+            while (th2 - tl > 1) {
+                const int tm = (tl + th2) >> 1;
+                if (ts[tm] < u)
+                    tl = tm;
+                else
+                    th2 = tm;
+            }
+            lo = static_cast<int64_t>(tl) * kTile;
+            hi = min(N, lo + kTile);
+            if (hi == N) hi = N;   // the forced cp[N-1] = 1.0 closes the last tile
+        }
         while (lo < hi) {
             const int64_t mid = (lo + hi) >> 1;
             if (__ldg(cp + mid) < u)

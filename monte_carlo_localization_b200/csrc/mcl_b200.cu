@@ -91,8 +91,8 @@ struct mcl_ctx {
     int T = 0, C = 0;
     double* d_tile_sum = nullptr;
     StepFn* d_chunk_fn = nullptr;
-    StepFn* d_chunk_pre = nullptr;
-    uint8_t* d_chunk_flag = nullptr;
+    StepFn* d_opq_pre = nullptr;
+    int* d_opq_idx = nullptr;
     int* d_tile_opq = nullptr;
     int64_t* d_tile_elem = nullptr;
     int* d_list_chunk = nullptr;
@@ -140,8 +140,8 @@ ExactArgs exact_args(mcl_ctx* c, const double* src, const double* div, double* t
     a.C = c->C;
     a.tile_sum = c->d_tile_sum;
     a.chunk_fn = c->d_chunk_fn;
-    a.chunk_pre = c->d_chunk_pre;
-    a.chunk_flag = c->d_chunk_flag;
+    a.opq_pre = c->d_opq_pre;
+    a.opq_idx = c->d_opq_idx;
     a.tile_opq = c->d_tile_opq;
     a.tile_elem = c->d_tile_elem;
     a.list_chunk = c->d_list_chunk;
@@ -309,6 +309,8 @@ int update_local(mcl_ctx* c, const double* action_dev, const float* obs_dev, con
     ma.idx_out = c->d_idx;
     ma.u = u_dev;
     ma.z = z_dev;
+    ma.tile_start = c->d_tile_start;
+    ma.T = c->T;
     ma.action = action_dev;
     ma.disp_x = c->prm.motion_dispersion_x;
     ma.disp_y = c->prm.motion_dispersion_y;
@@ -317,7 +319,8 @@ int update_local(mcl_ctx* c, const double* action_dev, const float* obs_dev, con
     ma.update_no = c->update_no;
     ma.centre = c->d_centre;
     const int mblocks = static_cast<int>((c->cnt + kMotionThreads - 1) / kMotionThreads);
-    k_resample_motion<<<dim3(mblocks, c->F), kMotionThreads, 0, s>>>(ma);
+    const size_t msmem = (c->T > 1 && c->T <= kMaxSearchTiles) ? sizeof(double) * c->T : 0;
+    k_resample_motion<<<dim3(mblocks, c->F), kMotionThreads, msmem, s>>>(ma);
     c->launches++;
     if (c->sort_enabled) {
         SortArgs sa{};
@@ -497,8 +500,8 @@ int mcl_create(const mcl_params* p, int device, mcl_ctx** out) {
     const size_t FT = static_cast<size_t>(c->F) * c->T, FC = static_cast<size_t>(c->F) * c->C;
     CK(dalloc(&c->d_tile_sum, FT));
     CK(dalloc(&c->d_chunk_fn, FC));
-    CK(dalloc(&c->d_chunk_pre, FC));
-    CK(dalloc(&c->d_chunk_flag, FC));
+    CK(dalloc(&c->d_opq_pre, FC));
+    CK(dalloc(&c->d_opq_idx, FC));
     CK(dalloc(&c->d_tile_opq, FT));
     CK(dalloc(&c->d_tile_elem, FT * 3));
     CK(dalloc(&c->d_list_chunk, FC));
@@ -541,7 +544,7 @@ int mcl_destroy(mcl_ctx* c) {
     cudaDeviceSynchronize();
     void* ptrs[] = {c->d_grid, c->d_v8, c->d_v4, c->d_free, c->d_tabT, c->d_step2idx, c->d_px[0], c->d_px[1], c->d_py[0],
                     c->d_py[1], c->d_pt[0], c->d_pt[1], c->d_wraw, c->d_wn, c->d_cdf, c->d_idx, c->d_steps, c->d_u, c->d_z,
-                    c->d_action, c->d_obs, c->d_slice, c->d_tile_sum, c->d_chunk_fn, c->d_chunk_pre, c->d_chunk_flag,
+                    c->d_action, c->d_obs, c->d_slice, c->d_tile_sum, c->d_chunk_fn, c->d_opq_pre, c->d_opq_idx,
                     c->d_tile_opq, c->d_tile_elem, c->d_list_chunk, c->d_list_fn, c->d_anchors, c->d_anchor_val,
                     c->d_tile_start, c->d_S1, c->d_S2, c->d_scratch_total, c->d_partial, c->d_pose, c->d_centre, c->d_replays,
                     c->d_hist, c->d_perm};
