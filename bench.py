@@ -185,7 +185,7 @@ def run_reference(args):
     if rank != 0:
         return
     n_ref = args.ref_particles
-    cb = cpu_reference_arm(n_ref, args.steps, max(args.warmup, 1))
+    cb = cpu_reference_arm(n_ref, args.steps, max(min(args.warmup, 3), 1))
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_update"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -259,6 +259,10 @@ def run_gpu(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    # clocks are sampled from the start of the warm-up to the end of the timed region (the timed
+    # region alone can be shorter than nvidia-smi's first report)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     # ---- warm-up ---------------------------------------------------------------------------
     t = 0
     for _ in range(W):
@@ -271,8 +275,6 @@ def run_gpu(args):
     snap_p, snap_w = ctx.get_particles(), ctx.get_weights()
 
     # ---- timed: inputs resident in HBM -----------------------------------------------------
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     launches0 = ctx.kernel_launches()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     ctx.set_profiling(True)
@@ -381,8 +383,8 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--particles", type=int, default=N_PER_GPU, help="particles per GPU")
     ap.add_argument("--ref-particles", type=int, default=100000,
@@ -392,7 +394,7 @@ def main():
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args)   # each step ~0.4 s of CPU work at the default --ref-particles
     else:
         run_gpu(args)
 
