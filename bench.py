@@ -45,12 +45,13 @@ METRIC = "MCL ray-casts/s (particles x beams x updates/s)"
 UNIT = "rays/s"
 
 
-def workload_config(n_gpus: int, n_particles: int, R: int) -> dict:
+def workload_config(n_gpus: int, n_particles: int, R: int, shard_mode: str = "p2p") -> dict:
     return {"workload": "BASELINE configs[2]: %s, %d particles x %d beams per GPU, tracking replay" % (
         MAP_NAME, n_particles, R),
             "map": MAP_NAME, "particles_per_gpu": n_particles, "particles_global": n_particles * n_gpus,
             "beams": R, "max_range_px": 207,
-            "sharding": "single GPU" if n_gpus == 1 else "particle-sharded x%d, exact global resampling" % n_gpus,
+            "sharding": "single GPU" if n_gpus == 1 else "particle-sharded x%d, exact global resampling, %s exchange" % (
+                n_gpus, shard_mode),
             "l2": "flushed between timed steps (256 MiB write)", "rng": "device Philox (no injected noise)"}
 
 
@@ -225,7 +226,8 @@ def run_gpu(args):
 
     if world > 1:
         from monte_carlo_localization_b200.sharded import ShardedFilter
-        flt = ShardedFilter(grid, angles, n_local=N, rank=rank, world=world, device=local_rank, seed=20250 + 3)
+        flt = ShardedFilter(grid, angles, n_local=N, rank=rank, world=world, device=local_rank, seed=20250 + 3,
+                            mode=args.shard_mode)
         ctx = flt.ctx
     else:
         flt = None
@@ -272,7 +274,7 @@ def run_gpu(args):
     # snapshot of the filter at the start of the timed region, so that the e2e leg below
     # replays exactly the same K steps from exactly the same state
     t_start = t
-    snap_p, snap_w = ctx.get_particles(), ctx.get_weights()
+    snap_p, snap_w = flt.gather_state() if flt is not None else (ctx.get_particles(), ctx.get_weights())
 
     # ---- timed: inputs resident in HBM -----------------------------------------------------
     launches0 = ctx.kernel_launches()
@@ -371,7 +373,7 @@ def run_gpu(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "updates_per_s": 1e3 / ms_per_step,
-                "config": workload_config(world, N, R), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+                "config": workload_config(world, N, R, args.shard_mode), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
                 "roofline": roof, "cpu_baseline": cb, "stage_ms": stage,
                 "wall_ms_per_step_incl_flush": 1e3 * wall / K,
                 "pose_error_m": pose_err if flt is None else None}
@@ -390,6 +392,8 @@ def main():
     ap.add_argument("--ref-particles", type=int, default=100000,
                     help="particles of the bounded CPU sample (reference arm / cpu_baseline)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--shard-mode", default="p2p", choices=["p2p", "allgather"],
+                    help="multi-GPU exchange: NVLink peer reads of source poses + weight all-gather, or full all-gather")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

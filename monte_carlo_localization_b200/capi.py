@@ -90,6 +90,11 @@ SIGNATURES = {
     "mcl_exchange_buffers_dev": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
                                            C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "mcl_update_finish_dev": (C.c_int, [C.c_void_p]),
+    "mcl_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "mcl_ipc_import": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "mcl_set_peer_pointers": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "mcl_state_pointers_dev": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "mcl_p2p_buffers_dev": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
 }
 
 _lib = None
@@ -343,6 +348,32 @@ class MclContext:
 
     def update_finish_dev(self):
         self._check(self._L.mcl_update_finish_dev(self._h), "mcl_update_finish_dev")
+
+    IPC_BLOB = 6 * 64   # six cudaIpcMemHandle_t
+
+    def ipc_export(self) -> bytes:
+        buf = C.create_string_buffer(self.IPC_BLOB)
+        self._check(self._L.mcl_ipc_export(self._h, buf, self.IPC_BLOB), "mcl_ipc_export")
+        return bytes(buf.raw)
+
+    def ipc_import(self, world: int, rank: int, blobs: bytes):
+        if len(blobs) != world * self.IPC_BLOB:
+            raise ValueError("expected %d bytes of IPC handles" % (world * self.IPC_BLOB))
+        self._check(self._L.mcl_ipc_import(self._h, world, rank, C.c_char_p(blobs)), "mcl_ipc_import")
+
+    def state_pointers_dev(self):
+        ptrs = (C.c_void_p * 6)()
+        self._check(self._L.mcl_state_pointers_dev(self._h, ptrs), "mcl_state_pointers_dev")
+        return [int(p) for p in ptrs]
+
+    def set_peer_pointers(self, world: int, rank: int, ptrs):
+        arr = (C.c_void_p * (6 * world))(*[C.c_void_p(p) for p in ptrs])
+        self._check(self._L.mcl_set_peer_pointers(self._h, world, rank, arr), "mcl_set_peer_pointers")
+
+    def p2p_buffers_dev(self):
+        w, part = C.c_void_p(), C.c_void_p()
+        self._check(self._L.mcl_p2p_buffers_dev(self._h, C.byref(w), C.byref(part)), "mcl_p2p_buffers_dev")
+        return int(w.value), int(part.value)
 
     def set_stream(self, cuda_stream_ptr: int):
         self._check(self._L.mcl_set_stream(self._h, C.c_void_p(cuda_stream_ptr)), "mcl_set_stream")

@@ -404,6 +404,12 @@ struct MotionArgs {
     int32_t* idx_out;         // [F][N]
     const double* u;          // [F][N] injected or nullptr
     const double* z;          // [F][3N] injected or nullptr
+    // peer-to-peer sharding: source poses are read from the owning rank's buffer over NVLink.
+    // peer_x/y/t[q] = rank q's state arrays (addressed by GLOBAL index); nullptr = local arrays
+    const double* const* peer_x;
+    const double* const* peer_y;
+    const double* const* peer_t;
+    int64_t n_local;
     const double* tile_start; // [F][T] exact CDF value before each 4096-particle tile (from the walk)
     int T;
     const double* action;     // [F][3] device
@@ -525,7 +531,19 @@ __global__ void __launch_bounds__(kMotionThreads) k_resample_motion(MotionArgs a
         if (lo >= N) lo = N - 1;  // unreachable for u < 1 == cp[N-1]; keeps reads in range
         if (N < 2) lo = 0;        // libstdc++ clears the table for fewer than 2 weights
         a.idx_out[fo + i] = static_cast<int32_t>(lo);
-        const double x = a.sx[fo + lo], y = a.sy[fo + lo], th = a.st[fo + lo];
+        double x, y, th;
+        if (a.peer_x) {
+            // the slot's source lives on rank q; its arrays are mapped into this address space
+            // (CUDA IPC), so these are plain loads that travel over NVLink
+            const int q = static_cast<int>(lo / a.n_local);
+            x = a.peer_x[q][lo];
+            y = a.peer_y[q][lo];
+            th = a.peer_t[q][lo];
+        } else {
+            x = a.sx[fo + lo];
+            y = a.sy[fo + lo];
+            th = a.st[fo + lo];
+        }
         double nt;
         if (m.straight) {
             double s, c;
@@ -843,6 +861,44 @@ __global__ void __launch_bounds__(kNormThreads) k_normalize_pose(NormArgs a) {
         p[2] = as;
         p[3] = ac;
     }
+}
+
+// P2P sharding: fold the per-block pose partial sums of the rank's own slots (written by
+// k_normalize_pose run over the slice with raw weights) into four doubles, in block order
+__global__ void __launch_bounds__(256) k_sum_partials(const double* partial, int nblk, double* out4) {
+    __shared__ double sm[8];
+    double v[4] = {0, 0, 0, 0};
+    for (int b = threadIdx.x; b < nblk; b += 256) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] += partial[static_cast<int64_t>(b) * 4 + q];
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[q] = block_sum<256>(v[q], sm);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) out4[q] = v[q];
+    }
+}
+
+__global__ void k_normalize_only(const double* w_raw, const double* total, double* wn, int64_t n) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double tot = total[0];
+    const double w = w_raw[i];
+    wn[i] = tot > 0.0 ? __ddiv_rn(w, tot) : w;   // `if (sum_weights > 0)` (:680)
+}
+
+// pose from the gathered per-rank partial sums (rank order => identical on every rank)
+__global__ void k_pose_from_partials(const double* partials, int world, const double* total, double* pose_out) {
+    if (threadIdx.x || blockIdx.x) return;
+    double v[4] = {0, 0, 0, 0};
+    for (int q = 0; q < world; ++q)
+        for (int k = 0; k < 4; ++k) v[k] += partials[4 * q + k];
+    const double tot = total[0];
+    const double s = tot > 0.0 ? tot : 1.0;
+    pose_out[0] = v[0] / s;
+    pose_out[1] = v[1] / s;
+    pose_out[2] = atan2(v[2], v[3]);
 }
 
 __global__ void __launch_bounds__(256) k_pose_final(const double* partial, int nblk, double* pose_out) {

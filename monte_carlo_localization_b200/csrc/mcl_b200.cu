@@ -117,6 +117,12 @@ struct mcl_ctx {
     // particle shard: this context computes output slots [lo, lo+cnt) of the filter
     int64_t lo = 0, cnt = 0;
     bool local_pending = false;
+    // peer-to-peer sharding
+    bool p2p = false;
+    int world = 1, rank = 0;
+    const double** d_peer_tab = nullptr;     // device: [buf 2][array 3][world] pointers
+    std::vector<void*> ipc_opened;
+    double* d_partials = nullptr;            // [world][4] pose partial sums (rank's own at [rank])
     // pinned staging for the host-facing update
     double* h_action = nullptr;
     float* h_obs = nullptr;
@@ -309,6 +315,12 @@ int update_local(mcl_ctx* c, const double* action_dev, const float* obs_dev, con
     ma.idx_out = c->d_idx;
     ma.u = u_dev;
     ma.z = z_dev;
+    if (c->p2p) {
+        ma.peer_x = c->d_peer_tab + static_cast<size_t>(src * 3 + 0) * c->world;
+        ma.peer_y = c->d_peer_tab + static_cast<size_t>(src * 3 + 1) * c->world;
+        ma.peer_t = c->d_peer_tab + static_cast<size_t>(src * 3 + 2) * c->world;
+        ma.n_local = c->N / c->world;
+    }
     ma.tile_start = c->d_tile_start;
     ma.T = c->T;
     ma.action = action_dev;
@@ -370,6 +382,22 @@ int update_local(mcl_ctx* c, const double* action_dev, const float* obs_dev, con
     else
         k_raycast_weight<4><<<dim3(rblocks, c->F), kRayThreads, smem, s>>>(ra);
     c->launches++;
+    if (c->p2p) {
+        // unnormalised pose sums of the rank's own slots (deterministic two-stage reduction)
+        NormArgs na{};
+        na.N = c->cnt;
+        na.w_raw = c->d_wraw + c->lo;
+        na.total = nullptr;
+        na.wn = nullptr;
+        na.px = c->d_px[dst] + c->lo;
+        na.py = c->d_py[dst] + c->lo;
+        na.pt = c->d_pt[dst] + c->lo;
+        na.partial = c->d_partial;
+        na.nblk = c->norm_blocks;
+        k_normalize_pose<<<dim3(c->norm_blocks, 1), kNormThreads, 0, s>>>(na);
+        k_sum_partials<<<1, 256, 0, s>>>(c->d_partial, c->norm_blocks, c->d_partials + 4 * c->rank);
+        c->launches += 2;
+    }
     if (c->profiling) CK(cudaEventRecord(c->ev[3], s));
     CK(cudaGetLastError());
     c->local_pending = true;
@@ -383,8 +411,16 @@ int update_finish(mcl_ctx* c) {
     const int dst = c->cur ^ 1;
     int rc = run_exact(c, c->d_wraw, nullptr, c->d_S1, nullptr, 0, true);
     if (rc) return rc;
-    rc = launch_pose(c, c->d_wraw, c->d_S1, c->d_wn, dst);
-    if (rc) return rc;
+    if (c->p2p) {
+        // poses of other ranks are not local: normalise all weights, pose from the gathered partials
+        const int64_t n = c->N;
+        k_normalize_only<<<static_cast<unsigned>((n + 255) / 256), 256, 0, c->stream>>>(c->d_wraw, c->d_S1, c->d_wn, n);
+        k_pose_from_partials<<<1, 32, 0, c->stream>>>(c->d_partials, c->world, c->d_S1, c->d_pose);
+        c->launches += 2;
+    } else {
+        rc = launch_pose(c, c->d_wraw, c->d_S1, c->d_wn, dst);
+        if (rc) return rc;
+    }
     if (c->profiling) CK(cudaEventRecord(c->ev[4], c->stream));
     CK(cudaGetLastError());
     c->cur = dst;
@@ -550,6 +586,9 @@ int mcl_destroy(mcl_ctx* c) {
                     c->d_hist, c->d_perm};
     for (void* p : ptrs)
         if (p) cudaFree(p);
+    for (void* p : c->ipc_opened) cudaIpcCloseMemHandle(p);
+    if (c->d_peer_tab) cudaFree(c->d_peer_tab);
+    if (c->d_partials) cudaFree(c->d_partials);
     if (c->h_action) cudaFreeHost(c->h_action);
     if (c->h_obs) cudaFreeHost(c->h_obs);
     if (c->h_pose) cudaFreeHost(c->h_pose);
@@ -1052,6 +1091,90 @@ int mcl_exchange_buffers_dev(mcl_ctx* c, void* ptrs_out[4], int64_t* n_total, in
     if (n_total) *n_total = c->N;
     if (lo) *lo = c->lo;
     if (count) *count = c->cnt;
+    return MCL_OK;
+}
+
+static int install_peers(mcl_ctx* c, int world, int rank, const std::vector<const double*>& tab) {
+    if (c->F != 1) return fail(MCL_ERR_INVALID, "peer-to-peer sharding applies to a single filter");
+    if (world < 1 || rank < 0 || rank >= world || c->N % world) return fail(MCL_ERR_INVALID, "bad world/rank %d/%d for %lld particles", world, rank, (long long)c->N);
+    if (c->d_peer_tab) cudaFree(c->d_peer_tab);
+    if (c->d_partials) cudaFree(c->d_partials);
+    c->d_peer_tab = nullptr;
+    c->d_partials = nullptr;
+    CK(cudaMalloc(reinterpret_cast<void**>(&c->d_peer_tab), sizeof(double*) * tab.size()));
+    CK(cudaMemcpy(c->d_peer_tab, tab.data(), sizeof(double*) * tab.size(), cudaMemcpyHostToDevice));
+    CK(dalloc(&c->d_partials, static_cast<size_t>(4) * world));
+    CK(cudaMemset(c->d_partials, 0, sizeof(double) * 4 * world));
+    c->world = world;
+    c->rank = rank;
+    c->lo = (c->N / world) * rank;
+    c->cnt = c->N / world;
+    c->p2p = true;
+    return MCL_OK;
+}
+
+int mcl_ipc_export(mcl_ctx* c, void* handles_out, size_t capacity) {
+    if (!c || !handles_out) return fail(MCL_ERR_INVALID, "null argument");
+    if (capacity < 6 * sizeof(cudaIpcMemHandle_t)) return fail(MCL_ERR_INVALID, "need %zu bytes", 6 * sizeof(cudaIpcMemHandle_t));
+    CK(cudaSetDevice(c->device));
+    auto* h = static_cast<cudaIpcMemHandle_t*>(handles_out);
+    for (int b = 0; b < 2; ++b) {
+        CK(cudaIpcGetMemHandle(&h[b * 3 + 0], c->d_px[b]));
+        CK(cudaIpcGetMemHandle(&h[b * 3 + 1], c->d_py[b]));
+        CK(cudaIpcGetMemHandle(&h[b * 3 + 2], c->d_pt[b]));
+    }
+    return MCL_OK;
+}
+
+int mcl_ipc_import(mcl_ctx* c, int world, int rank, const void* handles) {
+    if (!c || !handles) return fail(MCL_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    const auto* h = static_cast<const cudaIpcMemHandle_t*>(handles);
+    std::vector<const double*> tab(static_cast<size_t>(6) * world, nullptr);   // [buf][arr][world]
+    for (int q = 0; q < world; ++q) {
+        for (int k = 0; k < 6; ++k) {
+            const double* ptr;
+            if (q == rank) {
+                const int b = k / 3, a = k % 3;
+                ptr = a == 0 ? c->d_px[b] : (a == 1 ? c->d_py[b] : c->d_pt[b]);
+            } else {
+                void* p = nullptr;
+                CK(cudaIpcOpenMemHandle(&p, h[q * 6 + k], cudaIpcMemLazyEnablePeerAccess));
+                c->ipc_opened.push_back(p);
+                ptr = static_cast<const double*>(p);
+            }
+            tab[static_cast<size_t>(k) * world + q] = ptr;
+        }
+    }
+    return install_peers(c, world, rank, tab);
+}
+
+int mcl_set_peer_pointers(mcl_ctx* c, int world, int rank, const void* const* ptrs) {
+    if (!c || !ptrs) return fail(MCL_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    std::vector<const double*> tab(static_cast<size_t>(6) * world, nullptr);
+    for (int q = 0; q < world; ++q)
+        for (int k = 0; k < 6; ++k) tab[static_cast<size_t>(k) * world + q] = static_cast<const double*>(ptrs[q * 6 + k]);
+    return install_peers(c, world, rank, tab);
+}
+
+int mcl_state_pointers_dev(mcl_ctx* c, void* ptrs_out[6]) {
+    if (!c || !ptrs_out) return fail(MCL_ERR_INVALID, "null argument");
+    for (int b = 0; b < 2; ++b) {
+        ptrs_out[b * 3 + 0] = c->d_px[b];
+        ptrs_out[b * 3 + 1] = c->d_py[b];
+        ptrs_out[b * 3 + 2] = c->d_pt[b];
+    }
+    return MCL_OK;
+}
+
+int mcl_p2p_buffers_dev(mcl_ctx* c, void** w_raw_dev, void** partials_dev) {
+    if (!c || !w_raw_dev || !partials_dev) return fail(MCL_ERR_INVALID, "null argument");
+    if (!c->p2p) return fail(MCL_ERR_INVALID, "peer-to-peer sharding is not set up");
+    *w_raw_dev = c->d_wraw;
+    *partials_dev = c->d_partials;
     return MCL_OK;
 }
 

@@ -70,11 +70,18 @@ class _DevArray:
 class ShardedFilter:
     """One rank's share of a particle-sharded global filter (needs torch.distributed + NCCL)."""
 
-    def __init__(self, grid, angles, n_local: int, rank: int, world: int, device: int = 0, seed: int = 0, **params):
+    def __init__(self, grid, angles, n_local: int, rank: int, world: int, device: int = 0, seed: int = 0,
+                 mode: str = "p2p", **params):
+        """mode "allgather": all four state arrays are all-gathered every update (32 B/particle).
+        mode "p2p": ranks map each other's state arrays with CUDA IPC; the resampling kernel reads
+        source poses from their owner over NVLink and only raw weights + 4 pose partial sums per
+        rank are all-gathered (8 B/particle)."""
         import torch
         from .capi import MclContext
+        if mode not in ("allgather", "p2p"):
+            raise ValueError("mode must be 'allgather' or 'p2p'")
         self.torch = torch
-        self.rank, self.world, self.device = rank, world, device
+        self.rank, self.world, self.device, self.mode = rank, world, device, mode
         self.plan = ShardPlan(n_local * world, world)
         self.ctx = MclContext(device=device, max_particles=self.plan.n_global, seed=seed, **params)
         self.ctx.set_map(grid)
@@ -82,7 +89,12 @@ class ShardedFilter:
         lo, cnt = self.plan.slots(rank)
         self.ctx.set_shard(lo, cnt)
         self._alias = {}
-        self._pinned = None
+        if mode == "p2p":
+            import torch.distributed as dist
+            blobs = [None] * world
+            dist.all_gather_object(blobs, self.ctx.ipc_export())
+            self.ctx.ipc_import(world, rank, b"".join(blobs))
+            dist.barrier()
 
     def init_pose(self, pose, normals_3n=None):
         # every rank initialises the full state; the device RNG is keyed by the global slot,
@@ -98,10 +110,33 @@ class ShardedFilter:
 
     def update_dev(self, action_dev_ptr: int, obs_dev_ptr: int, u_dev_ptr: int = 0, z_dev_ptr: int = 0):
         """One MCL update; inputs on the device; the ctx must launch on torch's current stream."""
+        import torch.distributed as dist
         self.ctx.update_local_dev(action_dev_ptr, obs_dev_ptr, u_dev_ptr, z_dev_ptr)
-        ptrs, n, _, _ = self.ctx.exchange_buffers_dev()
-        exchange([self._tensor(p, n) for p in ptrs], self.plan, self.rank)
+        if self.mode == "p2p":
+            w_ptr, part_ptr = self.ctx.p2p_buffers_dev()
+            exchange([self._tensor(w_ptr, self.plan.n_global)], self.plan, self.rank)
+            part = self._tensor(part_ptr, 4 * self.world)
+            dist.all_gather_into_tensor(part, part[4 * self.rank:4 * self.rank + 4])
+        else:
+            ptrs, n, _, _ = self.ctx.exchange_buffers_dev()
+            exchange([self._tensor(p, n) for p in ptrs], self.plan, self.rank)
         self.ctx.update_finish_dev()
+
+    def gather_state(self):
+        """(particles [3, N], weights [N]) of the whole filter on every rank (collective)."""
+        import torch.distributed as dist
+        torch = self.torch
+        p = torch.from_numpy(self.ctx.get_particles()).cuda(self.device)
+        if self.mode == "p2p":   # only the own slice of the poses is current
+            lo, cnt = self.plan.slots(self.rank)
+            for k in range(3):
+                row = p[k].contiguous()
+                dist.all_gather_into_tensor(row, row[lo:lo + cnt].clone())
+                p[k] = row
+        return p.cpu().numpy(), self.ctx.get_weights()
+
+    def set_state(self, particles, weights):
+        self.ctx.set_particles(particles, weights)
 
     def update(self, action, obs, u=None, z3n=None):
         """Host-facing update: action/scan (and optional injected noise for the WHOLE filter)

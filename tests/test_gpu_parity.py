@@ -264,3 +264,63 @@ def test_particle_shards_reproduce_single_filter():
         prev_p, prev_w = z["particles"][t], z["weights"][t]
     for c in ranks:
         c.close()
+
+
+def test_p2p_shards_reproduce_single_filter():
+    """Peer-to-peer sharding, two emulated ranks on one GPU: each rank reads its slots' source
+    poses from the owner's arrays (mcl_set_peer_pointers), only raw weights and pose partial
+    sums are exchanged.  Must equal the golden single-filter update."""
+    import torch
+    from monte_carlo_localization_b200 import maps
+    from monte_carlo_localization_b200.sharded import ShardPlan, _DevArray
+    z = load_golden("update_sibal1_4000.npz")
+    g = maps.load_named_map("sibal1")
+    N, world = int(z["N"]), 2
+    plan = ShardPlan(N, world)
+    ranks = [_ctx(g, z["angles"], N) for _ in range(world)]
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    all_ptrs = []
+    for c in ranks:
+        c.set_stream(stream.cuda_stream)
+        all_ptrs += c.state_pointers_dev()
+    for r, c in enumerate(ranks):
+        c.set_peer_pointers(world, r, all_ptrs)
+    prev_p, prev_w = z["init_particles"], z["init_weights"]
+    for t in range(len(z["u"])):
+        a = torch.from_numpy(z["actions"][t].copy()).cuda()
+        o = torch.from_numpy(z["obs"][t].copy()).cuda()
+        u = torch.from_numpy(z["u"][t].copy()).cuda()
+        zz = torch.from_numpy(z["z"][t].copy()).cuda()
+        for r, c in enumerate(ranks):
+            # only the owner's slice has to be current: poison the rest to prove peers are used
+            lo, cnt = plan.slots(r)
+            p = np.full_like(prev_p, 1e6)
+            p[:, lo:lo + cnt] = prev_p[:, lo:lo + cnt]
+            c.set_particles(p, prev_w)
+        bufs = []
+        for c in ranks:
+            c.update_local_dev(a.data_ptr(), o.data_ptr(), u.data_ptr(), zz.data_ptr())
+            w_ptr, part_ptr = c.p2p_buffers_dev()
+            bufs.append((torch.as_tensor(_DevArray(w_ptr, N), device="cuda"),
+                         torch.as_tensor(_DevArray(part_ptr, 4 * world), device="cuda")))
+        for r in range(world):          # the two all-gathers, emulated with copies
+            for q in range(world):
+                if q != r:
+                    lo, cnt = plan.slots(q)
+                    bufs[r][0][lo:lo + cnt].copy_(bufs[q][0][lo:lo + cnt])
+                    bufs[r][1][4 * q:4 * q + 4].copy_(bufs[q][1][4 * q:4 * q + 4])
+        torch.cuda.synchronize()
+        for r, c in enumerate(ranks):
+            c.update_finish_dev()
+            pose = c.read_pose()
+            lo, cnt = plan.slots(r)
+            assert np.array_equal(c.resample_indices()[lo:lo + cnt], z["idx"][t][lo:lo + cnt])
+            assert_weights_close(c.get_weights(), z["weights"][t])
+            assert_pose_close(pose, z["pose"][t])
+            got = c.get_particles()[:, lo:lo + cnt]
+            assert np.abs(got - z["particles"][t][:, lo:lo + cnt]).max() < 1e-9
+        assert np.array_equal(ranks[0].get_weights(), ranks[1].get_weights())
+        prev_p, prev_w = z["particles"][t], z["weights"][t]
+    for c in ranks:
+        c.close()
