@@ -768,8 +768,9 @@ __global__ void __launch_bounds__(kRayThreads, 1) k_raycast_weight(RayArgs a) {
     uint32_t win_saddr;
     asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(win_saddr) : "l"(smem_win));
     const RefGrid rg{mp.grid, mp.W, mp.H, mp.res, mp.ox, mp.oy};
-    const int tw = M + 1;
+    const int tw = pin_reg(M + 1);
     const double* slice = a.slice + static_cast<int64_t>(f) * R * tw;
+    asm volatile("mov.b64 %0, %0;" : "+l"(slice));   // keep the table base in registers across rays
     const int32_t* perm = a.perm ? a.perm + fo + a.lo : nullptr;
     int replays = 0;
 
