@@ -41,6 +41,9 @@ struct MapDev {
 struct WindowV4S {
     uint32_t saddr;          // shared address of the window's first byte
     int offx, offy, pitch;
+    __device__ __forceinline__ int get_p(uint32_t px, uint32_t py) const {
+        return get(static_cast<int>(px >> kFrac), static_cast<int>(py >> kFrac));
+    }
     __device__ __forceinline__ int get(int lx, int ly) const {
         const int x = lx + offx, y = ly + offy;
         uint32_t b;
@@ -51,11 +54,18 @@ struct WindowV4S {
 
 // One byte per cell: the march reads the full 8-bit skip code with a single LDS.U8.
 struct WindowV8S {
-    uint32_t saddr;
-    int offx, offy, pitch;
+    uint32_t base;           // shared address of window cell (offx, offy): saddr + offy * pitch + offx
+    int pitch;
+    // main lookup straight from the fixed-point position: shift+add, shift, multiply-add, LDS
+    __device__ __forceinline__ int get_p(uint32_t px, uint32_t py) const {
+        uint32_t b;
+        const uint32_t t = (px >> kFrac) + base;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b) : "r"((py >> kFrac) * static_cast<uint32_t>(pitch) + t));
+        return static_cast<int>(b);
+    }
     __device__ __forceinline__ int get(int lx, int ly) const {
         uint32_t b;
-        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b) : "r"(saddr + static_cast<uint32_t>((ly + offy) * pitch + lx + offx)));
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b) : "r"(base + static_cast<uint32_t>(ly * pitch + lx)));
         return static_cast<int>(b);
     }
 };
@@ -795,8 +805,12 @@ __global__ void __launch_bounds__(kRayThreads, 1) k_raycast_weight(RayArgs a) {
             const int fqx = static_cast<int>(floor(qx)), fqy = static_cast<int>(floor(qy));
             const RayStart st = make_ray_start(qx, qy, fqx, fqy);
             const bool in_win = (mp.ww > 0) && fqx >= vx0 && fqx < vx1 && fqy >= vy0 && fqy < vy1;
-            using WinAcc = typename std::conditional<WBITS == 8, WindowV8S, WindowV4S>::type;
-            const WinAcc wacc{win_saddr, pin_reg(st.bx - wx0), pin_reg(st.by - wy0), pitch};
+            WindowV8S wacc8{0, 0};
+            WindowV4S wacc4{0, 0, 0, 0};
+            if (WBITS == 8)
+                wacc8 = WindowV8S{static_cast<uint32_t>(pin_reg(static_cast<int>(win_saddr) + (st.by - wy0) * pitch + (st.bx - wx0))), pitch};
+            else
+                wacc4 = WindowV4S{win_saddr, pin_reg(st.bx - wx0), pin_reg(st.by - wy0), pitch};
             const GlobalV8 gacc = make_global_v8(mp.v8, mp.PW, st.bx, st.by);
             for (int j = 0; j < R; ++j) {
                 int dxf, dyf;
@@ -804,7 +818,8 @@ __global__ void __launch_bounds__(kRayThreads, 1) k_raycast_weight(RayArgs a) {
                 const ReplayArgs ra{x, y, th, a.beams.angle[j]};
                 int r;
                 if (in_win)
-                    r = march_ray(wacc, st, dxf, dyf, M, rg, ra, &replays);
+                    r = WBITS == 8 ? march_ray(wacc8, st, dxf, dyf, M, rg, ra, &replays)
+                                   : march_ray(wacc4, st, dxf, dyf, M, rg, ra, &replays);
                 else
                     r = march_ray(gacc, st, dxf, dyf, M, rg, ra, &replays);
                 acc = __dmul_rn(acc, __ldg(slice + static_cast<unsigned>(j * tw + r)));

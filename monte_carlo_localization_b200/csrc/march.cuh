@@ -101,6 +101,7 @@ MCL_HD RayStart make_ray_start(double qx, double qy, int fqx, int fqy) {
 struct GlobalV8 {
     const uint8_t* base;   // &v8[by * PW + bx]
     int PW;
+    MCL_HD int get_p(uint32_t px, uint32_t py) const { return get(static_cast<int>(px >> kFrac), static_cast<int>(py >> kFrac)); }
     MCL_HD int get(int lx, int ly) const {
 #if defined(__CUDA_ARCH__)
         return __ldg(base + static_cast<int64_t>(ly) * PW + lx);
@@ -118,6 +119,7 @@ MCL_HD GlobalV8 make_global_v8(const uint8_t* v8, int PW, int bx, int by) {
 struct WindowV4 {
     const uint8_t* w4;   // wh rows of pitch bytes
     int offx, offy, pitch;   // bx - wx0, by - wy0
+    MCL_HD int get_p(uint32_t px, uint32_t py) const { return get(static_cast<int>(px >> kFrac), static_cast<int>(py >> kFrac)); }
     MCL_HD int get(int lx, int ly) const {
         const int x = lx + offx, y = ly + offy;
         const int b = w4[y * pitch + (x >> 1)];
@@ -211,7 +213,7 @@ MCL_HD int march_ray(const Acc& acc, const RayStart& st, int dxf, int dyf, int M
     do {
         const uint32_t px = st.p0x + static_cast<uint32_t>(k * dxf);
         const uint32_t py = st.p0y + static_cast<uint32_t>(k * dyf);
-        int v = acc.get(static_cast<int>(px >> kFrac), static_cast<int>(py >> kFrac));   // ray-local cell
+        int v = acc.get_p(px, py);   // skip code of the sample's cell
         if (v < 2) {
             // code 0 (blocked) or 1 (next to blocked): the class of this very sample matters
             const uint32_t tx = (px + kEtaFix) & kFracMask, ty = (py + kEtaFix) & kFracMask;
