@@ -324,3 +324,145 @@ def test_p2p_shards_reproduce_single_filter():
         prev_p, prev_w = z["particles"][t], z["weights"][t]
     for c in ranks:
         c.close()
+
+
+def test_full_size_update_1m_spielberg_vs_oracle():
+    """BASELINE config 3 at full size: one update of 1,048,576 particles x 60 beams on
+    Spielberg_map against the oracle (indices and range steps exact), plus the size-independent
+    properties of the outputs."""
+    from monte_carlo_localization_b200 import maps, synth
+    from oracle import bindings as ob
+    g = maps.load_named_map("Spielberg_map")
+    angles_full = synth.laser_angles()
+    angles = synth.downsample(angles_full)
+    N = 1 << 20
+    orc = ob.Oracle(g, angles, max_particles=N)
+    gt, actions = synth.trajectory(g, 2, 8.0)
+    ns = ob.NoiseStream(31337)
+    orc.init_pose(gt[0], ns.normal(3 * N))
+    scan = synth.scan_from_pose(orc.calc_range_many, gt[1], angles_full, np.random.default_rng(9))
+    obs = scan[::18]
+    # non-uniform weights so the CDF is not trivial
+    w = np.random.default_rng(10).random(N) ** 3 + 1e-9
+    w /= w.sum()
+    p0, _ = orc.get_state()
+    orc.set_state(p0, w)
+    c = _ctx(g, angles, N)
+    c.set_particles(p0, w)
+    u, z = ns.update_noise(N)
+    idx = orc.update(actions[0], obs, u, z)
+    pose_ref = orc.expected_pose()
+    pose = c.update(actions[0], obs, u, z)
+    got_idx = c.resample_indices()
+    assert np.array_equal(got_idx, idx)
+    want = steps_from_ranges(orc.ranges(), g.resolution_f64, orc.M)
+    got = c.range_steps()
+    assert (got != want).sum() == 0
+    wn = c.get_weights()
+    assert_weights_close(wn, orc.get_state()[1])
+    assert_pose_close(pose, pose_ref)
+    # properties that hold at any size
+    cdf = c.cdf()
+    assert cdf[-1] == 1.0 and (np.diff(cdf) >= 0).all()
+    order = np.argsort(u, kind="stable")
+    assert (np.diff(got_idx[order]) >= 0).all()          # the index is monotone in the draw
+    assert np.bincount(got_idx, minlength=N).sum() == N   # replication counts
+    assert abs(wn.sum() - 1.0) < 1e-9 and (wn > 0).all()
+    assert got.max() <= c.M
+    c.close()
+
+
+def test_edge_cases_match_oracle():
+    """Degenerate inputs the reference can meet: particles outside the map and on its border,
+    zero / max-range / out-of-range / NaN scan readings, a zero action, one dominant weight."""
+    from monte_carlo_localization_b200 import maps
+    from oracle import bindings as ob
+    z = load_golden("update_sibal1_4000.npz")
+    g = maps.load_named_map("sibal1")
+    N = int(z["N"])
+    res = g.resolution_f64
+    rng = np.random.default_rng(3)
+    p = z["init_particles"].copy()
+    p[0, :500] = g.origin[0] - rng.uniform(0, 3, 500)                      # left of the map
+    p[1, 500:1000] = g.origin[1] + g.height * res + rng.uniform(0, 3, 500)  # above the map
+    p[0, 1000:1200] = g.origin[0] + rng.integers(-2, 3, 200) * res          # on / next to the border lattice
+    p[1, 1200:1400] = g.origin[1] + rng.integers(-2, 3, 200) * res
+    p[0, 1400:1450] = 1e7                                                   # absurdly far away
+    w = np.full(N, 1e-12)
+    w[1234] = 1.0                                                           # one particle holds the mass
+    w /= w.sum()
+    obs = z["obs"][0].copy()
+    obs[0] = 0.0
+    obs[1] = 12.0
+    obs[2] = 50.0          # beyond max range: clamps to MAX_RANGE_PX (:552)
+    obs[3] = np.inf
+    obs[4] = np.nan        # reference: UB; x86 yields row 0
+    for action in ([0.0, 0.0, 0.0], [0.0005, 0.0, 0.0005], [0.5, 0.0, -0.2], [-0.05, 0.3, 0.0]):
+        orc = ob.Oracle(g, z["angles"], max_particles=N)
+        orc.set_state(p, w)
+        c = _ctx(g, z["angles"], N)
+        c.set_particles(p, w)
+        idx = orc.update(action, obs, z["u"][0], z["z"][0])
+        pose = c.update(action, obs, z["u"][0], z["z"][0])
+        assert np.array_equal(c.resample_indices(), idx)
+        assert np.array_equal(c.range_steps(), steps_from_ranges(orc.ranges(), res, orc.M))
+        assert_weights_close(c.get_weights(), orc.get_state()[1])
+        assert_pose_close(pose, orc.expected_pose())
+        c.close()
+    # a second update from the spread-out state (many particles outside the map)
+    orc = ob.Oracle(g, z["angles"], max_particles=N)
+    orc.set_state(p, np.full(N, 1.0 / N))
+    c = _ctx(g, z["angles"], N)
+    c.set_particles(p, np.full(N, 1.0 / N))
+    for t in range(2):
+        idx = orc.update(z["actions"][t], obs, z["u"][t], z["z"][t])
+        c.update(z["actions"][t], obs, z["u"][t], z["z"][t])
+        assert np.array_equal(c.resample_indices(), idx)
+        assert np.array_equal(c.range_steps(), steps_from_ranges(orc.ranges(), res, orc.M))
+        assert_weights_close(c.get_weights(), orc.get_state()[1])
+    c.close()
+
+
+def test_global_init_and_error_paths():
+    """initialize_global with injected draws equals the oracle; error conventions of the ABI."""
+    from monte_carlo_localization_b200 import MclContext, MclError, capi, maps
+    from oracle import bindings as ob
+    z = load_golden("update_sibal1_4000.npz")
+    g = maps.load_named_map("sibal1")
+    N = 4000
+    orc = ob.Oracle(g, z["angles"], max_particles=N)
+    c = _ctx(g, z["angles"], N)
+    assert c.num_free_cells() == orc.num_free_cells() == 26948
+    cell, th = ob.NoiseStream(5).global_init(N, orc.num_free_cells())
+    orc.init_global(cell, th)
+    c.init_global(cell, th)
+    assert np.array_equal(c.get_particles(), orc.get_state()[0])
+    assert np.array_equal(c.get_weights(), orc.get_state()[1])
+    c.init_global()                      # device RNG: every particle on a free cell's corner
+    p = c.get_particles()
+    col = np.round((p[0] - g.origin[0]) / g.resolution_f64).astype(int)
+    row = np.round((p[1] - g.origin[1]) / g.resolution_f64).astype(int)
+    assert (g.data[row, col] == 0).all() and (p[2] >= 0).all() and (p[2] < 2 * np.pi).all()
+    # wrong beam count, straight through the C ABI
+    import ctypes as C
+    act = np.zeros(3)
+    bad = np.zeros(7, dtype=np.float32)
+    pose = np.zeros(3)
+    rc = c._L.mcl_update(c._h, act.ctypes.data_as(capi.c_double_p), bad.ctypes.data_as(capi.c_float_p), 7, None,
+                         pose.ctypes.data_as(capi.c_double_p))
+    assert rc == capi.MCL_ERR_INVALID and b"num_beams" in c._L.mcl_last_error()
+    c.close()
+    c2 = MclContext(max_particles=16)
+    with pytest.raises(MclError) as e:   # update before a map: the reference's cast_ray returns max range (:613)
+        c2.calc_range_many(np.zeros((3, 4)))
+    assert e.value.status == capi.MCL_ERR_NO_MAP
+    occupied = maps.OccupancyGrid(np.full((20, 20), 100, dtype=np.int8), np.float32(0.05), (0.0, 0.0, 0.0))
+    c2.set_map(occupied)
+    with pytest.raises(MclError) as e:   # "No free space found in map!" (:423-427)
+        c2.init_global()
+    assert e.value.status == capi.MCL_ERR_NO_FREE_SPACE
+    fine = maps.OccupancyGrid(np.zeros((20, 20), dtype=np.int8), np.float32(0.01), (0.0, 0.0, 0.0))
+    with pytest.raises(MclError) as e:   # MAX_RANGE_PX = 1200 > 254
+        c2.set_map(fine)
+    assert e.value.status == capi.MCL_ERR_UNSUPPORTED
+    c2.close()
