@@ -762,16 +762,43 @@ __global__ void __launch_bounds__(kRayThreads, 1) k_raycast_weight(RayArgs a) {
         vx1 = (wx0 + mp.ww >= mp.PW) ? mp.PW - 2 : wx0 + mp.ww - M - 2;
         vy0 = (wy0 == 0) ? 2 : wy0 + M + 2;
         vy1 = (wy0 + mp.wh >= mp.PH) ? mp.PH - 2 : wy0 + mp.wh - M - 2;
-        const int vec_per_row = pitch >> 4;  // 16-byte vectors per window row
-        const int total = vec_per_row * mp.wh;
+        // Stage the window with the bulk-copy engine (TMA, cp.async.bulk): one global->shared
+        // copy per window row, completion counted in bytes on an mbarrier.  Rows are 16-byte
+        // aligned on both sides (PW, ww, wx0 are multiples of 32 cells).
         const int gpitch = WBITS == 8 ? mp.PW : (mp.PW >> 1);
         const uint8_t* gsrc = WBITS == 8 ? mp.v8 + wx0 : mp.v4 + (wx0 >> 1);
-        for (int i = threadIdx.x; i < total; i += kRayThreads) {
-            const int row = i / vec_per_row, col = i - row * vec_per_row;
-            const uint4 v = __ldg(reinterpret_cast<const uint4*>(gsrc + static_cast<int64_t>(wy0 + row) * gpitch) + col);
-            reinterpret_cast<uint4*>(smem_win + row * pitch)[col] = v;
+        __shared__ __align__(8) unsigned long long win_bar;
+        const uint32_t bar = static_cast<uint32_t>(__cvta_generic_to_shared(&win_bar));
+        const uint32_t dst0 = static_cast<uint32_t>(__cvta_generic_to_shared(smem_win));
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t total = static_cast<uint32_t>(pitch) * static_cast<uint32_t>(mp.wh);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(total) : "memory");
+        }
+        __syncthreads();
+        for (int row = threadIdx.x; row < mp.wh; row += kRayThreads) {
+            const uint8_t* src = gsrc + static_cast<int64_t>(wy0 + row) * gpitch;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             dst0 + static_cast<uint32_t>(row * pitch)),
+                         "l"(src), "r"(static_cast<uint32_t>(pitch)), "r"(bar)
+                         : "memory");
+        }
+        {   // every thread waits for phase 0 of the barrier: all bytes have landed
+            uint32_t done = 0;
+            while (!done) {
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\t"
+                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+                    "selp.u32 %0, 1, 0, p;\n\t}"
+                    : "=r"(done)
+                    : "r"(bar)
+                    : "memory");
+            }
+        }
     }
     // shared-space address of the window; the volatile asm keeps it in a register instead of
     // being rematerialised (S2R + LEA) inside the march loop
