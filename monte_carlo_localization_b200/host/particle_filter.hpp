@@ -86,6 +86,21 @@ class ParticleFilter {
     // velocity/angular velocity as odomCB stores them (:328-329); returns false if skipped
     bool update(double dt, double current_velocity, double current_angular_vel);
 
+    // --- the node's update shell without ROS ---
+    // odomCB (:325-352): twist -> velocities, pose -> last_pose_, odometry tracking update
+    void odomCB(const Vector3d& odom_pose, double linear_velocity, double angular_velocity);
+    // clicked_pose (:355-374): re-initialise around a pose and start odometry tracking from it
+    void clicked_pose(const Vector3d& pose);
+    // timer_update (:720-846) with the wall-clock dt passed in: action synthesis (odometry, or the
+    // decaying start-up jitter :767-772), MCL + expected_pose, odometry-tracking re-anchor with
+    // delay compensation (:781-807).  Returns false when the tick is skipped (:722, :750, :758).
+    bool timer_update(double dt);
+    // get_current_pose (:892-916): odometry tracking > filter estimate > particle mean > last odom
+    Vector3d get_current_pose();
+    // mean MCL time the delay compensation uses (:792-795), milliseconds
+    double mean_mcl_ms() const { return mcl_count_ ? mcl_total_ms_ / mcl_count_ : 0.0; }
+    bool odom_tracking_active() const { return odom_tracking_active_; }
+
     // --- state access (visualize() :944-963, get_current_pose :892-916) ---
     std::vector<double> particles() const;          // column-major N x 3
     std::vector<double> weights() const;
@@ -108,6 +123,15 @@ class ParticleFilter {
     Vector3d inferred_pose_{{0, 0, 0}};
     int iters_ = 0;
     double last_update_ms_ = 0.0;
+    // update-shell state (particle_filter.hpp:104-113, 170-178)
+    void initialize_odom_tracking(const Vector3d& initial_pose, bool from_rviz = true);   // :988-1002
+    void update_odom_pose(const Vector3d& current_odom);                                  // :1004-1013
+    Vector3d last_pose_{{0, 0, 0}}, odom_pose_{{0, 0, 0}}, odom_reference_pose_{{0, 0, 0}}, odom_reference_odom_{{0, 0, 0}};
+    bool odom_initialized_ = false, pose_initialized_from_rviz_ = false, odom_tracking_active_ = false;
+    double current_velocity_ = 0.0, current_angular_vel_ = 0.0;
+    double mcl_total_ms_ = 0.0;
+    int mcl_count_ = 0;
+    uint64_t jitter_state_ = 0x243F6A8885A308D3ull;   // start-up jitter noise (:769-771)
 };
 
 }  // namespace particle_filter_cpp

@@ -81,9 +81,16 @@ int main(int argc, char** argv) {
             q[2 * nb + i] = gt[2] + static_cast<double>(amin + i * ainc);
         }
         const std::vector<float> scan = pf.calc_range_many(q);
+        // the node's loop: scan callback, odometry callback, timer tick
         pf.lidarCB(amin, ainc, scan);
-        if (!pf.update(dt, vel, 0.0)) {
+        pf.odomCB(Vector3d{{100.0 + gt[0], -50.0 + gt[1], gt[2]}}, vel, 0.0);   // odom frame != map frame
+        if (!pf.timer_update(dt)) {
             std::fprintf(stderr, "update skipped\n");
+            return 1;
+        }
+        const Vector3d cur = pf.get_current_pose();   // what publish_tf would send (:839-845)
+        if (!pf.is_pose_valid(cur) || std::hypot(cur[0] - gt[0], cur[1] - gt[1]) > 1.0) {
+            std::fprintf(stderr, "get_current_pose off: [%.3f %.3f %.3f]\n", cur[0], cur[1], cur[2]);
             return 1;
         }
         const Vector3d p = pf.inferred_pose();
