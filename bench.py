@@ -229,6 +229,7 @@ def run_gpu(args):
         flt = ShardedFilter(grid, angles, n_local=N, rank=rank, world=world, device=local_rank, seed=20250 + 3,
                             mode=args.shard_mode)
         ctx = flt.ctx
+        args.shard_mode = flt.mode      # "allgather" if the peer mapping was refused on this host
     else:
         flt = None
         ctx = MclContext(device=local_rank, max_particles=N, seed=20250 + 3)

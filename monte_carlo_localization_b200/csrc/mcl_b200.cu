@@ -485,20 +485,9 @@ int mcl_device_count(void) {
     return n;
 }
 
-int mcl_create(const mcl_params* p, int device, mcl_ctx** out) {
-    if (!p || !out) return fail(MCL_ERR_INVALID, "null argument");
-    *out = nullptr;
-    if (p->max_particles < 1) return fail(MCL_ERR_INVALID, "max_particles must be >= 1");
-    if (p->num_filters < 1) return fail(MCL_ERR_INVALID, "num_filters must be >= 1");
-    if (!(p->squash_factor > 0) || !(p->max_range > 0)) return fail(MCL_ERR_INVALID, "squash_factor / max_range must be positive");
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
-        cudaGetLastError();
-        return fail(MCL_ERR_NO_DEVICE, "no CUDA device visible; the MCL update has no CPU fallback");
-    }
-    if (device < 0 || device >= ndev) return fail(MCL_ERR_INVALID, "device %d not in [0,%d)", device, ndev);
-    CK(cudaSetDevice(device));
-    auto* c = new mcl_ctx();
+int mcl_destroy(mcl_ctx* c);
+
+static int create_buffers(mcl_ctx* c, const mcl_params* p, int device) {
     c->prm = *p;
     c->device = device;
     c->F = p->num_filters;
@@ -570,6 +559,30 @@ int mcl_create(const mcl_params* p, int device, mcl_ctx** out) {
     CK(cudaFuncSetAttribute(k_raycast_weight<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kWindowBudget)));
     CK(cudaFuncSetAttribute(k_raycast_weight<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kWindowBudget)));
     CK(cudaDeviceSynchronize());
+    return MCL_OK;
+}
+
+int mcl_create(const mcl_params* p, int device, mcl_ctx** out) {
+    if (!p || !out) return fail(MCL_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (p->max_particles < 1) return fail(MCL_ERR_INVALID, "max_particles must be >= 1");
+    if (p->num_filters < 1) return fail(MCL_ERR_INVALID, "num_filters must be >= 1");
+    if (!(p->squash_factor > 0) || !(p->max_range > 0)) return fail(MCL_ERR_INVALID, "squash_factor / max_range must be positive");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(MCL_ERR_NO_DEVICE, "no CUDA device visible; the MCL update has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return fail(MCL_ERR_INVALID, "device %d not in [0,%d)", device, ndev);
+    CK(cudaSetDevice(device));
+    auto* c = new mcl_ctx();
+    const int rc = create_buffers(c, p, device);
+    if (rc != MCL_OK) {
+        const std::string keep = g_err;   // mcl_destroy must not clobber the reason
+        mcl_destroy(c);
+        g_err = keep;
+        return rc;
+    }
     *out = c;
     return MCL_OK;
 }

@@ -83,17 +83,33 @@ class ShardedFilter:
         self.torch = torch
         self.rank, self.world, self.device, self.mode = rank, world, device, mode
         self.plan = ShardPlan(n_local * world, world)
-        self.ctx = MclContext(device=device, max_particles=self.plan.n_global, seed=seed, **params)
-        self.ctx.set_map(grid)
-        self.ctx.set_beam_angles(angles)
-        lo, cnt = self.plan.slots(rank)
-        self.ctx.set_shard(lo, cnt)
+
+        def make_ctx():
+            c = MclContext(device=device, max_particles=self.plan.n_global, seed=seed, **params)
+            c.set_map(grid)
+            c.set_beam_angles(angles)
+            c.set_shard(*self.plan.slots(rank))
+            return c
+
+        self.ctx = make_ctx()
         self._alias = {}
+        self.p2p_error = None
         if mode == "p2p":
             import torch.distributed as dist
-            blobs = [None] * world
-            dist.all_gather_object(blobs, self.ctx.ipc_export())
-            self.ctx.ipc_import(world, rank, b"".join(blobs))
+            ok = 1
+            try:
+                blobs = [None] * world
+                dist.all_gather_object(blobs, self.ctx.ipc_export())
+                self.ctx.ipc_import(world, rank, b"".join(blobs))
+            except Exception as e:   # e.g. peer access or CUDA IPC not permitted on this host
+                ok, self.p2p_error = 0, str(e)
+            flag = torch.tensor([ok], dtype=torch.int32, device="cuda:%d" % device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                # every rank falls back together: all four state arrays are all-gathered instead
+                self.mode = "allgather"
+                self.ctx.close()
+                self.ctx = make_ctx()
             dist.barrier()
 
     def init_pose(self, pose, normals_3n=None):
