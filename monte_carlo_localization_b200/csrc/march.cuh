@@ -204,29 +204,46 @@ MCL_NOINLINE int resolve_uncertain(const Acc& acc, uint32_t px, uint32_t py, int
 
 // March one ray.  (dxf, dyf) = round(cos a * 2^23), round(sin a * 2^23).  Returns the step
 // index r in [0, M] (M == no hit).  `replays` (nullable) counts exact replays for diagnostics.
+//
+// The hot loop contains no call and no break: a sample that needs the exact path parks the
+// loop counter beyond M, the loop ends through its own condition, the out-of-line resolver
+// runs and the loop is re-entered.  (A call inside the loop forces the loop invariants to be
+// reloaded every iteration; a break out of the near-wall branch makes the branch unstructured,
+// and the lanes of a warp then stop reconverging inside the loop.)
 template <class Acc>
 MCL_HD int march_ray(const Acc& acc, const RayStart& st, int dxf, int dyf, int M, const RefGrid& g,
                      const ReplayArgs& ra, int* replays) {
-    // Single back edge, no early return: lanes that finish simply drop out of the loop, which
-    // keeps the per-iteration control overhead to one predicated branch.
+    constexpr int kPark = 1 << 20;
     int k = 1, r = M;
-    do {
+    for (;;) {
+        int pending_k = 0;   // sample to resolve exactly (0 = none)
+        do {
+            const uint32_t px = st.p0x + static_cast<uint32_t>(k * dxf);
+            const uint32_t py = st.p0y + static_cast<uint32_t>(k * dyf);
+            int v = acc.get_p(px, py);   // skip code of the sample's cell
+            if (v < 2) {
+                // code 0 (blocked) or 1 (next to blocked): the class of this very sample matters
+                const uint32_t tx = (px + kEtaFix) & kFracMask, ty = (py + kEtaFix) & kFracMask;
+                if ((tx < ty ? tx : ty) < 2u * kEtaFix) {
+                    pending_k = k;   // within kEta of a cell edge
+                    k = kPark;
+                } else if (v == 0) {
+                    r = k - 1;
+                    k = kPark;
+                }
+                v = 2;
+            }
+            k += v - 1;
+        } while (k <= M);
+        if (pending_k == 0) return r;
+        k = pending_k;
         const uint32_t px = st.p0x + static_cast<uint32_t>(k * dxf);
         const uint32_t py = st.p0y + static_cast<uint32_t>(k * dyf);
-        int v = acc.get_p(px, py);   // skip code of the sample's cell
-        if (v < 2) {
-            // code 0 (blocked) or 1 (next to blocked): the class of this very sample matters
-            const uint32_t tx = (px + kEtaFix) & kFracMask, ty = (py + kEtaFix) & kFracMask;
-            if ((tx < ty ? tx : ty) < 2u * kEtaFix) v = resolve_uncertain(acc, px, py, v, g, ra, k, replays);
-            if (v == 0) {
-                r = k - 1;
-                k = 1 << 20;      // ends the loop
-            }
-            v = 2;
-        }
-        k += v - 1;
-    } while (k <= M);
-    return r;
+        const int v = resolve_uncertain(acc, px, py, acc.get_p(px, py), g, ra, k, replays);
+        if (v == 0) return k - 1;
+        k += 1;
+        if (k > M) return M;
+    }
 }
 
 }  // namespace mclb200
