@@ -734,14 +734,15 @@ constexpr int kRayThreads = 1024;
 // One lane = one particle; the lane walks its R beams in order and folds the table
 // entries into the weight product in the reference's multiplication order (:564-579).
 // Lanes of a warp hold heading-neighbours (perm), so their rays and trip counts agree.
-template <int WBITS>
+// MC > 0: MAX_RANGE_PX known at compile time (the loop bound becomes an immediate); 0: run time
+template <int WBITS, int MC>
 __global__ void __launch_bounds__(kRayThreads, 1) k_raycast_weight(RayArgs a) {
     extern __shared__ __align__(16) uint8_t smem_win[];
     const int f = blockIdx.y;
     const MapDev& mp = a.map;
     const int64_t N = a.N;
     const int64_t fo = static_cast<int64_t>(f) * N;
-    const int M = pin_reg(mp.M);
+    const int M = MC > 0 ? MC : pin_reg(mp.M);
     const int R = a.beams.R;
 
     // ---- stage the window of the skip map around the cloud centre --------------------------

@@ -377,10 +377,26 @@ int update_local(mcl_ctx* c, const double* action_dev, const float* obs_dev, con
     const int per_sm = smem > 100 * 1024 ? 1 : 2;
     const int budget = std::max(1, (c->num_sms * per_sm) / std::min(c->F, c->num_sms * per_sm));
     const int rblocks = static_cast<int>(std::min<int64_t>((c->cnt + kRayThreads - 1) / kRayThreads, budget));
-    if (c->map.wbits == 8)
-        k_raycast_weight<8><<<dim3(rblocks, c->F), kRayThreads, smem, s>>>(ra);
-    else
-        k_raycast_weight<4><<<dim3(rblocks, c->F), kRayThreads, smem, s>>>(ra);
+    // MAX_RANGE_PX of the usual map resolutions is baked into specialised instances
+    // (0.05 m -> 239, 0.0504 m -> 238, 0.05796 m -> 207); anything else takes the generic one
+    const dim3 rgrid(rblocks, c->F);
+#define MCL_LAUNCH_RAY(WB, MCV) k_raycast_weight<WB, MCV><<<rgrid, kRayThreads, smem, s>>>(ra)
+    if (c->map.wbits == 8) {
+        switch (c->M) {
+            case 207: MCL_LAUNCH_RAY(8, 207); break;
+            case 238: MCL_LAUNCH_RAY(8, 238); break;
+            case 239: MCL_LAUNCH_RAY(8, 239); break;
+            default: MCL_LAUNCH_RAY(8, 0); break;
+        }
+    } else {
+        switch (c->M) {
+            case 207: MCL_LAUNCH_RAY(4, 207); break;
+            case 238: MCL_LAUNCH_RAY(4, 238); break;
+            case 239: MCL_LAUNCH_RAY(4, 239); break;
+            default: MCL_LAUNCH_RAY(4, 0); break;
+        }
+    }
+#undef MCL_LAUNCH_RAY
     c->launches++;
     if (c->p2p) {
         // unnormalised pose sums of the rank's own slots (deterministic two-stage reduction)
@@ -556,8 +572,17 @@ static int create_buffers(mcl_ctx* c, const mcl_params* p, int device) {
     CK(cudaMallocHost(reinterpret_cast<void**>(&c->h_action), sizeof(double) * 3 * c->F));
     CK(cudaMallocHost(reinterpret_cast<void**>(&c->h_obs), sizeof(float) * kMaxBeams * c->F));
     CK(cudaMallocHost(reinterpret_cast<void**>(&c->h_pose), sizeof(double) * 3 * c->F));
-    CK(cudaFuncSetAttribute(k_raycast_weight<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kWindowBudget)));
-    CK(cudaFuncSetAttribute(k_raycast_weight<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kWindowBudget)));
+#define MCL_RAY_SMEM(WB, MCV) \
+    CK(cudaFuncSetAttribute(k_raycast_weight<WB, MCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kWindowBudget)))
+    MCL_RAY_SMEM(8, 0);
+    MCL_RAY_SMEM(8, 207);
+    MCL_RAY_SMEM(8, 238);
+    MCL_RAY_SMEM(8, 239);
+    MCL_RAY_SMEM(4, 0);
+    MCL_RAY_SMEM(4, 207);
+    MCL_RAY_SMEM(4, 238);
+    MCL_RAY_SMEM(4, 239);
+#undef MCL_RAY_SMEM
     CK(cudaDeviceSynchronize());
     return MCL_OK;
 }
