@@ -90,6 +90,8 @@ struct BeamDev {
 struct ExactArgs {
     const double* src;       // [F][N] addends (before the optional division)
     const double* div;       // [F] divisor or nullptr
+    const double* approx_div;  // [F] or nullptr: tile_sum holds sums of src * approx_div (the weights
+                               // before normalisation); only the approximate prefix is rescaled
     int64_t N;
     int T;                   // tiles per filter
     int C;                   // chunks per filter = T * kTileChunks
@@ -175,6 +177,10 @@ __global__ void __launch_bounds__(kTileChunks) k_exact_chunks(ExactArgs a) {
     double pre = 0.0;
     for (int tt = tid; tt < t; tt += kTileChunks) pre += a.tile_sum[static_cast<int64_t>(f) * a.T + tt];
     pre = block_sum<kTileChunks>(pre, smd);
+    if (a.approx_div) {
+        const double ad = a.approx_div[f];
+        if (ad > 0.0) pre = pre / ad;   // `if (sum_weights > 0)`: otherwise the weights were left as they were
+    }
     if (use_div) pre = pre / div;
 
     const int64_t base = (static_cast<int64_t>(t) * kTileChunks + tid) * kChunk;
@@ -833,6 +839,7 @@ __global__ void __launch_bounds__(kRayThreads, 1) k_raycast_weight(RayArgs a) {
             const int fqx = static_cast<int>(floor(qx)), fqy = static_cast<int>(floor(qy));
             const RayStart st = make_ray_start(qx, qy, fqx, fqy);
             const bool in_win = (mp.ww > 0) && fqx >= vx0 && fqx < vx1 && fqy >= vy0 && fqy < vy1;
+            const double cths = cth * static_cast<double>(kOne), sths = sth * static_cast<double>(kOne);
             WindowV8S wacc8{0, 0};
             WindowV4S wacc4{0, 0, 0, 0};
             if (WBITS == 8)
@@ -842,7 +849,7 @@ __global__ void __launch_bounds__(kRayThreads, 1) k_raycast_weight(RayArgs a) {
             const GlobalV8 gacc = make_global_v8(mp.v8, mp.PW, st.bx, st.by);
             for (int j = 0; j < R; ++j) {
                 int dxf, dyf;
-                beam_direction_fixed(cth, sth, a.beams.cosa[j], a.beams.sina[j], &dxf, &dyf);
+                beam_direction_prescaled(cths, sths, a.beams.cosa[j], a.beams.sina[j], &dxf, &dyf);
                 const ReplayArgs ra{x, y, th, a.beams.angle[j]};
                 int r;
                 if (in_win)
@@ -872,6 +879,8 @@ struct NormArgs {
     const double* pt;
     double* partial;          // [F][nblk][4]
     int nblk;
+    unsigned int* done;       // [F] block-completion counters (zero on entry, reset on exit) or nullptr
+    double* pose_out;         // [F][3]: written by the last block to finish when `done` is given
 };
 constexpr int kNormThreads = 256;
 
@@ -904,6 +913,31 @@ __global__ void __launch_bounds__(kNormThreads) k_normalize_pose(NormArgs a) {
         p[1] = ay;
         p[2] = as;
         p[3] = ac;
+    }
+    if (!a.done) return;
+    // the last block of this filter folds the per-block partial sums in block order
+    // (deterministic) and writes the pose -- no second launch
+    __shared__ bool is_last;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        is_last = atomicAdd(a.done + f, 1u) == static_cast<unsigned>(gridDim.x) - 1u;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    double v[4] = {0, 0, 0, 0};
+    for (int b = threadIdx.x; b < a.nblk; b += kNormThreads) {
+        const volatile double* p = a.partial + (static_cast<int64_t>(f) * a.nblk + b) * 4;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] += p[q];
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[q] = block_sum<kNormThreads>(v[q], sm);
+    if (threadIdx.x == 0) {
+        a.pose_out[3 * f + 0] = v[0];
+        a.pose_out[3 * f + 1] = v[1];
+        a.pose_out[3 * f + 2] = atan2(v[2], v[3]);
+        a.done[f] = 0;
     }
 }
 

@@ -154,6 +154,8 @@ MCL_HD double p_coord(double c, double origin, double res, int pad_l) {
 // Fixed-point direction of beam (ca, sa) = (cos, sin)(beam angle) for a particle with heading
 // (cth, sth): cos/sin(theta + alpha) by angle addition, rounded to 2^-23.
 MCL_HD void beam_direction_fixed(double cth, double sth, double ca, double sa, int* dxf, int* dyf) {
+    // callers may pass (cth, sth) already multiplied by 2^23 (scale == 1): scaling by a power of
+    // two commutes with the roundings, so both forms give the same integers
     const double c = cth * ca - sth * sa;
     const double s = sth * ca + cth * sa;
 #if defined(__CUDA_ARCH__)
@@ -164,6 +166,15 @@ MCL_HD void beam_direction_fixed(double cth, double sth, double ca, double sa, i
     *dyf = static_cast<int>(__builtin_lrint(s * static_cast<double>(kOne)));
 #endif
 }
+
+#if defined(__CUDACC__)
+// (cths, sths) = (cos, sin)(theta) * 2^23, computed once per particle
+__device__ __forceinline__ void beam_direction_prescaled(double cths, double sths, double ca, double sa, int* dxf,
+                                                         int* dyf) {
+    *dxf = __double2int_rn(cths * ca - sths * sa);
+    *dyf = __double2int_rn(sths * ca + cths * sa);
+}
+#endif
 
 // Can a particle at P-coordinates (qx, qy) be marched at all?  Outside, its first sample is
 // already out of bounds for every beam (:632-636) and the step index is 0.

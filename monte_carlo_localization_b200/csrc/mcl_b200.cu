@@ -123,6 +123,10 @@ struct mcl_ctx {
     const double** d_peer_tab = nullptr;     // device: [buf 2][array 3][world] pointers
     std::vector<void*> ipc_opened;
     double* d_partials = nullptr;            // [world][4] pose partial sums (rank's own at [rank])
+    unsigned int* d_done = nullptr;          // [F] block-completion counters of k_normalize_pose
+    // what d_tile_sum currently holds: 0 nothing usable, 1 tile sums of w_norm, 2 tile sums of
+    // w_raw with w_norm = w_raw / S1 (rescaled on the fly for the approximate prefix)
+    int tile_state = 0;
     // pinned staging for the host-facing update
     double* h_action = nullptr;
     float* h_obs = nullptr;
@@ -137,10 +141,12 @@ struct mcl_ctx {
 
 namespace {
 
-ExactArgs exact_args(mcl_ctx* c, const double* src, const double* div, double* total, double* out, int force_one) {
+ExactArgs exact_args(mcl_ctx* c, const double* src, const double* div, const double* approx_div, double* total,
+                     double* out, int force_one) {
     ExactArgs a{};
     a.src = src;
     a.div = div;
+    a.approx_div = approx_div;
     a.N = c->N;
     a.T = c->T;
     a.C = c->C;
@@ -163,8 +169,8 @@ ExactArgs exact_args(mcl_ctx* c, const double* src, const double* div, double* t
 
 // sequential-order sum (and optionally prefix sums) of src[k] (/ div), see exact_sum.cuh
 int run_exact(mcl_ctx* c, const double* src, const double* div, double* total, double* out, int force_one,
-              bool need_tile_sums) {
-    ExactArgs a = exact_args(c, src, div, total, out, force_one);
+              bool need_tile_sums, const double* approx_div = nullptr) {
+    ExactArgs a = exact_args(c, src, div, approx_div, total, out, force_one);
     const dim3 gt(c->T, c->F);
     if (need_tile_sums) {
         k_tile_sums<<<gt, kTileChunks, 0, c->stream>>>(a);
@@ -263,10 +269,25 @@ int launch_pose(mcl_ctx* c, const double* w, const double* total, double* wn_out
     na.pt = c->d_pt[buf];
     na.partial = c->d_partial;
     na.nblk = c->norm_blocks;
+    na.done = c->d_done;
+    na.pose_out = c->d_pose;
     k_normalize_pose<<<dim3(c->norm_blocks, c->F), kNormThreads, 0, c->stream>>>(na);
-    k_pose_final<<<c->F, 256, 0, c->stream>>>(c->d_partial, c->norm_blocks, c->d_pose);
-    c->launches += 2;
+    c->launches += 1;
     CK(cudaGetLastError());
+    return MCL_OK;
+}
+
+// discrete_distribution(weights_): sum, normalise, partial_sum (random.tcc:2657-2678) of the
+// current normalised weights.  The approximate tile sums the exact kernels need are reused from
+// the last weight-sum pass whenever the weights have not been touched since.
+int build_cdf(mcl_ctx* c) {
+    const double* approx = c->tile_state == 2 ? c->d_S1 : nullptr;
+    int rc = run_exact(c, c->d_wn, nullptr, c->d_S2, nullptr, 0, c->tile_state == 0, approx);
+    if (rc) return rc;
+    if (c->tile_state == 0) c->tile_state = 1;
+    rc = run_exact(c, c->d_wn, c->d_S2, c->d_scratch_total, c->d_cdf, 1, false, approx);
+    if (rc) return rc;
+    c->cdf_valid = true;
     return MCL_OK;
 }
 
@@ -293,12 +314,8 @@ int update_local(mcl_ctx* c, const double* action_dev, const float* obs_dev, con
     k_prepare_obs<<<dim3(c->R, c->F), 256, 0, s>>>(oa);
     c->launches++;
 
-    // discrete_distribution(weights_): sum, normalise, partial_sum (random.tcc:2657-2678)
-    int rc = run_exact(c, c->d_wn, nullptr, c->d_S2, nullptr, 0, true);
+    int rc = build_cdf(c);
     if (rc) return rc;
-    rc = run_exact(c, c->d_wn, c->d_S2, c->d_scratch_total, c->d_cdf, 1, false);
-    if (rc) return rc;
-    c->cdf_valid = true;
     if (c->profiling) CK(cudaEventRecord(c->ev[1], s));
 
     MotionArgs ma{};
@@ -427,6 +444,7 @@ int update_finish(mcl_ctx* c) {
     const int dst = c->cur ^ 1;
     int rc = run_exact(c, c->d_wraw, nullptr, c->d_S1, nullptr, 0, true);
     if (rc) return rc;
+    c->tile_state = 2;   // d_tile_sum = tile sums of w_raw; w_norm = w_raw / S1 follows
     if (c->p2p) {
         // poses of other ranks are not local: normalise all weights, pose from the gathered partials
         const int64_t n = c->N;
@@ -559,6 +577,8 @@ static int create_buffers(mcl_ctx* c, const mcl_params* p, int device) {
     CK(dalloc(&c->d_pose, static_cast<size_t>(c->F) * 3));
     CK(cudaMemset(c->d_pose, 0, sizeof(double) * 3 * c->F));
     CK(dalloc(&c->d_centre, static_cast<size_t>(c->F) * 2));
+    CK(dalloc(&c->d_done, static_cast<size_t>(c->F)));
+    CK(cudaMemset(c->d_done, 0, sizeof(unsigned int) * c->F));
     {   // heading buckets: ~16 particles per bucket, power of two in [32, 4096]
         int B = 32;
         while (B < kMaxBuckets && static_cast<int64_t>(B) * 16 < c->N) B <<= 1;
@@ -621,7 +641,7 @@ int mcl_destroy(mcl_ctx* c) {
                     c->d_action, c->d_obs, c->d_slice, c->d_tile_sum, c->d_chunk_fn, c->d_opq_pre, c->d_opq_idx,
                     c->d_tile_opq, c->d_tile_elem, c->d_list_chunk, c->d_list_fn, c->d_anchors, c->d_anchor_val,
                     c->d_tile_start, c->d_S1, c->d_S2, c->d_scratch_total, c->d_partial, c->d_pose, c->d_centre, c->d_replays,
-                    c->d_hist, c->d_perm};
+                    c->d_hist, c->d_perm, c->d_done};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (void* p : c->ipc_opened) cudaIpcCloseMemHandle(p);
@@ -800,6 +820,7 @@ int mcl_init_pose(mcl_ctx* c, int filter, const double pose[3], const double* no
     cudaFree(d_pose);
     if (d_norm) cudaFree(d_norm);
     c->cdf_valid = false;
+    c->tile_state = 0;
     return MCL_OK;
 }
 
@@ -845,6 +866,7 @@ int mcl_init_global(mcl_ctx* c, int filter, const int32_t* cell, const double* t
     if (d_cell) cudaFree(d_cell);
     if (d_theta) cudaFree(d_theta);
     c->cdf_valid = false;
+    c->tile_state = 0;
     return MCL_OK;
 }
 
@@ -859,7 +881,10 @@ int mcl_set_particles(mcl_ctx* c, int filter, const double* P, const double* w) 
         CK(cudaMemcpy(c->d_py[c->cur] + fo, P + N, N * sizeof(double), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(c->d_pt[c->cur] + fo, P + 2 * N, N * sizeof(double), cudaMemcpyHostToDevice));
     }
-    if (w) CK(cudaMemcpy(c->d_wn + fo, w, N * sizeof(double), cudaMemcpyHostToDevice));
+    if (w) {
+        CK(cudaMemcpy(c->d_wn + fo, w, N * sizeof(double), cudaMemcpyHostToDevice));
+        c->tile_state = 0;
+    }
     c->cdf_valid = false;
     return MCL_OK;
 }
@@ -1055,11 +1080,8 @@ int mcl_sample_particles(mcl_ctx* c, int filter, int k, double* out) {
     if (!out || k < 1) return fail(MCL_ERR_INVALID, "bad arguments");
     CK(cudaSetDevice(c->device));
     // CDF of the current weights, as visualize() builds it (:949)
-    rc = run_exact(c, c->d_wn, nullptr, c->d_S2, nullptr, 0, true);
+    rc = build_cdf(c);
     if (rc) return rc;
-    rc = run_exact(c, c->d_wn, c->d_S2, c->d_scratch_total, c->d_cdf, 1, false);
-    if (rc) return rc;
-    c->cdf_valid = true;
     double* d_o = nullptr;
     CK(dalloc(&d_o, static_cast<size_t>(3) * k));
     const size_t fo = static_cast<size_t>(c->N) * filter;
