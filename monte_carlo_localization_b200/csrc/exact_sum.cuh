@@ -16,7 +16,7 @@
 // for a pair of integers (A[0], A[1]), and such maps compose associatively:
 //        (B o A)[p] = A[p] + B[(p + A[p]) & 1].
 // So: (1) a plain parallel scan gives every running sum to ~1e-10, which fixes its binade
-// except within a rigorous error band of a power of two; (2) every 16-addend chunk that is
+// except within a rigorous error band of a power of two; (2) every kChunk-addend chunk that is
 // safely inside one binade is summarised by its pair (two short sequential chains from the
 // even and the odd bottom of the binade); (3) pairs are combined with a parallel scan;
 // (4) the few chunks that may cross a binade ("opaque", a few dozen per million addends) are
@@ -29,8 +29,8 @@
 
 namespace mclb200 {
 
-constexpr int kChunk = 16;              // addends per chunk (one thread)
-constexpr int kTileChunks = 256;        // chunks per tile (one CTA)
+constexpr int kChunk = 8;               // addends per chunk (one thread)
+constexpr int kTileChunks = 512;        // chunks per tile (one CTA)
 constexpr int kTile = kChunk * kTileChunks;   // 4096 addends per tile
 
 // Step map of a run of addends inside one binade.  opaque => not representable; a[] unused.
