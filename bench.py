@@ -370,6 +370,9 @@ def run_gpu(args):
         if world == 1 and not args.no_cpu:
             cb = cpu_reference_arm(args.ref_particles, 3, 1)
             cb = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "buckets_ms_per_update")}
+            # the reference's shipped thread count (config/mcl_config.yaml:40 num_threads: 3), for context
+            shipped = cpu_reference_arm(max(1000, args.ref_particles // 4), 2, 1, threads=3)
+            cb["shipped_num_threads_3"] = {"value": shipped["value"], "unit": UNIT, "cores": 3, "sample": shipped["sample"]}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "updates_per_s": 1e3 / ms_per_step,

@@ -4,7 +4,7 @@
 //   exact sums / CDF   k_tile_sums, k_exact_chunks, k_exact_walk, k_exact_emit   (:658, :679)
 //   resample + motion  k_resample_motion                                         (:661-665, :449-503)
 //   ray cast + weight  k_prepare_obs, k_raycast_weight                           (:506-650)
-//   normalise + pose   k_normalize_pose, k_pose_final                            (:679-686, :696-716)
+//   normalise + pose   k_normalize_pose (the last block writes the pose)         (:679-686, :696-716)
 // blockIdx.y is the filter of a batch; every per-filter array is [F][...] contiguous.
 #pragma once
 #include <cuda_runtime.h>
@@ -977,24 +977,6 @@ __global__ void k_pose_from_partials(const double* partials, int world, const do
     pose_out[0] = v[0] / s;
     pose_out[1] = v[1] / s;
     pose_out[2] = atan2(v[2], v[3]);
-}
-
-__global__ void __launch_bounds__(256) k_pose_final(const double* partial, int nblk, double* pose_out) {
-    __shared__ double sm[8];
-    const int f = blockIdx.x;
-    double v[4] = {0, 0, 0, 0};
-    for (int b = threadIdx.x; b < nblk; b += 256) {
-        const double* p = partial + (static_cast<int64_t>(f) * nblk + b) * 4;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] += p[k];
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) v[k] = block_sum<256>(v[k], sm);
-    if (threadIdx.x == 0) {
-        pose_out[3 * f + 0] = v[0];
-        pose_out[3 * f + 1] = v[1];
-        pose_out[3 * f + 2] = atan2(v[2], v[3]);
-    }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -95,3 +95,17 @@ def test_trinary_rule():
     # rows flip: grid row 0 is the image's bottom row
     img2 = np.array([[0], [255]], dtype=np.uint8)
     assert maps.image_to_grid(img2, False, 0.65, 0.196).ravel().tolist() == [0, 100]
+
+
+def test_synthetic_levine_stand_in():
+    """The procedural stand-in for the missing levine.pgm honours maps/levine.yaml's geometry."""
+    from monte_carlo_localization_b200 import synth
+    g = maps.synth_levine()
+    assert (g.width, g.height) == (2048, 2048) and g.max_range_px() == 239
+    assert g.origin[:2] == (-51.224998, -51.224998)
+    free, occ, unk = g.counts()
+    assert free > 100000 and occ > 5000 and unk > 3000000
+    x, y, th = synth.centreline_loop(g, n_points=200, mask=(g.data == 0))
+    rows = ((y - g.origin[1]) / g.resolution_f64).astype(int)
+    cols = ((x - g.origin[0]) / g.resolution_f64).astype(int)
+    assert (g.data[rows, cols] == 0).mean() > 0.95      # the ground-truth loop runs through free space
