@@ -361,7 +361,14 @@ def run_gpu(args):
                     traffic = json.load(open(tp)).get("k_raycast_weight_dram_bytes_per_launch")
                 except Exception:
                     traffic = None
+            # gather-rate context for the same kernel: random byte reads/s the chip sustains from a
+            # shared-memory window and from a 4 MB L2-resident array
+            from monte_carlo_localization_b200 import capi as _capi
+            gather = {"shared_memory_peak_per_s": _capi.microbench_gather(True, device=local_rank),
+                      "l2_4mb_peak_per_s": _capi.microbench_gather(False, device=local_rank),
+                      "reference_samples_per_s": N * R * cbar / (stage["raycast_weight"] * 1e-3)}
             roof = {"bound": "hbm", "kernel": "k_raycast_weight", "achieved": ach, "peak": peak, "unit": "GB/s",
+                    "gather": gather,
                     "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg_bytes, "mean_cells_per_ray": cbar,
                     "kernel_ms": stage["raycast_weight"],

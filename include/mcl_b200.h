@@ -145,6 +145,12 @@ int mcl_kernel_launches(mcl_ctx* ctx, int64_t* count); /* kernels launched so fa
 /* Use the caller's CUDA stream (cudaStream_t passed as void*) instead of the ctx's own. */
 int mcl_set_stream(mcl_ctx* ctx, void* cuda_stream);
 
+/* Gather micro-benchmark (measurement aid): random single-byte reads per second from
+ * an L2-resident array of array_bytes (shared = 0) or from a shared-memory window (shared = 1,
+ * capped at 128 KB) -- the access pattern of the ray march without its arithmetic.  It gives the
+ * ray stage a gather-rate roofline next to the HBM one. */
+int mcl_microbench_gather(int device, int shared, size_t array_bytes, int iters_per_thread, double* gathers_per_second);
+
 /* ---- particle-sharded operation: one rank per GPU, ONE global filter ---------------------
  * The reference has no multi-process path; the coupling points of its update are the weight
  * sum (:679), the global CDF + source gather (:658-665) and the pose sums (:702-710).  Every

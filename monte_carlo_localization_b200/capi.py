@@ -85,6 +85,7 @@ SIGNATURES = {
     "mcl_set_keep_ranges": (C.c_int, [C.c_void_p, C.c_int]),
     "mcl_kernel_launches": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "mcl_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mcl_microbench_gather": (C.c_int, [C.c_int, C.c_int, C.c_size_t, C.c_int, c_double_p]),
     "mcl_set_shard": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64]),
     "mcl_update_local_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "mcl_exchange_buffers_dev": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
@@ -146,6 +147,16 @@ def default_params(**kw) -> MclParams:
             raise AttributeError("mcl_params has no field %r" % k)
         setattr(p, k, v)
     return p
+
+
+def microbench_gather(shared: bool, array_bytes: int = 4 << 20, iters: int = 4096, device: int = 0) -> float:
+    """Random single-byte gathers per second from shared memory or an L2-resident array."""
+    L = load_library()
+    out = C.c_double(0.0)
+    rc = L.mcl_microbench_gather(device, int(shared), array_bytes, iters, C.byref(out))
+    if rc != MCL_OK:
+        raise MclError(rc, "mcl_microbench_gather", L.mcl_last_error().decode(errors="replace"))
+    return float(out.value)
 
 
 class MclContext:

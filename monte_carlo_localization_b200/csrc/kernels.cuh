@@ -1112,6 +1112,37 @@ __global__ void k_sample_particles(const double* cdf, int64_t N, const double* p
     out[2 * k + i] = pt[lo];
 }
 
+// ------------------------------------------------------------------------------------------
+// gather micro-benchmark: random single-byte reads from an L2-resident array or
+// from a shared-memory window -- the access pattern of the ray march, without its arithmetic
+// ------------------------------------------------------------------------------------------
+template <bool SHARED>
+__global__ void __launch_bounds__(1024, 1) k_gather_bench(const uint8_t* __restrict__ arr, uint32_t mask, int iters,
+                                                         unsigned long long* sink) {
+    extern __shared__ __align__(16) uint8_t smem_win[];
+    if (SHARED) {
+        for (uint32_t i = threadIdx.x * 16u; i <= mask; i += blockDim.x * 16u)
+            *reinterpret_cast<uint4*>(smem_win + i) = __ldg(reinterpret_cast<const uint4*>(arr + i));
+        __syncthreads();
+    }
+    uint32_t s0 = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+    uint32_t s1 = s0 ^ 0x9e3779b9u, s2 = s0 + 0x85ebca6bu, s3 = s0 * 0xc2b2ae35u + 1u;
+    uint32_t acc = 0;
+    for (int it = 0; it < iters; ++it) {
+        // four independent address streams per thread (xorshift), like four rays in flight
+        s0 ^= s0 << 13; s0 ^= s0 >> 17; s0 ^= s0 << 5;
+        s1 ^= s1 << 13; s1 ^= s1 >> 17; s1 ^= s1 << 5;
+        s2 ^= s2 << 13; s2 ^= s2 >> 17; s2 ^= s2 << 5;
+        s3 ^= s3 << 13; s3 ^= s3 >> 17; s3 ^= s3 << 5;
+        if (SHARED) {
+            acc += smem_win[s0 & mask] + smem_win[s1 & mask] + smem_win[s2 & mask] + smem_win[s3 & mask];
+        } else {
+            acc += __ldg(arr + (s0 & mask)) + __ldg(arr + (s1 & mask)) + __ldg(arr + (s2 & mask)) + __ldg(arr + (s3 & mask));
+        }
+    }
+    if (acc == 0xffffffffu) atomicAdd(sink, 1ull);   // keeps the loads alive
+}
+
 __global__ void k_fill(double* p, int64_t n, double v) {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;

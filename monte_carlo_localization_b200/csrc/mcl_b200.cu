@@ -1244,6 +1244,54 @@ int mcl_update_finish_dev(mcl_ctx* c) {
     return update_finish(c);
 }
 
+int mcl_microbench_gather(int device, int shared, size_t array_bytes, int iters_per_thread, double* gathers_per_second) {
+    if (!gathers_per_second || iters_per_thread < 1) return fail(MCL_ERR_INVALID, "bad arguments");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(MCL_ERR_NO_DEVICE, "no CUDA device visible");
+    }
+    CK(cudaSetDevice(device));
+    // power-of-two size; the shared variant is capped by the 227 KB shared memory (128 KB window)
+    size_t bytes = 4096;
+    while (bytes * 2 <= array_bytes) bytes *= 2;
+    if (shared && bytes > 128 * 1024) bytes = 128 * 1024;
+    cudaDeviceProp prop{};
+    CK(cudaGetDeviceProperties(&prop, device));
+    uint8_t* d_arr = nullptr;
+    unsigned long long* d_sink = nullptr;
+    CK(dalloc(&d_arr, bytes));
+    CK(dalloc(&d_sink, size_t{1}));
+    CK(cudaMemset(d_arr, 1, bytes));
+    CK(cudaMemset(d_sink, 0, sizeof(unsigned long long)));
+    const int blocks = prop.multiProcessorCount, threads = 1024;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    const uint32_t mask = static_cast<uint32_t>(bytes - 1);
+    if (shared) CK(cudaFuncSetAttribute(k_gather_bench<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {   // first repetition warms up
+        CK(cudaEventRecord(e0));
+        if (shared)
+            k_gather_bench<true><<<blocks, threads, bytes>>>(d_arr, mask, iters_per_thread, d_sink);
+        else
+            k_gather_bench<false><<<blocks, threads>>>(d_arr, mask, iters_per_thread, d_sink);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    CK(cudaGetLastError());
+    *gathers_per_second = 4.0 * iters_per_thread * static_cast<double>(blocks) * threads / (best * 1e-3);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_arr);
+    cudaFree(d_sink);
+    return MCL_OK;
+}
+
 int mcl_set_stream(mcl_ctx* c, void* stream) {
     if (!c) return fail(MCL_ERR_INVALID, "null context");
     CK(cudaSetDevice(c->device));

@@ -466,3 +466,11 @@ def test_global_init_and_error_paths():
         c2.set_map(fine)
     assert e.value.status == capi.MCL_ERR_UNSUPPORTED
     c2.close()
+
+
+def test_gather_microbench_reports_rates():
+    """Measurement aid: random-byte gather rates from shared memory and from L2."""
+    from monte_carlo_localization_b200 import capi
+    sm = capi.microbench_gather(True, iters=512)
+    l2 = capi.microbench_gather(False, iters=512)
+    assert sm > 1e11 and l2 > 1e10 and sm > l2
