@@ -435,13 +435,6 @@ struct MotionArgs {
     double* centre;           // [F][2] accumulators (sum x, sum y)
 };
 
-// heading bucket of the coherence sort: particles with nearly equal headings cast nearly
-// identical rays, so a warp of bucket-neighbours marches in lock step
-__device__ __forceinline__ int theta_bucket(double th, int B) {
-    const int b = static_cast<int>((th + 3.14159265358979323846) * (static_cast<double>(B) * 0.15915494309189535));
-    return max(0, min(b, B - 1));
-}
-
 struct MotionScalars {
     double dt, vel, omega, radius, dtheta, vdt;
     int straight;

@@ -153,4 +153,52 @@ bool build_skip_map(const int8_t* data, int W, int H, SkipMap& out) {
     return true;
 }
 
+void build_gap_map(const SkipMap& sk, std::vector<float>& gap) {
+    const size_t n = static_cast<size_t>(sk.PW) * sk.PH;
+    std::vector<uint8_t> dil(n);
+    for (size_t i = 0; i < n; ++i) dil[i] = sk.v8[i] < 2;
+    std::vector<int64_t> d2;
+    edt_squared(dil, sk.PW, sk.PH, d2);
+    gap.resize(n);
+    for (size_t i = 0; i < n; ++i) {
+        const double d = std::sqrt(static_cast<double>(std::min<int64_t>(d2[i], int64_t{1} << 40)));
+        gap[i] = std::nextafterf(static_cast<float>(d), 0.0f);   // never above the true gap
+    }
+}
+
+void make_dir_sectors(int M, DirSector* out) {
+    const double pi = 3.14159265358979323846;
+    const double width = 2.0 * pi / kDirSectors;
+    for (int s = 0; s < kDirSectors; ++s) {
+        DirSector& sc = out[s];
+        const double a0 = s * width - kDirMargin, a1 = (s + 1) * width + kDirMargin;
+        const double mid = (s + 0.5) * width, half = width / 2 + kDirMargin;
+        sc.ux = std::cos(mid);
+        sc.uy = std::sin(mid);
+        sc.kappa = 2.0 * std::sin(half / 2) * (1.0 + 1e-9);
+        auto range = [&](bool sine, double* lo, double* hi) {
+            auto f = [&](double a) { return sine ? std::sin(a) : std::cos(a); };
+            *lo = std::min(f(a0), f(a1));
+            *hi = std::max(f(a0), f(a1));
+            for (int k = -4; k <= 12; ++k) {   // interior extrema at multiples of pi/2
+                const double e = k * pi / 2;
+                if (e > a0 && e < a1) {
+                    *lo = std::min(*lo, f(e));
+                    *hi = std::max(*hi, f(e));
+                }
+            }
+            *lo -= 1e-12;
+            *hi += 1e-12;
+        };
+        range(false, &sc.cmin, &sc.cmax);
+        range(true, &sc.smin, &sc.smax);
+        // cells reachable by samples 0..M of a ray starting anywhere in a cell, +-2 for the
+        // neighbour lookups of the edge test
+        sc.exl = static_cast<int>(std::floor(std::min(0.0, M * sc.cmin))) - 2;
+        sc.exh = static_cast<int>(std::floor(1.0 + std::max(0.0, M * sc.cmax))) + 2;
+        sc.eyl = static_cast<int>(std::floor(std::min(0.0, M * sc.smin))) - 2;
+        sc.eyh = static_cast<int>(std::floor(1.0 + std::max(0.0, M * sc.smax))) + 2;
+    }
+}
+
 }  // namespace mclb200

@@ -25,6 +25,8 @@
 #include <cstdint>
 #include <vector>
 
+#include "dirmap.cuh"
+
 namespace mclb200 {
 
 constexpr int kPadL = 8;   // P-cells left of / below reference cell 0 (incl. the trunc-duplicate)
@@ -44,5 +46,13 @@ bool build_skip_map(const int8_t* data, int W, int H, SkipMap& out);
 // Exact squared Euclidean distance transform to the set {mask != 0} (Felzenszwalb-
 // Huttenlocher lower envelopes); out[i] = squared distance in cells, big if no seed.
 void edt_squared(const std::vector<uint8_t>& mask, int W, int H, std::vector<int64_t>& out);
+
+// Euclidean gap (cells) between every P-cell's square and the nearest blocked cell's square
+// (0 for blocked cells and their 8-neighbours): the distance field the cone tracing of
+// dirmap.cuh queries.
+void build_gap_map(const SkipMap& sk, std::vector<float>& gap);
+
+// Geometry of the kDirSectors heading sectors for rays of at most M steps.
+void make_dir_sectors(int M, DirSector* out);
 
 }  // namespace mclb200

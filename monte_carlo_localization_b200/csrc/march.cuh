@@ -257,4 +257,67 @@ MCL_HD int march_ray(const Acc& acc, const RayStart& st, int dxf, int dyf, int M
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// March over a DIRECTIONAL skip map (dirmap.cuh): code 0x80 = blocked, bit 7 = "a neighbour is
+// blocked" (the landing sample needs the cell-edge test), low 7 bits = advance.  Same lattice
+// and the same exactness rule as march_ray; `rep` loads the particle pose only if a sample
+// must be replayed in FP64 (rep.load() -> ReplayArgs).
+// ------------------------------------------------------------------------------------------
+template <class Acc, class Rep>
+MCL_NOINLINE int resolve_uncertain_dir(const Acc& acc, uint32_t px, uint32_t py, int v, const RefGrid& g, const Rep& rep,
+                                       int k, int* replays) {
+    const bool hit = (v == 0x80);
+    const int cx = static_cast<int>(px >> kFrac), cy = static_cast<int>(py >> kFrac);
+    const uint32_t fx = px & kFracMask, fy = py & kFracMask;
+    const bool ux = ((fx + kEtaFix) & kFracMask) < 2u * kEtaFix;
+    const bool uy = ((fy + kEtaFix) & kFracMask) < 2u * kEtaFix;
+    const int nx = cx + (fx < kEtaFix ? -1 : 1);
+    const int ny = cy + (fy < kEtaFix ? -1 : 1);
+    bool differs = false;
+    if (ux) differs |= ((acc.get(nx, cy) == 0x80) != hit);
+    if (uy) differs |= ((acc.get(cx, ny) == 0x80) != hit);
+    if (ux && uy) differs |= ((acc.get(nx, ny) == 0x80) != hit);
+    if (!differs) return hit ? 1 : 0;
+    const ReplayArgs ra = rep.load();
+    double sn, cs;
+    sincos_ref(nf_add(ra.theta, static_cast<double>(ra.beam)), &sn, &cs);   // theta + angle (:533)
+    if (replays) ++*replays;
+    return replay_sample_is_hit(g, ra.x, ra.y, nf_mul(cs, g.res), nf_mul(sn, g.res), k) ? 1 : 0;
+}
+
+template <class Acc, class Rep>
+MCL_HD int march_ray_dir(const Acc& acc, const RayStart& st, int dxf, int dyf, int M, const RefGrid& g, const Rep& rep,
+                         int* replays) {
+    constexpr int kPark = 1 << 20;
+    int k = 1, r = M;
+    for (;;) {
+        int pending_k = 0;   // sample to resolve exactly (0 = none)
+        do {
+            const uint32_t px = st.p0x + static_cast<uint32_t>(k * dxf);
+            const uint32_t py = st.p0y + static_cast<uint32_t>(k * dyf);
+            int v = acc.get_p(px, py);
+            if (v >= 0x80) {
+                // blocked, or next to a blocked cell: the class of this very sample matters
+                const uint32_t tx = (px + kEtaFix) & kFracMask, ty = (py + kEtaFix) & kFracMask;
+                if ((tx < ty ? tx : ty) < 2u * kEtaFix) {
+                    pending_k = k;   // within kEta of a cell edge
+                    k = kPark;
+                } else if (v == 0x80) {
+                    r = k - 1;
+                    k = kPark;
+                }
+                v &= 0x7f;
+            }
+            k += v;
+        } while (k <= M);
+        if (pending_k == 0) return r;
+        k = pending_k;
+        const uint32_t px = st.p0x + static_cast<uint32_t>(k * dxf);
+        const uint32_t py = st.p0y + static_cast<uint32_t>(k * dyf);
+        if (resolve_uncertain_dir(acc, px, py, acc.get_p(px, py), g, rep, k, replays)) return k - 1;
+        k += 1;   // the sample's true cell may be the neighbour: take a single step
+        if (k > M) return M;
+    }
+}
+
 }  // namespace mclb200

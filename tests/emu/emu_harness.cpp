@@ -22,7 +22,43 @@ struct emu_map {
     std::vector<int8_t> grid;
     double res, ox, oy;
     int M;
+    // directional skip maps (dirmap.cuh), built sector by sector on first use
+    std::vector<float> gap;
+    DirSector sectors[kDirSectors];
+    std::vector<uint8_t> dir[kDirSectors];
 };
+
+// accessor over a whole sector map (the kernel's global-memory fallback)
+struct DirGlobal {
+    const uint8_t* base;
+    int PW;
+    long long* lookups;
+    int get_p(uint32_t px, uint32_t py) const {
+        if (lookups) ++*lookups;
+        return get(static_cast<int>(px >> kFrac), static_cast<int>(py >> kFrac));
+    }
+    int get(int lx, int ly) const { return base[static_cast<int64_t>(ly) * PW + lx]; }
+};
+struct ReplayNow {
+    ReplayArgs ra;
+    ReplayArgs load() const { return ra; }
+};
+
+static const std::vector<uint8_t>& emu_dir_sector(emu_map* m, int s) {
+    const SkipMap& sk = m->skip;
+    if (m->gap.empty()) {
+        build_gap_map(sk, m->gap);
+        make_dir_sectors(m->M, m->sectors);
+    }
+    std::vector<uint8_t>& d = m->dir[s];
+    if (d.empty()) {
+        d.resize(static_cast<size_t>(sk.PW) * sk.PH);
+        for (int cy = 0; cy < sk.PH; ++cy)
+            for (int cx = 0; cx < sk.PW; ++cx)
+                d[static_cast<size_t>(cy) * sk.PW + cx] = dir_code(sk.v8.data(), m->gap.data(), sk.PW, sk.PH, cx, cy, m->sectors[s]);
+    }
+    return d;
+}
 
 extern "C" {
 
@@ -103,6 +139,114 @@ long long emu_range_steps(const emu_map* m, const double* px, const double* py, 
         }
     }
     if (iters_out) *iters_out = iters;
+    return replays;
+}
+
+// One sector's directional map (PH*PW bytes), as the build kernel writes it.
+void emu_dir_map(emu_map* m, int sector, uint8_t* out) {
+    const std::vector<uint8_t>& d = emu_dir_sector(m, sector);
+    std::memcpy(out, d.data(), d.size());
+}
+
+// Step indices the way k_raycast_dir computes them: heading bucket -> sector per beam, march
+// over that sector's map; use_window: particles inside the box around the cloud centre read
+// a copy of the sector's window (the shared-memory path), the others the whole map.
+// lookups_out (nullable): skip-map lookups per ray.
+long long emu_range_steps_dir(emu_map* m, const double* px, const double* py, const double* pt, long long n,
+                              const float* angles, int R, int B, int use_window, int box, uint8_t* steps_out,
+                              int32_t* lookups_out) {
+    const SkipMap& sk = m->skip;
+    const int M = m->M;
+    emu_dir_sector(m, 0);
+    std::vector<double> ca(R), sa(R);
+    std::vector<int> io(R);
+    for (int j = 0; j < R; ++j) {
+        ca[j] = std::cos(static_cast<double>(angles[j]));
+        sa[j] = std::sin(static_cast<double>(angles[j]));
+        io[j] = dir_beam_offset(angles[j], B);
+    }
+    int shift = 0;
+    while ((B >> shift) > kDirSectors) ++shift;
+    // cloud centre -> box, like the kernel
+    double mx = 0, my = 0;
+    for (long long i = 0; i < n; ++i) {
+        mx += px[i];
+        my += py[i];
+    }
+    mx /= static_cast<double>(n);
+    my /= static_cast<double>(n);
+    const int bcx = static_cast<int>(std::floor((mx - m->ox) / m->res + kPadL));
+    const int bcy = static_cast<int>(std::floor((my - m->oy) / m->res + kPadL));
+    const int box_x0 = bcx - box / 2, box_y0 = bcy - box / 2;
+    std::vector<std::vector<uint8_t>> win(kDirSectors);
+    std::vector<DirWindow> wgeo(kDirSectors);
+    const RefGrid rg{m->grid.data(), sk.W, sk.H, m->res, m->ox, m->oy};
+    int replays = 0;
+    long long oob = 0;
+    for (long long i = 0; i < n; ++i) {
+        const double x = px[i], y = py[i], th = pt[i];
+        const double sth = std::sin(th), cth = std::cos(th);
+        const double qx = p_coord(x, m->ox, m->res, kPadL), qy = p_coord(y, m->oy, m->res, kPadL);
+        uint8_t* out = steps_out + i * R;
+        if (!p_inside(qx, qy, sk.PW, sk.PH)) {
+            for (int j = 0; j < R; ++j) {
+                out[j] = 0;
+                if (lookups_out) lookups_out[i * R + j] = 0;
+            }
+            continue;
+        }
+        const int fqx = static_cast<int>(std::floor(qx)), fqy = static_cast<int>(std::floor(qy));
+        const RayStart st = make_ray_start(qx, qy, fqx, fqy);
+        const int bucket = theta_bucket(th, B);
+        const bool in_box = use_window && fqx >= box_x0 && fqx < box_x0 + box && fqy >= box_y0 && fqy < box_y0 + box;
+        for (int j = 0; j < R; ++j) {
+            int dxf, dyf;
+            beam_direction_fixed(cth, sth, ca[j], sa[j], &dxf, &dyf);
+            const int s = dir_sector_of(bucket, io[j], B - 1, shift);
+            const std::vector<uint8_t>& d = emu_dir_sector(m, s);
+            const ReplayNow rep{ReplayArgs{x, y, th, angles[j]}};
+            long long lk = 0;
+            int r;
+            if (in_box) {
+                if (win[s].empty()) {
+                    wgeo[s] = dir_window(m->sectors[s], box_x0, box_y0, box, sk.PW, sk.PH);
+                    // poison outside the window so that a read beyond it would change the result
+                    win[s].assign(static_cast<size_t>(wgeo[s].pitch) * wgeo[s].rows, 0x80);
+                    for (int row = 0; row < wgeo[s].rows; ++row)
+                        std::memcpy(&win[s][static_cast<size_t>(row) * wgeo[s].pitch],
+                                    &d[static_cast<size_t>(wgeo[s].wy0 + row) * sk.PW + wgeo[s].wx0], wgeo[s].pitch);
+                }
+                const DirWindow& w = wgeo[s];
+                // bounds-checked accessor: the window must contain every cell the march reads
+                struct Checked {
+                    const uint8_t* w;
+                    int offx, offy, pitch, rows;
+                    long long* lookups;
+                    long long* oob;
+                    int get_p(uint32_t px_, uint32_t py_) const {
+                        ++*lookups;
+                        return get(static_cast<int>(px_ >> kFrac), static_cast<int>(py_ >> kFrac));
+                    }
+                    int get(int lx, int ly) const {
+                        const int xx = lx + offx, yy = ly + offy;
+                        if (xx < 0 || xx >= pitch || yy < 0 || yy >= rows) {
+                            ++*oob;   // a read beyond the window: reported as a failure
+                            return 0x80;
+                        }
+                        return w[static_cast<size_t>(yy) * pitch + xx];
+                    }
+                };
+                const Checked acc{win[s].data(), st.bx - w.wx0, st.by - w.wy0, w.pitch, w.rows, &lk, &oob};
+                r = march_ray_dir(acc, st, dxf, dyf, M, rg, rep, &replays);
+            } else {
+                const DirGlobal acc{d.data() + static_cast<int64_t>(st.by) * sk.PW + st.bx, sk.PW, &lk};
+                r = march_ray_dir(acc, st, dxf, dyf, M, rg, rep, &replays);
+            }
+            out[j] = static_cast<uint8_t>(r);
+            if (lookups_out) lookups_out[i * R + j] = static_cast<int32_t>(lk);
+        }
+    }
+    if (oob) return -oob;
     return replays;
 }
 

@@ -29,6 +29,11 @@ def lib():
         L.emu_range_steps.argtypes = [C.c_void_p] + [C.POINTER(C.c_double)] * 3 + [
             C.c_longlong, C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
             C.POINTER(C.c_uint8), C.POINTER(C.c_longlong)]
+        L.emu_dir_map.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint8)]
+        L.emu_range_steps_dir.restype = C.c_longlong
+        L.emu_range_steps_dir.argtypes = [C.c_void_p] + [C.POINTER(C.c_double)] * 3 + [
+            C.c_longlong, C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.c_int,
+            C.POINTER(C.c_uint8), C.POINTER(C.c_int32)]
         L.emu_exact_scan.restype = C.c_longlong
         L.emu_exact_scan.argtypes = [C.POINTER(C.c_double), C.c_longlong, C.c_int, C.c_double,
                                      C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int]
@@ -79,6 +84,28 @@ class EmuMap:
         rep = lib().emu_range_steps(self._h, _dp(x), _dp(y), _dp(th), n, a.ctypes.data_as(C.POINTER(C.c_float)), R,
                                     mode, wx0, wy0, ww, wh, out.ctypes.data_as(C.POINTER(C.c_uint8)), None)
         return out, int(rep)
+
+
+    def dir_map(self, sector):
+        out = np.empty((self.PH, self.PW), dtype=np.uint8)
+        lib().emu_dir_map(self._h, sector, out.ctypes.data_as(C.POINTER(C.c_uint8)))
+        return out
+
+    def range_steps_dir(self, x, y, th, angles, buckets=4096, window_box=0, want_lookups=False):
+        """Step indices [n, R] of the directional march (k_raycast_dir's logic); window_box > 0
+        routes particles inside that box around the cloud centre through a window copy."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        th = np.ascontiguousarray(th, dtype=np.float64)
+        a = np.ascontiguousarray(angles, dtype=np.float32)
+        n, R = len(x), len(a)
+        out = np.empty((n, R), dtype=np.uint8)
+        lk = np.empty((n, R), dtype=np.int32) if want_lookups else None
+        rep = lib().emu_range_steps_dir(self._h, _dp(x), _dp(y), _dp(th), n, a.ctypes.data_as(C.POINTER(C.c_float)), R,
+                                        buckets, int(window_box > 0), int(window_box),
+                                        out.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                        None if lk is None else lk.ctypes.data_as(C.POINTER(C.c_int32)))
+        return (out, int(rep), lk) if want_lookups else (out, int(rep))
 
 
 def exact_scan(src, div=None, want_prefix=True, force_last_one=False):

@@ -115,3 +115,83 @@ def test_skip_map_codes_are_conservative():
     v4 = em.v4()
     lo, hi = v4 & 15, v4 >> 4
     assert np.array_equal(lo, np.minimum(v8[:, 0::2], 15)) and np.array_equal(hi, np.minimum(v8[:, 1::2], 15))
+
+
+def _oracle_steps(g, angles, x, y, th):
+    n = len(x)
+    orc = ob.Oracle(g, angles, max_particles=n)
+    q = np.stack([np.repeat(x, len(angles)), np.repeat(y, len(angles)),
+                  (th[:, None] + angles[None, :].astype(np.float64)).reshape(-1)])
+    return steps_from_ranges(orc.calc_range_many(q), g.resolution_f64, orc.M).reshape(n, len(angles))
+
+
+@pytest.mark.parametrize("name", ["sibal1", "first_map"])
+@pytest.mark.parametrize("buckets", [2048, 4096])
+def test_directional_march_equals_reference_march(name, buckets):
+    """k_raycast_dir's logic (heading bucket -> sector map -> march_ray_dir) on stress poses:
+    cell corners, axis-aligned rays, poses outside the map; every sector gets used."""
+    g = maps.load_named_map(name)
+    angles = synth.beam_angles()
+    em = EmuMap(g)
+    n = 4000
+    x, y, th = _stress_poses(g, n, 11, angles)
+    want = _oracle_steps(g, angles, x, y, th)
+    got, replays = em.range_steps_dir(x, y, th, angles, buckets=buckets)
+    assert np.array_equal(got.astype(np.int64), want), "%d rays differ" % int((got != want).sum())
+    assert replays > 0
+
+
+def test_directional_window_covers_a_tracking_cloud():
+    """Tracking cloud on Spielberg: particles inside the box march a bounds-checked copy of each
+    sector's window (a read outside it fails the test), stragglers the whole sector map; the
+    directional maps need far fewer lookups than the isotropic skip map."""
+    full = maps.load_named_map("Spielberg_map")
+    angles = synth.beam_angles()
+    gt, _ = synth.trajectory(full, 60, 8.0)
+    pose = gt[30]
+    # crop 640 x 640 cells around the pose (the CPU build of 32 sector maps of the whole map is slow)
+    res = full.resolution_f64
+    c0 = max(0, int((pose[0] - full.origin[0]) / res) - 320)
+    r0 = max(0, int((pose[1] - full.origin[1]) / res) - 320)
+    g = maps.OccupancyGrid(np.ascontiguousarray(full.data[r0:r0 + 640, c0:c0 + 640]), full.resolution,
+                           (full.origin[0] + c0 * res, full.origin[1] + r0 * res, 0.0))
+    em = EmuMap(g)
+    rng = np.random.default_rng(5)
+    n = 1500
+    x = pose[0] + rng.normal(0, 0.15, n)
+    y = pose[1] + rng.normal(0, 0.15, n)
+    th = pose[2] + rng.normal(0, 0.25, n)
+    x[:20] += rng.normal(0, 6.0, 20)          # stragglers far outside the box
+    y[:20] += rng.normal(0, 6.0, 20)
+    want = _oracle_steps(g, angles, x, y, th)
+    got, replays, lk = em.range_steps_dir(x, y, th, angles, buckets=4096, window_box=64, want_lookups=True)
+    assert replays >= 0, "%d reads fell outside a sector window" % -replays
+    assert np.array_equal(got.astype(np.int64), want), "%d rays differ" % int((got != want).sum())
+    cbar = np.where(want < em.M, want + 1, em.M).mean()
+    assert lk.mean() < 0.1 * cbar     # an order of magnitude fewer lookups than cells sampled
+
+
+def test_directional_codes_respect_their_promise():
+    """Brute force on sibal1: from any sub-cell position and any direction of the sector, the
+    adv-1 samples after a cell of advance adv are not blocked."""
+    g = maps.load_named_map("sibal1")
+    em = EmuMap(g)
+    v8 = em.v8()
+    rng = np.random.default_rng(9)
+    width = 2 * np.pi / 32
+    for s in (0, 3, 8, 13, 21, 30):
+        d = em.dir_map(s)
+        assert ((d == 0x80) == (v8 == 0)).all()
+        assert (((d & 0x80) != 0) == (v8 < 2)).all()
+        assert ((d & 0x7f)[v8 > 0] >= 1).all()
+        ys, xs = np.nonzero((v8 >= 1) & ((d & 0x7f) > 1))
+        pick = rng.choice(len(ys), size=min(3000, len(ys)), replace=False)
+        for cy, cx in zip(ys[pick], xs[pick]):
+            adv = int(d[cy, cx] & 0x7f)
+            a = rng.uniform(s * width - 0.002, (s + 1) * width + 0.002, 6)
+            px = cx + rng.random(6)
+            py = cy + rng.random(6)
+            t = np.arange(1, adv)[:, None]
+            sx = np.floor(px[None, :] + t * np.cos(a)[None, :]).astype(int)
+            sy = np.floor(py[None, :] + t * np.sin(a)[None, :]).astype(int)
+            assert (v8[sy, sx] != 0).all(), (s, cx, cy, adv)
