@@ -235,6 +235,8 @@ def run_gpu(args):
         ctx = MclContext(device=local_rank, max_particles=N, seed=20250 + 3)
         ctx.set_map(grid)
         ctx.set_beam_angles(angles)
+    if args.ray_mode:
+        ctx.set_ray_mode(args.ray_mode)
     # the library launches on this (non-default) torch stream so torch CUDA events time its kernels
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
@@ -292,6 +294,7 @@ def run_gpu(args):
     barrier()
     wall = time.perf_counter() - wall0
     launches = ctx.kernel_launches() - launches0
+    ray_stage = ctx.ray_stage_info()      # which ray stage the last timed update ran
     dev_ms = float(sum(a.elapsed_time(b) for a, b in ev))
     clocks = sampler.stop()
 
@@ -384,7 +387,7 @@ def run_gpu(args):
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "updates_per_s": 1e3 / ms_per_step,
                 "config": workload_config(world, N, R, args.shard_mode), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-                "roofline": roof, "cpu_baseline": cb, "stage_ms": stage,
+                "roofline": roof, "cpu_baseline": cb, "stage_ms": stage, "ray_stage": ray_stage,
                 "wall_ms_per_step_incl_flush": 1e3 * wall / K,
                 "pose_error_m": pose_err}
         print(json.dumps(line))
@@ -402,6 +405,8 @@ def main():
     ap.add_argument("--ref-particles", type=int, default=100000,
                     help="particles of the bounded CPU sample (reference arm / cpu_baseline)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--ray-mode", type=int, default=0, choices=[0, 1, 2],
+                    help="0 auto (default), 1 isotropic skip-map kernel only, 2 directional stage always")
     ap.add_argument("--shard-mode", default="p2p", choices=["p2p", "allgather"],
                     help="multi-GPU exchange: NVLink peer reads of source poses + weight all-gather, or full all-gather")
     args = ap.parse_args()

@@ -145,6 +145,23 @@ int mcl_kernel_launches(mcl_ctx* ctx, int64_t* count); /* kernels launched so fa
 /* Use the caller's CUDA stream (cudaStream_t passed as void*) instead of the ctx's own. */
 int mcl_set_stream(mcl_ctx* ctx, void* cuda_stream);
 
+/* Ray stage selection.  One filter of more than 16384 particles gets, besides the isotropic
+ * skip-map kernel, the DIRECTIONAL stage: per-heading-sector skip maps built at mcl_set_map, rays
+ * grouped by sector, each sector's window staged in shared memory.  Both compute the reference's
+ * cast_ray (src/particle_filter.cpp:611-650) exactly; they differ only in how many samples they
+ * can prove irrelevant.  mode 0 (default): directional when at least 90 % of the particles lie in
+ * the window box around the cloud centre, decided on the device every update; 1: isotropic
+ * kernel only; 2: directional always (MCL_ERR_UNSUPPORTED if the context is not eligible). */
+int mcl_set_ray_mode(mcl_ctx* ctx, int mode);
+/* directional_ready: the context is eligible and its sector maps are built; last_mode: 1 if the
+ * last update ran the directional stage; box_cells: side of the window box; units: work units of
+ * the last update.  Any pointer may be NULL. */
+int mcl_ray_stage_info(mcl_ctx* ctx, int* directional_ready, int* last_mode, int* box_cells, int* units);
+
+/* Diagnostics: one sector's directional skip map (padded grid, *pw x *ph bytes, see
+ * csrc/dirmap.cuh for the code).  out may be NULL to query the size. */
+int mcl_get_dir_map(mcl_ctx* ctx, int sector, uint8_t* out, int* pw, int* ph);
+
 /* Gather micro-benchmark (measurement aid): random single-byte reads per second from
  * an L2-resident array of array_bytes (shared = 0) or from a shared-memory window (shared = 1,
  * capped at 128 KB) -- the access pattern of the ray march without its arithmetic.  It gives the

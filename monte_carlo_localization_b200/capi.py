@@ -85,6 +85,9 @@ SIGNATURES = {
     "mcl_set_keep_ranges": (C.c_int, [C.c_void_p, C.c_int]),
     "mcl_kernel_launches": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "mcl_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mcl_set_ray_mode": (C.c_int, [C.c_void_p, C.c_int]),
+    "mcl_ray_stage_info": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_int)] * 4),
+    "mcl_get_dir_map": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_uint8), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "mcl_microbench_gather": (C.c_int, [C.c_int, C.c_int, C.c_size_t, C.c_int, c_double_p]),
     "mcl_set_shard": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64]),
     "mcl_update_local_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
@@ -334,6 +337,23 @@ class MclContext:
 
     def set_keep_ranges(self, on: bool):
         self._check(self._L.mcl_set_keep_ranges(self._h, int(on)), "mcl_set_keep_ranges")
+
+    def set_ray_mode(self, mode: int):
+        """0 auto, 1 isotropic skip-map kernel only, 2 directional stage always."""
+        self._check(self._L.mcl_set_ray_mode(self._h, int(mode)), "mcl_set_ray_mode")
+
+    def ray_stage_info(self) -> dict:
+        v = [C.c_int(0) for _ in range(4)]
+        self._check(self._L.mcl_ray_stage_info(self._h, *[C.byref(x) for x in v]), "mcl_ray_stage_info")
+        return dict(zip(("directional_ready", "last_mode", "box_cells", "units"), (int(x.value) for x in v)))
+
+    def dir_map(self, sector: int) -> np.ndarray:
+        pw, ph = C.c_int(0), C.c_int(0)
+        self._check(self._L.mcl_get_dir_map(self._h, sector, None, C.byref(pw), C.byref(ph)), "mcl_get_dir_map")
+        out = np.empty((ph.value, pw.value), dtype=np.uint8)
+        self._check(self._L.mcl_get_dir_map(self._h, sector, out.ctypes.data_as(C.POINTER(C.c_uint8)), None, None),
+                    "mcl_get_dir_map")
+        return out
 
     def kernel_launches(self) -> int:
         n = C.c_int64(0)

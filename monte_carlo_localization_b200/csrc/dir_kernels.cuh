@@ -1,0 +1,441 @@
+// csrc/dir_kernels.cuh -- the directional ray stage (large single filters, tracking clouds).
+//
+// Replaces sensor_model's ray cast for every particle x beam (src/particle_filter.cpp:524-540,
+// :586-650) and its table product (:564-579) when one filter is large enough for the heading
+// sort to resolve sectors (>= kDirMinBuckets buckets):
+//   k_build_dir_maps   once per map: the kDirSectors directional skip maps (dirmap.cuh)
+//   k_dir_prepare      per update: ray-start records of the heading-sorted particles
+//   k_dir_plan         per update: per sector, the range of 1024-slot chunks of the heading-sorted
+//                      particles that cast rays into it; a work unit = (sector, chunk)
+//   k_raycast_dir      persistent CTAs pull units; the sector's window of the map is staged in
+//                      shared memory with cp.async.bulk; one lane = one particle, marching the two
+//                      or three beams of it that fall into the sector; step indices out
+//   k_weight_steps     table product in the reference's beam order + pow -> raw weights
+// Lanes of a warp hold heading-neighbours casting the same beam, so their rays share a sector,
+// a window and nearly a trip count.  If the cloud is not compact (fewer than 90 % of the
+// particles inside the window box, e.g. right after initialize_global) the plan hands the
+// update back to k_raycast_weight.
+#pragma once
+
+namespace mclb200 {
+
+constexpr int kDirThreads = 1024;     // threads of a ray CTA == sorted slots of one unit
+constexpr int kDirGrab = 16;          // units a CTA takes per visit to the global counter
+
+// ints of the plan buffer
+enum { kPlanMode = 0, kPlanUnits = 1, kPlanCounter = 2, kPlanInBox = 3, kPlanBoxX = 4, kPlanBoxY = 5, kPlanInts = 8 };
+
+struct DirBuildArgs {
+    const uint8_t* v8;
+    const float* gap;
+    const DirSector* sectors;
+    uint8_t* out;          // [S][PH*PW]
+    int PW, PH;
+};
+
+__global__ void __launch_bounds__(256) k_build_dir_maps(DirBuildArgs a) {
+    const int64_t cell = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+    const int64_t n = static_cast<int64_t>(a.PW) * a.PH;
+    if (cell >= n) return;
+    const int s = blockIdx.y;
+    const int cy = static_cast<int>(cell / a.PW), cx = static_cast<int>(cell - static_cast<int64_t>(cy) * a.PW);
+    a.out[static_cast<int64_t>(s) * n + cell] = dir_code(a.v8, a.gap, a.PW, a.PH, cx, cy, a.sectors[s]);
+}
+
+struct DirPrepArgs {
+    MapDev map;
+    int64_t N, lo, cnt;
+    const double* px;
+    const double* py;
+    const double* pt;
+    const int32_t* perm;       // sorted slot -> particle index relative to lo
+    const double* centre;      // [2] sums of x and y over the cnt particles
+    uint4* rec0;               // [cnt] p0x, p0y, bx | by << 16, bucket | flags << 16
+    double2* rec1;             // [cnt] cos(theta) * 2^23, sin(theta) * 2^23
+    int* plan;
+    int B, box;
+};
+
+// P-cell of the box corner: the box is centred on the cloud's mean position
+__device__ __forceinline__ void dir_box_origin(const double* centre, int64_t cnt, const MapDev& mp, int box, int* bx0, int* by0) {
+    const double mx = centre[0] / static_cast<double>(cnt), my = centre[1] / static_cast<double>(cnt);
+    const double qx = (mx - mp.ox) / mp.res + kPadL, qy = (my - mp.oy) / mp.res + kPadL;
+    const int cx = (qx > -1e9 && qx < 1e9) ? static_cast<int>(floor(qx)) : 0;
+    const int cy = (qy > -1e9 && qy < 1e9) ? static_cast<int>(floor(qy)) : 0;
+    *bx0 = cx - box / 2;
+    *by0 = cy - box / 2;
+}
+
+__global__ void __launch_bounds__(256) k_dir_prepare(DirPrepArgs a) {
+    __shared__ int s_cnt[8];
+    const int64_t pos = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+    int bx0, by0;
+    dir_box_origin(a.centre, a.cnt, a.map, a.box, &bx0, &by0);
+    int in_box = 0;
+    if (pos < a.cnt) {
+        const int64_t i = a.lo + a.perm[a.lo + pos];
+        const double x = a.px[i], y = a.py[i], th = a.pt[i];
+        double sth, cth;
+        sincos(th, &sth, &cth);
+        const double qx = p_coord(x, a.map.ox, a.map.res, kPadL);
+        const double qy = p_coord(y, a.map.oy, a.map.res, kPadL);
+        uint4 r0 = make_uint4(0u, 0u, 0u, static_cast<uint32_t>(theta_bucket(th, a.B)));
+        if (p_inside(qx, qy, a.map.PW, a.map.PH)) {
+            const int fqx = static_cast<int>(floor(qx)), fqy = static_cast<int>(floor(qy));
+            const RayStart st = make_ray_start(qx, qy, fqx, fqy);
+            in_box = fqx >= bx0 && fqx < bx0 + a.box && fqy >= by0 && fqy < by0 + a.box;
+            r0.x = st.p0x;
+            r0.y = st.p0y;
+            r0.z = (static_cast<uint32_t>(st.bx) & 0xffffu) | (static_cast<uint32_t>(st.by) << 16);
+            r0.w |= (1u | (in_box ? 2u : 0u)) << 16;
+        }
+        a.rec0[pos] = r0;
+        a.rec1[pos] = make_double2(cth * static_cast<double>(kOne), sth * static_cast<double>(kOne));
+    }
+    // particles inside the box (the plan's compactness test)
+    const unsigned m = __ballot_sync(kFullMask, in_box);
+    if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = __popc(m);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < 8; ++w) t += s_cnt[w];
+        if (t) atomicAdd(a.plan + kPlanInBox, t);
+    }
+}
+
+struct DirPlanArgs {
+    const int* hist;           // [B] heading histogram of the sort
+    int io[kMaxBeams];         // per-beam bucket offset (dir_beam_offset)
+    int* plan;
+    int* sec_tab;              // [S + 1] first unit of every sector | [S] first chunk of every sector
+    int64_t cnt;
+    int B, R, force;           // force: 0 decide by the in-box fraction, 2 always directional
+};
+
+constexpr int kPlanThreads = 1024;
+
+// Work decomposition of one update.  For sector s and beam j the particles whose beam-j ray lies
+// in s occupy one cyclic run of B/S heading buckets, i.e. one or two runs of sorted slots.  The
+// chunks (1024 slots) touched by any beam's run form the sector's chunk range; a UNIT is one
+// (sector, chunk) pair, numbered sector by sector so that consecutive units share a window.
+__global__ void __launch_bounds__(kPlanThreads) k_dir_plan(DirPlanArgs a) {
+    __shared__ int off[kMaxBuckets + 1];
+    __shared__ int wsum[kPlanThreads / 32];
+    __shared__ int cmin[kDirSectors], cmax[kDirSectors];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < kDirSectors) {
+        cmin[tid] = 0x7fffffff;
+        cmax[tid] = 0;
+    }
+    // ---- exclusive scan of the histogram: off[b] = first sorted slot of bucket b ----------
+    constexpr int kPer = kMaxBuckets / kPlanThreads;
+    int h[kPer], loc = 0;
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+        const int b = tid * kPer + q;
+        h[q] = b < a.B ? a.hist[b] : 0;
+        loc += h[q];
+    }
+    int v = loc;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(kFullMask, v, d);
+        if (lane >= d) v += o;
+    }
+    if (lane == 31) wsum[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        int w = wsum[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(kFullMask, w, d);
+            if (lane >= d) w += o;
+        }
+        wsum[lane] = w;
+    }
+    __syncthreads();
+    int excl = v - loc + (warp ? wsum[warp - 1] : 0);
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+        off[tid * kPer + q] = excl;
+        excl += h[q];
+    }
+    if (tid == kPlanThreads - 1) off[kMaxBuckets] = excl;
+    __syncthreads();
+    // ---- chunk range of every sector: union over (beam, half) of the chunks its slots touch
+    const int K = a.B / kDirSectors;
+    const int npieces = 2 * kDirSectors * a.R;
+    for (int p = tid; p < npieces; p += kPlanThreads) {
+        const int half = p & 1, sj = p >> 1, j = sj % a.R, s = sj / a.R;
+        const int bs = (s * K - a.io[j]) & (a.B - 1);          // first bucket of the run
+        const int be = bs + K;                                 // one past, may exceed B (wraps)
+        int lo_b, hi_b;
+        if (half == 0) {
+            lo_b = bs;
+            hi_b = be < a.B ? be : a.B;
+        } else {
+            lo_b = 0;
+            hi_b = be > a.B ? be - a.B : 0;
+        }
+        const int lo_s = off[lo_b], hi_s = off[hi_b];
+        if (hi_s > lo_s) {
+            atomicMin(&cmin[s], lo_s / kDirThreads);
+            atomicMax(&cmax[s], (hi_s - 1) / kDirThreads + 1);
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const int n = cmax[lane] > cmin[lane] ? cmax[lane] - cmin[lane] : 0;   // kDirSectors == 32 lanes
+        int w = n;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(kFullMask, w, d);
+            if (lane >= d) w += o;
+        }
+        a.sec_tab[lane] = w - n;
+        a.sec_tab[kDirSectors + 1 + lane] = n ? cmin[lane] : 0;
+        if (lane == 31) {
+            a.sec_tab[kDirSectors] = w;
+            const int in_box = a.plan[kPlanInBox];
+            const bool compact = static_cast<double>(in_box) >= 0.9 * static_cast<double>(a.cnt);
+            const bool dir = a.force == 2 || (a.force == 0 && compact);
+            a.plan[kPlanMode] = dir ? 1 : 0;
+            a.plan[kPlanUnits] = dir ? w : 0;
+            a.plan[kPlanCounter] = 0;
+            a.plan[kPlanInBox] = 0;
+        }
+    }
+}
+static_assert(kDirSectors == 32, "k_dir_plan scans the sectors with one warp");
+
+// Everything the rare exact-replay path needs, kept in device memory so that the hot path
+// carries one pointer: the reference grid and the pose arrays of the update's destination buffer.
+struct DirReplayCtx {
+    RefGrid grid;
+    const double* px;
+    const double* py;
+    const double* pt;
+    const int32_t* perm;       // already offset to the shard: perm[pos] is relative to lo
+    int64_t lo;
+    float angle[kMaxBeams];
+};
+struct ReplayLazy {
+    const DirReplayCtx* rc;
+    int pos, j;
+    __device__ __forceinline__ ReplayArgs load() const {
+        const int64_t i = rc->lo + rc->perm[pos];
+        return ReplayArgs{rc->px[i], rc->py[i], rc->pt[i], rc->angle[j]};
+    }
+    __device__ __forceinline__ RefGrid grid() const { return rc->grid; }
+};
+
+struct DirRayArgs {
+    MapDev map;
+    BeamDev beams;
+    int io[kMaxBeams];          // per-beam bucket offset
+    const DirSector* sectors;   // [S]
+    const uint8_t* dirmaps;     // [S][PH*PW]
+    const uint4* rec0;
+    const double2* rec1;
+    const int* sec_tab;         // [S + 1] first unit | [S] first chunk
+    int* plan;
+    const double* centre;
+    const DirReplayCtx* replay;
+    int64_t cnt, stride;
+    uint8_t* steps_sorted;      // [R][stride]
+    int64_t* replay_count;
+    int B, shift, box;
+    int win_bytes;              // shared-memory bytes reserved for the sector window
+};
+
+// dynamic shared memory of k_raycast_dir: window | rec0 prefetch [2][1024] | rec1 prefetch [2][1024]
+__host__ __device__ inline size_t dir_ray_smem(int win_bytes) {
+    return static_cast<size_t>(win_bytes) + 2 * kDirThreads * (sizeof(uint4) + sizeof(double2));
+}
+
+template <int MC>
+__global__ void __launch_bounds__(kDirThreads, 1) k_raycast_dir(DirRayArgs a) {
+    extern __shared__ __align__(16) uint8_t smem_win[];
+    __shared__ __align__(8) unsigned long long win_bar;
+    __shared__ unsigned s_u0;
+    __shared__ uint32_t s_units[kDirGrab];    // chunk << 6 | sector
+    __shared__ int s_sec[2 * kDirSectors + 2];
+    __shared__ int s_io[kMaxBeams];
+    if (a.plan[kPlanMode] != 1) return;
+    const unsigned n_units = static_cast<unsigned>(a.plan[kPlanUnits]);
+    const MapDev& mp = a.map;
+    const int M = MC > 0 ? MC : pin_reg(mp.M);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int R = a.beams.R;
+    const int cnt = static_cast<int>(a.cnt);
+    int bx0, by0;
+    dir_box_origin(a.centre, a.cnt, mp, a.box, &bx0, &by0);
+    const uint32_t bar = static_cast<uint32_t>(__cvta_generic_to_shared(&win_bar));
+    uint32_t win_saddr;
+    asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(win_saddr) : "l"(smem_win));
+    // thread-private prefetch slots of the ray-start records (two buffers)
+    const uint32_t rec0_s = win_saddr + static_cast<uint32_t>(a.win_bytes) + static_cast<uint32_t>(tid) * 16u;
+    const uint32_t rec1_s = rec0_s + 2u * kDirThreads * 16u;
+    if (tid < 2 * kDirSectors + 1) s_sec[tid] = a.sec_tab[tid];
+    if (tid < kMaxBeams) s_io[tid] = tid < R ? a.io[tid] : 0;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    const int64_t ncell = static_cast<int64_t>(mp.PW) * mp.PH;
+    const int K = a.B >> 5, Bmask = a.B - 1;
+    uint32_t phase = 0;
+    int cur_s = -1, replays = 0;
+    DirWindow wg{0, 0, 0, 0};
+    const uint8_t* smap = a.dirmaps;
+
+    // asynchronous copy of this thread's records of a unit into prefetch buffer `buf`
+    auto prefetch = [&](uint32_t unit, uint32_t buf) {
+        const int pos = static_cast<int>(unit >> 6) * kDirThreads + tid;
+        if (pos < cnt) {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(rec0_s + buf * (kDirThreads * 16u)), "l"(a.rec0 + pos) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(rec1_s + buf * (kDirThreads * 16u)), "l"(a.rec1 + pos) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    for (;;) {
+        __syncthreads();                    // s_u0 / s_units of the previous round have been read by everyone
+        if (tid == 0) s_u0 = atomicAdd(reinterpret_cast<unsigned*>(a.plan + kPlanCounter), static_cast<unsigned>(kDirGrab));
+        __syncthreads();
+        const unsigned u0 = s_u0;
+        if (u0 >= n_units) break;
+        const unsigned nu = min(static_cast<unsigned>(kDirGrab), n_units - u0);
+        if (tid < static_cast<int>(nu)) {
+            // sector of unit u: the last sector whose first unit is <= u (empty sectors share offsets)
+            const int u = static_cast<int>(u0) + tid;
+            int s = 0;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1)
+                if (s_sec[s + d] <= u) s += d;
+            s_units[tid] = (static_cast<uint32_t>(s_sec[kDirSectors + 1 + s] + (u - s_sec[s])) << 6) | static_cast<uint32_t>(s);
+        }
+        __syncthreads();
+        prefetch(s_units[0], 0u);
+        for (unsigned k = 0; k < nu; ++k) {
+            const uint32_t unit = s_units[k];
+            const int s = static_cast<int>(unit & 63u);
+            if (s != cur_s) {
+                // ---- stage sector s's window: one bulk copy per row, bytes counted on the mbarrier
+                __syncthreads();            // every warp has left the old window
+                wg = dir_window(a.sectors[s], bx0, by0, a.box, mp.PW, mp.PH);
+                smap = a.dirmaps + static_cast<int64_t>(s) * ncell;
+                if (tid == 0) {
+                    const uint32_t total = static_cast<uint32_t>(wg.pitch) * static_cast<uint32_t>(wg.rows);
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(total) : "memory");
+                }
+                __syncthreads();
+                const uint8_t* gsrc = smap + static_cast<int64_t>(wg.wy0) * mp.PW + wg.wx0;
+                for (int row = tid; row < wg.rows; row += kDirThreads) {
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                     win_saddr + static_cast<uint32_t>(row * wg.pitch)),
+                                 "l"(gsrc + static_cast<int64_t>(row) * mp.PW), "r"(static_cast<uint32_t>(wg.pitch)), "r"(bar)
+                                 : "memory");
+                }
+                uint32_t done = 0;
+                while (!done) {
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\t"
+                        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                        "selp.u32 %0, 1, 0, p;\n\t}"
+                        : "=r"(done)
+                        : "r"(bar), "r"(phase)
+                        : "memory");
+                }
+                phase ^= 1u;
+                cur_s = s;
+            }
+            // this unit's records have landed; start the copy of the next unit's
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            const uint32_t buf = k & 1u;
+            uint4 r0;
+            double2 cs;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r0.x), "=r"(r0.y), "=r"(r0.z), "=r"(r0.w) : "r"(rec0_s + buf * (kDirThreads * 16u)));
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(cs.x), "=d"(cs.y) : "r"(rec1_s + buf * (kDirThreads * 16u)));
+            if (k + 1 < nu) prefetch(s_units[k + 1], buf ^ 1u);
+            const int pos = static_cast<int>(unit >> 6) * kDirThreads + tid;
+            const bool valid = pos < cnt;
+            const int bucket = static_cast<int>(r0.w & 0xffffu), flags = static_cast<int>(r0.w >> 16);
+            // ---- beams with rays in this sector for some lane of the warp (lanes are bucket-sorted)
+            const int bmin = __reduce_min_sync(kFullMask, valid ? bucket : 0x7fffffff);
+            const int bmax = __reduce_max_sync(kFullMask, valid ? bucket : -1);
+            if (bmax < 0) continue;         // the whole warp is beyond the last particle
+            RayStart st;
+            st.p0x = r0.x;
+            st.p0y = r0.y;
+            st.bx = static_cast<int>(static_cast<int16_t>(r0.z & 0xffffu));
+            st.by = static_cast<int>(static_cast<int16_t>(r0.z >> 16));
+            const WindowV8S wacc{static_cast<uint32_t>(pin_reg(static_cast<int>(win_saddr) + (st.by - wg.wy0) * wg.pitch + (st.bx - wg.wx0))), wg.pitch};
+            const GlobalV8 gacc = make_global_v8(smap, mp.PW, st.bx, st.by);
+            for (int jb = 0; jb < R; jb += 32) {
+                const int jl = jb + lane;
+                // the warp's buckets shifted by the beam's offset: [start, start + len) cyclically; sector s = [0, K)
+                const int start = (bmin + (jl < R ? s_io[jl] : 0) - s * K) & Bmask;
+                unsigned mask = __ballot_sync(kFullMask, jl < R && (start < K || start + (bmax - bmin) >= a.B));
+                while (mask) {
+                    const int j = jb + __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    if (!valid || dir_sector_of(bucket, s_io[j], Bmask, a.shift) != s) continue;   // another unit's ray
+                    int r = 0;   // outside the map: the first sample is already out of bounds (:632-636)
+                    if (flags & 1) {
+                        int dxf, dyf;
+                        beam_direction_prescaled(cs.x, cs.y, a.beams.cosa[j], a.beams.sina[j], &dxf, &dyf);
+                        const ReplayLazy rep{a.replay, pos, j};
+                        if (flags & 2)
+                            r = march_ray_dir(wacc, st, dxf, dyf, M, rep, &replays);
+                        else
+                            r = march_ray_dir(gacc, st, dxf, dyf, M, rep, &replays);
+                    }
+                    a.steps_sorted[static_cast<int64_t>(j) * a.stride + pos] = static_cast<uint8_t>(r);
+                }
+            }
+        }
+    }
+    if (a.replay_count && replays) atomicAdd(reinterpret_cast<unsigned long long*>(a.replay_count), static_cast<unsigned long long>(replays));
+}
+
+struct WeightStepsArgs {
+    const int* plan;
+    const uint8_t* steps_sorted;   // [R][stride]
+    const int32_t* perm;
+    const double* slice;           // [R][M+1]
+    double* w_raw;                 // [N]
+    uint8_t* steps;                // [N*R] particle-major copy (get_ranges) or nullptr
+    int64_t lo, cnt, stride;
+    int R, tw;
+    double inv_squash;
+};
+
+// w = pow(prod_j table(obs_j, range_ij), 1/squash): entries multiplied in beam order like the
+// reference's loop (:564-579).  The step bytes and table entries of kBatch beams are loaded
+// before they are multiplied, so the loads of a batch are in flight together.
+__global__ void __launch_bounds__(256) k_weight_steps(WeightStepsArgs a) {
+    if (a.plan[kPlanMode] != 1) return;
+    const int64_t pos = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+    if (pos >= a.cnt) return;
+    constexpr int kBatch = 12;
+    double acc = 1.0;
+    for (int j0 = 0; j0 < a.R; j0 += kBatch) {
+        int r[kBatch];
+        double t[kBatch];
+#pragma unroll
+        for (int q = 0; q < kBatch; ++q)
+            r[q] = (j0 + q < a.R) ? static_cast<int>(__ldg(a.steps_sorted + static_cast<int64_t>(j0 + q) * a.stride + pos)) : 0;
+#pragma unroll
+        for (int q = 0; q < kBatch; ++q) t[q] = (j0 + q < a.R) ? __ldg(a.slice + (j0 + q) * a.tw + r[q]) : 1.0;
+#pragma unroll
+        for (int q = 0; q < kBatch; ++q)
+            if (j0 + q < a.R) acc = __dmul_rn(acc, t[q]);
+    }
+    const int64_t i = a.lo + a.perm[a.lo + pos];
+    a.w_raw[i] = pow(acc, a.inv_squash);
+    if (a.steps)   // diagnostics (mcl_get_ranges): particle-major copy of the step indices
+        for (int j = 0; j < a.R; ++j) a.steps[i * a.R + j] = a.steps_sorted[static_cast<int64_t>(j) * a.stride + pos];
+}
+
+}  // namespace mclb200

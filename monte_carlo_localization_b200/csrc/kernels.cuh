@@ -726,6 +726,7 @@ struct RayArgs {
     const double* centre;      // [F][2] sums of x and y over the filter's particles
     double inv_squash;
     int64_t* replay_count;     // diagnostics (nullable)
+    const int* plan;           // directional stage's plan (nullable): mode 1 = that stage does this update
 };
 
 constexpr int kRayThreads = 1024;
@@ -737,6 +738,7 @@ constexpr int kRayThreads = 1024;
 template <int WBITS, int MC>
 __global__ void __launch_bounds__(kRayThreads, 1) k_raycast_weight(RayArgs a) {
     extern __shared__ __align__(16) uint8_t smem_win[];
+    if (a.plan && a.plan[0] == 1) return;   // k_raycast_dir + k_weight_steps take this update (dir_kernels.cuh)
     const int f = blockIdx.y;
     const MapDev& mp = a.map;
     const int64_t N = a.N;
@@ -1142,3 +1144,5 @@ __global__ void k_fill(double* p, int64_t n, double v) {
 }
 
 }  // namespace mclb200
+
+#include "dir_kernels.cuh"

@@ -263,9 +263,10 @@ MCL_HD int march_ray(const Acc& acc, const RayStart& st, int dxf, int dyf, int M
 // and the same exactness rule as march_ray; `rep` loads the particle pose only if a sample
 // must be replayed in FP64 (rep.load() -> ReplayArgs).
 // ------------------------------------------------------------------------------------------
+// Returns bit 0 = the sample is a hit, bit 1 = the FP64 replay was needed.  `rep` is passed by
+// value (a few registers): rep.grid() is the reference grid, rep.load() the particle's pose.
 template <class Acc, class Rep>
-MCL_NOINLINE int resolve_uncertain_dir(const Acc& acc, uint32_t px, uint32_t py, int v, const RefGrid& g, const Rep& rep,
-                                       int k, int* replays) {
+MCL_NOINLINE int resolve_uncertain_dir(const Acc acc, uint32_t px, uint32_t py, int v, const Rep rep, int k) {
     const bool hit = (v == 0x80);
     const int cx = static_cast<int>(px >> kFrac), cy = static_cast<int>(py >> kFrac);
     const uint32_t fx = px & kFracMask, fy = py & kFracMask;
@@ -279,15 +280,14 @@ MCL_NOINLINE int resolve_uncertain_dir(const Acc& acc, uint32_t px, uint32_t py,
     if (ux && uy) differs |= ((acc.get(nx, ny) == 0x80) != hit);
     if (!differs) return hit ? 1 : 0;
     const ReplayArgs ra = rep.load();
+    const RefGrid g = rep.grid();
     double sn, cs;
     sincos_ref(nf_add(ra.theta, static_cast<double>(ra.beam)), &sn, &cs);   // theta + angle (:533)
-    if (replays) ++*replays;
-    return replay_sample_is_hit(g, ra.x, ra.y, nf_mul(cs, g.res), nf_mul(sn, g.res), k) ? 1 : 0;
+    return 2 | (replay_sample_is_hit(g, ra.x, ra.y, nf_mul(cs, g.res), nf_mul(sn, g.res), k) ? 1 : 0);
 }
 
 template <class Acc, class Rep>
-MCL_HD int march_ray_dir(const Acc& acc, const RayStart& st, int dxf, int dyf, int M, const RefGrid& g, const Rep& rep,
-                         int* replays) {
+MCL_HD int march_ray_dir(const Acc& acc, const RayStart& st, int dxf, int dyf, int M, const Rep& rep, int* replays) {
     constexpr int kPark = 1 << 20;
     int k = 1, r = M;
     for (;;) {
@@ -314,7 +314,9 @@ MCL_HD int march_ray_dir(const Acc& acc, const RayStart& st, int dxf, int dyf, i
         k = pending_k;
         const uint32_t px = st.p0x + static_cast<uint32_t>(k * dxf);
         const uint32_t py = st.p0y + static_cast<uint32_t>(k * dyf);
-        if (resolve_uncertain_dir(acc, px, py, acc.get_p(px, py), g, rep, k, replays)) return k - 1;
+        const int res = resolve_uncertain_dir(acc, px, py, acc.get_p(px, py), rep, k);
+        *replays += res >> 1;
+        if (res & 1) return k - 1;
         k += 1;   // the sample's true cell may be the neighbour: take a single step
         if (k > M) return M;
     }

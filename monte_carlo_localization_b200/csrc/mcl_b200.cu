@@ -114,6 +114,22 @@ struct mcl_ctx {
     int* d_hist = nullptr;      // [F][2B]: histogram | scatter cursors
     int32_t* d_perm = nullptr;
     bool sort_enabled = true;
+    // directional ray stage (dir_kernels.cuh): one large filter, heading sort fine enough
+    bool dir_ready = false;
+    int ray_mode = 0;                 // 0 auto, 1 isotropic kernel only, 2 directional forced
+    DirSector sectors[kDirSectors];
+    uint8_t* d_dirmaps = nullptr;     // [S][PH*PW]
+    DirSector* d_sectors = nullptr;
+    int beam_io[kMaxBeams] = {};
+    int* d_sec_tab = nullptr;         // [S+1] first unit | [S] first chunk, per sector
+    DirReplayCtx* d_replay_ctx = nullptr;   // [2]: one per state buffer
+    uint4* d_rec0 = nullptr;          // [N]
+    double2* d_rec1 = nullptr;        // [N]
+    int* d_plan = nullptr;
+    uint8_t* d_steps_sorted = nullptr;   // [R][stride]
+    int64_t dir_stride = 0;
+    int dir_box = 0;
+    size_t dir_smem = 0;
     // particle shard: this context computes output slots [lo, lo+cnt) of the filter
     int64_t lo = 0, cnt = 0;
     bool local_pending = false;
@@ -251,6 +267,101 @@ int ensure_slice(mcl_ctx* c) {
     return MCL_OK;
 }
 
+constexpr size_t kDirWindowBudget = 112 * 1024;   // one sector window (half of shared memory: room to double-buffer)
+
+void free_dir(mcl_ctx* c) {
+    for (void* p : {static_cast<void*>(c->d_dirmaps), static_cast<void*>(c->d_sectors), static_cast<void*>(c->d_sec_tab), static_cast<void*>(c->d_replay_ctx),
+                    static_cast<void*>(c->d_rec0), static_cast<void*>(c->d_rec1),
+                    static_cast<void*>(c->d_plan), static_cast<void*>(c->d_steps_sorted)})
+        if (p) cudaFree(p);
+    c->d_dirmaps = nullptr;
+    c->d_sectors = nullptr;
+    c->d_sec_tab = nullptr;
+    c->d_replay_ctx = nullptr;
+    c->d_rec0 = nullptr;
+    c->d_rec1 = nullptr;
+    c->d_plan = nullptr;
+    c->d_steps_sorted = nullptr;
+    c->dir_ready = false;
+}
+
+// the exact-replay context of the directional ray kernel, one per state buffer
+int upload_replay_ctx(mcl_ctx* c) {
+    if (!c->d_replay_ctx) return MCL_OK;
+    DirReplayCtx h[2];
+    for (int b = 0; b < 2; ++b) {
+        h[b].grid = RefGrid{c->d_grid, c->map.W, c->map.H, c->res, c->ox, c->oy};
+        h[b].px = c->d_px[b];
+        h[b].py = c->d_py[b];
+        h[b].pt = c->d_pt[b];
+        h[b].perm = c->d_perm + c->lo;
+        h[b].lo = c->lo;
+        for (int j = 0; j < kMaxBeams; ++j) h[b].angle[j] = j < c->R ? c->beams.angle[j] : 0.0f;
+    }
+    CK(cudaMemcpy(c->d_replay_ctx, h, sizeof(h), cudaMemcpyHostToDevice));
+    return MCL_OK;
+}
+
+// Directional ray stage: eligible for ONE large filter whose heading sort has at least
+// kDirMinBuckets buckets.  Builds the sector maps on the device (k_build_dir_maps) and the
+// per-update work buffers.  Called whenever the map or the beam table changes.
+int ensure_dir(mcl_ctx* c, bool map_changed) {
+    if (!c->have_map || !c->have_beams) return MCL_OK;
+    const bool eligible = c->F == 1 && c->B >= kDirMinBuckets && c->skip.PW <= 32767 && c->skip.PH <= 32767 && c->R <= 127;
+    if (!eligible) {
+        free_dir(c);
+        return MCL_OK;
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    const size_t ncell = static_cast<size_t>(c->skip.PW) * c->skip.PH;
+    if (map_changed || !c->d_dirmaps) {
+        free_dir(c);
+        make_dir_sectors(c->M, c->sectors);
+        c->dir_box = dir_choose_box(c->sectors, kDirWindowBudget);
+        if (c->dir_box == 0 || ncell * kDirSectors > (size_t{8} << 30)) return MCL_OK;   // stays on the isotropic kernel
+        size_t smem = 0;
+        for (int s = 0; s < kDirSectors; ++s) {
+            const DirSector& sc = c->sectors[s];
+            smem = std::max(smem, static_cast<size_t>((c->dir_box + sc.exh - sc.exl + 30) & ~15) *
+                                      static_cast<size_t>(c->dir_box + sc.eyh - sc.eyl));
+        }
+        c->dir_smem = smem;
+        std::vector<float> gap;
+        build_gap_map(c->skip, gap);
+        float* d_gap = nullptr;
+        CK(dalloc(&d_gap, ncell));
+        CK(cudaMemcpy(d_gap, gap.data(), ncell * sizeof(float), cudaMemcpyHostToDevice));
+        CK(dalloc(&c->d_sectors, static_cast<size_t>(kDirSectors)));
+        CK(cudaMemcpy(c->d_sectors, c->sectors, sizeof(c->sectors), cudaMemcpyHostToDevice));
+        CK(dalloc(&c->d_dirmaps, ncell * kDirSectors));
+        DirBuildArgs ba{c->d_v8, d_gap, c->d_sectors, c->d_dirmaps, c->skip.PW, c->skip.PH};
+        k_build_dir_maps<<<dim3(static_cast<unsigned>((ncell + 255) / 256), kDirSectors), 256, 0, c->stream>>>(ba);
+        c->launches++;
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(c->stream));
+        cudaFree(d_gap);
+        CK(dalloc(&c->d_plan, static_cast<size_t>(kPlanInts)));
+        CK(cudaMemset(c->d_plan, 0, sizeof(int) * kPlanInts));
+        CK(dalloc(&c->d_rec0, static_cast<size_t>(c->N)));
+        CK(dalloc(&c->d_rec1, static_cast<size_t>(c->N)));
+    }
+    // per-beam-table buffers
+    for (void* p : {static_cast<void*>(c->d_sec_tab), static_cast<void*>(c->d_steps_sorted), static_cast<void*>(c->d_replay_ctx)})
+        if (p) cudaFree(p);
+    c->d_sec_tab = nullptr;
+    c->d_steps_sorted = nullptr;
+    c->d_replay_ctx = nullptr;
+    for (int j = 0; j < c->R; ++j) c->beam_io[j] = dir_beam_offset(c->beams.angle[j], c->B);
+    CK(dalloc(&c->d_sec_tab, static_cast<size_t>(2 * kDirSectors + 2)));
+    CK(dalloc(&c->d_replay_ctx, size_t{2}));
+    const int64_t nchunks = (c->N + kDirThreads - 1) / kDirThreads;
+    c->dir_stride = nchunks * kDirThreads;
+    CK(dalloc(&c->d_steps_sorted, static_cast<size_t>(c->R) * c->dir_stride));
+    if (dir_ray_smem(static_cast<int>((c->dir_smem + 15) & ~size_t{15})) > kWindowBudget) return MCL_OK;   // stays on the isotropic kernel
+    c->dir_ready = true;
+    return upload_replay_ctx(c);
+}
+
 int check_filter(const mcl_ctx* c, int filter, bool allow_all) {
     if (!c) return fail(MCL_ERR_INVALID, "null context");
     if (filter == -1 && allow_all) return MCL_OK;
@@ -371,6 +482,36 @@ int update_local(mcl_ctx* c, const double* action_dev, const float* obs_dev, con
         k_sort_scatter<<<gs, kSortThreads, 0, s>>>(sa);
         c->launches += 2;
     }
+    const bool dir = c->dir_ready && c->sort_enabled && c->ray_mode != 1;
+    if (dir) {
+        DirPrepArgs pa{};
+        pa.map = c->map;
+        pa.N = c->N;
+        pa.lo = c->lo;
+        pa.cnt = c->cnt;
+        pa.px = c->d_px[dst];
+        pa.py = c->d_py[dst];
+        pa.pt = c->d_pt[dst];
+        pa.perm = c->d_perm;
+        pa.centre = c->d_centre;
+        pa.rec0 = c->d_rec0;
+        pa.rec1 = c->d_rec1;
+        pa.plan = c->d_plan;
+        pa.B = c->B;
+        pa.box = c->dir_box;
+        k_dir_prepare<<<static_cast<unsigned>((c->cnt + 255) / 256), 256, 0, s>>>(pa);
+        DirPlanArgs la{};
+        la.hist = c->d_hist;
+        std::memcpy(la.io, c->beam_io, sizeof(la.io));
+        la.plan = c->d_plan;
+        la.sec_tab = c->d_sec_tab;
+        la.cnt = c->cnt;
+        la.B = c->B;
+        la.R = c->R;
+        la.force = c->ray_mode;
+        k_dir_plan<<<1, kPlanThreads, 0, s>>>(la);
+        c->launches += 2;
+    }
     if (c->profiling) CK(cudaEventRecord(c->ev[2], s));
 
     RayArgs ra{};
@@ -389,6 +530,7 @@ int update_local(mcl_ctx* c, const double* action_dev, const float* obs_dev, con
     ra.centre = c->d_centre;
     ra.inv_squash = 1.0 / c->prm.squash_factor;
     ra.replay_count = c->d_replays;
+    ra.plan = dir ? c->d_plan : nullptr;
     const size_t smem = static_cast<size_t>(c->map.wbits == 8 ? c->map.ww : c->map.ww / 2) * c->map.wh;
     // persistent blocks: one per SM when the window fills shared memory, a few otherwise
     const int per_sm = smem > 100 * 1024 ? 1 : 2;
@@ -415,6 +557,52 @@ int update_local(mcl_ctx* c, const double* action_dev, const float* obs_dev, con
     }
 #undef MCL_LAUNCH_RAY
     c->launches++;
+    if (dir) {
+        DirRayArgs da{};
+        da.map = c->map;
+        da.beams = c->beams;
+        std::memcpy(da.io, c->beam_io, sizeof(da.io));
+        da.sectors = c->d_sectors;
+        da.dirmaps = c->d_dirmaps;
+        da.rec0 = c->d_rec0;
+        da.rec1 = c->d_rec1;
+        da.sec_tab = c->d_sec_tab;
+        da.replay = c->d_replay_ctx + dst;
+        da.plan = c->d_plan;
+        da.centre = c->d_centre;
+        da.cnt = c->cnt;
+        da.stride = c->dir_stride;
+        da.steps_sorted = c->d_steps_sorted;
+        da.replay_count = c->d_replays;
+        da.B = c->B;
+        da.shift = 0;
+        while ((c->B >> da.shift) > kDirSectors) ++da.shift;
+        da.box = c->dir_box;
+        da.win_bytes = static_cast<int>((c->dir_smem + 15) & ~size_t{15});
+        const size_t dsmem = dir_ray_smem(da.win_bytes);
+        const int dblocks = static_cast<int>(std::min<int64_t>(c->num_sms, (c->cnt * c->R + kDirThreads - 1) / kDirThreads));
+        switch (c->M) {
+            case 207: k_raycast_dir<207><<<dblocks, kDirThreads, dsmem, s>>>(da); break;
+            case 238: k_raycast_dir<238><<<dblocks, kDirThreads, dsmem, s>>>(da); break;
+            case 239: k_raycast_dir<239><<<dblocks, kDirThreads, dsmem, s>>>(da); break;
+            default: k_raycast_dir<0><<<dblocks, kDirThreads, dsmem, s>>>(da); break;
+        }
+        WeightStepsArgs wa{};
+        wa.plan = c->d_plan;
+        wa.steps_sorted = c->d_steps_sorted;
+        wa.perm = c->d_perm;
+        wa.slice = c->d_slice;
+        wa.w_raw = c->d_wraw;
+        wa.steps = c->keep_ranges ? c->d_steps : nullptr;
+        wa.lo = c->lo;
+        wa.cnt = c->cnt;
+        wa.stride = c->dir_stride;
+        wa.R = c->R;
+        wa.tw = c->M + 1;
+        wa.inv_squash = 1.0 / c->prm.squash_factor;
+        k_weight_steps<<<static_cast<unsigned>((c->cnt + 255) / 256), 256, 0, s>>>(wa);
+        c->launches += 2;
+    }
     if (c->p2p) {
         // unnormalised pose sums of the rank's own slots (deterministic two-stage reduction)
         NormArgs na{};
@@ -603,6 +791,10 @@ static int create_buffers(mcl_ctx* c, const mcl_params* p, int device) {
     MCL_RAY_SMEM(4, 238);
     MCL_RAY_SMEM(4, 239);
 #undef MCL_RAY_SMEM
+    CK(cudaFuncSetAttribute(k_raycast_dir<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kWindowBudget)));
+    CK(cudaFuncSetAttribute(k_raycast_dir<207>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kWindowBudget)));
+    CK(cudaFuncSetAttribute(k_raycast_dir<238>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kWindowBudget)));
+    CK(cudaFuncSetAttribute(k_raycast_dir<239>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kWindowBudget)));
     CK(cudaDeviceSynchronize());
     return MCL_OK;
 }
@@ -644,6 +836,7 @@ int mcl_destroy(mcl_ctx* c) {
                     c->d_hist, c->d_perm, c->d_done};
     for (void* p : ptrs)
         if (p) cudaFree(p);
+    free_dir(c);
     for (void* p : c->ipc_opened) cudaIpcCloseMemHandle(p);
     if (c->d_peer_tab) cudaFree(c->d_peer_tab);
     if (c->d_partials) cudaFree(c->d_partials);
@@ -740,7 +933,9 @@ int mcl_set_map(mcl_ctx* c, const int8_t* data, int width, int height, float res
     build_sensor_table(c, c->table);
     int rc = upload_table(c);
     if (rc) return rc;
-    return ensure_slice(c);
+    rc = ensure_slice(c);
+    if (rc) return rc;
+    return ensure_dir(c, true);
 }
 
 int mcl_max_range_px(const mcl_ctx* c) { return c ? c->M : 0; }
@@ -779,7 +974,9 @@ int mcl_set_beam_angles(mcl_ctx* c, const float* angles, int n) {
         c->d_steps = nullptr;
     }
     if (c->keep_ranges) CK(dalloc(&c->d_steps, static_cast<size_t>(c->F) * c->N * c->R));
-    return ensure_slice(c);
+    const int rc = ensure_slice(c);
+    if (rc) return rc;
+    return ensure_dir(c, false);
 }
 
 int mcl_num_free_cells(const mcl_ctx* c) { return c ? static_cast<int>(c->skip.free_cells.size()) : 0; }
@@ -1129,7 +1326,9 @@ int mcl_set_shard(mcl_ctx* c, int64_t lo, int64_t count) {
     if (c->local_pending) return fail(MCL_ERR_INVALID, "update in flight");
     c->lo = lo;
     c->cnt = count;
-    return MCL_OK;
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    return upload_replay_ctx(c);
 }
 
 int mcl_update_local_dev(mcl_ctx* c, const double* action_dev, const float* obs_dev, int num_beams, const double* u_dev,
@@ -1289,6 +1488,46 @@ int mcl_microbench_gather(int device, int shared, size_t array_bytes, int iters_
     cudaEventDestroy(e1);
     cudaFree(d_arr);
     cudaFree(d_sink);
+    return MCL_OK;
+}
+
+int mcl_set_ray_mode(mcl_ctx* c, int mode) {
+    if (!c) return fail(MCL_ERR_INVALID, "null context");
+    if (mode < 0 || mode > 2) return fail(MCL_ERR_INVALID, "ray mode %d not in {0 auto, 1 isotropic, 2 directional}", mode);
+    if (mode == 2 && !c->dir_ready)
+        return fail(MCL_ERR_UNSUPPORTED, "the directional ray stage needs one filter of more than %d particles, a map and a beam table",
+                    16 * (kDirMinBuckets / 2));
+    c->ray_mode = mode;
+    return MCL_OK;
+}
+
+int mcl_ray_stage_info(mcl_ctx* c, int* directional_ready, int* last_mode, int* box_cells, int* units) {
+    if (!c) return fail(MCL_ERR_INVALID, "null context");
+    CK(cudaSetDevice(c->device));
+    int plan[kPlanInts] = {0};
+    if (c->dir_ready) {
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaMemcpy(plan, c->d_plan, sizeof(plan), cudaMemcpyDeviceToHost));
+    }
+    if (directional_ready) *directional_ready = c->dir_ready ? 1 : 0;
+    if (last_mode) *last_mode = plan[kPlanMode];
+    if (box_cells) *box_cells = c->dir_ready ? c->dir_box : 0;
+    if (units) *units = plan[kPlanUnits];
+    return MCL_OK;
+}
+
+int mcl_get_dir_map(mcl_ctx* c, int sector, uint8_t* out, int* pw, int* ph) {
+    if (!c) return fail(MCL_ERR_INVALID, "null context");
+    if (!c->dir_ready) return fail(MCL_ERR_UNSUPPORTED, "the directional ray stage is not active for this context");
+    if (sector < 0 || sector >= kDirSectors) return fail(MCL_ERR_INVALID, "sector %d not in [0,%d)", sector, kDirSectors);
+    if (pw) *pw = c->skip.PW;
+    if (ph) *ph = c->skip.PH;
+    if (out) {
+        CK(cudaSetDevice(c->device));
+        CK(cudaStreamSynchronize(c->stream));
+        const size_t ncell = static_cast<size_t>(c->skip.PW) * c->skip.PH;
+        CK(cudaMemcpy(out, c->d_dirmaps + ncell * sector, ncell, cudaMemcpyDeviceToHost));
+    }
     return MCL_OK;
 }
 

@@ -41,7 +41,9 @@ struct DirGlobal {
 };
 struct ReplayNow {
     ReplayArgs ra;
+    RefGrid rg;
     ReplayArgs load() const { return ra; }
+    RefGrid grid() const { return rg; }
 };
 
 static const std::vector<uint8_t>& emu_dir_sector(emu_map* m, int s) {
@@ -204,7 +206,7 @@ long long emu_range_steps_dir(emu_map* m, const double* px, const double* py, co
             beam_direction_fixed(cth, sth, ca[j], sa[j], &dxf, &dyf);
             const int s = dir_sector_of(bucket, io[j], B - 1, shift);
             const std::vector<uint8_t>& d = emu_dir_sector(m, s);
-            const ReplayNow rep{ReplayArgs{x, y, th, angles[j]}};
+            const ReplayNow rep{ReplayArgs{x, y, th, angles[j]}, rg};
             long long lk = 0;
             int r;
             if (in_box) {
@@ -237,10 +239,10 @@ long long emu_range_steps_dir(emu_map* m, const double* px, const double* py, co
                     }
                 };
                 const Checked acc{win[s].data(), st.bx - w.wx0, st.by - w.wy0, w.pitch, w.rows, &lk, &oob};
-                r = march_ray_dir(acc, st, dxf, dyf, M, rg, rep, &replays);
+                r = march_ray_dir(acc, st, dxf, dyf, M, rep, &replays);
             } else {
                 const DirGlobal acc{d.data() + static_cast<int64_t>(st.by) * sk.PW + st.bx, sk.PW, &lk};
-                r = march_ray_dir(acc, st, dxf, dyf, M, rg, rep, &replays);
+                r = march_ray_dir(acc, st, dxf, dyf, M, rep, &replays);
             }
             out[j] = static_cast<uint8_t>(r);
             if (lookups_out) lookups_out[i * R + j] = static_cast<int32_t>(lk);

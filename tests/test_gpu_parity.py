@@ -474,3 +474,92 @@ def test_gather_microbench_reports_rates():
     sm = capi.microbench_gather(True, iters=512)
     l2 = capi.microbench_gather(False, iters=512)
     assert sm > 1e11 and l2 > 1e10 and sm > l2
+
+
+def _tracking_case(name, N, speed, seed):
+    from monte_carlo_localization_b200 import maps, synth
+    from oracle import bindings as ob
+    g = maps.load_named_map(name)
+    angles_full = synth.laser_angles()
+    angles = synth.downsample(angles_full)
+    orc = ob.Oracle(g, angles, max_particles=N)
+    gt, actions = synth.trajectory(g, 40, speed)
+    ns = ob.NoiseStream(seed)
+    orc.init_pose(gt[20], ns.normal(3 * N))
+    scan = synth.scan_from_pose(orc.calc_range_many, gt[21], angles_full, np.random.default_rng(seed))
+    return g, angles, orc, ns, actions[20], scan[::18]
+
+
+@pytest.mark.parametrize("name,N,speed", [("Spielberg_map", 200000, 8.0), ("basement_fixed", 50000, 3.0),
+                                          ("sibal1", 20000, 3.0)])
+def test_directional_stage_equals_isotropic_kernel_and_oracle(name, N, speed):
+    """The two ray stages compute the same cast_ray: step indices and raw weights are
+    bit-identical between them, and equal to the oracle's."""
+    g, angles, orc, ns, action, obs = _tracking_case(name, N, speed, 77)
+    p0, w0 = orc.get_state()
+    u, z = ns.update_noise(N)
+    c = _ctx(g, angles, N)
+    info = c.ray_stage_info()
+    assert info["directional_ready"] == 1 and info["box_cells"] >= 64
+    out = {}
+    for mode in (1, 2, 0):
+        c.set_ray_mode(mode)
+        c.set_particles(p0, w0)
+        pose = c.update(action, obs, u, z)
+        out[mode] = (c.range_steps().copy(), c.raw_weights().copy(), c.get_weights().copy(), pose.copy())
+        assert c.ray_stage_info()["last_mode"] == (0 if mode == 1 else 1)
+    for k in range(4):
+        assert np.array_equal(out[1][k], out[2][k]), "stage outputs differ in item %d" % k
+        assert np.array_equal(out[0][k], out[2][k])
+    idx = orc.update(action, obs, u, z)
+    assert np.array_equal(c.resample_indices(), idx)
+    want = steps_from_ranges(orc.ranges(), g.resolution_f64, orc.M)
+    assert (out[2][0] != want).sum() == 0
+    assert_weights_close(out[2][2], orc.get_state()[1])
+    assert_pose_close(out[2][3], orc.expected_pose())
+    c.close()
+
+
+def test_directional_maps_equal_cpu_build():
+    """k_build_dir_maps writes the bytes the CPU harness computes from the same source."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(__file__))
+    from emu_bindings import EmuMap
+    from monte_carlo_localization_b200 import maps, synth
+    g = maps.load_named_map("sibal1")
+    c = _ctx(g, synth.beam_angles(), 20000)
+    em = EmuMap(g)
+    for s in (0, 5, 8, 17, 31):
+        assert np.array_equal(c.dir_map(s), em.dir_map(s)), "sector %d differs" % s
+    c.close()
+
+
+def test_scattered_cloud_falls_back_to_isotropic_kernel():
+    """After initialize_global the cloud is not compact: the plan keeps the isotropic kernel;
+    forcing the directional stage (all particles on the global-memory path) gives the same."""
+    from monte_carlo_localization_b200 import maps, synth
+    from oracle import bindings as ob
+    g = maps.load_named_map("sibal1")
+    angles = synth.beam_angles()
+    N = 30000
+    orc = ob.Oracle(g, angles, max_particles=N)
+    cell, th = ob.NoiseStream(8).global_init(N, orc.num_free_cells())
+    orc.init_global(cell, th)
+    p0, w0 = orc.get_state()
+    ns = ob.NoiseStream(9)
+    u, z = ns.update_noise(N)
+    obs = np.full(len(angles), 3.0, dtype=np.float32)
+    action = np.array([0.05, 0.0, 0.01])
+    c = _ctx(g, angles, N)
+    res = {}
+    for mode in (0, 2):
+        c.set_ray_mode(mode)
+        c.set_particles(p0, w0)
+        c.update(action, obs, u, z)
+        res[mode] = (c.range_steps().copy(), c.raw_weights().copy())
+        assert c.ray_stage_info()["last_mode"] == (1 if mode == 2 else 0)
+    assert np.array_equal(res[0][0], res[2][0]) and np.array_equal(res[0][1], res[2][1])
+    orc.update(action, obs, u, z)
+    want = steps_from_ranges(orc.ranges(), g.resolution_f64, orc.M)
+    assert (res[2][0] != want).sum() == 0
+    c.close()
