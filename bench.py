@@ -355,13 +355,19 @@ def run_gpu(args):
         peak, peak_src = measured_peak_gbs()
         roof = None
         if stage is not None and cbar is not None and stage["raycast_weight"] > 0:
-            alg_bytes = N * R * cbar + N * (24 + 8)     # cells the reference samples + pose read + weight write
-            ach = alg_bytes / (stage["raycast_weight"] * 1e-3) / 1e9
+            # dominant kernel: the ray march.  k_raycast_dir (directional stage) when the plan chose it,
+            # else k_raycast_weight; its own CUDA-event time (stage "ray_march") is the denominator
+            directional = ray_stage.get("last_mode") == 1
+            kname = "k_raycast_dir" if directional else "k_raycast_weight"
+            k_ms = stage.get("ray_march") or stage["raycast_weight"]
+            # cells the reference samples (1 B each) + ray-start record read + step/weight write
+            alg_bytes = N * R * cbar + (N * R * 1 + N * 32 * 2 if directional else N * (24 + 8))
+            ach = alg_bytes / (k_ms * 1e-3) / 1e9
             traffic = None
             tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
             if os.path.exists(tp):
                 try:
-                    traffic = json.load(open(tp)).get("k_raycast_weight_dram_bytes_per_launch")
+                    traffic = json.load(open(tp)).get(kname + "_dram_bytes_per_launch")
                 except Exception:
                     traffic = None
             # gather-rate context for the same kernel: random byte reads/s the chip sustains from a
@@ -369,13 +375,14 @@ def run_gpu(args):
             from monte_carlo_localization_b200 import capi as _capi
             gather = {"shared_memory_peak_per_s": _capi.microbench_gather(True, device=local_rank),
                       "l2_4mb_peak_per_s": _capi.microbench_gather(False, device=local_rank),
-                      "reference_samples_per_s": N * R * cbar / (stage["raycast_weight"] * 1e-3)}
-            roof = {"bound": "hbm", "kernel": "k_raycast_weight", "achieved": ach, "peak": peak, "unit": "GB/s",
+                      "reference_samples_per_s": N * R * cbar / (k_ms * 1e-3)}
+            roof = {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peak, "unit": "GB/s",
                     "gather": gather,
                     "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg_bytes, "mean_cells_per_ray": cbar,
-                    "kernel_ms": stage["raycast_weight"],
-                    "note": "grid/skip map is L2+shared-memory resident; bytes are the reference's per-sample reads"}
+                    "kernel_ms": k_ms,
+                    "note": "skip maps are L2+shared-memory resident; algorithmic bytes are the reference's per-sample "
+                            "grid reads, most of which the kernel proves unnecessary, so frac can exceed 1"}
         cb = None
         if world == 1 and not args.no_cpu:
             cb = cpu_reference_arm(args.ref_particles, 3, 1)

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MCL_B200_ABI_VERSION 1
+#define MCL_B200_ABI_VERSION 2
 
 typedef enum mcl_status {
     MCL_OK = 0,
@@ -69,6 +69,7 @@ typedef struct mcl_noise {
  * when profiling is enabled with mcl_set_profiling). */
 typedef struct mcl_stage_ms {
     float cdf, resample_motion, raycast_weight, normalize_pose, total;
+    float ray_march;   /* the ray kernel alone (raycast_weight also covers the table product) */
 } mcl_stage_ms;
 
 typedef struct mcl_ctx mcl_ctx;

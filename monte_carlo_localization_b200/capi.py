@@ -44,7 +44,7 @@ class MclNoise(C.Structure):
 
 class MclStageMs(C.Structure):
     _fields_ = [("cdf", C.c_float), ("resample_motion", C.c_float), ("raycast_weight", C.c_float),
-                ("normalize_pose", C.c_float), ("total", C.c_float)]
+                ("normalize_pose", C.c_float), ("total", C.c_float), ("ray_march", C.c_float)]
 
 
 # every symbol include/mcl_b200.h declares: name -> (restype, argtypes)

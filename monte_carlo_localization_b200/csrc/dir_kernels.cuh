@@ -4,7 +4,8 @@
 // :586-650) and its table product (:564-579) when one filter is large enough for the heading
 // sort to resolve sectors (>= kDirMinBuckets buckets):
 //   k_build_dir_maps   once per map: the kDirSectors directional skip maps (dirmap.cuh)
-//   k_dir_prepare      per update: ray-start records of the heading-sorted particles
+//   (k_resample_motion) per update: every particle's ray-start record, in slot order
+//   k_dir_gather       per update: the records moved to heading-sorted order (one 32 B gather each)
 //   k_dir_plan         per update: per sector, the range of 1024-slot chunks of the heading-sorted
 //                      particles that cast rays into it; a work unit = (sector, chunk)
 //   k_raycast_dir      persistent CTAs pull units; the sector's window of the map is staged in
@@ -42,18 +43,18 @@ __global__ void __launch_bounds__(256) k_build_dir_maps(DirBuildArgs a) {
     a.out[static_cast<int64_t>(s) * n + cell] = dir_code(a.v8, a.gap, a.PW, a.PH, cx, cy, a.sectors[s]);
 }
 
+// k_dir_gather: ray-start records from slot order into heading-sorted order
 struct DirPrepArgs {
     MapDev map;
-    int64_t N, lo, cnt;
-    const double* px;
-    const double* py;
-    const double* pt;
-    const int32_t* perm;       // sorted slot -> particle index relative to lo
-    const double* centre;      // [2] sums of x and y over the cnt particles
-    uint4* rec0;               // [cnt] p0x, p0y, bx | by << 16, bucket | flags << 16
-    double2* rec1;             // [cnt] cos(theta) * 2^23, sin(theta) * 2^23
+    const double* centre;      // [2] sums of x and y over the shard's particles
+    const uint4* rec0_in;      // [cnt] records in slot order (k_resample_motion)
+    const double2* rec1_in;
+    uint4* rec0;               // [cnt] records in heading-sorted order
+    double2* rec1;
+    const int32_t* perm;       // sorted slot -> slot index (both relative to the shard)
     int* plan;
-    int B, box;
+    int64_t cnt;
+    int box;
 };
 
 // P-cell of the box corner: the box is centred on the cloud's mean position
@@ -66,33 +67,51 @@ __device__ __forceinline__ void dir_box_origin(const double* centre, int64_t cnt
     *by0 = cy - box / 2;
 }
 
-__global__ void __launch_bounds__(256) k_dir_prepare(DirPrepArgs a) {
+// Ray-start record of one particle:
+//   rec0 = p0x, p0y (9.23 fixed-point start), bx | by << 16 (P-cell of local coordinate 0),
+//          heading bucket | flags << 16 (bit 0: inside the map, bit 1: inside the window box)
+//   rec1 = cos(theta) * 2^23, sin(theta) * 2^23
+__device__ __forceinline__ void dir_write_record(const MapDev& mp, uint4* rec0, double2* rec1, int64_t slot, double x, double y,
+                                                 double th, int bucket) {
+    double sth, cth;
+    sincos(th, &sth, &cth);
+    const double qx = p_coord(x, mp.ox, mp.res, kPadL);
+    const double qy = p_coord(y, mp.oy, mp.res, kPadL);
+    uint4 r0 = make_uint4(0u, 0u, 0u, static_cast<uint32_t>(bucket));
+    if (p_inside(qx, qy, mp.PW, mp.PH)) {
+        const int fqx = static_cast<int>(floor(qx)), fqy = static_cast<int>(floor(qy));
+        const RayStart st = make_ray_start(qx, qy, fqx, fqy);
+        r0.x = st.p0x;
+        r0.y = st.p0y;
+        r0.z = (static_cast<uint32_t>(st.bx) & 0xffffu) | (static_cast<uint32_t>(st.by) << 16);
+        r0.w |= 1u << 16;
+    }
+    rec0[slot] = r0;
+    rec1[slot] = make_double2(cth * static_cast<double>(kOne), sth * static_cast<double>(kOne));
+}
+
+// Moves every particle's record (written in slot order by k_resample_motion) to its heading-
+// sorted slot, one 32-byte gather per particle, and sets the window-box flag -- the box needs the
+// cloud centre, which is complete only after the motion kernel.
+__global__ void __launch_bounds__(256) k_dir_gather(DirPrepArgs a) {
     __shared__ int s_cnt[8];
     const int64_t pos = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
     int bx0, by0;
     dir_box_origin(a.centre, a.cnt, a.map, a.box, &bx0, &by0);
     int in_box = 0;
     if (pos < a.cnt) {
-        const int64_t i = a.lo + a.perm[a.lo + pos];
-        const double x = a.px[i], y = a.py[i], th = a.pt[i];
-        double sth, cth;
-        sincos(th, &sth, &cth);
-        const double qx = p_coord(x, a.map.ox, a.map.res, kPadL);
-        const double qy = p_coord(y, a.map.oy, a.map.res, kPadL);
-        uint4 r0 = make_uint4(0u, 0u, 0u, static_cast<uint32_t>(theta_bucket(th, a.B)));
-        if (p_inside(qx, qy, a.map.PW, a.map.PH)) {
-            const int fqx = static_cast<int>(floor(qx)), fqy = static_cast<int>(floor(qy));
-            const RayStart st = make_ray_start(qx, qy, fqx, fqy);
+        const int i = a.perm[pos];
+        uint4 r0 = a.rec0_in[i];
+        const double2 r1 = a.rec1_in[i];
+        if (r0.w >> 16) {
+            const int fqx = static_cast<int>(static_cast<int16_t>(r0.z & 0xffffu)) + kLocalOrigin;
+            const int fqy = static_cast<int>(static_cast<int16_t>(r0.z >> 16)) + kLocalOrigin;
             in_box = fqx >= bx0 && fqx < bx0 + a.box && fqy >= by0 && fqy < by0 + a.box;
-            r0.x = st.p0x;
-            r0.y = st.p0y;
-            r0.z = (static_cast<uint32_t>(st.bx) & 0xffffu) | (static_cast<uint32_t>(st.by) << 16);
-            r0.w |= (1u | (in_box ? 2u : 0u)) << 16;
+            if (in_box) r0.w |= 2u << 16;
         }
         a.rec0[pos] = r0;
-        a.rec1[pos] = make_double2(cth * static_cast<double>(kOne), sth * static_cast<double>(kOne));
+        a.rec1[pos] = r1;
     }
-    // particles inside the box (the plan's compactness test)
     const unsigned m = __ballot_sync(kFullMask, in_box);
     if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = __popc(m);
     __syncthreads();
@@ -285,6 +304,7 @@ __global__ void __launch_bounds__(kDirThreads, 1) k_raycast_dir(DirRayArgs a) {
     const int64_t ncell = static_cast<int64_t>(mp.PW) * mp.PH;
     const int K = a.B >> 5, Bmask = a.B - 1;
     uint32_t phase = 0;
+    unsigned seen = 0;
     int cur_s = -1, replays = 0;
     DirWindow wg{0, 0, 0, 0};
     const uint8_t* smap = a.dirmaps;
@@ -301,11 +321,15 @@ __global__ void __launch_bounds__(kDirThreads, 1) k_raycast_dir(DirRayArgs a) {
 
     for (;;) {
         __syncthreads();                    // s_u0 / s_units of the previous round have been read by everyone
-        if (tid == 0) s_u0 = atomicAdd(reinterpret_cast<unsigned*>(a.plan + kPlanCounter), static_cast<unsigned>(kDirGrab));
+        // guided self-scheduling: large grabs first, small ones towards the end of the unit list
+        const unsigned left = n_units > seen ? n_units - seen : 0u;
+        const unsigned grab = max(2u, min(static_cast<unsigned>(kDirGrab), left / (2u * gridDim.x)));
+        if (tid == 0) s_u0 = atomicAdd(reinterpret_cast<unsigned*>(a.plan + kPlanCounter), grab);
         __syncthreads();
         const unsigned u0 = s_u0;
         if (u0 >= n_units) break;
-        const unsigned nu = min(static_cast<unsigned>(kDirGrab), n_units - u0);
+        seen = u0 + grab;
+        const unsigned nu = min(grab, n_units - u0);
         if (tid < static_cast<int>(nu)) {
             // sector of unit u: the last sector whose first unit is <= u (empty sectors share offsets)
             const int u = static_cast<int>(u0) + tid;
@@ -372,6 +396,7 @@ __global__ void __launch_bounds__(kDirThreads, 1) k_raycast_dir(DirRayArgs a) {
             st.by = static_cast<int>(static_cast<int16_t>(r0.z >> 16));
             const WindowV8S wacc{static_cast<uint32_t>(pin_reg(static_cast<int>(win_saddr) + (st.by - wg.wy0) * wg.pitch + (st.bx - wg.wx0))), wg.pitch};
             const GlobalV8 gacc = make_global_v8(smap, mp.PW, st.bx, st.by);
+            uint8_t* const out = a.steps_sorted + pos;
             for (int jb = 0; jb < R; jb += 32) {
                 const int jl = jb + lane;
                 // the warp's buckets shifted by the beam's offset: [start, start + len) cyclically; sector s = [0, K)
@@ -391,7 +416,7 @@ __global__ void __launch_bounds__(kDirThreads, 1) k_raycast_dir(DirRayArgs a) {
                         else
                             r = march_ray_dir(gacc, st, dxf, dyf, M, rep, &replays);
                     }
-                    a.steps_sorted[static_cast<int64_t>(j) * a.stride + pos] = static_cast<uint8_t>(r);
+                    out[static_cast<uint64_t>(static_cast<uint32_t>(j)) * static_cast<uint32_t>(a.stride)] = static_cast<uint8_t>(r);
                 }
             }
         }
@@ -412,30 +437,41 @@ struct WeightStepsArgs {
 };
 
 // w = pow(prod_j table(obs_j, range_ij), 1/squash): entries multiplied in beam order like the
-// reference's loop (:564-579).  The step bytes and table entries of kBatch beams are loaded
-// before they are multiplied, so the loads of a batch are in flight together.
-__global__ void __launch_bounds__(256) k_weight_steps(WeightStepsArgs a) {
+// reference's loop (:564-579).  One thread = four consecutive sorted slots: the step bytes arrive
+// as 32-bit words (128 B per warp and beam), kBatch beams in flight, four independent products.
+constexpr int kWeightThreads = 256;
+__global__ void __launch_bounds__(kWeightThreads) k_weight_steps(WeightStepsArgs a) {
     if (a.plan[kPlanMode] != 1) return;
-    const int64_t pos = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+    const int64_t pos = (static_cast<int64_t>(blockIdx.x) * kWeightThreads + threadIdx.x) * 4;
     if (pos >= a.cnt) return;
-    constexpr int kBatch = 12;
-    double acc = 1.0;
+    constexpr int kBatch = 10;
+    double acc[4] = {1.0, 1.0, 1.0, 1.0};
     for (int j0 = 0; j0 < a.R; j0 += kBatch) {
-        int r[kBatch];
-        double t[kBatch];
+        uint32_t w[kBatch];
 #pragma unroll
         for (int q = 0; q < kBatch; ++q)
-            r[q] = (j0 + q < a.R) ? static_cast<int>(__ldg(a.steps_sorted + static_cast<int64_t>(j0 + q) * a.stride + pos)) : 0;
+            w[q] = (j0 + q < a.R) ? __ldg(reinterpret_cast<const uint32_t*>(a.steps_sorted + static_cast<int64_t>(j0 + q) * a.stride + pos)) : 0u;
 #pragma unroll
-        for (int q = 0; q < kBatch; ++q) t[q] = (j0 + q < a.R) ? __ldg(a.slice + (j0 + q) * a.tw + r[q]) : 1.0;
+        for (int q = 0; q < kBatch; ++q) {
+            if (j0 + q < a.R) {
+                const double* row = a.slice + (j0 + q) * a.tw;
 #pragma unroll
-        for (int q = 0; q < kBatch; ++q)
-            if (j0 + q < a.R) acc = __dmul_rn(acc, t[q]);
+                for (int e = 0; e < 4; ++e) {
+                    const int r = static_cast<int>((w[q] >> (8 * e)) & 255u);   // slots beyond cnt hold zeros or stale (valid) steps
+                    acc[e] = __dmul_rn(acc[e], __ldg(row + r));
+                }
+            }
+        }
     }
-    const int64_t i = a.lo + a.perm[a.lo + pos];
-    a.w_raw[i] = pow(acc, a.inv_squash);
-    if (a.steps)   // diagnostics (mcl_get_ranges): particle-major copy of the step indices
-        for (int j = 0; j < a.R; ++j) a.steps[i * a.R + j] = a.steps_sorted[static_cast<int64_t>(j) * a.stride + pos];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        if (pos + e < a.cnt) {
+            const int64_t i = a.lo + a.perm[a.lo + pos + e];
+            a.w_raw[i] = pow(acc[e], a.inv_squash);
+            if (a.steps)   // diagnostics (mcl_get_ranges): particle-major copy of the step indices
+                for (int j = 0; j < a.R; ++j) a.steps[i * a.R + j] = a.steps_sorted[static_cast<int64_t>(j) * a.stride + pos + e];
+        }
+    }
 }
 
 }  // namespace mclb200

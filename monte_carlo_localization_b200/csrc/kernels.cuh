@@ -20,6 +20,7 @@
 namespace mclb200 {
 
 constexpr int kMaxBeams = 128;
+constexpr int kMaxBuckets = 4096;     // heading buckets of the coherence sort
 
 // Everything the ray/weight kernels need to know about the map and the beams.  Passed by
 // value: kernel parameters live in the constant bank, so the beam tables below are read
@@ -83,6 +84,12 @@ struct BeamDev {
     double cosa[kMaxBeams];     // cos((double)angle)
     double sina[kMaxBeams];
 };
+
+}  // namespace mclb200
+
+#include "dir_kernels.cuh"
+
+namespace mclb200 {
 
 // ------------------------------------------------------------------------------------------
 // exact sequential sums
@@ -433,6 +440,12 @@ struct MotionArgs {
     uint64_t seed;
     uint64_t update_no;
     double* centre;           // [F][2] accumulators (sum x, sum y)
+    // directional ray stage (dir_kernels.cuh): ray-start records in slot order, or nullptr;
+    // the heading sort's scatter pass moves them to their sorted slots
+    uint4* rec0;
+    double2* rec1;
+    MapDev map;
+    int B;
 };
 
 struct MotionScalars {
@@ -575,6 +588,7 @@ __global__ void __launch_bounds__(kMotionThreads) k_resample_motion(MotionArgs a
         a.dx[fo + i] = nx;
         a.dy[fo + i] = ny;
         a.dt[fo + i] = nt;
+        if (a.rec0) dir_write_record(a.map, a.rec0, a.rec1, li, nx, ny, nt, theta_bucket(nt, a.B));
         if (!(fabs(nx) < 1e12) || !(fabs(ny) < 1e12)) nx = ny = 0.0;  // keep the window centre finite
     }
     // cloud centre for the shared-memory window of the ray kernel
@@ -604,7 +618,6 @@ struct SortArgs {
     int64_t chunk;        // particles per block (multiple of kSortThreads)
 };
 constexpr int kSortThreads = 1024;
-constexpr int kMaxBuckets = 4096;
 
 __global__ void __launch_bounds__(kSortThreads) k_sort_hist(SortArgs a) {
     __shared__ int cnt[kMaxBuckets];
@@ -1144,5 +1157,3 @@ __global__ void k_fill(double* p, int64_t n, double v) {
 }
 
 }  // namespace mclb200
-
-#include "dir_kernels.cuh"

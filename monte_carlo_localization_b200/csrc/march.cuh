@@ -286,34 +286,38 @@ MCL_NOINLINE int resolve_uncertain_dir(const Acc acc, uint32_t px, uint32_t py, 
     return 2 | (replay_sample_is_hit(g, ra.x, ra.y, nf_mul(cs, g.res), nf_mul(sn, g.res), k) ? 1 : 0);
 }
 
+// A sample is "near an edge" for the hot loop if its fraction lies within 2^-14 cell of a cell
+// edge -- a superset of the kEta band that costs two logic operations; the resolver applies the
+// exact band.
+constexpr uint32_t kEdgeMask = kFracMask & ~511u;
+static_assert(2u * kEtaFix <= 512u, "the coarse edge band must contain the kEta band");
+
 template <class Acc, class Rep>
 MCL_HD int march_ray_dir(const Acc& acc, const RayStart& st, int dxf, int dyf, int M, const Rep& rep, int* replays) {
     constexpr int kPark = 1 << 20;
-    int k = 1, r = M;
+    int k = 1;
     for (;;) {
-        int pending_k = 0;   // sample to resolve exactly (0 = none)
+        int kstop = 0;   // sample at which the loop stopped: blocked cell, or a near-wall sample close to an edge
         do {
             const uint32_t px = st.p0x + static_cast<uint32_t>(k * dxf);
             const uint32_t py = st.p0y + static_cast<uint32_t>(k * dyf);
             int v = acc.get_p(px, py);
             if (v >= 0x80) {
                 // blocked, or next to a blocked cell: the class of this very sample matters
-                const uint32_t tx = (px + kEtaFix) & kFracMask, ty = (py + kEtaFix) & kFracMask;
-                if ((tx < ty ? tx : ty) < 2u * kEtaFix) {
-                    pending_k = k;   // within kEta of a cell edge
-                    k = kPark;
-                } else if (v == 0x80) {
-                    r = k - 1;
+                const bool clear = (((px + kEtaFix) & kEdgeMask) != 0u) & (((py + kEtaFix) & kEdgeMask) != 0u) & (v != 0x80);
+                if (!clear) {
+                    kstop = k;
                     k = kPark;
                 }
                 v &= 0x7f;
             }
             k += v;
         } while (k <= M);
-        if (pending_k == 0) return r;
-        k = pending_k;
+        if (kstop == 0) return M;
+        k = kstop;
         const uint32_t px = st.p0x + static_cast<uint32_t>(k * dxf);
         const uint32_t py = st.p0y + static_cast<uint32_t>(k * dyf);
+        if ((((px + kEtaFix) & kEdgeMask) != 0u) & (((py + kEtaFix) & kEdgeMask) != 0u)) return k - 1;   // blocked, clear of edges
         const int res = resolve_uncertain_dir(acc, px, py, acc.get_p(px, py), rep, k);
         *replays += res >> 1;
         if (res & 1) return k - 1;

@@ -123,8 +123,8 @@ struct mcl_ctx {
     int beam_io[kMaxBeams] = {};
     int* d_sec_tab = nullptr;         // [S+1] first unit | [S] first chunk, per sector
     DirReplayCtx* d_replay_ctx = nullptr;   // [2]: one per state buffer
-    uint4* d_rec0 = nullptr;          // [N]
-    double2* d_rec1 = nullptr;        // [N]
+    uint4* d_rec0 = nullptr;          // [2][N]: slot order | heading-sorted order
+    double2* d_rec1 = nullptr;        // [2][N]
     int* d_plan = nullptr;
     uint8_t* d_steps_sorted = nullptr;   // [R][stride]
     int64_t dir_stride = 0;
@@ -342,8 +342,8 @@ int ensure_dir(mcl_ctx* c, bool map_changed) {
         cudaFree(d_gap);
         CK(dalloc(&c->d_plan, static_cast<size_t>(kPlanInts)));
         CK(cudaMemset(c->d_plan, 0, sizeof(int) * kPlanInts));
-        CK(dalloc(&c->d_rec0, static_cast<size_t>(c->N)));
-        CK(dalloc(&c->d_rec1, static_cast<size_t>(c->N)));
+        CK(dalloc(&c->d_rec0, static_cast<size_t>(2 * c->N)));
+        CK(dalloc(&c->d_rec1, static_cast<size_t>(2 * c->N)));
     }
     // per-beam-table buffers
     for (void* p : {static_cast<void*>(c->d_sec_tab), static_cast<void*>(c->d_steps_sorted), static_cast<void*>(c->d_replay_ctx)})
@@ -357,6 +357,7 @@ int ensure_dir(mcl_ctx* c, bool map_changed) {
     const int64_t nchunks = (c->N + kDirThreads - 1) / kDirThreads;
     c->dir_stride = nchunks * kDirThreads;
     CK(dalloc(&c->d_steps_sorted, static_cast<size_t>(c->R) * c->dir_stride));
+    CK(cudaMemset(c->d_steps_sorted, 0, static_cast<size_t>(c->R) * c->dir_stride));   // slots beyond the shard stay valid steps
     if (dir_ray_smem(static_cast<int>((c->dir_smem + 15) & ~size_t{15})) > kWindowBudget) return MCL_OK;   // stays on the isotropic kernel
     c->dir_ready = true;
     return upload_replay_ctx(c);
@@ -429,7 +430,12 @@ int update_local(mcl_ctx* c, const double* action_dev, const float* obs_dev, con
     if (rc) return rc;
     if (c->profiling) CK(cudaEventRecord(c->ev[1], s));
 
+    const bool dir = c->dir_ready && c->sort_enabled && c->ray_mode != 1;
     MotionArgs ma{};
+    ma.rec0 = dir ? c->d_rec0 : nullptr;
+    ma.rec1 = dir ? c->d_rec1 : nullptr;
+    ma.map = c->map;
+    ma.B = c->B;
     ma.N = c->N;
     ma.lo = c->lo;
     ma.cnt = c->cnt;
@@ -482,24 +488,19 @@ int update_local(mcl_ctx* c, const double* action_dev, const float* obs_dev, con
         k_sort_scatter<<<gs, kSortThreads, 0, s>>>(sa);
         c->launches += 2;
     }
-    const bool dir = c->dir_ready && c->sort_enabled && c->ray_mode != 1;
     if (dir) {
         DirPrepArgs pa{};
         pa.map = c->map;
-        pa.N = c->N;
-        pa.lo = c->lo;
-        pa.cnt = c->cnt;
-        pa.px = c->d_px[dst];
-        pa.py = c->d_py[dst];
-        pa.pt = c->d_pt[dst];
-        pa.perm = c->d_perm;
         pa.centre = c->d_centre;
-        pa.rec0 = c->d_rec0;
-        pa.rec1 = c->d_rec1;
+        pa.rec0_in = c->d_rec0;
+        pa.rec1_in = c->d_rec1;
+        pa.rec0 = c->d_rec0 + c->N;
+        pa.rec1 = c->d_rec1 + c->N;
+        pa.perm = c->d_perm + c->lo;
         pa.plan = c->d_plan;
-        pa.B = c->B;
+        pa.cnt = c->cnt;
         pa.box = c->dir_box;
-        k_dir_prepare<<<static_cast<unsigned>((c->cnt + 255) / 256), 256, 0, s>>>(pa);
+        k_dir_gather<<<static_cast<unsigned>((c->cnt + 255) / 256), 256, 0, s>>>(pa);
         DirPlanArgs la{};
         la.hist = c->d_hist;
         std::memcpy(la.io, c->beam_io, sizeof(la.io));
@@ -564,8 +565,8 @@ int update_local(mcl_ctx* c, const double* action_dev, const float* obs_dev, con
         std::memcpy(da.io, c->beam_io, sizeof(da.io));
         da.sectors = c->d_sectors;
         da.dirmaps = c->d_dirmaps;
-        da.rec0 = c->d_rec0;
-        da.rec1 = c->d_rec1;
+        da.rec0 = c->d_rec0 + c->N;
+        da.rec1 = c->d_rec1 + c->N;
         da.sec_tab = c->d_sec_tab;
         da.replay = c->d_replay_ctx + dst;
         da.plan = c->d_plan;
@@ -587,6 +588,7 @@ int update_local(mcl_ctx* c, const double* action_dev, const float* obs_dev, con
             case 239: k_raycast_dir<239><<<dblocks, kDirThreads, dsmem, s>>>(da); break;
             default: k_raycast_dir<0><<<dblocks, kDirThreads, dsmem, s>>>(da); break;
         }
+        if (c->profiling) CK(cudaEventRecord(c->ev[5], s));
         WeightStepsArgs wa{};
         wa.plan = c->d_plan;
         wa.steps_sorted = c->d_steps_sorted;
@@ -600,9 +602,10 @@ int update_local(mcl_ctx* c, const double* action_dev, const float* obs_dev, con
         wa.R = c->R;
         wa.tw = c->M + 1;
         wa.inv_squash = 1.0 / c->prm.squash_factor;
-        k_weight_steps<<<static_cast<unsigned>((c->cnt + 255) / 256), 256, 0, s>>>(wa);
+        k_weight_steps<<<static_cast<unsigned>((c->cnt + 4 * kWeightThreads - 1) / (4 * kWeightThreads)), kWeightThreads, 0, s>>>(wa);
         c->launches += 2;
     }
+    if (!dir && c->profiling) CK(cudaEventRecord(c->ev[5], s));
     if (c->p2p) {
         // unnormalised pose sums of the rank's own slots (deterministic two-stage reduction)
         NormArgs na{};
@@ -1222,6 +1225,8 @@ int mcl_update(mcl_ctx* c, const double* action, const float* obs, int num_beams
         c->last_ms.normalize_pose = t;
         cudaEventElapsedTime(&t, c->ev[0], c->ev[4]);
         c->last_ms.total = t;
+        cudaEventElapsedTime(&t, c->ev[2], c->ev[5]);
+        c->last_ms.ray_march = t;
     }
     return MCL_OK;
 }
