@@ -43,14 +43,21 @@ __global__ void __launch_bounds__(256) k_build_dir_maps(DirBuildArgs a) {
     a.out[static_cast<int64_t>(s) * n + cell] = dir_code(a.v8, a.gap, a.PW, a.PH, cx, cy, a.sectors[s]);
 }
 
+// Ray-start record of one particle (32 bytes = one memory sector):
+//   a = p0x, p0y (9.23 fixed-point start), bx | by << 16 (P-cell of local coordinate 0),
+//       heading bucket | flags << 16 (bit 0: inside the map, bit 1: inside the window box)
+//   b = cos(theta) * 2^23, sin(theta) * 2^23
+struct __align__(32) DirRec {
+    uint4 a;
+    double2 b;
+};
+
 // k_dir_gather: ray-start records from slot order into heading-sorted order
 struct DirPrepArgs {
     MapDev map;
     const double* centre;      // [2] sums of x and y over the shard's particles
-    const uint4* rec0_in;      // [cnt] records in slot order (k_resample_motion)
-    const double2* rec1_in;
-    uint4* rec0;               // [cnt] records in heading-sorted order
-    double2* rec1;
+    const DirRec* rec_in;      // [cnt] records in slot order (k_resample_motion)
+    DirRec* rec;               // [cnt] records in heading-sorted order
     const int32_t* perm;       // sorted slot -> slot index (both relative to the shard)
     int* plan;
     int64_t cnt;
@@ -67,12 +74,8 @@ __device__ __forceinline__ void dir_box_origin(const double* centre, int64_t cnt
     *by0 = cy - box / 2;
 }
 
-// Ray-start record of one particle:
-//   rec0 = p0x, p0y (9.23 fixed-point start), bx | by << 16 (P-cell of local coordinate 0),
-//          heading bucket | flags << 16 (bit 0: inside the map, bit 1: inside the window box)
-//   rec1 = cos(theta) * 2^23, sin(theta) * 2^23
-__device__ __forceinline__ void dir_write_record(const MapDev& mp, uint4* rec0, double2* rec1, int64_t slot, double x, double y,
-                                                 double th, int bucket) {
+__device__ __forceinline__ void dir_write_record(const MapDev& mp, DirRec* rec, int64_t slot, double x, double y, double th,
+                                                 int bucket) {
     double sth, cth;
     sincos(th, &sth, &cth);
     const double qx = p_coord(x, mp.ox, mp.res, kPadL);
@@ -86,8 +89,8 @@ __device__ __forceinline__ void dir_write_record(const MapDev& mp, uint4* rec0, 
         r0.z = (static_cast<uint32_t>(st.bx) & 0xffffu) | (static_cast<uint32_t>(st.by) << 16);
         r0.w |= 1u << 16;
     }
-    rec0[slot] = r0;
-    rec1[slot] = make_double2(cth * static_cast<double>(kOne), sth * static_cast<double>(kOne));
+    rec[slot].a = r0;
+    rec[slot].b = make_double2(cth * static_cast<double>(kOne), sth * static_cast<double>(kOne));
 }
 
 // Moves every particle's record (written in slot order by k_resample_motion) to its heading-
@@ -101,16 +104,16 @@ __global__ void __launch_bounds__(256) k_dir_gather(DirPrepArgs a) {
     int in_box = 0;
     if (pos < a.cnt) {
         const int i = a.perm[pos];
-        uint4 r0 = a.rec0_in[i];
-        const double2 r1 = a.rec1_in[i];
+        uint4 r0 = a.rec_in[i].a;
+        const double2 r1 = a.rec_in[i].b;
         if (r0.w >> 16) {
             const int fqx = static_cast<int>(static_cast<int16_t>(r0.z & 0xffffu)) + kLocalOrigin;
             const int fqy = static_cast<int>(static_cast<int16_t>(r0.z >> 16)) + kLocalOrigin;
             in_box = fqx >= bx0 && fqx < bx0 + a.box && fqy >= by0 && fqy < by0 + a.box;
             if (in_box) r0.w |= 2u << 16;
         }
-        a.rec0[pos] = r0;
-        a.rec1[pos] = r1;
+        a.rec[pos].a = r0;
+        a.rec[pos].b = r1;
     }
     const unsigned m = __ballot_sync(kFullMask, in_box);
     if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = __popc(m);
@@ -254,8 +257,7 @@ struct DirRayArgs {
     int io[kMaxBeams];          // per-beam bucket offset
     const DirSector* sectors;   // [S]
     const uint8_t* dirmaps;     // [S][PH*PW]
-    const uint4* rec0;
-    const double2* rec1;
+    const DirRec* rec;          // heading-sorted ray-start records
     const int* sec_tab;         // [S + 1] first unit | [S] first chunk
     int* plan;
     const double* centre;
@@ -313,8 +315,8 @@ __global__ void __launch_bounds__(kDirThreads, 1) k_raycast_dir(DirRayArgs a) {
     auto prefetch = [&](uint32_t unit, uint32_t buf) {
         const int pos = static_cast<int>(unit >> 6) * kDirThreads + tid;
         if (pos < cnt) {
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(rec0_s + buf * (kDirThreads * 16u)), "l"(a.rec0 + pos) : "memory");
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(rec1_s + buf * (kDirThreads * 16u)), "l"(a.rec1 + pos) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(rec0_s + buf * (kDirThreads * 16u)), "l"(&a.rec[pos].a) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(rec1_s + buf * (kDirThreads * 16u)), "l"(&a.rec[pos].b) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -446,22 +448,29 @@ __global__ void __launch_bounds__(kWeightThreads) k_weight_steps(WeightStepsArgs
     if (pos >= a.cnt) return;
     constexpr int kBatch = 10;
     double acc[4] = {1.0, 1.0, 1.0, 1.0};
-    for (int j0 = 0; j0 < a.R; j0 += kBatch) {
+    const uint32_t* sp = reinterpret_cast<const uint32_t*>(a.steps_sorted + pos);   // stride and pos are multiples of 4
+    const size_t wstride = static_cast<size_t>(a.stride) / 4;
+    const double* row = a.slice;
+    int j = 0;
+    for (; j + kBatch <= a.R; j += kBatch) {
         uint32_t w[kBatch];
 #pragma unroll
-        for (int q = 0; q < kBatch; ++q)
-            w[q] = (j0 + q < a.R) ? __ldg(reinterpret_cast<const uint32_t*>(a.steps_sorted + static_cast<int64_t>(j0 + q) * a.stride + pos)) : 0u;
+        for (int q = 0; q < kBatch; ++q) w[q] = __ldcs(sp + q * wstride);   // streamed: the table rows stay in L1
 #pragma unroll
         for (int q = 0; q < kBatch; ++q) {
-            if (j0 + q < a.R) {
-                const double* row = a.slice + (j0 + q) * a.tw;
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int r = static_cast<int>((w[q] >> (8 * e)) & 255u);   // slots beyond cnt hold zeros or stale (valid) steps
-                    acc[e] = __dmul_rn(acc[e], __ldg(row + r));
-                }
-            }
+            for (int e = 0; e < 4; ++e)   // slots beyond cnt hold zeros or stale (valid) steps
+                acc[e] = __dmul_rn(acc[e], __ldg(row + q * a.tw + ((w[q] >> (8 * e)) & 255u)));
         }
+        sp += kBatch * wstride;
+        row += kBatch * a.tw;
+    }
+    for (; j < a.R; ++j) {
+        const uint32_t w = __ldcs(sp);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[e] = __dmul_rn(acc[e], __ldg(row + ((w >> (8 * e)) & 255u)));
+        sp += wstride;
+        row += a.tw;
     }
 #pragma unroll
     for (int e = 0; e < 4; ++e) {

@@ -442,8 +442,7 @@ struct MotionArgs {
     double* centre;           // [F][2] accumulators (sum x, sum y)
     // directional ray stage (dir_kernels.cuh): ray-start records in slot order, or nullptr;
     // the heading sort's scatter pass moves them to their sorted slots
-    uint4* rec0;
-    double2* rec1;
+    DirRec* rec;
     MapDev map;
     int B;
 };
@@ -588,7 +587,7 @@ __global__ void __launch_bounds__(kMotionThreads) k_resample_motion(MotionArgs a
         a.dx[fo + i] = nx;
         a.dy[fo + i] = ny;
         a.dt[fo + i] = nt;
-        if (a.rec0) dir_write_record(a.map, a.rec0, a.rec1, li, nx, ny, nt, theta_bucket(nt, a.B));
+        if (a.rec) dir_write_record(a.map, a.rec, li, nx, ny, nt, theta_bucket(nt, a.B));
         if (!(fabs(nx) < 1e12) || !(fabs(ny) < 1e12)) nx = ny = 0.0;  // keep the window centre finite
     }
     // cloud centre for the shared-memory window of the ray kernel

@@ -123,8 +123,7 @@ struct mcl_ctx {
     int beam_io[kMaxBeams] = {};
     int* d_sec_tab = nullptr;         // [S+1] first unit | [S] first chunk, per sector
     DirReplayCtx* d_replay_ctx = nullptr;   // [2]: one per state buffer
-    uint4* d_rec0 = nullptr;          // [2][N]: slot order | heading-sorted order
-    double2* d_rec1 = nullptr;        // [2][N]
+    DirRec* d_rec = nullptr;          // [2][N]: slot order | heading-sorted order
     int* d_plan = nullptr;
     uint8_t* d_steps_sorted = nullptr;   // [R][stride]
     int64_t dir_stride = 0;
@@ -271,15 +270,14 @@ constexpr size_t kDirWindowBudget = 112 * 1024;   // one sector window (half of 
 
 void free_dir(mcl_ctx* c) {
     for (void* p : {static_cast<void*>(c->d_dirmaps), static_cast<void*>(c->d_sectors), static_cast<void*>(c->d_sec_tab), static_cast<void*>(c->d_replay_ctx),
-                    static_cast<void*>(c->d_rec0), static_cast<void*>(c->d_rec1),
+                    static_cast<void*>(c->d_rec),
                     static_cast<void*>(c->d_plan), static_cast<void*>(c->d_steps_sorted)})
         if (p) cudaFree(p);
     c->d_dirmaps = nullptr;
     c->d_sectors = nullptr;
     c->d_sec_tab = nullptr;
     c->d_replay_ctx = nullptr;
-    c->d_rec0 = nullptr;
-    c->d_rec1 = nullptr;
+    c->d_rec = nullptr;
     c->d_plan = nullptr;
     c->d_steps_sorted = nullptr;
     c->dir_ready = false;
@@ -342,8 +340,7 @@ int ensure_dir(mcl_ctx* c, bool map_changed) {
         cudaFree(d_gap);
         CK(dalloc(&c->d_plan, static_cast<size_t>(kPlanInts)));
         CK(cudaMemset(c->d_plan, 0, sizeof(int) * kPlanInts));
-        CK(dalloc(&c->d_rec0, static_cast<size_t>(2 * c->N)));
-        CK(dalloc(&c->d_rec1, static_cast<size_t>(2 * c->N)));
+        CK(dalloc(&c->d_rec, static_cast<size_t>(2 * c->N)));
     }
     // per-beam-table buffers
     for (void* p : {static_cast<void*>(c->d_sec_tab), static_cast<void*>(c->d_steps_sorted), static_cast<void*>(c->d_replay_ctx)})
@@ -432,8 +429,7 @@ int update_local(mcl_ctx* c, const double* action_dev, const float* obs_dev, con
 
     const bool dir = c->dir_ready && c->sort_enabled && c->ray_mode != 1;
     MotionArgs ma{};
-    ma.rec0 = dir ? c->d_rec0 : nullptr;
-    ma.rec1 = dir ? c->d_rec1 : nullptr;
+    ma.rec = dir ? c->d_rec : nullptr;
     ma.map = c->map;
     ma.B = c->B;
     ma.N = c->N;
@@ -492,10 +488,8 @@ int update_local(mcl_ctx* c, const double* action_dev, const float* obs_dev, con
         DirPrepArgs pa{};
         pa.map = c->map;
         pa.centre = c->d_centre;
-        pa.rec0_in = c->d_rec0;
-        pa.rec1_in = c->d_rec1;
-        pa.rec0 = c->d_rec0 + c->N;
-        pa.rec1 = c->d_rec1 + c->N;
+        pa.rec_in = c->d_rec;
+        pa.rec = c->d_rec + c->N;
         pa.perm = c->d_perm + c->lo;
         pa.plan = c->d_plan;
         pa.cnt = c->cnt;
@@ -565,8 +559,7 @@ int update_local(mcl_ctx* c, const double* action_dev, const float* obs_dev, con
         std::memcpy(da.io, c->beam_io, sizeof(da.io));
         da.sectors = c->d_sectors;
         da.dirmaps = c->d_dirmaps;
-        da.rec0 = c->d_rec0 + c->N;
-        da.rec1 = c->d_rec1 + c->N;
+        da.rec = c->d_rec + c->N;
         da.sec_tab = c->d_sec_tab;
         da.replay = c->d_replay_ctx + dst;
         da.plan = c->d_plan;
