@@ -297,6 +297,7 @@ __global__ void __launch_bounds__(kDirThreads, 1) k_raycast_dir(DirRayArgs a) {
     // thread-private prefetch slots of the ray-start records (two buffers)
     const uint32_t rec0_s = win_saddr + static_cast<uint32_t>(a.win_bytes) + static_cast<uint32_t>(tid) * 16u;
     const uint32_t rec1_s = rec0_s + 2u * kDirThreads * 16u;
+    const uint32_t io_saddr = static_cast<uint32_t>(__cvta_generic_to_shared(s_io)) + static_cast<uint32_t>(lane) * 4u;
     if (tid < 2 * kDirSectors + 1) s_sec[tid] = a.sec_tab[tid];
     if (tid < kMaxBeams) s_io[tid] = tid < R ? a.io[tid] : 0;
     if (tid == 0) {
@@ -402,12 +403,14 @@ __global__ void __launch_bounds__(kDirThreads, 1) k_raycast_dir(DirRayArgs a) {
             for (int jb = 0; jb < R; jb += 32) {
                 const int jl = jb + lane;
                 // the warp's buckets shifted by the beam's offset: [start, start + len) cyclically; sector s = [0, K)
-                const int start = (bmin + (jl < R ? s_io[jl] : 0) - s * K) & Bmask;
+                uint32_t io_l;   // s_io[jl] (entries beyond R are 0 and masked below); plain LDS from a register address
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(io_l) : "r"(io_saddr + static_cast<uint32_t>(jb * 4)));
+                const int start = (bmin + static_cast<int>(io_l) - s * K) & Bmask;
                 unsigned mask = __ballot_sync(kFullMask, jl < R && (start < K || start + (bmax - bmin) >= a.B));
                 while (mask) {
                     const int j = jb + __ffs(mask) - 1;
                     mask &= mask - 1;
-                    if (!valid || dir_sector_of(bucket, s_io[j], Bmask, a.shift) != s) continue;   // another unit's ray
+                    if (!valid || dir_sector_of(bucket, a.io[j], Bmask, a.shift) != s) continue;   // another unit's ray
                     int r = 0;   // outside the map: the first sample is already out of bounds (:632-636)
                     if (flags & 1) {
                         int dxf, dyf;

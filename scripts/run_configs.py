@@ -58,12 +58,13 @@ def config1():
             "updates_per_s": 200 / sec, "rays_per_s": 4000 * 60 * 200 / sec, "median_pose_err_m": float(np.median(errs))}
 
 
-def config2(steps=1000):
+def config2(steps=1000, ray_mode=0):
     g = maps.load_named_map("basement_fixed")
     N = 100000
     ctx = MclContext(max_particles=N, seed=20252)
     ctx.set_map(g)
     ctx.set_beam_angles(synth.beam_angles())
+    ctx.set_ray_mode(ray_mode)
     gt, actions, obs = replay(ctx, g, steps + 20, 3.0, 779)
     ctx.init_pose(gt[0])
     timed_updates(ctx, actions, obs, gt, 20)
@@ -71,7 +72,7 @@ def config2(steps=1000):
     return {"config": 2, "map": "basement_fixed (levine stand-in: levine.pgm is missing from the reference checkout)",
             "particles": N, "beams": 60, "updates": steps, "ms_per_update": 1e3 * sec / steps, "updates_per_s": steps / sec,
             "rays_per_s": N * 60 * steps / sec, "median_pose_err_m": float(np.median(errs)),
-            "max_pose_err_m": float(np.max(errs))}
+            "max_pose_err_m": float(np.max(errs)), "ray_mode": ray_mode, "ray_stage": ctx.ray_stage_info()}
 
 
 def config4(F=1024, steps=20):
@@ -104,11 +105,12 @@ def config4(F=1024, steps=20):
             "frac_filters_within_0.3m": float(np.mean(err < 0.3))}
 
 
-def config5(N=2000000, max_updates=60):
+def config5(N=2000000, max_updates=60, ray_mode=0):
     g = maps.load_named_map("basement_fixed")
     ctx = MclContext(max_particles=N, seed=20255)
     ctx.set_map(g)
     ctx.set_beam_angles(synth.beam_angles())
+    ctx.set_ray_mode(ray_mode)
     gt, actions, obs = replay(ctx, g, max_updates, 3.0, 782)
     ctx.init_global()
     streak, conv, times = 0, None, []
@@ -126,7 +128,7 @@ def config5(N=2000000, max_updates=60):
             "converged_at_update": conv, "ms_per_update_first5": 1e3 * float(np.mean(times[:5])),
             "ms_per_update_last5": 1e3 * float(np.mean(times[-5:])),
             "time_to_converge_s": None if conv is None else float(np.sum(times[:conv + 9])),
-            "final_pose_err_m": float(d)}
+            "final_pose_err_m": float(d), "ray_mode": ray_mode, "ray_stage": ctx.ray_stage_info()}
 
 
 if __name__ == "__main__":
@@ -135,14 +137,15 @@ if __name__ == "__main__":
     ap.add_argument("--n5", type=int, default=2000000)
     ap.add_argument("--steps2", type=int, default=1000)
     ap.add_argument("--filters4", type=int, default=1024)
+    ap.add_argument("--ray-mode", type=int, default=0, help="0 auto, 1 isotropic kernel only, 2 directional stage always")
     a = ap.parse_args()
     for c in a.configs.split(","):
         if c == "1":
             print(json.dumps(config1()))
         elif c == "2":
-            print(json.dumps(config2(a.steps2)))
+            print(json.dumps(config2(a.steps2, a.ray_mode)))
         elif c == "4":
             print(json.dumps(config4(a.filters4)))
         elif c == "5":
-            print(json.dumps(config5(a.n5)))
+            print(json.dumps(config5(a.n5, ray_mode=a.ray_mode)))
         sys.stdout.flush()

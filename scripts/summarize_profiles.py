@@ -126,7 +126,109 @@ def launch_summary(path):
     open(os.path.join(ROOT, "profiles", "r1_final_launches.md"), "w").write("\n".join(out) + "\n")
 
 
+def dir_summary(rep, launches_csv, tag):
+    """Summaries for the directional ray stage (k_raycast_dir): profiles/<tag>_ray_ncu.md,
+    profiles/<tag>_launches.md (+ .csv copy) and the kernel's DRAM traffic in ncu_traffic.json."""
+    raw = page(rep, "raw")
+    hdr, units = raw[0], raw[1]
+    r = [x for x in raw[2:] if "k_raycast_dir" in x[hdr.index("Kernel Name")]][0]
+    vals = {k: (r[hdr.index(k)], units[hdr.index(k)]) for k in KEYS if k in hdr}
+    kname = r[hdr.index("Kernel Name")]
+    src_rows = page(rep, "source")
+    # the source page lists every captured kernel; take the first k_raycast_dir block
+    src, take = [], False
+    for x in src_rows:
+        if x and x[0] == "Kernel Name":
+            if take:
+                break
+            take = "k_raycast_dir" in x[1]
+            continue
+        if take and len(x) >= 10 and x[0] != "Address":
+            src.append(x)
+    tot = sum(int(x[5]) for x in src)
+    rays = 1048576 * 60 / 32.0
+    b = collections.OrderedDict([("march loop, skip path", 0), ("march loop, near-wall path", 0),
+                                 ("per ray and per 32-beam round (direction, sector test, store)", 0),
+                                 ("per unit (record prefetch, window base, beam mask)", 0),
+                                 ("rare (window staging, scheduling, exact replay)", 0)])
+    for x in src:
+        ie = int(x[5])
+        q = ie / rays
+        key = (list(b)[0] if q >= 5.2 else list(b)[1] if q >= 3 else list(b)[2] if q >= 0.7 else list(b)[3] if q >= 0.2 else list(b)[4])
+        b[key] += ie
+    dram = to_bytes(*vals["dram__bytes_read.sum"]) + to_bytes(*vals["dram__bytes_write.sum"])
+    sass = " ".join(x[1] for x in src)
+    md = ["# %s -- ncu --set full (directional ray stage)" % kname, "",
+          "Command (under gpurun, after the same command exited 0 without ncu):", "",
+          "    ncu --set full --clock-control none --import-source on -k regex:k_raycast_dir -s 6 -c 1 \\",
+          "        -o gpurun_out/prof_%s python bench.py --steps 3 --warmup 3 --no-cpu" % tag, "",
+          "Workload: Spielberg_map, 1,048,576 particles x 60 beams (62.9 M rays), tracking cloud.",
+          "Times under ncu are cold-cache and serialised: compare shares, not absolutes.", "",
+          "| metric | value | unit |", "|---|---|---|"]
+    md += ["| `%s` | %s | %s |" % (k, v[0], v[1]) for k, v in vals.items()]
+    md += ["", "DRAM traffic per launch: %.1f MB (ray-start records in, step bytes out, sector windows mostly from L2)." % (dram / 1e6),
+           "Algorithmic bytes per launch (SURVEY 8d): N*R*C-bar grid bytes of the reference's march + 64 B/particle records + 1 B/ray steps.",
+           "Shared-memory lookups of the sector windows: %s wavefronts, %s of them bank-conflict replays." % (
+               vals["l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"][0], vals["l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"][0]),
+           "", "SASS evidence: UBLKCP (cp.async.bulk window staging) %s, SYNCS (mbarrier) %s, LDGSTS (cp.async record prefetch) %s, LDS.U8 lookups %s; "
+           "no HMMA/UTC*MMA (no dense contraction on this path)." % tuple(
+               "present" if t in sass else "absent" for t in ("UBLKCP", "SYNCS", "LDGSTS", "LDS.U8")),
+           "", "Executed warp instructions by region (source page, `Instructions Executed`):", "",
+           "| region | warp instructions | share | per warp-ray |", "|---|---|---|---|"]
+    md += ["| %s | %.3e | %.1f %% | %.0f |" % (k, v, 100 * v / tot, v / rays) for k, v in b.items()]
+    md += ["| total | %.3e | | %.0f |" % (tot, tot / rays), "",
+           "Reading: warp-issue bound (issue active %s %% of peak; tensor, FP64 and LSU pipes far from saturated), SIMT lane efficiency %s of 32."
+           % (vals["smsp__issue_active.avg.pct_of_peak_sustained_active"][0][:4], vals["smsp__thread_inst_executed_per_inst_executed.ratio"][0])]
+    open(os.path.join(ROOT, "profiles", tag + "_ray_ncu.md"), "w").write("\n".join(md) + "\n")
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    t = json.load(open(tp)) if os.path.exists(tp) else {}
+    t["k_raycast_dir_dram_bytes_per_launch"] = dram
+    t["k_raycast_dir_source"] = "profiles/%s_ray_ncu.md (ncu --set full, one launch, 1M x 60 Spielberg)" % tag
+    json.dump(t, open(tp, "w"))
+    # launch list
+    import shutil
+    shutil.copy(launches_csv, os.path.join(ROOT, "profiles", tag + "_launches.csv"))
+    rows = list(csv.reader(open(launches_csv)))
+    hi = [i for i, rr in enumerate(rows) if "Kernel Name" in rr][0]
+    h2 = rows[hi]
+    kn, mv = h2.index("Kernel Name"), h2.index("Metric Value")
+    agg = collections.OrderedDict()
+    for rr in rows[hi + 2:]:
+        if len(rr) <= mv:
+            continue
+        try:
+            v = float(rr[mv].replace(",", ""))
+        except ValueError:
+            continue
+        agg.setdefault(rr[kn].split("(")[0][:60], []).append(v)
+    skip = ("k_range_queries", "k_init_pose", "k_fill", "k_build_dir_maps", "k_gather_bench")
+    upd = {k: v for k, v in agg.items() if "mclb200" in k and not any(x in k for x in skip)}
+    n_upd = len(upd[[k for k in upd if "k_raycast_dir" in k][0]])
+    # the diagnostics pass of bench.py (per-ray steps kept) inflates k_weight_steps: use the median
+    med = {k: sorted(v)[len(v) // 2] for k, v in upd.items()}
+    tot_med = sum(med[k] * len(v) / n_upd for k, v in upd.items())
+    out = ["# Launch list of `python bench.py --steps 3 --warmup 3 --no-cpu` (directional ray stage)", "",
+           "`ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv`; raw CSV: `profiles/%s_launches.csv`." % tag,
+           "Per-launch times are cold-cache and serialised by ncu; the SHARES are what must agree with the CUDA-event stage",
+           "times of the bench line.  Median per launch (bench.py's C-bar pass keeps per-ray steps in a few updates, which",
+           "inflates `k_weight_steps` there).", "",
+           "Kernels of one MCL update (%d updates captured):" % n_upd, "",
+           "| kernel | launches / update | median us / launch | share of update |", "|---|---|---|---|"]
+    for k, v in upd.items():
+        out.append("| `%s` | %.0f | %.1f | %.1f %% |" % (k.replace("void ", "").replace("mclb200::", ""), len(v) / n_upd,
+                                                        med[k] / 1e3, 100 * med[k] * len(v) / n_upd / tot_med))
+    out.append("| total per update | %d | %.1f | |" % (round(sum(len(v) for v in upd.values()) / n_upd), tot_med / 1e3))
+    bd = agg.get("mclb200::k_build_dir_maps", [0])
+    out += ["", "Outside the update: `k_build_dir_maps` once per map (%.1f ms for the 32 sector maps of Spielberg_map), `k_range_queries` "
+            "(synthetic scan generation), `k_init_pose`, `k_fill`, the gather micro-benchmark and the L2-flush fill of bench.py." % (bd[0] / 1e6)]
+    open(os.path.join(ROOT, "profiles", tag + "_launches.md"), "w").write("\n".join(out) + "\n")
+    print("wrote profiles/%s_ray_ncu.md, profiles/%s_launches.md, profiles/ncu_traffic.json" % (tag, tag))
+
+
 if __name__ == "__main__":
-    ray_summary(sys.argv[1])
-    launch_summary(sys.argv[2])
-    print("wrote profiles/r1_final_ray_ncu.md, profiles/r1_final_launches.md, profiles/ncu_traffic.json")
+    if len(sys.argv) >= 4 and sys.argv[1] == "--dir":
+        dir_summary(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else "r1_dir")
+    else:
+        ray_summary(sys.argv[1])
+        launch_summary(sys.argv[2])
+        print("wrote profiles/r1_final_ray_ncu.md, profiles/r1_final_launches.md, profiles/ncu_traffic.json")
