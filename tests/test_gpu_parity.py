@@ -563,3 +563,102 @@ def test_scattered_cloud_falls_back_to_isotropic_kernel():
     want = steps_from_ranges(orc.ranges(), g.resolution_f64, orc.M)
     assert (res[2][0] != want).sum() == 0
     c.close()
+
+
+def test_directional_stage_edge_cases_match_oracle():
+    """The directional stage on degenerate inputs: a cloud at the map border (clipped windows),
+    particles outside the map and outside the window box, NaN / inf / out-of-range scan readings,
+    headings at +-pi (bucket wrap-around), one dominant weight."""
+    from monte_carlo_localization_b200 import maps, synth
+    from oracle import bindings as ob
+    g = maps.load_named_map("sibal1")
+    angles = synth.beam_angles()
+    N = 24000
+    res = g.resolution_f64
+    rng = np.random.default_rng(12)
+    ns = ob.NoiseStream(99)
+    # cloud in the lower-left corner region of the map, heading west (around +-pi)
+    x = g.origin[0] + 1.0 + rng.normal(0, 0.3, N)
+    y = g.origin[1] + 1.2 + rng.normal(0, 0.3, N)
+    th = np.pi + rng.normal(0, 0.3, N)
+    th = (th + np.pi) % (2 * np.pi) - np.pi
+    th[:50] = np.pi                     # exactly on the wrap
+    th[50:100] = -np.pi
+    x[100:400] = g.origin[0] - rng.uniform(0, 2, 300)                # left of the map
+    y[400:700] = g.origin[1] + rng.integers(-2, 3, 300) * res       # on / next to the border lattice
+    x[700:900] += rng.normal(0, 5.0, 200)                            # far outside the window box
+    x[900:920] = 1e7
+    p = np.stack([x, y, th])
+    w = np.full(N, 1e-9)
+    w[4321] = 1.0
+    w /= w.sum()
+    obs = np.full(len(angles), 2.0, dtype=np.float32)
+    obs[0], obs[1], obs[2], obs[3], obs[4] = 0.0, 12.0, 50.0, np.inf, np.nan
+    c = _ctx(g, angles, N)
+    c.set_ray_mode(2)
+    for k, action in enumerate(([0.0, 0.0, 0.0], [0.3, 0.0, -0.2])):
+        u, z = ns.update_noise(N)
+        orc = ob.Oracle(g, angles, max_particles=N)
+        orc.set_state(p, w)
+        c.set_particles(p, w)
+        idx = orc.update(action, obs, u, z)
+        pose = c.update(action, obs, u, z)
+        assert c.ray_stage_info()["last_mode"] == 1
+        assert np.array_equal(c.resample_indices(), idx)
+        assert np.array_equal(c.range_steps(), steps_from_ranges(orc.ranges(), res, orc.M))
+        assert_weights_close(c.get_weights(), orc.get_state()[1])
+        assert_pose_close(pose, orc.expected_pose())
+        w = np.full(N, 1.0 / N)          # second round: uniform weights, every particle survives
+    c.close()
+
+
+def test_directional_stage_in_particle_shards():
+    """Two emulated ranks on one GPU, each large enough for the directional stage: the sharded
+    update (local slots -> exchange -> finish) equals the single-filter update bit for bit."""
+    import torch
+    from monte_carlo_localization_b200.sharded import ShardPlan, _DevArray
+    N, world = 40000, 2
+    g, angles, orc, ns, action, obs = _tracking_case("sibal1", N, 3.0, 5)
+    p0, w0 = orc.get_state()
+    u, z = ns.update_noise(N)
+    single = _ctx(g, angles, N)
+    single.set_particles(p0, w0)
+    pose_single = single.update(action, obs, u, z)
+    assert single.ray_stage_info()["last_mode"] == 1
+    plan = ShardPlan(N, world)
+    ranks = []
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    for r in range(world):
+        c = _ctx(g, angles, N)
+        c.set_shard(*plan.slots(r))
+        c.set_stream(stream.cuda_stream)
+        ranks.append(c)
+    a = torch.from_numpy(np.asarray(action, dtype=np.float64).copy()).cuda()
+    o = torch.from_numpy(obs.copy()).cuda()
+    ud = torch.from_numpy(u.copy()).cuda()
+    zd = torch.from_numpy(z.copy()).cuda()
+    bufs = []
+    for c in ranks:
+        c.set_particles(p0, w0)
+        c.update_local_dev(a.data_ptr(), o.data_ptr(), ud.data_ptr(), zd.data_ptr())
+        ptrs, n, lo, cnt = c.exchange_buffers_dev()
+        bufs.append([torch.as_tensor(_DevArray(p, n), device="cuda") for p in ptrs])
+    for r in range(world):              # the all-gather, emulated with copies
+        for q in range(world):
+            if q != r:
+                lo, cnt = plan.slots(q)
+                for k in range(4):
+                    bufs[r][k][lo:lo + cnt].copy_(bufs[q][k][lo:lo + cnt])
+    torch.cuda.synchronize()
+    for r, c in enumerate(ranks):
+        c.update_finish_dev()
+        pose = c.read_pose()
+        assert c.ray_stage_info()["last_mode"] == 1
+        assert np.array_equal(c.get_weights(), single.get_weights())
+        assert np.array_equal(c.get_particles(), single.get_particles())
+        assert np.array_equal(pose, pose_single)
+        lo, cnt = plan.slots(r)
+        assert np.array_equal(c.range_steps()[lo:lo + cnt], single.range_steps()[lo:lo + cnt])
+    for c in ranks + [single]:
+        c.close()
