@@ -117,6 +117,11 @@ class ShardedFilter:
         # so all ranks hold identical particles
         self.ctx.init_pose(pose, normals_3n)
 
+    def init_global(self):
+        """initialize_global (src/particle_filter.cpp:401-446) with the device RNG: keyed by the
+        global slot, so every rank holds the same particles."""
+        self.ctx.init_global()
+
     def _tensor(self, ptr: int, n: int):
         t = self._alias.get(ptr)
         if t is None:
