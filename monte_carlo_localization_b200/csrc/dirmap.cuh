@@ -153,10 +153,11 @@ MCL_HD DirWindow dir_window(const DirSector& sc, int box_x0, int box_y0, int box
     int y1 = box_y0 + box + sc.eyh;
     y1 = y1 > PH ? PH : y1;
     DirWindow w;
-    w.wx0 = x0;
-    w.wy0 = y0;
+    w.wx0 = x0 < PW ? x0 : PW;
+    w.wy0 = y0 < PH ? y0 : PH;
     w.pitch = x1 > x0 ? x1 - x0 : 0;
     w.rows = y1 > y0 ? y1 - y0 : 0;
+    if (w.pitch == 0 || w.rows == 0) w.pitch = w.rows = 0;   // the box lies beside the grid: no particle uses the window
     return w;
 }
 

@@ -144,6 +144,32 @@ long long emu_range_steps(const emu_map* m, const double* px, const double* py, 
     return replays;
 }
 
+// Host-side helpers of the directional stage, exposed for property tests.
+int emu_dir_constants(int* sectors, double* margin) {
+    *sectors = kDirSectors;
+    *margin = kDirMargin;
+    return kDirMinBuckets;
+}
+int emu_dir_sector(double theta, float alpha, int B) {
+    int shift = 0;
+    while ((B >> shift) > kDirSectors) ++shift;
+    return dir_sector_of(theta_bucket(theta, B), dir_beam_offset(alpha, B), B - 1, shift);
+}
+// window geometry for a box at (bx0, by0): out = wx0, wy0, pitch, rows per sector; returns the box side
+// dir_choose_box picks for `capacity` bytes
+int emu_dir_windows(emu_map* m, int bx0, int by0, long long capacity, int* out) {
+    emu_dir_sector(m, 0);
+    const int box = dir_choose_box(m->sectors, static_cast<size_t>(capacity));
+    for (int s = 0; s < kDirSectors; ++s) {
+        const DirWindow w = dir_window(m->sectors[s], bx0, by0, box, m->skip.PW, m->skip.PH);
+        out[4 * s + 0] = w.wx0;
+        out[4 * s + 1] = w.wy0;
+        out[4 * s + 2] = w.pitch;
+        out[4 * s + 3] = w.rows;
+    }
+    return box;
+}
+
 // One sector's directional map (PH*PW bytes), as the build kernel writes it.
 void emu_dir_map(emu_map* m, int sector, uint8_t* out) {
     const std::vector<uint8_t>& d = emu_dir_sector(m, sector);

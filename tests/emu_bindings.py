@@ -30,6 +30,9 @@ def lib():
             C.c_longlong, C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
             C.POINTER(C.c_uint8), C.POINTER(C.c_longlong)]
         L.emu_dir_map.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint8)]
+        L.emu_dir_constants.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_double)]
+        L.emu_dir_sector.argtypes = [C.c_double, C.c_float, C.c_int]
+        L.emu_dir_windows.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.POINTER(C.c_int)]
         L.emu_range_steps_dir.restype = C.c_longlong
         L.emu_range_steps_dir.argtypes = [C.c_void_p] + [C.POINTER(C.c_double)] * 3 + [
             C.c_longlong, C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.c_int,
@@ -106,6 +109,22 @@ class EmuMap:
                                         out.ctypes.data_as(C.POINTER(C.c_uint8)),
                                         None if lk is None else lk.ctypes.data_as(C.POINTER(C.c_int32)))
         return (out, int(rep), lk) if want_lookups else (out, int(rep))
+
+
+def dir_constants():
+    s, m = C.c_int(0), C.c_double(0)
+    min_buckets = lib().emu_dir_constants(C.byref(s), C.byref(m))
+    return s.value, m.value, min_buckets
+
+
+def dir_sector(theta, alpha, buckets):
+    return lib().emu_dir_sector(float(theta), C.c_float(float(alpha)), int(buckets))
+
+
+def dir_windows(em, bx0, by0, capacity):
+    out = np.zeros(4 * 32, dtype=np.int32)
+    box = lib().emu_dir_windows(em._h, int(bx0), int(by0), int(capacity), out.ctypes.data_as(C.POINTER(C.c_int)))
+    return box, out.reshape(32, 4)
 
 
 def exact_scan(src, div=None, want_prefix=True, force_last_one=False):

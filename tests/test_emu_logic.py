@@ -195,3 +195,43 @@ def test_directional_codes_respect_their_promise():
             sx = np.floor(px[None, :] + t * np.cos(a)[None, :]).astype(int)
             sy = np.floor(py[None, :] + t * np.sin(a)[None, :]).astype(int)
             assert (v8[sy, sx] != 0).all(), (s, cx, cy, adv)
+
+
+def test_sector_of_a_ray_contains_its_direction():
+    """Host arithmetic of the directional stage: the sector chosen from (heading bucket, beam)
+    by integer arithmetic contains the ray's real direction up to the map's validity margin, for
+    every admissible bucket count, headings on the +-pi seam and arbitrary beam tables."""
+    from emu_bindings import dir_constants, dir_sector
+    S, margin, min_buckets = dir_constants()
+    assert S == 32 and min_buckets == 2048
+    width = 2 * np.pi / S
+    rng = np.random.default_rng(21)
+    thetas = np.concatenate([rng.uniform(-np.pi, np.pi, 4000), [np.pi, -np.pi, 0.0, np.nextafter(np.pi, 0), -np.nextafter(np.pi, 0)],
+                             (np.arange(64) - 32) * (2 * np.pi / 64)])
+    alphas = np.concatenate([synth.beam_angles(), rng.uniform(-3.2, 3.2, 40).astype(np.float32), np.float32([0.0, 3.1415927, -3.1415927])])
+    for B in (2048, 4096):
+        worst = 0.0
+        for th in thetas:
+            for al in alphas[rng.integers(0, len(alphas), 12)]:
+                s = dir_sector(th, al, B)
+                a = (th + float(al)) % (2 * np.pi)
+                lo, hi = s * width, (s + 1) * width
+                # cyclic distance of a to the interval [lo, hi]
+                d = 0.0 if lo <= a <= hi else min(abs(a - lo), abs(a - hi), abs(a - lo - 2 * np.pi), abs(a - hi + 2 * np.pi),
+                                                  abs(a - lo + 2 * np.pi), abs(a - hi - 2 * np.pi))
+                worst = max(worst, d)
+        assert worst <= np.pi / B + 1e-9 < margin, (B, worst)
+
+
+def test_sector_windows_fit_shared_memory_and_stay_inside_the_grid():
+    from emu_bindings import dir_windows
+    for name in ("sibal1", "Spielberg_map", "basement_fixed"):
+        em = EmuMap(maps.load_named_map(name))
+        cap = 112 * 1024
+        for bx0, by0 in ((-500, -500), (0, 0), (em.PW // 2, em.PH // 2), (em.PW - 30, em.PH - 30), (em.PW + 400, 7)):
+            box, w = dir_windows(em, bx0, by0, cap)
+            assert box >= 64 and box % 16 == 0
+            assert (w[:, 2] * w[:, 3] <= cap).all()
+            assert (w[:, 0] % 16 == 0).all() and (w[:, 2] % 16 == 0).all()
+            assert (w[:, 0] >= 0).all() and (w[:, 1] >= 0).all()
+            assert (w[:, 0] + w[:, 2] <= em.PW).all() and (w[:, 1] + w[:, 3] <= em.PH).all()
