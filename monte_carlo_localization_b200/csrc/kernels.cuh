@@ -888,6 +888,7 @@ struct NormArgs {
     int nblk;
     unsigned int* done;       // [F] block-completion counters (zero on entry, reset on exit) or nullptr
     double* pose_out;         // [F][3]: written by the last block to finish when `done` is given
+    double* pose_host;        // same values into mapped pinned host memory (nullable): saves the D2H copy
 };
 constexpr int kNormThreads = 256;
 
@@ -941,9 +942,15 @@ __global__ void __launch_bounds__(kNormThreads) k_normalize_pose(NormArgs a) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) v[q] = block_sum<kNormThreads>(v[q], sm);
     if (threadIdx.x == 0) {
+        const double th = atan2(v[2], v[3]);
         a.pose_out[3 * f + 0] = v[0];
         a.pose_out[3 * f + 1] = v[1];
-        a.pose_out[3 * f + 2] = atan2(v[2], v[3]);
+        a.pose_out[3 * f + 2] = th;
+        if (a.pose_host) {
+            a.pose_host[3 * f + 0] = v[0];
+            a.pose_host[3 * f + 1] = v[1];
+            a.pose_host[3 * f + 2] = th;
+        }
         a.done[f] = 0;
     }
 }
@@ -974,7 +981,7 @@ __global__ void k_normalize_only(const double* w_raw, const double* total, doubl
 }
 
 // pose from the gathered per-rank partial sums (rank order => identical on every rank)
-__global__ void k_pose_from_partials(const double* partials, int world, const double* total, double* pose_out) {
+__global__ void k_pose_from_partials(const double* partials, int world, const double* total, double* pose_out, double* pose_host) {
     if (threadIdx.x || blockIdx.x) return;
     double v[4] = {0, 0, 0, 0};
     for (int q = 0; q < world; ++q)
@@ -984,6 +991,11 @@ __global__ void k_pose_from_partials(const double* partials, int world, const do
     pose_out[0] = v[0] / s;
     pose_out[1] = v[1] / s;
     pose_out[2] = atan2(v[2], v[3]);
+    if (pose_host) {
+        pose_host[0] = pose_out[0];
+        pose_host[1] = pose_out[1];
+        pose_host[2] = pose_out[2];
+    }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -143,9 +143,12 @@ struct mcl_ctx {
     // w_raw with w_norm = w_raw / S1 (rescaled on the fly for the approximate prefix)
     int tile_state = 0;
     // pinned staging for the host-facing update
+    // pinned staging of the host-facing update: [F][3] doubles of action followed by [F][R] floats of
+    // scan in ONE buffer (one H2D copy per update); d_action / d_obs alias the device twin
     double* h_action = nullptr;
     float* h_obs = nullptr;
     double* h_pose = nullptr;
+    double* d_pose_mapped = nullptr;   // device alias of h_pose (mapped pinned memory): the pose kernel writes it directly
     uint64_t update_no = 0, init_no = 0;
     int64_t launches = 0;
     bool profiling = false;
@@ -262,7 +265,6 @@ int ensure_slice(mcl_ctx* c) {
         CK(dalloc(&c->d_slice, need));
         c->slice_elems = need;
     }
-    if (!c->d_obs) CK(dalloc(&c->d_obs, static_cast<size_t>(c->F) * kMaxBeams));
     return MCL_OK;
 }
 
@@ -380,6 +382,7 @@ int launch_pose(mcl_ctx* c, const double* w, const double* total, double* wn_out
     na.nblk = c->norm_blocks;
     na.done = c->d_done;
     na.pose_out = c->d_pose;
+    na.pose_host = c->d_pose_mapped;
     k_normalize_pose<<<dim3(c->norm_blocks, c->F), kNormThreads, 0, c->stream>>>(na);
     c->launches += 1;
     CK(cudaGetLastError());
@@ -633,7 +636,7 @@ int update_finish(mcl_ctx* c) {
         // poses of other ranks are not local: normalise all weights, pose from the gathered partials
         const int64_t n = c->N;
         k_normalize_only<<<static_cast<unsigned>((n + 255) / 256), 256, 0, c->stream>>>(c->d_wraw, c->d_S1, c->d_wn, n);
-        k_pose_from_partials<<<1, 32, 0, c->stream>>>(c->d_partials, c->world, c->d_S1, c->d_pose);
+        k_pose_from_partials<<<1, 32, 0, c->stream>>>(c->d_partials, c->world, c->d_S1, c->d_pose, c->d_pose_mapped);
         c->launches += 2;
     } else {
         rc = launch_pose(c, c->d_wraw, c->d_S1, c->d_wn, dst);
@@ -772,10 +775,18 @@ static int create_buffers(mcl_ctx* c, const mcl_params* p, int device) {
     }
     CK(dalloc(&c->d_replays, size_t{1}));
     CK(cudaMemset(c->d_replays, 0, sizeof(int64_t)));
-    CK(dalloc(&c->d_action, static_cast<size_t>(c->F) * 3));
-    CK(cudaMallocHost(reinterpret_cast<void**>(&c->h_action), sizeof(double) * 3 * c->F));
-    CK(cudaMallocHost(reinterpret_cast<void**>(&c->h_obs), sizeof(float) * kMaxBeams * c->F));
-    CK(cudaMallocHost(reinterpret_cast<void**>(&c->h_pose), sizeof(double) * 3 * c->F));
+    {
+        const size_t in_bytes = sizeof(double) * 3 * c->F + sizeof(float) * kMaxBeams * c->F;
+        void* d_in = nullptr;
+        CK(cudaMalloc(&d_in, in_bytes));
+        c->d_action = static_cast<double*>(d_in);
+        c->d_obs = reinterpret_cast<float*>(c->d_action + 3 * c->F);
+        CK(cudaMallocHost(reinterpret_cast<void**>(&c->h_action), in_bytes));
+        c->h_obs = reinterpret_cast<float*>(c->h_action + 3 * c->F);
+        CK(cudaHostAlloc(reinterpret_cast<void**>(&c->h_pose), sizeof(double) * 3 * c->F, cudaHostAllocMapped));
+        std::memset(c->h_pose, 0, sizeof(double) * 3 * c->F);
+        CK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->d_pose_mapped), c->h_pose, 0));
+    }
 #define MCL_RAY_SMEM(WB, MCV) \
     CK(cudaFuncSetAttribute(k_raycast_weight<WB, MCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kWindowBudget)))
     MCL_RAY_SMEM(8, 0);
@@ -826,7 +837,7 @@ int mcl_destroy(mcl_ctx* c) {
     cudaDeviceSynchronize();
     void* ptrs[] = {c->d_grid, c->d_v8, c->d_v4, c->d_free, c->d_tabT, c->d_step2idx, c->d_px[0], c->d_px[1], c->d_py[0],
                     c->d_py[1], c->d_pt[0], c->d_pt[1], c->d_wraw, c->d_wn, c->d_cdf, c->d_idx, c->d_steps, c->d_u, c->d_z,
-                    c->d_action, c->d_obs, c->d_slice, c->d_tile_sum, c->d_chunk_fn, c->d_opq_pre, c->d_opq_idx,
+                    c->d_action, c->d_slice, c->d_tile_sum, c->d_chunk_fn, c->d_opq_pre, c->d_opq_idx,
                     c->d_tile_opq, c->d_tile_elem, c->d_list_chunk, c->d_list_fn, c->d_anchors, c->d_anchor_val,
                     c->d_tile_start, c->d_S1, c->d_S2, c->d_scratch_total, c->d_partial, c->d_pose, c->d_centre, c->d_replays,
                     c->d_hist, c->d_perm, c->d_done};
@@ -837,7 +848,6 @@ int mcl_destroy(mcl_ctx* c) {
     if (c->d_peer_tab) cudaFree(c->d_peer_tab);
     if (c->d_partials) cudaFree(c->d_partials);
     if (c->h_action) cudaFreeHost(c->h_action);
-    if (c->h_obs) cudaFreeHost(c->h_obs);
     if (c->h_pose) cudaFreeHost(c->h_pose);
     for (auto& e : c->ev)
         if (e) cudaEventDestroy(e);
@@ -1174,8 +1184,7 @@ int mcl_update(mcl_ctx* c, const double* action, const float* obs, int num_beams
     cudaStream_t s = c->stream;
     std::memcpy(c->h_action, action, sizeof(double) * 3 * c->F);
     std::memcpy(c->h_obs, obs, sizeof(float) * c->R * c->F);
-    CK(cudaMemcpyAsync(c->d_action, c->h_action, sizeof(double) * 3 * c->F, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(c->d_obs, c->h_obs, sizeof(float) * c->R * c->F, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(c->d_action, c->h_action, sizeof(double) * 3 * c->F + sizeof(float) * c->R * c->F, cudaMemcpyHostToDevice, s));
     const double* u_dev = nullptr;
     const double* z_dev = nullptr;
     if (noise) {
@@ -1203,7 +1212,7 @@ int mcl_update(mcl_ctx* c, const double* action, const float* obs, int num_beams
     }
     int rc = update_device(c, c->d_action, c->d_obs, u_dev, z_dev);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(c->h_pose, c->d_pose, sizeof(double) * 3 * c->F, cudaMemcpyDeviceToHost, s));
+    // the pose kernel has written the pose into h_pose (mapped pinned memory): no D2H copy call
     CK(cudaStreamSynchronize(s));
     if (pose_out) std::memcpy(pose_out, c->h_pose, sizeof(double) * 3 * c->F);
     if (c->profiling) {
