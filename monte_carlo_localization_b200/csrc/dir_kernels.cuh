@@ -306,6 +306,8 @@ __global__ void __launch_bounds__(kDirThreads, 1) k_raycast_dir(DirRayArgs a) {
     }
     const int64_t ncell = static_cast<int64_t>(mp.PW) * mp.PH;
     const int K = a.B >> 5, Bmask = a.B - 1;
+    const uint32_t io_r0 = static_cast<uint32_t>(pin_reg(lane < R ? a.io[lane] : 0));
+    const uint32_t io_r1 = static_cast<uint32_t>(pin_reg(lane + 32 < R ? a.io[lane + 32] : 0));
     uint32_t phase = 0;
     unsigned seen = 0;
     int cur_s = -1, replays = 0;
@@ -403,8 +405,13 @@ __global__ void __launch_bounds__(kDirThreads, 1) k_raycast_dir(DirRayArgs a) {
             for (int jb = 0; jb < R; jb += 32) {
                 const int jl = jb + lane;
                 // the warp's buckets shifted by the beam's offset: [start, start + len) cyclically; sector s = [0, K)
-                uint32_t io_l;   // s_io[jl] (entries beyond R are 0 and masked below); plain LDS from a register address
-                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(io_l) : "r"(io_saddr + static_cast<uint32_t>(jb * 4)));
+                uint32_t io_l;   // io[jl]: beams 0..63 live in two registers per lane, the rest in shared memory
+                if (jb == 0)
+                    io_l = io_r0;
+                else if (jb == 32)
+                    io_l = io_r1;
+                else
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(io_l) : "r"(io_saddr + static_cast<uint32_t>(jb * 4)));
                 const int start = (bmin + static_cast<int>(io_l) - s * K) & Bmask;
                 unsigned mask = __ballot_sync(kFullMask, jl < R && (start < K || start + (bmax - bmin) >= a.B));
                 while (mask) {

@@ -709,10 +709,20 @@ struct ObsArgs {
     double* slice;             // [F][R][M+1]  slice[j][r] = table(obs_idx_j, range_idx(r))
     int R, M;
     double res;
+    double* centre;            // [F][2] cleared here for k_resample_motion's sums
+    int* hist;                 // [nhist] heading histogram + scatter cursors, cleared here (nullable)
+    int nhist;
 };
 
 __global__ void k_prepare_obs(ObsArgs a) {
     const int j = blockIdx.x, f = blockIdx.y;
+    {   // per-update accumulators: cleared by the whole grid, ahead of the kernels that add to them
+        const int nthreads = gridDim.x * gridDim.y * blockDim.x;
+        const int gtid = (blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+        if (a.hist)
+            for (int i = gtid; i < a.nhist; i += nthreads) a.hist[i] = 0;
+        if (gtid < 2 * static_cast<int>(gridDim.y)) a.centre[gtid] = 0.0;
+    }
     // obs_px = obs / res, clamp, round (:549-554, :570, :573)
     float opx = static_cast<float>(static_cast<double>(a.obs[f * a.R + j]) / a.res);
     if (opx > static_cast<float>(a.M)) opx = static_cast<float>(a.M);

@@ -413,8 +413,6 @@ int update_local(mcl_ctx* c, const double* action_dev, const float* obs_dev, con
     cudaStream_t s = c->stream;
     if (c->profiling) CK(cudaEventRecord(c->ev[0], s));
 
-    CK(cudaMemsetAsync(c->d_centre, 0, sizeof(double) * 2 * c->F, s));
-    if (c->sort_enabled) CK(cudaMemsetAsync(c->d_hist, 0, sizeof(int) * 2 * c->B * c->F, s));
     ObsArgs oa{};
     oa.obs = obs_dev;
     oa.tabT = c->d_tabT;
@@ -423,6 +421,10 @@ int update_local(mcl_ctx* c, const double* action_dev, const float* obs_dev, con
     oa.R = c->R;
     oa.M = c->M;
     oa.res = c->res;
+    // the same launch clears the per-update accumulators (cloud centre, heading histogram + cursors)
+    oa.centre = c->d_centre;
+    oa.hist = c->sort_enabled ? c->d_hist : nullptr;
+    oa.nhist = 2 * c->B * c->F;
     k_prepare_obs<<<dim3(c->R, c->F), 256, 0, s>>>(oa);
     c->launches++;
 
