@@ -4,6 +4,7 @@ functional checks) on the GPU box and print one JSON summary per config.
 
   config 1  sibal1, 4000 particles, single update (parity is in tests/test_gpu_parity.py)
   config 2  levine stand-in (basement_fixed), 100k particles, 1000-step replay, 1 GPU
+  config 2s the same on the procedural levine stand-in (maps.synth_levine)
   config 4  1024 independent 4000-particle filters on sibal1 (one GPU's share of the batch
             is 128 filters; run at 1024 here to show the whole batch on one B200)
   config 5  global initialisation on the levine stand-in: particles uniform over free space,
@@ -58,8 +59,10 @@ def config1():
             "updates_per_s": 200 / sec, "rays_per_s": 4000 * 60 * 200 / sec, "median_pose_err_m": float(np.median(errs))}
 
 
-def config2(steps=1000, ray_mode=0):
-    g = maps.load_named_map("basement_fixed")
+def config2(steps=1000, ray_mode=0, levine_synth=False):
+    # levine.pgm is missing from the reference checkout: two stand-ins, the shipped
+    # basement_fixed map and a procedural corridor loop honouring maps/levine.yaml
+    g = maps.synth_levine() if levine_synth else maps.load_named_map("basement_fixed")
     N = 100000
     ctx = MclContext(max_particles=N, seed=20252)
     ctx.set_map(g)
@@ -69,7 +72,8 @@ def config2(steps=1000, ray_mode=0):
     ctx.init_pose(gt[0])
     timed_updates(ctx, actions, obs, gt, 20)
     sec, errs = timed_updates(ctx, actions[20:], obs[20:], gt[20:], steps)
-    return {"config": 2, "map": "basement_fixed (levine stand-in: levine.pgm is missing from the reference checkout)",
+    return {"config": 2, "map": ("levine_synth (procedural stand-in honouring maps/levine.yaml)" if levine_synth else
+                                 "basement_fixed (levine stand-in: levine.pgm is missing from the reference checkout)"),
             "particles": N, "beams": 60, "updates": steps, "ms_per_update": 1e3 * sec / steps, "updates_per_s": steps / sec,
             "rays_per_s": N * 60 * steps / sec, "median_pose_err_m": float(np.median(errs)),
             "max_pose_err_m": float(np.max(errs)), "ray_mode": ray_mode, "ray_stage": ctx.ray_stage_info()}
@@ -140,7 +144,9 @@ if __name__ == "__main__":
     ap.add_argument("--ray-mode", type=int, default=0, help="0 auto, 1 isotropic kernel only, 2 directional stage always")
     a = ap.parse_args()
     for c in a.configs.split(","):
-        if c == "1":
+        if c == "2s":
+            print(json.dumps(config2(a.steps2, a.ray_mode, levine_synth=True)))
+        elif c == "1":
             print(json.dumps(config1()))
         elif c == "2":
             print(json.dumps(config2(a.steps2, a.ray_mode)))
