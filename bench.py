@@ -365,13 +365,23 @@ def run_gpu(args):
             # cells the reference samples (1 B each) + ray-start record read + step/weight write
             alg_bytes = N * R * cbar + (N * R * 1 + N * 32 * 2 if directional else N * (24 + 8))
             ach = alg_bytes / (k_ms * 1e-3) / 1e9
-            traffic = None
+            traffic, issue = None, None
             tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
             if os.path.exists(tp):
                 try:
-                    traffic = json.load(open(tp)).get(kname + "_dram_bytes_per_launch")
+                    prof = json.load(open(tp))
+                    traffic = prof.get(kname + "_dram_bytes_per_launch")
+                    # what actually bounds the kernel: warp-instruction issue.  Instructions per launch from the
+                    # committed ncu capture of this workload, time measured live, peak = 4 schedulers x SMs x clock
+                    winst = prof.get(kname + "_warp_instructions_per_launch")
+                    if winst and clocks.get("sm_mhz"):
+                        sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+                        peak_issue = 4.0 * sms * clocks["sm_mhz"] * 1e6
+                        issue = {"warp_instructions_per_launch": winst, "source": "profiles/ncu_traffic.json (ncu capture)",
+                                 "achieved_per_s": winst / (k_ms * 1e-3), "peak_per_s": peak_issue,
+                                 "frac": winst / (k_ms * 1e-3) / peak_issue}
                 except Exception:
-                    traffic = None
+                    traffic, issue = None, None
             # gather-rate context for the same kernel: random byte reads/s the chip sustains from a
             # shared-memory window and from a 4 MB L2-resident array
             from monte_carlo_localization_b200 import capi as _capi
@@ -379,7 +389,7 @@ def run_gpu(args):
                       "l2_4mb_peak_per_s": _capi.microbench_gather(False, device=local_rank),
                       "reference_samples_per_s": N * R * cbar / (k_ms * 1e-3)}
             roof = {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peak, "unit": "GB/s",
-                    "gather": gather,
+                    "gather": gather, "issue": issue,
                     "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg_bytes, "mean_cells_per_ray": cbar,
                     "kernel_ms": k_ms,

@@ -85,6 +85,7 @@ SIGNATURES = {
     "mcl_set_keep_ranges": (C.c_int, [C.c_void_p, C.c_int]),
     "mcl_kernel_launches": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "mcl_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mcl_set_graphs": (C.c_int, [C.c_void_p, C.c_int]),
     "mcl_set_ray_mode": (C.c_int, [C.c_void_p, C.c_int]),
     "mcl_ray_stage_info": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_int)] * 4),
     "mcl_get_dir_map": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_uint8), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
@@ -337,6 +338,10 @@ class MclContext:
 
     def set_keep_ranges(self, on: bool):
         self._check(self._L.mcl_set_keep_ranges(self._h, int(on)), "mcl_set_keep_ranges")
+
+    def set_graphs(self, on: bool):
+        """CUDA-graph replay of the steady-state host-facing update (default on)."""
+        self._check(self._L.mcl_set_graphs(self._h, int(on)), "mcl_set_graphs")
 
     def set_ray_mode(self, mode: int):
         """0 auto, 1 isotropic skip-map kernel only, 2 directional stage always."""

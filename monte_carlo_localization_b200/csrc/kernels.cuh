@@ -438,7 +438,7 @@ struct MotionArgs {
     const double* action;     // [F][3] device
     double disp_x, disp_y, disp_t;
     uint64_t seed;
-    uint64_t update_no;
+    const unsigned long long* update_no;   // device counter of completed updates (keys the Philox stream)
     double* centre;           // [F][2] accumulators (sum x, sum y)
     // directional ray stage (dir_kernels.cuh): ray-start records in slot order, or nullptr;
     // the heading sort's scatter pass moves them to their sorted slots
@@ -499,6 +499,7 @@ __global__ void __launch_bounds__(kMotionThreads) k_resample_motion(MotionArgs a
     const int64_t N = a.N;
     const int64_t fo = static_cast<int64_t>(f) * N;
     const MotionScalars m = motion_scalars(a.action[3 * f + 0], a.action[3 * f + 2]);
+    const uint64_t update_no = *a.update_no;
     double nx = 0.0, ny = 0.0;
     if (li < a.cnt) {
         // noise: injected arrays in the reference's draw order, else Philox keyed by
@@ -508,11 +509,11 @@ __global__ void __launch_bounds__(kMotionThreads) k_resample_motion(MotionArgs a
         const bool need_rng = (a.u == nullptr) || (a.z == nullptr);
         if (need_rng) {
             r0 = philox4x32_10(static_cast<uint32_t>(i), static_cast<uint32_t>(i >> 32), static_cast<uint32_t>(f), 0u,
-                               static_cast<uint32_t>(a.seed) ^ static_cast<uint32_t>(a.update_no),
-                               static_cast<uint32_t>(a.seed >> 32) ^ static_cast<uint32_t>(a.update_no >> 32) ^ 0x5bd1e995u);
+                               static_cast<uint32_t>(a.seed) ^ static_cast<uint32_t>(update_no),
+                               static_cast<uint32_t>(a.seed >> 32) ^ static_cast<uint32_t>(update_no >> 32) ^ 0x5bd1e995u);
             r1 = philox4x32_10(static_cast<uint32_t>(i), static_cast<uint32_t>(i >> 32), static_cast<uint32_t>(f), 1u,
-                               static_cast<uint32_t>(a.seed) ^ static_cast<uint32_t>(a.update_no),
-                               static_cast<uint32_t>(a.seed >> 32) ^ static_cast<uint32_t>(a.update_no >> 32) ^ 0x5bd1e995u);
+                               static_cast<uint32_t>(a.seed) ^ static_cast<uint32_t>(update_no),
+                               static_cast<uint32_t>(a.seed >> 32) ^ static_cast<uint32_t>(update_no >> 32) ^ 0x5bd1e995u);
         }
         u = a.u ? a.u[fo + i] : canonical_from_words(r0.v[0], r0.v[1]);
         if (a.z) {
@@ -899,6 +900,7 @@ struct NormArgs {
     unsigned int* done;       // [F] block-completion counters (zero on entry, reset on exit) or nullptr
     double* pose_out;         // [F][3]: written by the last block to finish when `done` is given
     double* pose_host;        // same values into mapped pinned host memory (nullable): saves the D2H copy
+    unsigned long long* update_no;   // incremented once when the update's pose is written (nullable)
 };
 constexpr int kNormThreads = 256;
 
@@ -962,6 +964,7 @@ __global__ void __launch_bounds__(kNormThreads) k_normalize_pose(NormArgs a) {
             a.pose_host[3 * f + 2] = th;
         }
         a.done[f] = 0;
+        if (a.update_no && f == 0) *a.update_no += 1ull;   // this update is complete: the next one draws fresh noise
     }
 }
 
@@ -991,7 +994,8 @@ __global__ void k_normalize_only(const double* w_raw, const double* total, doubl
 }
 
 // pose from the gathered per-rank partial sums (rank order => identical on every rank)
-__global__ void k_pose_from_partials(const double* partials, int world, const double* total, double* pose_out, double* pose_host) {
+__global__ void k_pose_from_partials(const double* partials, int world, const double* total, double* pose_out, double* pose_host,
+                                     unsigned long long* update_no) {
     if (threadIdx.x || blockIdx.x) return;
     double v[4] = {0, 0, 0, 0};
     for (int q = 0; q < world; ++q)
@@ -1006,6 +1010,7 @@ __global__ void k_pose_from_partials(const double* partials, int world, const do
         pose_host[1] = pose_out[1];
         pose_host[2] = pose_out[2];
     }
+    *update_no += 1ull;
 }
 
 // ------------------------------------------------------------------------------------------

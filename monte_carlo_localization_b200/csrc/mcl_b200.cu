@@ -150,6 +150,11 @@ struct mcl_ctx {
     double* h_pose = nullptr;
     double* d_pose_mapped = nullptr;   // device alias of h_pose (mapped pinned memory): the pose kernel writes it directly
     uint64_t update_no = 0, init_no = 0;
+    unsigned long long* d_update_no = nullptr;   // device twin of update_no, read by k_resample_motion
+    // CUDA graphs of the steady-state host-facing update, one per state-buffer parity
+    bool graphs_enabled = true;
+    cudaGraphExec_t gexec[2] = {nullptr, nullptr};
+    int64_t graph_launches = 0;
     int64_t launches = 0;
     bool profiling = false;
     cudaEvent_t ev[6] = {};
@@ -158,6 +163,15 @@ struct mcl_ctx {
 };
 
 namespace {
+
+// the captured update graphs bake in buffer pointers, launch shapes and the stream's kernels:
+// every setter that can change one of them drops the graphs (they are re-captured on demand)
+void drop_graphs(mcl_ctx* c) {
+    for (auto& g : c->gexec) {
+        if (g) cudaGraphExecDestroy(g);
+        g = nullptr;
+    }
+}
 
 ExactArgs exact_args(mcl_ctx* c, const double* src, const double* div, const double* approx_div, double* total,
                      double* out, int force_one) {
@@ -244,6 +258,7 @@ void build_sensor_table(const mcl_ctx* c, std::vector<double>& tab) {
 }
 
 int upload_table(mcl_ctx* c) {
+    drop_graphs(c);
     const int tw = c->M + 1;
     std::vector<double> tabT(static_cast<size_t>(tw) * tw);
     for (int d = 0; d < tw; ++d)
@@ -257,6 +272,7 @@ int upload_table(mcl_ctx* c) {
 }
 
 int ensure_slice(mcl_ctx* c) {
+    drop_graphs(c);
     if (!c->have_map || !c->have_beams) return MCL_OK;
     const size_t need = static_cast<size_t>(c->F) * c->R * (c->M + 1);
     if (need > c->slice_elems) {
@@ -271,6 +287,7 @@ int ensure_slice(mcl_ctx* c) {
 constexpr size_t kDirWindowBudget = 112 * 1024;   // one sector window (half of shared memory: room to double-buffer)
 
 void free_dir(mcl_ctx* c) {
+    drop_graphs(c);
     for (void* p : {static_cast<void*>(c->d_dirmaps), static_cast<void*>(c->d_sectors), static_cast<void*>(c->d_sec_tab), static_cast<void*>(c->d_replay_ctx),
                     static_cast<void*>(c->d_rec),
                     static_cast<void*>(c->d_plan), static_cast<void*>(c->d_steps_sorted)})
@@ -369,7 +386,7 @@ int check_filter(const mcl_ctx* c, int filter, bool allow_all) {
     return MCL_OK;
 }
 
-int launch_pose(mcl_ctx* c, const double* w, const double* total, double* wn_out, int buf) {
+int launch_pose(mcl_ctx* c, const double* w, const double* total, double* wn_out, int buf, bool count_update) {
     NormArgs na{};
     na.N = c->N;
     na.w_raw = w;
@@ -383,6 +400,7 @@ int launch_pose(mcl_ctx* c, const double* w, const double* total, double* wn_out
     na.done = c->d_done;
     na.pose_out = c->d_pose;
     na.pose_host = c->d_pose_mapped;
+    na.update_no = count_update ? c->d_update_no : nullptr;
     k_normalize_pose<<<dim3(c->norm_blocks, c->F), kNormThreads, 0, c->stream>>>(na);
     c->launches += 1;
     CK(cudaGetLastError());
@@ -463,7 +481,7 @@ int update_local(mcl_ctx* c, const double* action_dev, const float* obs_dev, con
     ma.disp_y = c->prm.motion_dispersion_y;
     ma.disp_t = c->prm.motion_dispersion_theta;
     ma.seed = c->prm.seed;
-    ma.update_no = c->update_no;
+    ma.update_no = c->d_update_no;
     ma.centre = c->d_centre;
     const int mblocks = static_cast<int>((c->cnt + kMotionThreads - 1) / kMotionThreads);
     const size_t msmem = (c->T > 1 && c->T <= kMaxSearchTiles) ? sizeof(double) * c->T : 0;
@@ -638,10 +656,10 @@ int update_finish(mcl_ctx* c) {
         // poses of other ranks are not local: normalise all weights, pose from the gathered partials
         const int64_t n = c->N;
         k_normalize_only<<<static_cast<unsigned>((n + 255) / 256), 256, 0, c->stream>>>(c->d_wraw, c->d_S1, c->d_wn, n);
-        k_pose_from_partials<<<1, 32, 0, c->stream>>>(c->d_partials, c->world, c->d_S1, c->d_pose, c->d_pose_mapped);
+        k_pose_from_partials<<<1, 32, 0, c->stream>>>(c->d_partials, c->world, c->d_S1, c->d_pose, c->d_pose_mapped, c->d_update_no);
         c->launches += 2;
     } else {
-        rc = launch_pose(c, c->d_wraw, c->d_S1, c->d_wn, dst);
+        rc = launch_pose(c, c->d_wraw, c->d_S1, c->d_wn, dst, true);
         if (rc) return rc;
     }
     if (c->profiling) CK(cudaEventRecord(c->ev[4], c->stream));
@@ -775,6 +793,8 @@ static int create_buffers(mcl_ctx* c, const mcl_params* p, int device) {
         CK(dalloc(&c->d_hist, static_cast<size_t>(2) * B * c->F));
         CK(dalloc(&c->d_perm, FN));
     }
+    CK(dalloc(&c->d_update_no, size_t{1}));
+    CK(cudaMemset(c->d_update_no, 0, sizeof(unsigned long long)));
     CK(dalloc(&c->d_replays, size_t{1}));
     CK(cudaMemset(c->d_replays, 0, sizeof(int64_t)));
     {
@@ -846,6 +866,8 @@ int mcl_destroy(mcl_ctx* c) {
     for (void* p : ptrs)
         if (p) cudaFree(p);
     free_dir(c);
+    drop_graphs(c);
+    if (c->d_update_no) cudaFree(c->d_update_no);
     for (void* p : c->ipc_opened) cudaIpcCloseMemHandle(p);
     if (c->d_peer_tab) cudaFree(c->d_peer_tab);
     if (c->d_partials) cudaFree(c->d_partials);
@@ -1212,7 +1234,42 @@ int mcl_update(mcl_ctx* c, const double* action, const float* obs, int num_beams
             z_dev = c->d_z;
         }
     }
-    int rc = update_device(c, c->d_action, c->d_obs, u_dev, z_dev);
+    // Steady state (no injected noise, no diagnostics, whole filter on this GPU, weights untouched
+    // since the last update): the ~18 launches of an update are replayed as ONE CUDA graph.
+    const bool graph_ok = c->graphs_enabled && !noise && !c->profiling && !c->keep_ranges && !c->p2p && c->lo == 0 &&
+                          c->cnt == c->N && c->tile_state == 2 && !c->local_pending;
+    int rc = MCL_OK;
+    if (graph_ok && c->gexec[c->cur]) {
+        CK(cudaGraphLaunch(c->gexec[c->cur], s));
+        c->cur ^= 1;             // what update_device does on the host side
+        c->update_no++;
+        c->launches += c->graph_launches;
+    } else if (graph_ok && cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        const int parity = c->cur;
+        const int64_t before = c->launches;
+        rc = update_device(c, c->d_action, c->d_obs, nullptr, nullptr);
+        cudaGraph_t g = nullptr;
+        const cudaError_t e = cudaStreamEndCapture(s, &g);
+        if (rc == MCL_OK && e == cudaSuccess && g && cudaGraphInstantiate(&c->gexec[parity], g, 0) == cudaSuccess) {
+            c->graph_launches = c->launches - before;
+            cudaGraphDestroy(g);
+            CK(cudaGraphLaunch(c->gexec[parity], s));
+        } else {
+            // capture refused (e.g. an enclosing capture): run this update directly and stop trying
+            if (g) cudaGraphDestroy(g);
+            cudaGetLastError();
+            c->gexec[parity] = nullptr;
+            c->graphs_enabled = false;
+            if (rc != MCL_OK) return rc;
+            c->cur ^= 1;         // undo the host-side bookkeeping of the captured (never executed) update
+            c->update_no--;
+            c->launches = before;
+            rc = update_device(c, c->d_action, c->d_obs, nullptr, nullptr);
+        }
+    } else {
+        if (graph_ok) cudaGetLastError();
+        rc = update_device(c, c->d_action, c->d_obs, u_dev, z_dev);
+    }
     if (rc) return rc;
     // the pose kernel has written the pose into h_pose (mapped pinned memory): no D2H copy call
     CK(cudaStreamSynchronize(s));
@@ -1240,7 +1297,7 @@ int mcl_expected_pose(mcl_ctx* c, int filter, double pose_out[3]) {
     if (rc) return rc;
     if (!pose_out) return fail(MCL_ERR_INVALID, "null output");
     CK(cudaSetDevice(c->device));
-    rc = launch_pose(c, c->d_wn, nullptr, nullptr, c->cur);
+    rc = launch_pose(c, c->d_wn, nullptr, nullptr, c->cur, false);
     if (rc) return rc;
     CK(cudaMemcpyAsync(c->h_pose, c->d_pose, sizeof(double) * 3 * c->F, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -1335,6 +1392,7 @@ int mcl_set_shard(mcl_ctx* c, int64_t lo, int64_t count) {
     if (c->local_pending) return fail(MCL_ERR_INVALID, "update in flight");
     c->lo = lo;
     c->cnt = count;
+    drop_graphs(c);
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
     return upload_replay_ctx(c);
@@ -1500,6 +1558,15 @@ int mcl_microbench_gather(int device, int shared, size_t array_bytes, int iters_
     return MCL_OK;
 }
 
+int mcl_set_graphs(mcl_ctx* c, int enabled) {
+    if (!c) return fail(MCL_ERR_INVALID, "null context");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    c->graphs_enabled = enabled != 0;
+    drop_graphs(c);
+    return MCL_OK;
+}
+
 int mcl_set_ray_mode(mcl_ctx* c, int mode) {
     if (!c) return fail(MCL_ERR_INVALID, "null context");
     if (mode < 0 || mode > 2) return fail(MCL_ERR_INVALID, "ray mode %d not in {0 auto, 1 isotropic, 2 directional}", mode);
@@ -1507,6 +1574,7 @@ int mcl_set_ray_mode(mcl_ctx* c, int mode) {
         return fail(MCL_ERR_UNSUPPORTED, "the directional ray stage needs one filter of more than %d particles, a map and a beam table",
                     16 * (kDirMinBuckets / 2));
     c->ray_mode = mode;
+    drop_graphs(c);
     return MCL_OK;
 }
 
@@ -1545,6 +1613,7 @@ int mcl_set_stream(mcl_ctx* c, void* stream) {
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
     c->stream = stream ? static_cast<cudaStream_t>(stream) : c->own_stream;
+    drop_graphs(c);
     return MCL_OK;
 }
 

@@ -183,6 +183,7 @@ def dir_summary(rep, launches_csv, tag):
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     t = json.load(open(tp)) if os.path.exists(tp) else {}
     t["k_raycast_dir_dram_bytes_per_launch"] = dram
+    t["k_raycast_dir_warp_instructions_per_launch"] = float(vals["smsp__inst_executed.sum"][0].replace(",", ""))
     t["k_raycast_dir_source"] = "profiles/%s_ray_ncu.md (ncu --set full, one launch, 1M x 60 Spielberg)" % tag
     json.dump(t, open(tp, "w"))
     # launch list

@@ -662,3 +662,42 @@ def test_directional_stage_in_particle_shards():
         assert np.array_equal(c.range_steps()[lo:lo + cnt], single.range_steps()[lo:lo + cnt])
     for c in ranks + [single]:
         c.close()
+
+
+@pytest.mark.parametrize("name,N", [("sibal1", 4000), ("sibal1", 30000)])
+def test_graph_replay_equals_direct_launches(name, N):
+    """The host-facing update replays its steady state as a CUDA graph: particles, weights and
+    poses are bit-identical to the launch-by-launch path over a run of device-RNG updates,
+    including across a re-initialisation (which drops out of and re-enters the steady state)."""
+    from monte_carlo_localization_b200 import MclContext, maps, synth
+    g = maps.load_named_map(name)
+    angles_full = synth.laser_angles()
+    angles = synth.downsample(angles_full)
+    ctxs = []
+    for graphs in (True, False):
+        c = MclContext(max_particles=N, seed=4711)
+        c.set_map(g)
+        c.set_beam_angles(angles)
+        c.set_graphs(graphs)
+        ctxs.append(c)
+    gt, actions = synth.trajectory(g, 14, 3.0)
+    rng = np.random.default_rng(3)
+    obs = [synth.scan_from_pose(ctxs[0].calc_range_many, gt[t + 1], angles_full, rng)[::18] for t in range(14)]
+    launches = []
+    for c in ctxs:
+        c.init_pose(gt[0])
+        n0 = c.kernel_launches()
+        poses = [c.update(actions[t], obs[t]).copy() for t in range(8)]
+        c.init_pose(gt[8])                    # weights touched: the next update runs launch by launch
+        poses += [c.update(actions[t], obs[t]).copy() for t in range(8, 14)]
+        launches.append(c.kernel_launches() - n0)
+        c._poses = np.stack(poses)
+    a, b = ctxs
+    assert np.array_equal(a._poses, b._poses)
+    assert np.array_equal(a.get_particles(), b.get_particles())
+    assert np.array_equal(a.get_weights(), b.get_weights())
+    assert launches[0] == launches[1]          # the launch counter counts the kernels of a replayed graph too
+    err = np.hypot(*(a._poses[-1][:2] - gt[14][:2]))
+    assert err < 0.5
+    for c in ctxs:
+        c.close()
