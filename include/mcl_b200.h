@@ -152,7 +152,7 @@ int mcl_set_stream(mcl_ctx* ctx, void* cuda_stream);
  * graphs are dropped and re-captured whenever a setter changes a buffer, the stream or a mode. */
 int mcl_set_graphs(mcl_ctx* ctx, int enabled);
 
-/* Ray stage selection.  One filter of more than 16384 particles gets, besides the isotropic
+/* Ray stage selection.  One filter of at least 1024 particles gets, besides the isotropic
  * skip-map kernel, the DIRECTIONAL stage: per-heading-sector skip maps built at mcl_set_map, rays
  * grouped by sector, each sector's window staged in shared memory.  Both compute the reference's
  * cast_ray (src/particle_filter.cpp:611-650) exactly; they differ only in how many samples they

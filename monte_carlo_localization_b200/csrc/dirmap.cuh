@@ -39,6 +39,7 @@ constexpr int kDirMaxAdv = 127;
 constexpr int kDirBlocked = 0x80;
 constexpr int kDirNear = 0x80;
 constexpr int kDirMinBuckets = 2048;     // heading buckets of the sort: bucket half-width < margin
+constexpr int kDirMinParticles = 1024;   // smaller single filters stay on the isotropic kernel
 
 struct DirSector {
     double ux, uy;                    // unit vector of the sector's mid direction

@@ -411,6 +411,110 @@ __global__ void __launch_bounds__(kTileChunks) k_exact_emit(ExactArgs a) {
     }
 }
 
+// T == 1 (a filter of at most kTile = 4096 particles is ONE tile): chunks, walk and emit of the
+// exact sequential sum in a single CTA per filter -- one launch per pass instead of two or three,
+// which is what a small filter's update time is made of.  Same arithmetic as the three kernels
+// above with the tile prefix fixed at 0: chunk step maps, the ordered serial pass over the opaque
+// chunks (their addends re-read from global memory by thread 0: they are rare), the total, and
+// the prefix sums.
+__global__ void __launch_bounds__(kTileChunks) k_exact_single(ExactArgs a) {
+    __shared__ double smd[kTileChunks / 32];
+    __shared__ RFn smr[kTileChunks / 32];
+    __shared__ RFn sm_inc[kTileChunks];
+    __shared__ ScanElem sms[kTileChunks / 32];
+    __shared__ ScanElem sm_se[kTileChunks];
+    __shared__ double sm_anchor[kTileChunks];   // exact running sum after an opaque chunk, by chunk index
+    __shared__ StepFn sm_pre[kTileChunks];      // step map from the previous anchor (or 0) to each opaque chunk, by rank
+    __shared__ int sm_opq[kTileChunks];         // opaque chunk indices in order
+    __shared__ int wcnt[kTileChunks / 32];
+    const int f = blockIdx.y, tid = threadIdx.x;
+    const double* src = a.src + static_cast<int64_t>(f) * a.N;
+    const bool use_div = a.div != nullptr;
+    const double div = use_div ? a.div[f] : 1.0;
+
+    const int64_t base = static_cast<int64_t>(tid) * kChunk;
+    double v[kChunk];
+    load_chunk(v, src, base, a.N, use_div, div);
+    double c = 0.0;
+#pragma unroll
+    for (int i = 0; i < kChunk; ++i) c += v[i];
+    const double incl = block_scan_inclusive<kTileChunks>(c, AddOp(), smd, 0.0);
+    const double s_in = 0.0 + (incl - c);
+    const double s_out = s_in + c;
+    StepFn fn = fn_identity();
+    int opaque = 0;
+    if (base < a.N) {
+        const int64_t cnt = (base + kChunk < a.N) ? base + kChunk : a.N;
+        const int e = chunk_safe_binade(s_in, s_out, cnt);
+        if (e < 0) {
+            fn = fn_opaque();
+            opaque = 1;
+        } else {
+            fn = chunk_step_fn(v, kChunk, e);
+        }
+    }
+    const RFn ident{fn_identity(), 0};
+    const RFn el = opaque ? RFn{fn_identity(), 1} : RFn{fn, 0};
+    const RFn inc = block_scan_inclusive<kTileChunks>(el, RFnOp(), smr, ident);
+    sm_inc[tid] = inc;
+    const unsigned bal = __ballot_sync(kFullMask, opaque);
+    if ((tid & 31) == 0) wcnt[tid >> 5] = __popc(bal);
+    __syncthreads();
+    const RFn exc = tid ? sm_inc[tid - 1] : ident;
+    int orank = __popc(bal & ((1u << (tid & 31)) - 1u));
+    int nopq = 0;
+#pragma unroll
+    for (int w = 0; w < kTileChunks / 32; ++w) {
+        if (w < (tid >> 5)) orank += wcnt[w];
+        nopq += wcnt[w];
+    }
+    if (opaque) {
+        sm_opq[orank] = tid;
+        sm_pre[orank] = exc.f;
+    }
+    __syncthreads();
+    // serial pass over the opaque chunks in order, each from its exact input
+    if (tid == 0) {
+        double V = 0.0;
+        for (int r = 0; r < nopq; ++r) {
+            const int ch = sm_opq[r];
+            double w8[kChunk];
+            load_chunk(w8, src, static_cast<int64_t>(ch) * kChunk, a.N, use_div, div);
+            V = chunk_seq_eval(w8, kChunk, fn_apply(sm_pre[r], V));
+            sm_anchor[ch] = V;
+        }
+        const RFn run = sm_inc[kTileChunks - 1];
+        a.total[f] = fn_apply(run.f, run.reset ? V : 0.0);
+    }
+    if (!a.out) return;
+    __syncthreads();
+    // prefix sums: every chunk's exact input from a scan of step maps and anchors, then 8 adds
+    ScanElem se = opaque ? se_abs(sm_anchor[tid]) : se_fn(fn);
+    if (tid == 0) se = se_combine(se_abs(0.0), se);
+    const ScanElem seid = se_fn(fn_identity());
+    const ScanElem sinc = block_scan_inclusive<kTileChunks>(se, SEOp(), sms, seid);
+    sm_se[tid] = sinc;
+    __syncthreads();
+    double s = tid ? bits_dbl(sm_se[tid - 1].a0) : 0.0;
+    if (base >= a.N) return;
+    double* out = a.out + static_cast<int64_t>(f) * a.N;
+#pragma unroll
+    for (int i = 0; i < kChunk; ++i) {
+        s = __dadd_rn(s, v[i]);
+        v[i] = s;
+    }
+    if (a.force_last_one && a.N - 1 >= base && a.N - 1 < base + kChunk) v[a.N - 1 - base] = 1.0;
+    if (base + kChunk <= a.N) {
+        double2* p = reinterpret_cast<double2*>(out + base);
+#pragma unroll
+        for (int i = 0; i < kChunk / 2; ++i) p[i] = make_double2(v[2 * i], v[2 * i + 1]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < kChunk; ++i)
+            if (base + i < a.N) out[base + i] = v[i];
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // resample (:658-665) + motion model (:449-503)
 // ------------------------------------------------------------------------------------------

@@ -204,6 +204,12 @@ int run_exact(mcl_ctx* c, const double* src, const double* div, double* total, d
               bool need_tile_sums, const double* approx_div = nullptr) {
     ExactArgs a = exact_args(c, src, div, approx_div, total, out, force_one);
     const dim3 gt(c->T, c->F);
+    if (c->T == 1) {   // a filter of one tile: the whole pass is one CTA per filter
+        k_exact_single<<<gt, kTileChunks, 0, c->stream>>>(a);
+        c->launches++;
+        CK(cudaGetLastError());
+        return MCL_OK;
+    }
     if (need_tile_sums) {
         k_tile_sums<<<gt, kTileChunks, 0, c->stream>>>(a);
         c->launches++;
@@ -789,6 +795,9 @@ static int create_buffers(mcl_ctx* c, const mcl_params* p, int device) {
     {   // heading buckets: ~16 particles per bucket, power of two in [32, 4096]
         int B = 32;
         while (B < kMaxBuckets && static_cast<int64_t>(B) * 16 < c->N) B <<= 1;
+        // a single filter of at least kDirMinParticles runs the directional ray stage, whose sector
+        // arithmetic needs buckets narrower than the sector maps' margin
+        if (c->F == 1 && c->N >= kDirMinParticles && B < kDirMinBuckets) B = kDirMinBuckets;
         c->B = B;
         CK(dalloc(&c->d_hist, static_cast<size_t>(2) * B * c->F));
         CK(dalloc(&c->d_perm, FN));
@@ -1436,7 +1445,8 @@ static int install_peers(mcl_ctx* c, int world, int rank, const std::vector<cons
     c->lo = (c->N / world) * rank;
     c->cnt = c->N / world;
     c->p2p = true;
-    return MCL_OK;
+    drop_graphs(c);
+    return upload_replay_ctx(c);   // the shard moved: the exact-replay context of the directional stage follows it
 }
 
 int mcl_ipc_export(mcl_ctx* c, void* handles_out, size_t capacity) {
@@ -1571,8 +1581,8 @@ int mcl_set_ray_mode(mcl_ctx* c, int mode) {
     if (!c) return fail(MCL_ERR_INVALID, "null context");
     if (mode < 0 || mode > 2) return fail(MCL_ERR_INVALID, "ray mode %d not in {0 auto, 1 isotropic, 2 directional}", mode);
     if (mode == 2 && !c->dir_ready)
-        return fail(MCL_ERR_UNSUPPORTED, "the directional ray stage needs one filter of more than %d particles, a map and a beam table",
-                    16 * (kDirMinBuckets / 2));
+        return fail(MCL_ERR_UNSUPPORTED, "the directional ray stage needs one filter of at least %d particles, a map and a beam table",
+                    kDirMinParticles);
     c->ray_mode = mode;
     drop_graphs(c);
     return MCL_OK;

@@ -21,16 +21,19 @@ def _ctx(grid, angles, N, **kw):
     return c
 
 
+@pytest.mark.parametrize("ray_mode", [0, 1], ids=["auto", "isotropic"])
 @pytest.mark.parametrize("fixture", ["update_sibal1_4000.npz", "update_Spielberg_map_2000.npz",
                                      "update_basement_fixed_1000.npz"])
-def test_golden_updates_teacher_forced(fixture):
+def test_golden_updates_teacher_forced(fixture, ray_mode):
     """Every update starts from the reference's own state, so each stage is compared on
-    identical inputs: indices and ranges must match exactly."""
+    identical inputs: indices and ranges must match exactly.  Run with the ray stage chosen on the
+    device (directional for the compact clouds of >= 1024 particles) and with the isotropic kernel."""
     from monte_carlo_localization_b200 import maps
     z = load_golden(fixture)
     g = maps.load_named_map(str(z["map"]))
     N = int(z["N"])
     c = _ctx(g, z["angles"], N)
+    c.set_ray_mode(ray_mode)
     prev_p, prev_w = z["init_particles"], z["init_weights"]
     for t in range(len(z["u"])):
         c.set_particles(prev_p, prev_w)
@@ -46,6 +49,8 @@ def test_golden_updates_teacher_forced(fixture):
         assert np.abs(p[2] - z["particles"][t][2]).max() < 1e-9
         assert_pose_close(pose, z["pose"][t])
         prev_p, prev_w = z["particles"][t], z["weights"][t]
+    info = c.ray_stage_info()
+    assert info["last_mode"] == (1 if (ray_mode == 0 and N >= 1024) else 0)
     c.close()
 
 
