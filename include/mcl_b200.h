@@ -158,7 +158,9 @@ int mcl_set_graphs(mcl_ctx* ctx, int enabled);
  * cast_ray (src/particle_filter.cpp:611-650) exactly; they differ only in how many samples they
  * can prove irrelevant.  mode 0 (default): directional when at least 90 % of the particles lie in
  * the window box around the cloud centre, decided on the device every update; 1: isotropic
- * kernel only; 2: directional always (MCL_ERR_UNSUPPORTED if the context is not eligible). */
+ * kernel only; 2: directional always (MCL_ERR_UNSUPPORTED if the context is not eligible).  A BATCH of
+ * filters whose whole padded map fits one window can run the directional stage over the pool of all
+ * filters' particles; that is opt-in (mode 2): on such small maps the isotropic kernel measured faster. */
 int mcl_set_ray_mode(mcl_ctx* ctx, int mode);
 /* directional_ready: the context is eligible and its sector maps are built; last_mode: 1 if the
  * last update ran the directional stage; box_cells: side of the window box; units: work units of

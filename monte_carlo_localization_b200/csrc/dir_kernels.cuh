@@ -12,6 +12,9 @@
 //                      shared memory with cp.async.bulk; one lane = one particle, marching the two
 //                      or three beams of it that fall into the sector; step indices out
 //   k_weight_steps     table product in the reference's beam order + pow -> raw weights
+// A BATCH of filters whose whole padded map fits one window (small maps) runs the same stage over
+// the pool of all filters' particles ("pool mode"): slots are (filter, heading-sorted) order, every
+// sector's window is the whole sector map, every (sector, chunk) pair is a unit.
 // Lanes of a warp hold heading-neighbours casting the same beam, so their rays share a sector,
 // a window and nearly a trip count.  If the cloud is not compact (fewer than 90 % of the
 // particles inside the window box, e.g. right after initialize_global) the plan hands the
@@ -58,10 +61,12 @@ struct DirPrepArgs {
     const double* centre;      // [2] sums of x and y over the shard's particles
     const DirRec* rec_in;      // [cnt] records in slot order (k_resample_motion)
     DirRec* rec;               // [cnt] records in heading-sorted order
-    const int32_t* perm;       // sorted slot -> slot index (both relative to the shard)
+    const int32_t* perm;       // sorted slot -> slot index (both relative to the shard / to the slot's filter)
     int* plan;
     int64_t cnt;
+    int64_t nfil;              // particles per filter (pool mode: slot / nfil is the filter); >= cnt otherwise
     int box;
+    int whole;                 // pool mode: the window is the whole map, every particle inside the map is "in the box"
 };
 
 // P-cell of the box corner: the box is centred on the cloud's mean position
@@ -103,13 +108,13 @@ __global__ void __launch_bounds__(256) k_dir_gather(DirPrepArgs a) {
     dir_box_origin(a.centre, a.cnt, a.map, a.box, &bx0, &by0);
     int in_box = 0;
     if (pos < a.cnt) {
-        const int i = a.perm[pos];
+        const int64_t i = (pos / a.nfil) * a.nfil + a.perm[pos];
         uint4 r0 = a.rec_in[i].a;
         const double2 r1 = a.rec_in[i].b;
         if (r0.w >> 16) {
             const int fqx = static_cast<int>(static_cast<int16_t>(r0.z & 0xffffu)) + kLocalOrigin;
             const int fqy = static_cast<int>(static_cast<int16_t>(r0.z >> 16)) + kLocalOrigin;
-            in_box = fqx >= bx0 && fqx < bx0 + a.box && fqy >= by0 && fqy < by0 + a.box;
+            in_box = a.whole || (fqx >= bx0 && fqx < bx0 + a.box && fqy >= by0 && fqy < by0 + a.box);
             if (in_box) r0.w |= 2u << 16;
         }
         a.rec[pos].a = r0;
@@ -132,6 +137,7 @@ struct DirPlanArgs {
     int* sec_tab;              // [S + 1] first unit of every sector | [S] first chunk of every sector
     int64_t cnt;
     int B, R, force;           // force: 0 decide by the in-box fraction, 2 always directional
+    int all_chunks;            // pool mode: every sector covers every chunk (slots are not globally heading-sorted)
 };
 
 constexpr int kPlanThreads = 1024;
@@ -155,7 +161,7 @@ __global__ void __launch_bounds__(kPlanThreads) k_dir_plan(DirPlanArgs a) {
 #pragma unroll
     for (int q = 0; q < kPer; ++q) {
         const int b = tid * kPer + q;
-        h[q] = b < a.B ? a.hist[b] : 0;
+        h[q] = (b < a.B && !a.all_chunks) ? a.hist[b] : 0;   // pool mode: the sort's histograms are per filter, not used
         loc += h[q];
     }
     int v = loc;
@@ -206,6 +212,11 @@ __global__ void __launch_bounds__(kPlanThreads) k_dir_plan(DirPlanArgs a) {
         }
     }
     __syncthreads();
+    if (a.all_chunks && tid < kDirSectors) {
+        cmin[tid] = 0;
+        cmax[tid] = static_cast<int>((a.cnt + kDirThreads - 1) / kDirThreads);
+    }
+    __syncthreads();
     if (warp == 0) {
         const int n = cmax[lane] > cmin[lane] ? cmax[lane] - cmin[lane] : 0;   // kDirSectors == 32 lanes
         int w = n;
@@ -237,15 +248,16 @@ struct DirReplayCtx {
     const double* px;
     const double* py;
     const double* pt;
-    const int32_t* perm;       // already offset to the shard: perm[pos] is relative to lo
+    const int32_t* perm;       // already offset to the shard: perm[pos] is relative to lo (to the slot's filter in pool mode)
     int64_t lo;
+    int64_t nfil;              // particles per filter in pool mode, >= the slot count otherwise
     float angle[kMaxBeams];
 };
 struct ReplayLazy {
     const DirReplayCtx* rc;
     int pos, j;
     __device__ __forceinline__ ReplayArgs load() const {
-        const int64_t i = rc->lo + rc->perm[pos];
+        const int64_t i = rc->lo + (pos / rc->nfil) * rc->nfil + rc->perm[pos];
         return ReplayArgs{rc->px[i], rc->py[i], rc->pt[i], rc->angle[j]};
     }
     __device__ __forceinline__ RefGrid grid() const { return rc->grid; }
@@ -267,6 +279,7 @@ struct DirRayArgs {
     int64_t* replay_count;
     int B, shift, box;
     int win_bytes;              // shared-memory bytes reserved for the sector window
+    int whole;                  // pool mode: the window of every sector is its whole map
 };
 
 // dynamic shared memory of k_raycast_dir: window | rec0 prefetch [2][1024] | rec1 prefetch [2][1024]
@@ -352,7 +365,7 @@ __global__ void __launch_bounds__(kDirThreads, 1) k_raycast_dir(DirRayArgs a) {
             if (s != cur_s) {
                 // ---- stage sector s's window: one bulk copy per row, bytes counted on the mbarrier
                 __syncthreads();            // every warp has left the old window
-                wg = dir_window(a.sectors[s], bx0, by0, a.box, mp.PW, mp.PH);
+                wg = a.whole ? DirWindow{0, 0, mp.PW, mp.PH} : dir_window(a.sectors[s], bx0, by0, a.box, mp.PW, mp.PH);
                 smap = a.dirmaps + static_cast<int64_t>(s) * ncell;
                 if (tid == 0) {
                     const uint32_t total = static_cast<uint32_t>(wg.pitch) * static_cast<uint32_t>(wg.rows);
@@ -444,6 +457,7 @@ struct WeightStepsArgs {
     double* w_raw;                 // [N]
     uint8_t* steps;                // [N*R] particle-major copy (get_ranges) or nullptr
     int64_t lo, cnt, stride;
+    int64_t nfil;                  // particles per filter in pool mode (slot / nfil is the filter), >= cnt otherwise
     int R, tw;
     double inv_squash;
 };
@@ -458,6 +472,13 @@ __global__ void __launch_bounds__(kWeightThreads) k_weight_steps(WeightStepsArgs
     if (pos >= a.cnt) return;
     constexpr int kBatch = 10;
     double acc[4] = {1.0, 1.0, 1.0, 1.0};
+    int64_t fil[4];   // filter of each slot (0 unless pool mode): its rows of the table slice
+    int foff[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        fil[e] = min(pos + e, a.cnt - 1) / a.nfil;
+        foff[e] = static_cast<int>(fil[e]) * a.R * a.tw;
+    }
     const uint32_t* sp = reinterpret_cast<const uint32_t*>(a.steps_sorted + pos);   // stride and pos are multiples of 4
     const size_t wstride = static_cast<size_t>(a.stride) / 4;
     const double* row = a.slice;
@@ -470,7 +491,7 @@ __global__ void __launch_bounds__(kWeightThreads) k_weight_steps(WeightStepsArgs
         for (int q = 0; q < kBatch; ++q) {
 #pragma unroll
             for (int e = 0; e < 4; ++e)   // slots beyond cnt hold zeros or stale (valid) steps
-                acc[e] = __dmul_rn(acc[e], __ldg(row + q * a.tw + ((w[q] >> (8 * e)) & 255u)));
+                acc[e] = __dmul_rn(acc[e], __ldg(row + foff[e] + q * a.tw + ((w[q] >> (8 * e)) & 255u)));
         }
         sp += kBatch * wstride;
         row += kBatch * a.tw;
@@ -478,17 +499,17 @@ __global__ void __launch_bounds__(kWeightThreads) k_weight_steps(WeightStepsArgs
     for (; j < a.R; ++j) {
         const uint32_t w = __ldcs(sp);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) acc[e] = __dmul_rn(acc[e], __ldg(row + ((w >> (8 * e)) & 255u)));
+        for (int e = 0; e < 4; ++e) acc[e] = __dmul_rn(acc[e], __ldg(row + foff[e] + ((w >> (8 * e)) & 255u)));
         sp += wstride;
         row += a.tw;
     }
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         if (pos + e < a.cnt) {
-            const int64_t i = a.lo + a.perm[a.lo + pos + e];
+            const int64_t i = a.lo + fil[e] * a.nfil + a.perm[a.lo + pos + e];
             a.w_raw[i] = pow(acc[e], a.inv_squash);
             if (a.steps)   // diagnostics (mcl_get_ranges): particle-major copy of the step indices
-                for (int j = 0; j < a.R; ++j) a.steps[i * a.R + j] = a.steps_sorted[static_cast<int64_t>(j) * a.stride + pos + e];
+                for (int jj = 0; jj < a.R; ++jj) a.steps[i * a.R + jj] = a.steps_sorted[static_cast<int64_t>(jj) * a.stride + pos + e];
         }
     }
 }

@@ -548,7 +548,7 @@ struct MotionArgs {
     // the heading sort's scatter pass moves them to their sorted slots
     DirRec* rec;
     MapDev map;
-    int B;
+    int B;                    // heading buckets of the directional stage's sector arithmetic
 };
 
 struct MotionScalars {
@@ -692,7 +692,7 @@ __global__ void __launch_bounds__(kMotionThreads) k_resample_motion(MotionArgs a
         a.dx[fo + i] = nx;
         a.dy[fo + i] = ny;
         a.dt[fo + i] = nt;
-        if (a.rec) dir_write_record(a.map, a.rec, li, nx, ny, nt, theta_bucket(nt, a.B));
+        if (a.rec) dir_write_record(a.map, a.rec, fo + li, nx, ny, nt, theta_bucket(nt, a.B));
         if (!(fabs(nx) < 1e12) || !(fabs(ny) < 1e12)) nx = ny = 0.0;  // keep the window centre finite
     }
     // cloud centre for the shared-memory window of the ray kernel

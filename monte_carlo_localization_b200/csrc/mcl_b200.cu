@@ -116,6 +116,8 @@ struct mcl_ctx {
     bool sort_enabled = true;
     // directional ray stage (dir_kernels.cuh): one large filter, heading sort fine enough
     bool dir_ready = false;
+    bool dir_pool = false;            // batch of filters on a map that fits one window: the stage runs over the pool
+    int dir_B = 0;                    // heading buckets of the sector arithmetic (the sort's B for one filter)
     int ray_mode = 0;                 // 0 auto, 1 isotropic kernel only, 2 directional forced
     DirSector sectors[kDirSectors];
     uint8_t* d_dirmaps = nullptr;     // [S][PH*PW]
@@ -319,6 +321,7 @@ int upload_replay_ctx(mcl_ctx* c) {
         h[b].pt = c->d_pt[b];
         h[b].perm = c->d_perm + c->lo;
         h[b].lo = c->lo;
+        h[b].nfil = c->dir_pool ? c->N : (int64_t{1} << 40);
         for (int j = 0; j < kMaxBeams; ++j) h[b].angle[j] = j < c->R ? c->beams.angle[j] : 0.0f;
     }
     CK(cudaMemcpy(c->d_replay_ctx, h, sizeof(h), cudaMemcpyHostToDevice));
@@ -330,13 +333,16 @@ int upload_replay_ctx(mcl_ctx* c) {
 // per-update work buffers.  Called whenever the map or the beam table changes.
 int ensure_dir(mcl_ctx* c, bool map_changed) {
     if (!c->have_map || !c->have_beams) return MCL_OK;
-    const bool eligible = c->F == 1 && c->B >= kDirMinBuckets && c->skip.PW <= 32767 && c->skip.PH <= 32767 && c->R <= 127;
+    const size_t ncell = static_cast<size_t>(c->skip.PW) * c->skip.PH;
+    // one filter: windows around the cloud; a batch: only when the whole padded map is one window
+    const bool pool = c->F > 1 && ncell <= kDirWindowBudget && static_cast<int64_t>(c->F) * c->N < (int64_t{1} << 31) - 2048;
+    const bool eligible = ((c->F == 1 && c->B >= kDirMinBuckets) || pool) && c->skip.PW <= 32767 && c->skip.PH <= 32767 && c->R <= 127;
     if (!eligible) {
         free_dir(c);
         return MCL_OK;
     }
     CK(cudaStreamSynchronize(c->stream));
-    const size_t ncell = static_cast<size_t>(c->skip.PW) * c->skip.PH;
+    const int64_t pool_n = static_cast<int64_t>(c->F) * c->N;   // slots of the stage (== N for one filter)
     if (map_changed || !c->d_dirmaps) {
         free_dir(c);
         make_dir_sectors(c->M, c->sectors);
@@ -348,7 +354,7 @@ int ensure_dir(mcl_ctx* c, bool map_changed) {
             smem = std::max(smem, static_cast<size_t>((c->dir_box + sc.exh - sc.exl + 30) & ~15) *
                                       static_cast<size_t>(c->dir_box + sc.eyh - sc.eyl));
         }
-        c->dir_smem = smem;
+        c->dir_smem = pool ? ncell : smem;
         std::vector<float> gap;
         build_gap_map(c->skip, gap);
         float* d_gap = nullptr;
@@ -365,18 +371,20 @@ int ensure_dir(mcl_ctx* c, bool map_changed) {
         cudaFree(d_gap);
         CK(dalloc(&c->d_plan, static_cast<size_t>(kPlanInts)));
         CK(cudaMemset(c->d_plan, 0, sizeof(int) * kPlanInts));
-        CK(dalloc(&c->d_rec, static_cast<size_t>(2 * c->N)));
+        CK(dalloc(&c->d_rec, static_cast<size_t>(2 * pool_n)));
     }
+    c->dir_pool = pool;
+    c->dir_B = pool ? kMaxBuckets : c->B;
     // per-beam-table buffers
     for (void* p : {static_cast<void*>(c->d_sec_tab), static_cast<void*>(c->d_steps_sorted), static_cast<void*>(c->d_replay_ctx)})
         if (p) cudaFree(p);
     c->d_sec_tab = nullptr;
     c->d_steps_sorted = nullptr;
     c->d_replay_ctx = nullptr;
-    for (int j = 0; j < c->R; ++j) c->beam_io[j] = dir_beam_offset(c->beams.angle[j], c->B);
+    for (int j = 0; j < c->R; ++j) c->beam_io[j] = dir_beam_offset(c->beams.angle[j], c->dir_B);
     CK(dalloc(&c->d_sec_tab, static_cast<size_t>(2 * kDirSectors + 2)));
     CK(dalloc(&c->d_replay_ctx, size_t{2}));
-    const int64_t nchunks = (c->N + kDirThreads - 1) / kDirThreads;
+    const int64_t nchunks = (pool_n + kDirThreads - 1) / kDirThreads;
     c->dir_stride = nchunks * kDirThreads;
     CK(dalloc(&c->d_steps_sorted, static_cast<size_t>(c->R) * c->dir_stride));
     CK(cudaMemset(c->d_steps_sorted, 0, static_cast<size_t>(c->R) * c->dir_stride));   // slots beyond the shard stay valid steps
@@ -456,11 +464,12 @@ int update_local(mcl_ctx* c, const double* action_dev, const float* obs_dev, con
     if (rc) return rc;
     if (c->profiling) CK(cudaEventRecord(c->ev[1], s));
 
-    const bool dir = c->dir_ready && c->sort_enabled && c->ray_mode != 1;
+    // a batch's pool mode is opt-in (ray mode 2): measured slower than the isotropic kernel on small maps
+    const bool dir = c->dir_ready && c->sort_enabled && c->ray_mode != 1 && (!c->dir_pool || c->ray_mode == 2);
     MotionArgs ma{};
     ma.rec = dir ? c->d_rec : nullptr;
     ma.map = c->map;
-    ma.B = c->B;
+    ma.B = c->dir_B;
     ma.N = c->N;
     ma.lo = c->lo;
     ma.cnt = c->cnt;
@@ -517,70 +526,76 @@ int update_local(mcl_ctx* c, const double* action_dev, const float* obs_dev, con
         DirPrepArgs pa{};
         pa.map = c->map;
         pa.centre = c->d_centre;
+        const int64_t slots = c->dir_pool ? static_cast<int64_t>(c->F) * c->N : c->cnt;
         pa.rec_in = c->d_rec;
-        pa.rec = c->d_rec + c->N;
+        pa.rec = c->d_rec + static_cast<int64_t>(c->F) * c->N;
         pa.perm = c->d_perm + c->lo;
         pa.plan = c->d_plan;
-        pa.cnt = c->cnt;
+        pa.cnt = slots;
+        pa.nfil = c->dir_pool ? c->N : (int64_t{1} << 40);
         pa.box = c->dir_box;
-        k_dir_gather<<<static_cast<unsigned>((c->cnt + 255) / 256), 256, 0, s>>>(pa);
+        pa.whole = c->dir_pool ? 1 : 0;
+        k_dir_gather<<<static_cast<unsigned>((slots + 255) / 256), 256, 0, s>>>(pa);
         DirPlanArgs la{};
         la.hist = c->d_hist;
         std::memcpy(la.io, c->beam_io, sizeof(la.io));
         la.plan = c->d_plan;
         la.sec_tab = c->d_sec_tab;
-        la.cnt = c->cnt;
-        la.B = c->B;
+        la.cnt = slots;
+        la.B = c->dir_B;
         la.R = c->R;
-        la.force = c->ray_mode;
+        la.force = c->dir_pool ? 2 : c->ray_mode;   // the pool has no cloud box to be outside of
+        la.all_chunks = c->dir_pool ? 1 : 0;
         k_dir_plan<<<1, kPlanThreads, 0, s>>>(la);
         c->launches += 2;
     }
     if (c->profiling) CK(cudaEventRecord(c->ev[2], s));
 
-    RayArgs ra{};
-    ra.map = c->map;
-    ra.beams = c->beams;
-    ra.N = c->N;
-    ra.lo = c->lo;
-    ra.cnt = c->cnt;
-    ra.px = c->d_px[dst];
-    ra.py = c->d_py[dst];
-    ra.pt = c->d_pt[dst];
-    ra.perm = c->sort_enabled ? c->d_perm : nullptr;
-    ra.slice = c->d_slice;
-    ra.w_raw = c->d_wraw;
-    ra.steps = c->keep_ranges ? c->d_steps : nullptr;
-    ra.centre = c->d_centre;
-    ra.inv_squash = 1.0 / c->prm.squash_factor;
-    ra.replay_count = c->d_replays;
-    ra.plan = dir ? c->d_plan : nullptr;
-    const size_t smem = static_cast<size_t>(c->map.wbits == 8 ? c->map.ww : c->map.ww / 2) * c->map.wh;
-    // persistent blocks: one per SM when the window fills shared memory, a few otherwise
-    const int per_sm = smem > 100 * 1024 ? 1 : 2;
-    const int budget = std::max(1, (c->num_sms * per_sm) / std::min(c->F, c->num_sms * per_sm));
-    const int rblocks = static_cast<int>(std::min<int64_t>((c->cnt + kRayThreads - 1) / kRayThreads, budget));
-    // MAX_RANGE_PX of the usual map resolutions is baked into specialised instances
-    // (0.05 m -> 239, 0.0504 m -> 238, 0.05796 m -> 207); anything else takes the generic one
-    const dim3 rgrid(rblocks, c->F);
+    if (!(dir && c->dir_pool)) {   // the pool mode of the directional stage has no fallback to hand the update to
+        RayArgs ra{};
+        ra.map = c->map;
+        ra.beams = c->beams;
+        ra.N = c->N;
+        ra.lo = c->lo;
+        ra.cnt = c->cnt;
+        ra.px = c->d_px[dst];
+        ra.py = c->d_py[dst];
+        ra.pt = c->d_pt[dst];
+        ra.perm = c->sort_enabled ? c->d_perm : nullptr;
+        ra.slice = c->d_slice;
+        ra.w_raw = c->d_wraw;
+        ra.steps = c->keep_ranges ? c->d_steps : nullptr;
+        ra.centre = c->d_centre;
+        ra.inv_squash = 1.0 / c->prm.squash_factor;
+        ra.replay_count = c->d_replays;
+        ra.plan = dir ? c->d_plan : nullptr;
+        const size_t smem = static_cast<size_t>(c->map.wbits == 8 ? c->map.ww : c->map.ww / 2) * c->map.wh;
+        // persistent blocks: one per SM when the window fills shared memory, a few otherwise
+        const int per_sm = smem > 100 * 1024 ? 1 : 2;
+        const int budget = std::max(1, (c->num_sms * per_sm) / std::min(c->F, c->num_sms * per_sm));
+        const int rblocks = static_cast<int>(std::min<int64_t>((c->cnt + kRayThreads - 1) / kRayThreads, budget));
+        // MAX_RANGE_PX of the usual map resolutions is baked into specialised instances
+        // (0.05 m -> 239, 0.0504 m -> 238, 0.05796 m -> 207); anything else takes the generic one
+        const dim3 rgrid(rblocks, c->F);
 #define MCL_LAUNCH_RAY(WB, MCV) k_raycast_weight<WB, MCV><<<rgrid, kRayThreads, smem, s>>>(ra)
-    if (c->map.wbits == 8) {
-        switch (c->M) {
-            case 207: MCL_LAUNCH_RAY(8, 207); break;
-            case 238: MCL_LAUNCH_RAY(8, 238); break;
-            case 239: MCL_LAUNCH_RAY(8, 239); break;
-            default: MCL_LAUNCH_RAY(8, 0); break;
+        if (c->map.wbits == 8) {
+            switch (c->M) {
+                case 207: MCL_LAUNCH_RAY(8, 207); break;
+                case 238: MCL_LAUNCH_RAY(8, 238); break;
+                case 239: MCL_LAUNCH_RAY(8, 239); break;
+                default: MCL_LAUNCH_RAY(8, 0); break;
+            }
+        } else {
+            switch (c->M) {
+                case 207: MCL_LAUNCH_RAY(4, 207); break;
+                case 238: MCL_LAUNCH_RAY(4, 238); break;
+                case 239: MCL_LAUNCH_RAY(4, 239); break;
+                default: MCL_LAUNCH_RAY(4, 0); break;
+            }
         }
-    } else {
-        switch (c->M) {
-            case 207: MCL_LAUNCH_RAY(4, 207); break;
-            case 238: MCL_LAUNCH_RAY(4, 238); break;
-            case 239: MCL_LAUNCH_RAY(4, 239); break;
-            default: MCL_LAUNCH_RAY(4, 0); break;
-        }
-    }
 #undef MCL_LAUNCH_RAY
-    c->launches++;
+        c->launches++;
+    }
     if (dir) {
         DirRayArgs da{};
         da.map = c->map;
@@ -588,22 +603,24 @@ int update_local(mcl_ctx* c, const double* action_dev, const float* obs_dev, con
         std::memcpy(da.io, c->beam_io, sizeof(da.io));
         da.sectors = c->d_sectors;
         da.dirmaps = c->d_dirmaps;
-        da.rec = c->d_rec + c->N;
+        const int64_t slots = c->dir_pool ? static_cast<int64_t>(c->F) * c->N : c->cnt;
+        da.rec = c->d_rec + static_cast<int64_t>(c->F) * c->N;
         da.sec_tab = c->d_sec_tab;
         da.replay = c->d_replay_ctx + dst;
         da.plan = c->d_plan;
         da.centre = c->d_centre;
-        da.cnt = c->cnt;
+        da.cnt = slots;
         da.stride = c->dir_stride;
         da.steps_sorted = c->d_steps_sorted;
         da.replay_count = c->d_replays;
-        da.B = c->B;
+        da.B = c->dir_B;
         da.shift = 0;
-        while ((c->B >> da.shift) > kDirSectors) ++da.shift;
+        while ((c->dir_B >> da.shift) > kDirSectors) ++da.shift;
         da.box = c->dir_box;
+        da.whole = c->dir_pool ? 1 : 0;
         da.win_bytes = static_cast<int>((c->dir_smem + 15) & ~size_t{15});
         const size_t dsmem = dir_ray_smem(da.win_bytes);
-        const int dblocks = static_cast<int>(std::min<int64_t>(c->num_sms, (c->cnt * c->R + kDirThreads - 1) / kDirThreads));
+        const int dblocks = static_cast<int>(std::min<int64_t>(c->num_sms, (slots * c->R + kDirThreads - 1) / kDirThreads));
         switch (c->M) {
             case 207: k_raycast_dir<207><<<dblocks, kDirThreads, dsmem, s>>>(da); break;
             case 238: k_raycast_dir<238><<<dblocks, kDirThreads, dsmem, s>>>(da); break;
@@ -619,12 +636,13 @@ int update_local(mcl_ctx* c, const double* action_dev, const float* obs_dev, con
         wa.w_raw = c->d_wraw;
         wa.steps = c->keep_ranges ? c->d_steps : nullptr;
         wa.lo = c->lo;
-        wa.cnt = c->cnt;
+        wa.cnt = slots;
+        wa.nfil = c->dir_pool ? c->N : (int64_t{1} << 40);
         wa.stride = c->dir_stride;
         wa.R = c->R;
         wa.tw = c->M + 1;
         wa.inv_squash = 1.0 / c->prm.squash_factor;
-        k_weight_steps<<<static_cast<unsigned>((c->cnt + 4 * kWeightThreads - 1) / (4 * kWeightThreads)), kWeightThreads, 0, s>>>(wa);
+        k_weight_steps<<<static_cast<unsigned>((slots + 4 * kWeightThreads - 1) / (4 * kWeightThreads)), kWeightThreads, 0, s>>>(wa);
         c->launches += 2;
     }
     if (!dir && c->profiling) CK(cudaEventRecord(c->ev[5], s));

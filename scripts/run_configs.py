@@ -79,12 +79,13 @@ def config2(steps=1000, ray_mode=0, levine_synth=False):
             "max_pose_err_m": float(np.max(errs)), "ray_mode": ray_mode, "ray_stage": ctx.ray_stage_info()}
 
 
-def config4(F=1024, steps=20):
+def config4(F=1024, steps=20, ray_mode=0):
     g = maps.load_named_map("sibal1")
     N = 4000
     ctx = MclContext(max_particles=N, num_filters=F, seed=20254)
     ctx.set_map(g)
     ctx.set_beam_angles(synth.beam_angles())
+    ctx.set_ray_mode(ray_mode)
     stride = 1
     gt, actions, obs = replay(ctx, g, steps + 5, 3.0, 781, batch=F, phase_stride=stride)
     for f in range(F):   # every car starts at its own phase of the lap
@@ -106,7 +107,7 @@ def config4(F=1024, steps=20):
     return {"config": 4, "map": "sibal1", "filters": F, "particles_per_filter": N, "beams": 60, "batch_steps": steps,
             "ms_per_batch_step": 1e3 * sec / steps, "filter_updates_per_s": F * steps / sec,
             "rays_per_s": F * N * 60 * steps / sec, "median_pose_err_m": float(np.median(err)),
-            "frac_filters_within_0.3m": float(np.mean(err < 0.3))}
+            "frac_filters_within_0.3m": float(np.mean(err < 0.3)), "ray_mode": ray_mode, "ray_stage": ctx.ray_stage_info()}
 
 
 def config5(N=2000000, max_updates=60, ray_mode=0):
@@ -151,7 +152,7 @@ if __name__ == "__main__":
         elif c == "2":
             print(json.dumps(config2(a.steps2, a.ray_mode)))
         elif c == "4":
-            print(json.dumps(config4(a.filters4)))
+            print(json.dumps(config4(a.filters4, ray_mode=a.ray_mode)))
         elif c == "5":
             print(json.dumps(config5(a.n5, ray_mode=a.ray_mode)))
         sys.stdout.flush()

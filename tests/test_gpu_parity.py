@@ -706,3 +706,49 @@ def test_graph_replay_equals_direct_launches(name, N):
     assert err < 0.5
     for c in ctxs:
         c.close()
+
+
+def test_batch_pool_directional_stage_equals_isotropic_kernel():
+    """A batch of filters on a map that fits one window runs the directional stage over the pool
+    of all filters' particles: step indices, raw weights, weights and poses are bit-identical
+    to the isotropic kernel's, filter by filter, and filter 0 equals the oracle."""
+    from monte_carlo_localization_b200 import MclContext, maps, synth
+    from oracle import bindings as ob
+    g = maps.load_named_map("sibal1")
+    angles_full = synth.laser_angles()
+    angles = synth.downsample(angles_full)
+    F, N = 5, 3000            # 3000 is not a multiple of 32: warps and 4-slot groups straddle filters
+    gt, actions = synth.trajectory(g, 30, 3.0)
+    ns = ob.NoiseStream(321)
+    orcs, states = [], []
+    for f in range(F):
+        o = ob.Oracle(g, angles, max_particles=N)
+        o.init_pose(gt[5 * f], ns.normal(3 * N))
+        orcs.append(o)
+        states.append(o.get_state())
+    obs = np.stack([synth.scan_from_pose(orcs[0].calc_range_many, gt[5 * f + 1], angles_full, np.random.default_rng(f))[::18]
+                    for f in range(F)]).astype(np.float32)
+    act = np.stack([actions[5 * f] for f in range(F)])
+    noise = [ns.update_noise(N) for _ in range(F)]
+    out = {}
+    for mode in (1, 2):        # pool mode is opt-in for batches (auto keeps the isotropic kernel)
+        c = MclContext(max_particles=N, num_filters=F)
+        c.set_map(g)
+        c.set_beam_angles(angles)
+        c.set_keep_ranges(True)
+        c.set_ray_mode(mode)
+        for f in range(F):
+            c.set_particles(states[f][0], states[f][1], filter=f)
+        poses = c.update(act, obs, np.stack([n[0] for n in noise]), np.stack([n[1] for n in noise]))
+        assert c.ray_stage_info()["last_mode"] == (0 if mode == 1 else 1)
+        out[mode] = [(c.range_steps(f).copy(), c.raw_weights(f).copy(), c.get_weights(f).copy()) for f in range(F)] + [poses.copy()]
+        c.close()
+    out[0] = out[2]
+    for f in range(F):
+        for k in range(3):
+            assert np.array_equal(out[0][f][k], out[1][f][k]), "filter %d item %d differs" % (f, k)
+    assert np.array_equal(out[0][F], out[1][F])
+    idx = orcs[0].update(act[0], obs[0], noise[0][0], noise[0][1])
+    want = steps_from_ranges(orcs[0].ranges(), g.resolution_f64, orcs[0].M)
+    assert (out[0][0][0] != want).sum() == 0
+    assert_weights_close(out[0][0][2], orcs[0].get_state()[1])
