@@ -466,18 +466,21 @@ struct WeightStepsArgs {
 // reference's loop (:564-579).  One thread = four consecutive sorted slots: the step bytes arrive
 // as 32-bit words (128 B per warp and beam), kBatch beams in flight, four independent products.
 constexpr int kWeightThreads = 256;
+template <bool POOL>   // POOL: slots of several filters (slot / nfil is the filter, each with its own table slice)
 __global__ void __launch_bounds__(kWeightThreads) k_weight_steps(WeightStepsArgs a) {
     if (a.plan[kPlanMode] != 1) return;
     const int64_t pos = (static_cast<int64_t>(blockIdx.x) * kWeightThreads + threadIdx.x) * 4;
     if (pos >= a.cnt) return;
     constexpr int kBatch = 10;
     double acc[4] = {1.0, 1.0, 1.0, 1.0};
-    int64_t fil[4];   // filter of each slot (0 unless pool mode): its rows of the table slice
-    int foff[4];
+    int fil[4] = {0, 0, 0, 0};    // filter of each slot: its rows of the table slice
+    int foff[4] = {0, 0, 0, 0};
+    if (POOL) {
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        fil[e] = min(pos + e, a.cnt - 1) / a.nfil;
-        foff[e] = static_cast<int>(fil[e]) * a.R * a.tw;
+        for (int e = 0; e < 4; ++e) {
+            fil[e] = static_cast<int>(min(pos + e, a.cnt - 1) / a.nfil);
+            foff[e] = fil[e] * a.R * a.tw;
+        }
     }
     const uint32_t* sp = reinterpret_cast<const uint32_t*>(a.steps_sorted + pos);   // stride and pos are multiples of 4
     const size_t wstride = static_cast<size_t>(a.stride) / 4;
@@ -506,7 +509,7 @@ __global__ void __launch_bounds__(kWeightThreads) k_weight_steps(WeightStepsArgs
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         if (pos + e < a.cnt) {
-            const int64_t i = a.lo + fil[e] * a.nfil + a.perm[a.lo + pos + e];
+            const int64_t i = a.lo + (POOL ? fil[e] * a.nfil : int64_t{0}) + a.perm[a.lo + pos + e];
             a.w_raw[i] = pow(acc[e], a.inv_squash);
             if (a.steps)   // diagnostics (mcl_get_ranges): particle-major copy of the step indices
                 for (int jj = 0; jj < a.R; ++jj) a.steps[i * a.R + jj] = a.steps_sorted[static_cast<int64_t>(jj) * a.stride + pos + e];

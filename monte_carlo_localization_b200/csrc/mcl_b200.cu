@@ -642,7 +642,11 @@ int update_local(mcl_ctx* c, const double* action_dev, const float* obs_dev, con
         wa.R = c->R;
         wa.tw = c->M + 1;
         wa.inv_squash = 1.0 / c->prm.squash_factor;
-        k_weight_steps<<<static_cast<unsigned>((slots + 4 * kWeightThreads - 1) / (4 * kWeightThreads)), kWeightThreads, 0, s>>>(wa);
+        const unsigned wblocks = static_cast<unsigned>((slots + 4 * kWeightThreads - 1) / (4 * kWeightThreads));
+        if (c->dir_pool)
+            k_weight_steps<true><<<wblocks, kWeightThreads, 0, s>>>(wa);
+        else
+            k_weight_steps<false><<<wblocks, kWeightThreads, 0, s>>>(wa);
         c->launches += 2;
     }
     if (!dir && c->profiling) CK(cudaEventRecord(c->ev[5], s));
