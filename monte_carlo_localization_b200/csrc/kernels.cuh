@@ -117,7 +117,19 @@ struct ExactArgs {
     double* total;           // [F]     exact sequential sum
     double* out;             // [F][N]  prefix sums (emit) or nullptr
     int force_last_one;      // discrete_distribution sets _M_cp.back() = 1.0 (random.tcc:2677)
+    // coarse level of the CDF search (k_resample_motion): coarse[f][k] = out[(k+1)*8*coarse_m - 1],
+    // written by the emit step next to the prefix sums; coarse_m = 0: none
+    double* coarse;
+    int coarse_m, coarse_n;  // chunks per coarse entry (power of two), entries per filter
 };
+
+// emit step: the thread that holds the last chunk of a coarse segment publishes its final prefix sum
+__device__ __forceinline__ void emit_coarse(const ExactArgs& a, int f, int64_t chunk_in_filter, int64_t base, double last) {
+    if (a.coarse_m > 0 && ((chunk_in_filter + 1) & (a.coarse_m - 1)) == 0 && base + kChunk <= a.N) {
+        const int64_t k = (chunk_in_filter + 1) / a.coarse_m - 1;
+        if (k < a.coarse_n) a.coarse[static_cast<int64_t>(f) * a.coarse_n + k] = last;
+    }
+}
 
 struct RFn {
     StepFn f;
@@ -400,6 +412,7 @@ __global__ void __launch_bounds__(kTileChunks) k_exact_emit(ExactArgs a) {
         v[i] = s;
     }
     if (a.force_last_one && a.N - 1 >= base && a.N - 1 < base + kChunk) v[a.N - 1 - base] = 1.0;
+    emit_coarse(a, f, static_cast<int64_t>(t) * kTileChunks + tid, base, v[kChunk - 1]);
     if (base + kChunk <= a.N) {
         double2* p = reinterpret_cast<double2*>(out + base);
 #pragma unroll
@@ -504,6 +517,7 @@ __global__ void __launch_bounds__(kTileChunks) k_exact_single(ExactArgs a) {
         v[i] = s;
     }
     if (a.force_last_one && a.N - 1 >= base && a.N - 1 < base + kChunk) v[a.N - 1 - base] = 1.0;
+    emit_coarse(a, f, tid, base, v[kChunk - 1]);
     if (base + kChunk <= a.N) {
         double2* p = reinterpret_cast<double2*>(out + base);
 #pragma unroll
@@ -537,8 +551,9 @@ struct MotionArgs {
     const double* const* peer_y;
     const double* const* peer_t;
     int64_t n_local;
-    const double* tile_start; // [F][T] exact CDF value before each 4096-particle tile (from the walk)
-    int T;
+    // coarse level of the CDF search, staged in shared memory: coarse[f][k] = cdf[(k+1) << cshift) - 1]
+    const double* coarse;     // [F][nc] or nullptr
+    int nc, cshift;
     const double* action;     // [F][3] device
     double disp_x, disp_y, disp_t;
     uint64_t seed;
@@ -585,27 +600,30 @@ __device__ __forceinline__ double wrap_angle_dev(double a) {  // src/utils.cpp:4
     return a;
 }
 
-constexpr int kMotionThreads = 256;
+constexpr int kMotionThreads = 1024;
 
-constexpr int kMaxSearchTiles = 4096;   // coarse CDF level kept in shared memory (32 KB)
-
+// One thread per output slot, persistent blocks when the coarse CDF level is large (one staging of
+// the table per SM).  The search is lower_bound(cp, u) in two levels: the coarse entries are the
+// exact CDF values at the ends of 2^cshift-element segments, so the first segment whose end value
+// is >= u contains the answer.
 __global__ void __launch_bounds__(kMotionThreads) k_resample_motion(MotionArgs a) {
     __shared__ double sm[kMotionThreads / 32];
-    extern __shared__ double ts[];   // a.T doubles when the coarse level is used
+    extern __shared__ double ts[];   // a.nc doubles when the coarse level is used
     const int f = blockIdx.y;
-    const bool two_level = a.T > 1 && a.T <= kMaxSearchTiles;
+    const bool two_level = a.coarse != nullptr && a.nc > 0;
     if (two_level) {
-        for (int t = threadIdx.x; t < a.T; t += kMotionThreads) ts[t] = a.tile_start[static_cast<int64_t>(f) * a.T + t];
+        for (int t = threadIdx.x; t < a.nc; t += kMotionThreads) ts[t] = a.coarse[static_cast<int64_t>(f) * a.nc + t];
         __syncthreads();
     }
-    const int64_t li = static_cast<int64_t>(blockIdx.x) * kMotionThreads + threadIdx.x;
-    const int64_t i = a.lo + li;   // global slot: noise and RNG counters do not depend on the sharding
     const int64_t N = a.N;
     const int64_t fo = static_cast<int64_t>(f) * N;
     const MotionScalars m = motion_scalars(a.action[3 * f + 0], a.action[3 * f + 2]);
     const uint64_t update_no = *a.update_no;
-    double nx = 0.0, ny = 0.0;
-    if (li < a.cnt) {
+    double sum_x = 0.0, sum_y = 0.0;
+    for (int64_t li = static_cast<int64_t>(blockIdx.x) * kMotionThreads + threadIdx.x; li < a.cnt;
+         li += static_cast<int64_t>(gridDim.x) * kMotionThreads) {
+        const int64_t i = a.lo + li;   // global slot: noise and RNG counters do not depend on the sharding
+        double nx, ny;
         // noise: injected arrays in the reference's draw order, else Philox keyed by
         // (seed, update) and counted by (filter, particle)
         double u, z0, z1, z2;
@@ -633,19 +651,18 @@ __global__ void __launch_bounds__(kMotionThreads) k_resample_motion(MotionArgs a
         const double* cp = a.cdf + fo;
         int64_t lo = 0, hi = N;
         if (two_level) {
-            // coarse level: ts[t] = cp[t*kTile - 1]; every index below t*kTile has cp <= ts[t], so
-            // with t* the last tile whose ts < u the answer lies inside tile t*
-            int tl = 0, th2 = a.T;
-            while (th2 - tl > 1) {
-                const int tm = (tl + th2) >> 1;
-                if (ts[tm] < u)
-                    tl = tm;
+            // k* = first segment whose end value ts[k] = cp[((k+1) << cshift) - 1] is >= u (nc if none):
+            // everything before segment k* is < u, so the answer lies in it (or in the tail past the table)
+            int kl = 0, kh = a.nc;
+            while (kl < kh) {
+                const int km = (kl + kh) >> 1;
+                if (ts[km] < u)
+                    kl = km + 1;
                 else
-                    th2 = tm;
+                    kh = km;
             }
-            lo = static_cast<int64_t>(tl) * kTile;
-            hi = min(N, lo + kTile);
-            if (hi == N) hi = N;   // the forced cp[N-1] = 1.0 closes the last tile
+            lo = static_cast<int64_t>(kl) << a.cshift;
+            hi = min(N, lo + (int64_t{1} << a.cshift));
         }
         while (lo < hi) {
             const int64_t mid = (lo + hi) >> 1;
@@ -694,10 +711,12 @@ __global__ void __launch_bounds__(kMotionThreads) k_resample_motion(MotionArgs a
         a.dt[fo + i] = nt;
         if (a.rec) dir_write_record(a.map, a.rec, fo + li, nx, ny, nt, theta_bucket(nt, a.B));
         if (!(fabs(nx) < 1e12) || !(fabs(ny) < 1e12)) nx = ny = 0.0;  // keep the window centre finite
+        sum_x += nx;
+        sum_y += ny;
     }
     // cloud centre for the shared-memory window of the ray kernel
-    const double bx = block_sum<kMotionThreads>(nx, sm);
-    const double by = block_sum<kMotionThreads>(ny, sm);
+    const double bx = block_sum<kMotionThreads>(sum_x, sm);
+    const double by = block_sum<kMotionThreads>(sum_y, sm);
     if (threadIdx.x == 0) {
         atomicAdd(a.centre + 2 * f + 0, bx);
         atomicAdd(a.centre + 2 * f + 1, by);

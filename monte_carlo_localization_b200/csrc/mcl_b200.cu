@@ -100,6 +100,8 @@ struct mcl_ctx {
     double* d_anchors = nullptr;
     double* d_anchor_val = nullptr;
     double* d_tile_start = nullptr;
+    double* d_coarse = nullptr;      // [F][coarse_n] coarse level of the CDF search (exact values at segment ends)
+    int coarse_n = 0, coarse_shift = 0;
     double* d_S1 = nullptr;
     double* d_S2 = nullptr;
     double* d_scratch_total = nullptr;
@@ -198,6 +200,10 @@ ExactArgs exact_args(mcl_ctx* c, const double* src, const double* div, const dou
     a.total = total;
     a.out = out;
     a.force_last_one = force_one;
+    // the pass that emits the CDF also publishes the coarse level of its search
+    a.coarse = (out && c->coarse_n > 0) ? c->d_coarse : nullptr;
+    a.coarse_m = a.coarse ? (1 << c->coarse_shift) / kChunk : 0;
+    a.coarse_n = c->coarse_n;
     return a;
 }
 
@@ -489,8 +495,9 @@ int update_local(mcl_ctx* c, const double* action_dev, const float* obs_dev, con
         ma.peer_t = c->d_peer_tab + static_cast<size_t>(src * 3 + 2) * c->world;
         ma.n_local = c->N / c->world;
     }
-    ma.tile_start = c->d_tile_start;
-    ma.T = c->T;
+    ma.coarse = c->coarse_n > 0 ? c->d_coarse : nullptr;
+    ma.nc = c->coarse_n;
+    ma.cshift = c->coarse_shift;
     ma.action = action_dev;
     ma.disp_x = c->prm.motion_dispersion_x;
     ma.disp_y = c->prm.motion_dispersion_y;
@@ -498,8 +505,10 @@ int update_local(mcl_ctx* c, const double* action_dev, const float* obs_dev, con
     ma.seed = c->prm.seed;
     ma.update_no = c->d_update_no;
     ma.centre = c->d_centre;
-    const int mblocks = static_cast<int>((c->cnt + kMotionThreads - 1) / kMotionThreads);
-    const size_t msmem = (c->T > 1 && c->T <= kMaxSearchTiles) ? sizeof(double) * c->T : 0;
+    int mblocks = static_cast<int>((c->cnt + kMotionThreads - 1) / kMotionThreads);
+    const size_t msmem = sizeof(double) * static_cast<size_t>(c->coarse_n);
+    // a large table is staged once per SM by persistent blocks; a small one by every block
+    if (msmem > 16 * 1024) mblocks = std::min(mblocks, std::max(1, c->num_sms / std::min(c->F, c->num_sms)));
     k_resample_motion<<<dim3(mblocks, c->F), kMotionThreads, msmem, s>>>(ma);
     c->launches++;
     if (c->sort_enabled) {
@@ -803,6 +812,12 @@ static int create_buffers(mcl_ctx* c, const mcl_params* p, int device) {
     CK(dalloc(&c->d_anchors, FC));
     CK(dalloc(&c->d_anchor_val, FC));
     CK(dalloc(&c->d_tile_start, FT));
+    {   // coarse CDF level: segments of 64 particles, doubled until at most 16384 entries (128 KB of shared memory)
+        c->coarse_shift = 6;
+        while ((c->N >> c->coarse_shift) > 16384) ++c->coarse_shift;
+        c->coarse_n = static_cast<int>(c->N >> c->coarse_shift);
+        CK(dalloc(&c->d_coarse, static_cast<size_t>(c->F) * std::max(c->coarse_n, 1)));
+    }
     CK(dalloc(&c->d_S1, static_cast<size_t>(c->F)));
     CK(dalloc(&c->d_S2, static_cast<size_t>(c->F)));
     CK(dalloc(&c->d_scratch_total, static_cast<size_t>(c->F)));
@@ -851,6 +866,7 @@ static int create_buffers(mcl_ctx* c, const mcl_params* p, int device) {
     MCL_RAY_SMEM(4, 238);
     MCL_RAY_SMEM(4, 239);
 #undef MCL_RAY_SMEM
+    CK(cudaFuncSetAttribute(k_resample_motion, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * static_cast<int>(sizeof(double))));
     CK(cudaFuncSetAttribute(k_raycast_dir<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kWindowBudget)));
     CK(cudaFuncSetAttribute(k_raycast_dir<207>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kWindowBudget)));
     CK(cudaFuncSetAttribute(k_raycast_dir<238>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kWindowBudget)));
@@ -892,7 +908,7 @@ int mcl_destroy(mcl_ctx* c) {
                     c->d_py[1], c->d_pt[0], c->d_pt[1], c->d_wraw, c->d_wn, c->d_cdf, c->d_idx, c->d_steps, c->d_u, c->d_z,
                     c->d_action, c->d_slice, c->d_tile_sum, c->d_chunk_fn, c->d_opq_pre, c->d_opq_idx,
                     c->d_tile_opq, c->d_tile_elem, c->d_list_chunk, c->d_list_fn, c->d_anchors, c->d_anchor_val,
-                    c->d_tile_start, c->d_S1, c->d_S2, c->d_scratch_total, c->d_partial, c->d_pose, c->d_centre, c->d_replays,
+                    c->d_tile_start, c->d_coarse, c->d_S1, c->d_S2, c->d_scratch_total, c->d_partial, c->d_pose, c->d_centre, c->d_replays,
                     c->d_hist, c->d_perm, c->d_done};
     for (void* p : ptrs)
         if (p) cudaFree(p);
