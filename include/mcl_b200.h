@@ -146,9 +146,10 @@ int mcl_kernel_launches(mcl_ctx* ctx, int64_t* count); /* kernels launched so fa
 /* Use the caller's CUDA stream (cudaStream_t passed as void*) instead of the ctx's own. */
 int mcl_set_stream(mcl_ctx* ctx, void* cuda_stream);
 
-/* The host-facing mcl_update replays its steady state (no injected noise, no diagnostics, whole
+/* mcl_update and mcl_update_dev replay their steady state (no injected noise, no diagnostics, whole
  * filter on this GPU, weights untouched since the previous update) as ONE CUDA graph per
- * state-buffer parity instead of ~18 kernel launches; results are identical.  On by default;
+ * state-buffer parity instead of ~18 kernel launches; results are identical (mcl_update_dev first
+ * copies action and scan into the context's staging buffers, device to device).  On by default;
  * graphs are dropped and re-captured whenever a setter changes a buffer, the stream or a mode. */
 int mcl_set_graphs(mcl_ctx* ctx, int enabled);
 

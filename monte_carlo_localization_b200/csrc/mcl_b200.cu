@@ -713,6 +713,54 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
     return update_finish(c);
 }
 
+// One update from device-resident inputs, replayed as a CUDA graph when the update is in its steady
+// state (no diagnostics, whole filter on this GPU, weights untouched since the last update): the
+// ~18 launches become one.  The graph reads action and scan from the context's own staging
+// buffers, so foreign device pointers are first copied there (264 bytes, device to device).
+int update_steady(mcl_ctx* c, const double* action_dev, const float* obs_dev) {
+    cudaStream_t s = c->stream;
+    const bool graph_ok = c->graphs_enabled && !c->profiling && !c->keep_ranges && !c->p2p && c->lo == 0 && c->cnt == c->N &&
+                          c->tile_state == 2 && !c->local_pending;
+    if (!graph_ok) return update_device(c, action_dev, obs_dev, nullptr, nullptr);
+    if (action_dev != c->d_action)
+        CK(cudaMemcpyAsync(c->d_action, action_dev, sizeof(double) * 3 * c->F, cudaMemcpyDeviceToDevice, s));
+    if (obs_dev != c->d_obs)
+        CK(cudaMemcpyAsync(c->d_obs, obs_dev, sizeof(float) * c->R * c->F, cudaMemcpyDeviceToDevice, s));
+    if (c->gexec[c->cur]) {
+        CK(cudaGraphLaunch(c->gexec[c->cur], s));
+        c->cur ^= 1;             // what update_device does on the host side
+        c->update_no++;
+        c->launches += c->graph_launches;
+        return MCL_OK;
+    }
+    if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        c->graphs_enabled = false;
+        return update_device(c, c->d_action, c->d_obs, nullptr, nullptr);
+    }
+    const int parity = c->cur;
+    const int64_t before = c->launches;
+    int rc = update_device(c, c->d_action, c->d_obs, nullptr, nullptr);
+    cudaGraph_t g = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(s, &g);
+    if (rc == MCL_OK && e == cudaSuccess && g && cudaGraphInstantiate(&c->gexec[parity], g, 0) == cudaSuccess) {
+        c->graph_launches = c->launches - before;
+        cudaGraphDestroy(g);
+        CK(cudaGraphLaunch(c->gexec[parity], s));
+        return MCL_OK;
+    }
+    // capture refused (e.g. an enclosing capture): run this update directly and stop trying
+    if (g) cudaGraphDestroy(g);
+    cudaGetLastError();
+    c->gexec[parity] = nullptr;
+    c->graphs_enabled = false;
+    if (rc != MCL_OK) return rc;
+    c->cur ^= 1;                 // undo the host-side bookkeeping of the captured (never executed) update
+    c->update_no--;
+    c->launches = before;
+    return update_device(c, c->d_action, c->d_obs, nullptr, nullptr);
+}
+
 }  // namespace
 
 extern "C" {
@@ -1227,7 +1275,7 @@ int mcl_update_dev(mcl_ctx* c, const double* action_dev, const float* obs_dev, i
     if (!c || !action_dev || !obs_dev) return fail(MCL_ERR_INVALID, "null argument");
     if (num_beams != c->R) return fail(MCL_ERR_INVALID, "num_beams %d != configured %d", num_beams, c->R);
     CK(cudaSetDevice(c->device));
-    return update_device(c, action_dev, obs_dev, nullptr, nullptr);
+    return update_steady(c, action_dev, obs_dev);
 }
 
 int mcl_read_pose(mcl_ctx* c, double* pose_out) {
@@ -1281,42 +1329,7 @@ int mcl_update(mcl_ctx* c, const double* action, const float* obs, int num_beams
             z_dev = c->d_z;
         }
     }
-    // Steady state (no injected noise, no diagnostics, whole filter on this GPU, weights untouched
-    // since the last update): the ~18 launches of an update are replayed as ONE CUDA graph.
-    const bool graph_ok = c->graphs_enabled && !noise && !c->profiling && !c->keep_ranges && !c->p2p && c->lo == 0 &&
-                          c->cnt == c->N && c->tile_state == 2 && !c->local_pending;
-    int rc = MCL_OK;
-    if (graph_ok && c->gexec[c->cur]) {
-        CK(cudaGraphLaunch(c->gexec[c->cur], s));
-        c->cur ^= 1;             // what update_device does on the host side
-        c->update_no++;
-        c->launches += c->graph_launches;
-    } else if (graph_ok && cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-        const int parity = c->cur;
-        const int64_t before = c->launches;
-        rc = update_device(c, c->d_action, c->d_obs, nullptr, nullptr);
-        cudaGraph_t g = nullptr;
-        const cudaError_t e = cudaStreamEndCapture(s, &g);
-        if (rc == MCL_OK && e == cudaSuccess && g && cudaGraphInstantiate(&c->gexec[parity], g, 0) == cudaSuccess) {
-            c->graph_launches = c->launches - before;
-            cudaGraphDestroy(g);
-            CK(cudaGraphLaunch(c->gexec[parity], s));
-        } else {
-            // capture refused (e.g. an enclosing capture): run this update directly and stop trying
-            if (g) cudaGraphDestroy(g);
-            cudaGetLastError();
-            c->gexec[parity] = nullptr;
-            c->graphs_enabled = false;
-            if (rc != MCL_OK) return rc;
-            c->cur ^= 1;         // undo the host-side bookkeeping of the captured (never executed) update
-            c->update_no--;
-            c->launches = before;
-            rc = update_device(c, c->d_action, c->d_obs, nullptr, nullptr);
-        }
-    } else {
-        if (graph_ok) cudaGetLastError();
-        rc = update_device(c, c->d_action, c->d_obs, u_dev, z_dev);
-    }
+    int rc = noise ? update_device(c, c->d_action, c->d_obs, u_dev, z_dev) : update_steady(c, c->d_action, c->d_obs);
     if (rc) return rc;
     // the pose kernel has written the pose into h_pose (mapped pinned memory): no D2H copy call
     CK(cudaStreamSynchronize(s));
