@@ -2,8 +2,12 @@
 //
 // One update of the reference (src/particle_filter.cpp:652-716) becomes, per filter:
 //   exact sums / CDF   k_tile_sums, k_exact_chunks, k_exact_walk, k_exact_emit   (:658, :679)
+//                      (k_exact_single: all of a pass in one CTA for a filter of one tile)
 //   resample + motion  k_resample_motion                                         (:661-665, :449-503)
-//   ray cast + weight  k_prepare_obs, k_raycast_weight                           (:506-650)
+//   heading sort       k_sort_hist, k_sort_scatter (processing order only)
+//   ray cast + weight  k_prepare_obs, then either k_raycast_weight (isotropic skip map, weights in
+//                      its epilogue) or the directional stage of dir_kernels.cuh: k_dir_gather,
+//                      k_dir_plan, k_raycast_dir, k_weight_steps                   (:506-650)
 //   normalise + pose   k_normalize_pose (the last block writes the pose)         (:679-686, :696-716)
 // blockIdx.y is the filter of a batch; every per-filter array is [F][...] contiguous.
 #pragma once
