@@ -342,6 +342,15 @@ def run_gpu(args):
         ctx.set_keep_ranges(False)
         ctx.set_profiling(False)
         cbar = float(np.mean(cb_samples))
+    elif args.shard_stages:
+        # sharded filter: per-stage times of this rank from a profiled replay of the same steps
+        # ("exchange" = the NCCL all-gather between the local stages and the finish stage)
+        flt.set_state(snap_p, snap_w)
+        ctx.set_profiling(True)
+        for i in range(K):
+            flt.update(acts_h[i], obs_h[i])
+            stages.append(ctx.stage_ms())
+        ctx.set_profiling(False)
     stage = {k: float(np.mean([s_[k] for s_ in stages])) for k in stages[0]} if stages else None
 
     # ---- max over ranks --------------------------------------------------------------------
@@ -426,6 +435,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--ray-mode", type=int, default=0, choices=[0, 1, 2],
                     help="0 auto (default), 1 isotropic skip-map kernel only, 2 directional stage always")
+    ap.add_argument("--shard-stages", action="store_true", help="multi-GPU: also report rank 0's per-stage times (extra replay)")
     ap.add_argument("--shard-mode", default="p2p", choices=["p2p", "allgather"],
                     help="multi-GPU exchange: NVLink peer reads of source poses + weight all-gather, or full all-gather")
     args = ap.parse_args()

@@ -70,6 +70,7 @@ typedef struct mcl_noise {
 typedef struct mcl_stage_ms {
     float cdf, resample_motion, raycast_weight, normalize_pose, total;
     float ray_march;   /* the ray kernel alone (raycast_weight also covers the table product) */
+    float exchange;    /* sharded filter: between mcl_update_local_dev and mcl_update_finish_dev (the caller's all-gather) */
 } mcl_stage_ms;
 
 typedef struct mcl_ctx mcl_ctx;
@@ -200,16 +201,18 @@ int mcl_update_finish_dev(mcl_ctx* ctx);
  * every rank maps the other ranks' state arrays (CUDA IPC) and the resampling kernel reads
  * each slot's source pose straight from its owner over NVLink; only the raw weights
  * (8 B/particle) and four pose partial sums per rank are all-gathered.  Set-up, once:
- *   mcl_ipc_export on every rank -> exchange the 384-byte blobs -> mcl_ipc_import(world, rank,
+ *   mcl_ipc_export on every rank -> exchange the 512-byte blobs -> mcl_ipc_import(world, rank,
  *   blobs in rank order).  Per update: mcl_update_local_dev -> all-gather in place the two
  *   buffers of mcl_p2p_buffers_dev (w_raw: slice [lo, lo+count); partials: 4 doubles at
  *   [4*rank]) -> mcl_update_finish_dev.  After set-up only a rank's own slice of the state is
  *   current in its arrays.  mcl_set_peer_pointers does the same wiring from raw device
- *   pointers (several contexts in one process; mcl_state_pointers_dev lists them). */
+ *   pointers (several contexts in one process; mcl_state_pointers_dev lists them: x, y, theta of
+ *   both state buffers, then the packed 32-byte (x, y, theta, 0) copies of both buffers, which is
+ *   what the resampling kernel reads from a peer -- one NVLink transaction per source pose). */
 int mcl_ipc_export(mcl_ctx* ctx, void* handles_out, size_t capacity);
 int mcl_ipc_import(mcl_ctx* ctx, int world, int rank, const void* handles);
-int mcl_set_peer_pointers(mcl_ctx* ctx, int world, int rank, const void* const* ptrs /* world x 6 */);
-int mcl_state_pointers_dev(mcl_ctx* ctx, void* ptrs_out[6]);
+int mcl_set_peer_pointers(mcl_ctx* ctx, int world, int rank, const void* const* ptrs /* world x 8 */);
+int mcl_state_pointers_dev(mcl_ctx* ctx, void* ptrs_out[8]);
 int mcl_p2p_buffers_dev(mcl_ctx* ctx, void** w_raw_dev, void** partials_dev);
 
 #ifdef __cplusplus

@@ -44,7 +44,7 @@ class MclNoise(C.Structure):
 
 class MclStageMs(C.Structure):
     _fields_ = [("cdf", C.c_float), ("resample_motion", C.c_float), ("raycast_weight", C.c_float),
-                ("normalize_pose", C.c_float), ("total", C.c_float), ("ray_march", C.c_float)]
+                ("normalize_pose", C.c_float), ("total", C.c_float), ("ray_march", C.c_float), ("exchange", C.c_float)]
 
 
 # every symbol include/mcl_b200.h declares: name -> (restype, argtypes)
@@ -385,7 +385,7 @@ class MclContext:
     def update_finish_dev(self):
         self._check(self._L.mcl_update_finish_dev(self._h), "mcl_update_finish_dev")
 
-    IPC_BLOB = 6 * 64   # six cudaIpcMemHandle_t
+    IPC_BLOB = 8 * 64   # eight cudaIpcMemHandle_t: x, y, theta of both state buffers + their packed copies
 
     def ipc_export(self) -> bytes:
         buf = C.create_string_buffer(self.IPC_BLOB)
@@ -398,12 +398,12 @@ class MclContext:
         self._check(self._L.mcl_ipc_import(self._h, world, rank, C.c_char_p(blobs)), "mcl_ipc_import")
 
     def state_pointers_dev(self):
-        ptrs = (C.c_void_p * 6)()
+        ptrs = (C.c_void_p * 8)()
         self._check(self._L.mcl_state_pointers_dev(self._h, ptrs), "mcl_state_pointers_dev")
         return [int(p) for p in ptrs]
 
     def set_peer_pointers(self, world: int, rank: int, ptrs):
-        arr = (C.c_void_p * (6 * world))(*[C.c_void_p(p) for p in ptrs])
+        arr = (C.c_void_p * (8 * world))(*[C.c_void_p(p) for p in ptrs])
         self._check(self._L.mcl_set_peer_pointers(self._h, world, rank, arr), "mcl_set_peer_pointers")
 
     def p2p_buffers_dev(self):

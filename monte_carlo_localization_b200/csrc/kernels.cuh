@@ -555,6 +555,13 @@ struct MotionArgs {
     const double* const* peer_y;
     const double* const* peer_t;
     int64_t n_local;
+    // packed copy of the state, one 32-byte (x, y, theta, 0) entry per particle: the source-pose
+    // gather of the resampling touches one memory sector (one NVLink transaction from a peer)
+    // instead of three.  spose4 / peer_pose4 = source buffer (nullptr: not valid, use the SoA
+    // arrays), dpose4 = destination buffer, always written.
+    const double4* spose4;
+    const double4* const* peer_pose4;
+    double4* dpose4;
     // coarse level of the CDF search, staged in shared memory: coarse[f][k] = cdf[(k+1) << cshift) - 1]
     const double* coarse;     // [F][nc] or nullptr
     int nc, cshift;
@@ -679,13 +686,26 @@ __global__ void __launch_bounds__(kMotionThreads) k_resample_motion(MotionArgs a
         if (N < 2) lo = 0;        // libstdc++ clears the table for fewer than 2 weights
         a.idx_out[fo + i] = static_cast<int32_t>(lo);
         double x, y, th;
-        if (a.peer_x) {
+        if (a.peer_pose4) {
             // the slot's source lives on rank q; its arrays are mapped into this address space
-            // (CUDA IPC), so these are plain loads that travel over NVLink
+            // (CUDA IPC), so this is a plain 32-byte load that travels over NVLink
+            const int q = static_cast<int>(lo / a.n_local);
+            const double2* p4 = reinterpret_cast<const double2*>(a.peer_pose4[q] + lo);
+            const double2 xy = p4[0], tz = p4[1];
+            x = xy.x;
+            y = xy.y;
+            th = tz.x;
+        } else if (a.peer_x) {
             const int q = static_cast<int>(lo / a.n_local);
             x = a.peer_x[q][lo];
             y = a.peer_y[q][lo];
             th = a.peer_t[q][lo];
+        } else if (a.spose4) {
+            const double2* p4 = reinterpret_cast<const double2*>(a.spose4 + fo + lo);
+            const double2 xy = __ldg(p4), tz = __ldg(p4 + 1);
+            x = xy.x;
+            y = xy.y;
+            th = tz.x;
         } else {
             x = a.sx[fo + lo];
             y = a.sy[fo + lo];
@@ -713,6 +733,11 @@ __global__ void __launch_bounds__(kMotionThreads) k_resample_motion(MotionArgs a
         a.dx[fo + i] = nx;
         a.dy[fo + i] = ny;
         a.dt[fo + i] = nt;
+        {
+            double2* d4 = reinterpret_cast<double2*>(a.dpose4 + fo + i);
+            d4[0] = make_double2(nx, ny);
+            d4[1] = make_double2(nt, 0.0);
+        }
         if (a.rec) dir_write_record(a.map, a.rec, fo + li, nx, ny, nt, theta_bucket(nt, a.B));
         if (!(fabs(nx) < 1e12) || !(fabs(ny) < 1e12)) nx = ny = 0.0;  // keep the window centre finite
         sum_x += nx;

@@ -74,6 +74,8 @@ struct mcl_ctx {
     double* d_px[2] = {nullptr, nullptr};
     double* d_py[2] = {nullptr, nullptr};
     double* d_pt[2] = {nullptr, nullptr};
+    double4* d_pose4[2] = {nullptr, nullptr};   // packed (x, y, theta, 0) copy of the state written by k_resample_motion
+    bool pose4_ok[2] = {false, false};          // the packed copy of that buffer matches the SoA arrays
     int cur = 0;
     double* d_wraw = nullptr;
     double* d_wn = nullptr;
@@ -161,7 +163,8 @@ struct mcl_ctx {
     int64_t graph_launches = 0;
     int64_t launches = 0;
     bool profiling = false;
-    cudaEvent_t ev[6] = {};
+    bool ev_valid = false;            // the stage events of a whole update have been recorded
+    cudaEvent_t ev[7] = {};
     mcl_stage_ms last_ms{};
     bool cdf_valid = false;
 };
@@ -489,7 +492,13 @@ int update_local(mcl_ctx* c, const double* action_dev, const float* obs_dev, con
     ma.idx_out = c->d_idx;
     ma.u = u_dev;
     ma.z = z_dev;
+    // the packed source copy is usable if k_resample_motion wrote it (no set_particles / init since) and,
+    // for a shard, if the other ranks' slices are reachable too (p2p; the all-gather mode only moves the SoA arrays)
+    const bool packed = c->pose4_ok[src] && (c->p2p || c->cnt == c->N);
+    ma.spose4 = packed ? c->d_pose4[src] : nullptr;
+    ma.dpose4 = c->d_pose4[dst];
     if (c->p2p) {
+        ma.peer_pose4 = packed ? reinterpret_cast<const double4* const*>(c->d_peer_tab + static_cast<size_t>(6 + src) * c->world) : nullptr;
         ma.peer_x = c->d_peer_tab + static_cast<size_t>(src * 3 + 0) * c->world;
         ma.peer_y = c->d_peer_tab + static_cast<size_t>(src * 3 + 1) * c->world;
         ma.peer_t = c->d_peer_tab + static_cast<size_t>(src * 3 + 2) * c->world;
@@ -511,6 +520,7 @@ int update_local(mcl_ctx* c, const double* action_dev, const float* obs_dev, con
     if (msmem > 16 * 1024) mblocks = std::min(mblocks, std::max(1, c->num_sms / std::min(c->F, c->num_sms)));
     k_resample_motion<<<dim3(mblocks, c->F), kMotionThreads, msmem, s>>>(ma);
     c->launches++;
+    c->pose4_ok[dst] = true;
     if (c->sort_enabled) {
         SortArgs sa{};
         sa.N = c->N;
@@ -686,6 +696,7 @@ int update_local(mcl_ctx* c, const double* action_dev, const float* obs_dev, con
 int update_finish(mcl_ctx* c) {
     if (!c->local_pending) return fail(MCL_ERR_INVALID, "mcl_update_finish without mcl_update_local");
     const int dst = c->cur ^ 1;
+    if (c->profiling) CK(cudaEventRecord(c->ev[6], c->stream));
     int rc = run_exact(c, c->d_wraw, nullptr, c->d_S1, nullptr, 0, true);
     if (rc) return rc;
     c->tile_state = 2;   // d_tile_sum = tile sums of w_raw; w_norm = w_raw / S1 follows
@@ -699,7 +710,10 @@ int update_finish(mcl_ctx* c) {
         rc = launch_pose(c, c->d_wraw, c->d_S1, c->d_wn, dst, true);
         if (rc) return rc;
     }
-    if (c->profiling) CK(cudaEventRecord(c->ev[4], c->stream));
+    if (c->profiling) {
+        CK(cudaEventRecord(c->ev[4], c->stream));
+        c->ev_valid = true;
+    }
     CK(cudaGetLastError());
     c->cur = dst;
     c->update_no++;
@@ -713,14 +727,35 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
     return update_finish(c);
 }
 
+// per-stage device times of the last profiled update, from its CUDA events (the stream must have
+// passed the last of them)
+void read_stage_times(mcl_ctx* c) {
+    float t = 0;
+    cudaEventElapsedTime(&t, c->ev[0], c->ev[1]);
+    c->last_ms.cdf = t;
+    cudaEventElapsedTime(&t, c->ev[1], c->ev[2]);
+    c->last_ms.resample_motion = t;
+    cudaEventElapsedTime(&t, c->ev[2], c->ev[3]);
+    c->last_ms.raycast_weight = t;
+    cudaEventElapsedTime(&t, c->ev[6], c->ev[4]);
+    c->last_ms.normalize_pose = t;
+    cudaEventElapsedTime(&t, c->ev[0], c->ev[4]);
+    c->last_ms.total = t;
+    cudaEventElapsedTime(&t, c->ev[2], c->ev[5]);
+    c->last_ms.ray_march = t;
+    cudaEventElapsedTime(&t, c->ev[3], c->ev[6]);
+    c->last_ms.exchange = t;
+}
+
 // One update from device-resident inputs, replayed as a CUDA graph when the update is in its steady
 // state (no diagnostics, whole filter on this GPU, weights untouched since the last update): the
 // ~18 launches become one.  The graph reads action and scan from the context's own staging
 // buffers, so foreign device pointers are first copied there (264 bytes, device to device).
 int update_steady(mcl_ctx* c, const double* action_dev, const float* obs_dev) {
     cudaStream_t s = c->stream;
+    // (a captured graph reads the packed copy of the state: an update whose packed source is stale runs directly)
     const bool graph_ok = c->graphs_enabled && !c->profiling && !c->keep_ranges && !c->p2p && c->lo == 0 && c->cnt == c->N &&
-                          c->tile_state == 2 && !c->local_pending;
+                          c->tile_state == 2 && !c->local_pending && c->pose4_ok[c->cur];
     if (!graph_ok) return update_device(c, action_dev, obs_dev, nullptr, nullptr);
     if (action_dev != c->d_action)
         CK(cudaMemcpyAsync(c->d_action, action_dev, sizeof(double) * 3 * c->F, cudaMemcpyDeviceToDevice, s));
@@ -831,6 +866,8 @@ static int create_buffers(mcl_ctx* c, const mcl_params* p, int device) {
         CK(dalloc(&c->d_px[b], FN));
         CK(dalloc(&c->d_py[b], FN));
         CK(dalloc(&c->d_pt[b], FN));
+        CK(dalloc(&c->d_pose4[b], FN));
+        CK(cudaMemset(c->d_pose4[b], 0, FN * sizeof(double4)));
         CK(cudaMemset(c->d_px[b], 0, FN * sizeof(double)));   // particles_ = Zero (:106)
         CK(cudaMemset(c->d_py[b], 0, FN * sizeof(double)));
         CK(cudaMemset(c->d_pt[b], 0, FN * sizeof(double)));
@@ -952,7 +989,8 @@ int mcl_destroy(mcl_ctx* c) {
     if (!c) return MCL_OK;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    void* ptrs[] = {c->d_grid, c->d_v8, c->d_v4, c->d_free, c->d_tabT, c->d_step2idx, c->d_px[0], c->d_px[1], c->d_py[0],
+    void* ptrs[] = {c->d_pose4[0], c->d_pose4[1],
+                    c->d_grid, c->d_v8, c->d_v4, c->d_free, c->d_tabT, c->d_step2idx, c->d_px[0], c->d_px[1], c->d_py[0],
                     c->d_py[1], c->d_pt[0], c->d_pt[1], c->d_wraw, c->d_wn, c->d_cdf, c->d_idx, c->d_steps, c->d_u, c->d_z,
                     c->d_action, c->d_slice, c->d_tile_sum, c->d_chunk_fn, c->d_opq_pre, c->d_opq_idx,
                     c->d_tile_opq, c->d_tile_elem, c->d_list_chunk, c->d_list_fn, c->d_anchors, c->d_anchor_val,
@@ -1143,6 +1181,7 @@ int mcl_init_pose(mcl_ctx* c, int filter, const double pose[3], const double* no
     if (d_norm) cudaFree(d_norm);
     c->cdf_valid = false;
     c->tile_state = 0;
+    c->pose4_ok[c->cur] = false;   // the packed copy no longer matches the state arrays
     return MCL_OK;
 }
 
@@ -1189,6 +1228,7 @@ int mcl_init_global(mcl_ctx* c, int filter, const int32_t* cell, const double* t
     if (d_theta) cudaFree(d_theta);
     c->cdf_valid = false;
     c->tile_state = 0;
+    c->pose4_ok[c->cur] = false;   // the packed copy no longer matches the state arrays
     return MCL_OK;
 }
 
@@ -1202,6 +1242,7 @@ int mcl_set_particles(mcl_ctx* c, int filter, const double* P, const double* w) 
         CK(cudaMemcpy(c->d_px[c->cur] + fo, P, N * sizeof(double), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(c->d_py[c->cur] + fo, P + N, N * sizeof(double), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(c->d_pt[c->cur] + fo, P + 2 * N, N * sizeof(double), cudaMemcpyHostToDevice));
+        c->pose4_ok[c->cur] = false;   // the packed copy no longer matches the state arrays
     }
     if (w) {
         CK(cudaMemcpy(c->d_wn + fo, w, N * sizeof(double), cudaMemcpyHostToDevice));
@@ -1334,21 +1375,7 @@ int mcl_update(mcl_ctx* c, const double* action, const float* obs, int num_beams
     // the pose kernel has written the pose into h_pose (mapped pinned memory): no D2H copy call
     CK(cudaStreamSynchronize(s));
     if (pose_out) std::memcpy(pose_out, c->h_pose, sizeof(double) * 3 * c->F);
-    if (c->profiling) {
-        float t = 0;
-        cudaEventElapsedTime(&t, c->ev[0], c->ev[1]);
-        c->last_ms.cdf = t;
-        cudaEventElapsedTime(&t, c->ev[1], c->ev[2]);
-        c->last_ms.resample_motion = t;
-        cudaEventElapsedTime(&t, c->ev[2], c->ev[3]);
-        c->last_ms.raycast_weight = t;
-        cudaEventElapsedTime(&t, c->ev[3], c->ev[4]);
-        c->last_ms.normalize_pose = t;
-        cudaEventElapsedTime(&t, c->ev[0], c->ev[4]);
-        c->last_ms.total = t;
-        cudaEventElapsedTime(&t, c->ev[2], c->ev[5]);
-        c->last_ms.ray_march = t;
-    }
+    if (c->profiling && c->ev_valid) read_stage_times(c);
     return MCL_OK;
 }
 
@@ -1421,11 +1448,18 @@ int mcl_sample_particles(mcl_ctx* c, int filter, int k, double* out) {
 int mcl_set_profiling(mcl_ctx* c, int enabled) {
     if (!c) return fail(MCL_ERR_INVALID, "null context");
     c->profiling = enabled != 0;
+    c->ev_valid = false;
     return MCL_OK;
 }
 
 int mcl_get_stage_ms(mcl_ctx* c, mcl_stage_ms* out) {
     if (!c || !out) return fail(MCL_ERR_INVALID, "null argument");
+    if (c->profiling && c->ev_valid && !c->local_pending) {
+        // the device-resident and sharded entry points do not synchronise: wait for the last event here
+        CK(cudaSetDevice(c->device));
+        CK(cudaEventSynchronize(c->ev[4]));
+        read_stage_times(c);
+    }
     *out = c->last_ms;
     return MCL_OK;
 }
@@ -1452,6 +1486,7 @@ int mcl_set_shard(mcl_ctx* c, int64_t lo, int64_t count) {
     if (c->local_pending) return fail(MCL_ERR_INVALID, "update in flight");
     c->lo = lo;
     c->cnt = count;
+    c->pose4_ok[0] = c->pose4_ok[1] = false;
     drop_graphs(c);
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
@@ -1496,19 +1531,21 @@ static int install_peers(mcl_ctx* c, int world, int rank, const std::vector<cons
     c->lo = (c->N / world) * rank;
     c->cnt = c->N / world;
     c->p2p = true;
+    c->pose4_ok[0] = c->pose4_ok[1] = false;
     drop_graphs(c);
     return upload_replay_ctx(c);   // the shard moved: the exact-replay context of the directional stage follows it
 }
 
 int mcl_ipc_export(mcl_ctx* c, void* handles_out, size_t capacity) {
     if (!c || !handles_out) return fail(MCL_ERR_INVALID, "null argument");
-    if (capacity < 6 * sizeof(cudaIpcMemHandle_t)) return fail(MCL_ERR_INVALID, "need %zu bytes", 6 * sizeof(cudaIpcMemHandle_t));
+    if (capacity < 8 * sizeof(cudaIpcMemHandle_t)) return fail(MCL_ERR_INVALID, "need %zu bytes", 8 * sizeof(cudaIpcMemHandle_t));
     CK(cudaSetDevice(c->device));
     auto* h = static_cast<cudaIpcMemHandle_t*>(handles_out);
     for (int b = 0; b < 2; ++b) {
         CK(cudaIpcGetMemHandle(&h[b * 3 + 0], c->d_px[b]));
         CK(cudaIpcGetMemHandle(&h[b * 3 + 1], c->d_py[b]));
         CK(cudaIpcGetMemHandle(&h[b * 3 + 2], c->d_pt[b]));
+        CK(cudaIpcGetMemHandle(&h[6 + b], c->d_pose4[b]));
     }
     return MCL_OK;
 }
@@ -1518,16 +1555,17 @@ int mcl_ipc_import(mcl_ctx* c, int world, int rank, const void* handles) {
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
     const auto* h = static_cast<const cudaIpcMemHandle_t*>(handles);
-    std::vector<const double*> tab(static_cast<size_t>(6) * world, nullptr);   // [buf][arr][world]
+    std::vector<const double*> tab(static_cast<size_t>(8) * world, nullptr);   // [x y t of buf 0 | of buf 1 | pose4 buf 0 | buf 1][world]
     for (int q = 0; q < world; ++q) {
-        for (int k = 0; k < 6; ++k) {
+        for (int k = 0; k < 8; ++k) {
             const double* ptr;
             if (q == rank) {
                 const int b = k / 3, a = k % 3;
-                ptr = a == 0 ? c->d_px[b] : (a == 1 ? c->d_py[b] : c->d_pt[b]);
+                ptr = k >= 6 ? reinterpret_cast<const double*>(c->d_pose4[k - 6])
+                             : (a == 0 ? c->d_px[b] : (a == 1 ? c->d_py[b] : c->d_pt[b]));
             } else {
                 void* p = nullptr;
-                CK(cudaIpcOpenMemHandle(&p, h[q * 6 + k], cudaIpcMemLazyEnablePeerAccess));
+                CK(cudaIpcOpenMemHandle(&p, h[q * 8 + k], cudaIpcMemLazyEnablePeerAccess));
                 c->ipc_opened.push_back(p);
                 ptr = static_cast<const double*>(p);
             }
@@ -1541,18 +1579,19 @@ int mcl_set_peer_pointers(mcl_ctx* c, int world, int rank, const void* const* pt
     if (!c || !ptrs) return fail(MCL_ERR_INVALID, "null argument");
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
-    std::vector<const double*> tab(static_cast<size_t>(6) * world, nullptr);
+    std::vector<const double*> tab(static_cast<size_t>(8) * world, nullptr);
     for (int q = 0; q < world; ++q)
-        for (int k = 0; k < 6; ++k) tab[static_cast<size_t>(k) * world + q] = static_cast<const double*>(ptrs[q * 6 + k]);
+        for (int k = 0; k < 8; ++k) tab[static_cast<size_t>(k) * world + q] = static_cast<const double*>(ptrs[q * 8 + k]);
     return install_peers(c, world, rank, tab);
 }
 
-int mcl_state_pointers_dev(mcl_ctx* c, void* ptrs_out[6]) {
+int mcl_state_pointers_dev(mcl_ctx* c, void* ptrs_out[8]) {
     if (!c || !ptrs_out) return fail(MCL_ERR_INVALID, "null argument");
     for (int b = 0; b < 2; ++b) {
         ptrs_out[b * 3 + 0] = c->d_px[b];
         ptrs_out[b * 3 + 1] = c->d_py[b];
         ptrs_out[b * 3 + 2] = c->d_pt[b];
+        ptrs_out[6 + b] = c->d_pose4[b];
     }
     return MCL_OK;
 }

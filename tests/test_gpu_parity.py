@@ -752,3 +752,57 @@ def test_batch_pool_directional_stage_equals_isotropic_kernel():
     want = steps_from_ranges(orcs[0].ranges(), g.resolution_f64, orcs[0].M)
     assert (out[0][0][0] != want).sum() == 0
     assert_weights_close(out[0][0][2], orcs[0].get_state()[1])
+
+
+def test_p2p_shards_free_running_use_packed_peer_poses():
+    """Peer-to-peer sharding without teacher forcing: from the second update on, every slot's
+    source pose is ONE 32-byte read of the owner's packed (x, y, theta) copy.  Two emulated ranks
+    must stay bit-identical to the single filter over the whole run."""
+    import torch
+    from monte_carlo_localization_b200 import maps
+    from monte_carlo_localization_b200.sharded import ShardPlan, _DevArray
+    z = load_golden("update_sibal1_4000.npz")
+    g = maps.load_named_map("sibal1")
+    N, world = int(z["N"]), 2
+    plan = ShardPlan(N, world)
+    single = _ctx(g, z["angles"], N)
+    single.set_particles(z["init_particles"], z["init_weights"])
+    ranks = [_ctx(g, z["angles"], N) for _ in range(world)]
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    all_ptrs = []
+    for c in ranks:
+        c.set_stream(stream.cuda_stream)
+        all_ptrs += c.state_pointers_dev()
+    for r, c in enumerate(ranks):
+        c.set_peer_pointers(world, r, all_ptrs)
+        c.set_particles(z["init_particles"], z["init_weights"])
+    for t in range(len(z["u"])):
+        pose_single = single.update(z["actions"][t], z["obs"][t], z["u"][t], z["z"][t])
+        a = torch.from_numpy(z["actions"][t].copy()).cuda()
+        o = torch.from_numpy(z["obs"][t].copy()).cuda()
+        u = torch.from_numpy(z["u"][t].copy()).cuda()
+        zz = torch.from_numpy(z["z"][t].copy()).cuda()
+        bufs = []
+        for c in ranks:
+            c.update_local_dev(a.data_ptr(), o.data_ptr(), u.data_ptr(), zz.data_ptr())
+            w_ptr, part_ptr = c.p2p_buffers_dev()
+            bufs.append((torch.as_tensor(_DevArray(w_ptr, N), device="cuda"),
+                         torch.as_tensor(_DevArray(part_ptr, 4 * world), device="cuda")))
+        for r in range(world):          # the two all-gathers, emulated with copies
+            for q in range(world):
+                if q != r:
+                    lo, cnt = plan.slots(q)
+                    bufs[r][0][lo:lo + cnt].copy_(bufs[q][0][lo:lo + cnt])
+                    bufs[r][1][4 * q:4 * q + 4].copy_(bufs[q][1][4 * q:4 * q + 4])
+        torch.cuda.synchronize()
+        for r, c in enumerate(ranks):
+            c.update_finish_dev()
+            pose = c.read_pose()
+            lo, cnt = plan.slots(r)
+            assert np.array_equal(c.resample_indices()[lo:lo + cnt], single.resample_indices()[lo:lo + cnt]), "update %d" % t
+            assert np.array_equal(c.get_weights(), single.get_weights())
+            assert np.array_equal(c.get_particles()[:, lo:lo + cnt], single.get_particles()[:, lo:lo + cnt])
+            assert_pose_close(pose, pose_single)
+    for c in ranks + [single]:
+        c.close()
