@@ -691,15 +691,18 @@ __global__ void __launch_bounds__(kMotionThreads) k_resample_motion(MotionArgs a
             // (CUDA IPC), so this is a plain 32-byte load that travels over NVLink
             const int q = static_cast<int>(lo / a.n_local);
             const double2* p4 = reinterpret_cast<const double2*>(a.peer_pose4[q] + lo);
-            const double2 xy = p4[0], tz = p4[1];
+            // cache-volatile loads: the owner rewrites this buffer every other update, and a line kept in
+            // this GPU's caches from two updates ago must not be served (measured: plain 128-bit loads
+            // returned stale poses on a real 2-GPU run; scripts/check_sharded_equals_single.py)
+            const double2 xy = __ldcv(p4), tz = __ldcv(p4 + 1);
             x = xy.x;
             y = xy.y;
             th = tz.x;
         } else if (a.peer_x) {
             const int q = static_cast<int>(lo / a.n_local);
-            x = a.peer_x[q][lo];
-            y = a.peer_y[q][lo];
-            th = a.peer_t[q][lo];
+            x = __ldcv(a.peer_x[q] + lo);   // cache-volatile like the packed path: a peer rewrites these arrays every other update
+            y = __ldcv(a.peer_y[q] + lo);
+            th = __ldcv(a.peer_t[q] + lo);
         } else if (a.spose4) {
             const double2* p4 = reinterpret_cast<const double2*>(a.spose4 + fo + lo);
             const double2 xy = __ldg(p4), tz = __ldg(p4 + 1);

@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -494,7 +495,8 @@ int update_local(mcl_ctx* c, const double* action_dev, const float* obs_dev, con
     ma.z = z_dev;
     // the packed source copy is usable if k_resample_motion wrote it (no set_particles / init since) and,
     // for a shard, if the other ranks' slices are reachable too (p2p; the all-gather mode only moves the SoA arrays)
-    const bool packed = c->pose4_ok[src] && (c->p2p || c->cnt == c->N);
+    static const bool no_packed = std::getenv("MCL_NO_PACKED") != nullptr;   // debugging knob
+    const bool packed = !no_packed && c->pose4_ok[src] && (c->p2p || c->cnt == c->N);
     ma.spose4 = packed ? c->d_pose4[src] : nullptr;
     ma.dpose4 = c->d_pose4[dst];
     if (c->p2p) {
