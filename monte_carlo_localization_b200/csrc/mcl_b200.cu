@@ -495,8 +495,13 @@ int update_local(mcl_ctx* c, const double* action_dev, const float* obs_dev, con
     ma.z = z_dev;
     // the packed source copy is usable if k_resample_motion wrote it (no set_particles / init since) and,
     // for a shard, if the other ranks' slices are reachable too (p2p; the all-gather mode only moves the SoA arrays)
+    // Only the unsharded filter reads the packed copy.  For p2p shards the packed PEER reads measured
+    // 20 % faster than three SoA reads (one NVLink transaction per pose) but were not bit-exact against
+    // one GPU on a real 4-GPU run (scripts/check_sharded_equals_single.py), so they stay off until that
+    // is understood; the SoA peer reads are verified exact at 2 and 4 GPUs.
     static const bool no_packed = std::getenv("MCL_NO_PACKED") != nullptr;   // debugging knob
-    const bool packed = !no_packed && c->pose4_ok[src] && (c->p2p || c->cnt == c->N);
+    static const bool packed_peers = std::getenv("MCL_PACKED_PEERS") != nullptr;   // experiment
+    const bool packed = !no_packed && c->pose4_ok[src] && ((c->p2p && packed_peers) || (!c->p2p && c->cnt == c->N));
     ma.spose4 = packed ? c->d_pose4[src] : nullptr;
     ma.dpose4 = c->d_pose4[dst];
     if (c->p2p) {
