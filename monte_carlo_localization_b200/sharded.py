@@ -8,14 +8,18 @@ reference's semantics exactly:
   * every rank holds the whole filter state, but computes only output slots
     [rank * n_local, (rank + 1) * n_local) of the expensive per-particle stages
     (resample search, motion, ray cast, weights);
-  * ONE exchange step per update: an in-place all-gather of the four state arrays
-    (x, y, theta, raw weight) over NCCL / NVLink;
+  * ONE exchange step per update over NCCL / NVLink: in mode "p2p" an in-place all-gather of
+    the raw weights (+ four pose partial sums per rank), the source poses being read by the
+    resampling kernel straight from their owner's memory (CUDA IPC); in mode "allgather" an
+    in-place all-gather of all four state arrays (x, y, theta, raw weight);
   * the global weight sum, normalisation, pose and the next CDF are then computed on every
     rank from identical data with deterministic kernels, so all ranks stay bit-identical and
     the gathered result equals the single-filter update with the same noise.
 
 `ShardPlan` and `exchange` are backend-agnostic host logic (exercised with gloo on CPU in
 tests/test_sharded_gloo.py); `ShardedFilter` binds them to the CUDA context.
+scripts/check_sharded_equals_single.py checks on real GPUs that the sharded filter stays
+bit-identical to the same filter on one GPU.
 """
 from __future__ import annotations
 
