@@ -497,8 +497,9 @@ int update_local(mcl_ctx* c, const double* action_dev, const float* obs_dev, con
     // for a shard, if the other ranks' slices are reachable too (p2p; the all-gather mode only moves the SoA arrays)
     // Only the unsharded filter reads the packed copy.  For p2p shards the packed PEER reads measured
     // 20 % faster than three SoA reads (one NVLink transaction per pose) but were not bit-exact against
-    // one GPU on a real 4-GPU run (scripts/check_sharded_equals_single.py), so they stay off until that
-    // is understood; the SoA peer reads are verified exact at 2 and 4 GPUs.
+    // one GPU for a 1 M-particle filter on real 2- and 4-GPU runs (exact for 512 k particles;
+    // scripts/check_sharded_equals_single.py), so they stay off until that is understood; the SoA peer
+    // reads are verified exact at 2 and 4 GPUs.
     static const bool no_packed = std::getenv("MCL_NO_PACKED") != nullptr;   // debugging knob
     static const bool packed_peers = std::getenv("MCL_PACKED_PEERS") != nullptr;   // experiment
     const bool packed = !no_packed && c->pose4_ok[src] && ((c->p2p && packed_peers) || (!c->p2p && c->cnt == c->N));
