@@ -215,7 +215,20 @@ def run_gpu(args):
         raise SystemExit("--gpus %d needs torchrun (one rank per GPU)" % args.gpus)
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL prints its version banner on stdout when NCCL_DEBUG=VERSION is set in the environment;
+        # stdout must carry exactly ONE JSON line, so file descriptor 1 points at stderr while the
+        # communicator is created
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     grid = maps.load_named_map(MAP_NAME)
     angles = synth.beam_angles()
