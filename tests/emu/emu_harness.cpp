@@ -55,6 +55,7 @@ static const std::vector<uint8_t>& emu_dir_sector(emu_map* m, int s) {
     std::vector<uint8_t>& d = m->dir[s];
     if (d.empty()) {
         d.resize(static_cast<size_t>(sk.PW) * sk.PH);
+#pragma omp parallel for schedule(dynamic, 8)   // test harness only: rows of one sector map in parallel
         for (int cy = 0; cy < sk.PH; ++cy)
             for (int cx = 0; cx < sk.PW; ++cx)
                 d[static_cast<size_t>(cy) * sk.PW + cx] = dir_code(sk.v8.data(), m->gap.data(), sk.PW, sk.PH, cx, cy, m->sectors[s]);

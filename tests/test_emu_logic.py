@@ -237,17 +237,19 @@ def test_sector_windows_fit_shared_memory_and_stay_inside_the_grid():
             assert (w[:, 0] + w[:, 2] <= em.PW).all() and (w[:, 1] + w[:, 3] <= em.PH).all()
 
 
-def test_directional_march_reproduces_the_golden_range_steps():
-    """The committed golden fixture holds the step indices the UNMODIFIED reference produced for
+@pytest.mark.parametrize("fixture,name", [("update_sibal1_4000.npz", "sibal1"), ("update_basement_fixed_1000.npz", "basement_fixed"),
+                                          ("update_Spielberg_map_2000.npz", "Spielberg_map")])
+def test_directional_march_reproduces_the_golden_range_steps(fixture, name):
+    """The committed golden fixtures hold the step indices the UNMODIFIED reference produced for
     its own proposal particles; the directional march (CPU build of the kernel source, window
-    path included) reproduces them exactly for every update of the fixture."""
+    path included) reproduces them exactly for every update of every fixture."""
     from helpers import load_golden
-    z = load_golden("update_sibal1_4000.npz")
-    g = maps.load_named_map("sibal1")
+    z = load_golden(fixture)
+    g = maps.load_named_map(name)
     em = EmuMap(g)
     for t in range(len(z["u"])):
         p = z["particles"][t]          # the proposal the reference cast its rays from (:540)
-        for box in (0, 128):
+        for box in ((0, 128) if name == "sibal1" else (128,)):
             got, replays = em.range_steps_dir(p[0], p[1], p[2], z["angles"], buckets=2048, window_box=box)
             assert replays >= 0, "%d reads fell outside a sector window" % -replays
             assert np.array_equal(got, z["steps"][t]), "update %d box %d: %d rays differ" % (t, box, int((got != z["steps"][t]).sum()))
