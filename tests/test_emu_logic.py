@@ -125,8 +125,8 @@ def _oracle_steps(g, angles, x, y, th):
     return steps_from_ranges(orc.calc_range_many(q), g.resolution_f64, orc.M).reshape(n, len(angles))
 
 
-@pytest.mark.parametrize("name", ["sibal1", "first_map"])
-@pytest.mark.parametrize("buckets", [2048, 4096])
+@pytest.mark.parametrize("name,buckets", [("sibal1", 2048), ("sibal1", 4096), ("first_map", 2048), ("first_map", 4096),
+                                          ("basement_fixed", 4096), ("Spielberg_map", 2048)])
 def test_directional_march_equals_reference_march(name, buckets):
     """k_raycast_dir's logic (heading bucket -> sector map -> march_ray_dir) on stress poses:
     cell corners, axis-aligned rays, poses outside the map; every sector gets used."""
