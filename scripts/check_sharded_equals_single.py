@@ -45,6 +45,11 @@ def main():
     obs = np.stack([synth.scan_from_pose(flt.ctx.calc_range_many, gt[t + 1], angles_full, rng)[::18]
                     for t in range(a.updates)]).astype(np.float32)
     flt.init_pose(gt[0])
+    if os.environ.get("CHECK_BARRIER_AFTER_INIT"):
+        # every rank's initial state must be complete before any peer's first update reads it
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
     poses = [np.asarray(flt.update(actions[t], obs[t])).copy() for t in range(a.updates)]
     p, w = flt.gather_state()
     ok = True
