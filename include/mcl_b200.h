@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MCL_B200_ABI_VERSION 2
+#define MCL_B200_ABI_VERSION 3
 
 typedef enum mcl_status {
     MCL_OK = 0,
@@ -70,7 +70,7 @@ typedef struct mcl_noise {
 typedef struct mcl_stage_ms {
     float cdf, resample_motion, raycast_weight, normalize_pose, total;
     float ray_march;   /* the ray kernel alone (raycast_weight also covers the table product) */
-    float exchange;    /* sharded filter: between mcl_update_local_dev and mcl_update_finish_dev (the caller's all-gather) */
+    float exchange;    /* unused since ABI 3 (exchanges happen inside the kernels); kept for layout */
 } mcl_stage_ms;
 
 typedef struct mcl_ctx mcl_ctx;
@@ -120,6 +120,10 @@ int mcl_update(mcl_ctx* ctx, const double* action, const float* obs, int num_bea
  * left in device memory (mcl_pose_dev) and copied out by mcl_read_pose. */
 int mcl_update_dev(mcl_ctx* ctx, const double* action_dev, const float* obs_dev, int num_beams);
 int mcl_read_pose(mcl_ctx* ctx, double* pose_out);
+/* mcl_update_dev with injected noise already on the device (u_dev: N uniforms per filter, z_dev: 3 N
+ * normals per filter; a sharded rank: of the WHOLE filter; either may be NULL).  Never graph-replayed. */
+int mcl_update_dev_noise(mcl_ctx* ctx, const double* action_dev, const float* obs_dev, int num_beams,
+                         const double* u_dev, const double* z_dev);
 int mcl_synchronize(mcl_ctx* ctx);
 
 /* expected_pose() alone :696-716 over the current state. */
@@ -138,11 +142,23 @@ int mcl_get_raw_weights(mcl_ctx* ctx, int filter, double* weights_out);        /
 int mcl_get_cdf(mcl_ctx* ctx, int filter, double* cdf_out);                    /* discrete_distribution _M_cp */
 /* visualize() :946-958: k weighted samples of the particle set (k x 3 column-major). */
 int mcl_sample_particles(mcl_ctx* ctx, int filter, int k, double* particles_out);
+/* The same draw with the k canonical uniforms the reference's generator would produce injected
+ * (u; NULL = device RNG) and the drawn particle indices returned (idx_out, nullable): index i is
+ * lower_bound(_M_cp, u[i]) exactly as std::discrete_distribution::operator() (random.tcc:2709-2713). */
+int mcl_sample_particles_u(mcl_ctx* ctx, int filter, int k, const double* u, double* particles_out, int32_t* idx_out);
 
 /* Options / introspection. */
 int mcl_set_profiling(mcl_ctx* ctx, int enabled);
 int mcl_get_stage_ms(mcl_ctx* ctx, mcl_stage_ms* out);
-int mcl_set_keep_ranges(mcl_ctx* ctx, int enabled);   /* store per-ray steps for read-back */
+/* Device time of every kernel of the last profiled update, in launch order (CUDA events around each
+ * launch).  names_out: capacity x 48 bytes, NUL-terminated; ms_out: capacity floats; *count = kernels. */
+int mcl_get_kernel_ms(mcl_ctx* ctx, char* names_out, float* ms_out, int capacity, int* count);
+int mcl_set_keep_ranges(mcl_ctx* ctx, int enabled);
+/* Diagnostics: SM cycle counts of the phases of one kind of exact-sum pass (csrc/exact_kernels.cuh; 0 S1,
+ * 1 normalise+pose+S2, 2 S2 of stored weights, 3 cdf; < 0 off) in the updates that follow.  out (nullable, 8
+ * values, read and cleared): slowest CTA's tile phase | last CTA until it knows it is last | pose fold | tile
+ * scan | ordered opaque list | exchange | serial evaluation + tile starts | opaque chunks of this rank. */
+int mcl_debug_pass_cycles(mcl_ctx* ctx, int pass_kind, unsigned long long* out);   /* store per-ray steps for read-back */
 int mcl_kernel_launches(mcl_ctx* ctx, int64_t* count); /* kernels launched so far by this ctx */
 /* Use the caller's CUDA stream (cudaStream_t passed as void*) instead of the ctx's own. */
 int mcl_set_stream(mcl_ctx* ctx, void* cuda_stream);
@@ -179,41 +195,52 @@ int mcl_get_dir_map(mcl_ctx* ctx, int sector, uint8_t* out, int* pw, int* ph);
  * ray stage a gather-rate roofline next to the HBM one. */
 int mcl_microbench_gather(int device, int shared, size_t array_bytes, int iters_per_thread, double* gathers_per_second);
 
-/* ---- particle-sharded operation: one rank per GPU, ONE global filter ---------------------
- * The reference has no multi-process path; the coupling points of its update are the weight
- * sum (:679), the global CDF + source gather (:658-665) and the pose sums (:702-710).  Every
- * rank keeps the whole filter state (max_particles = global count) but computes only output
- * slots [lo, lo+count).  Per update:
- *   mcl_update_local_dev      CDF over all particles, then resample / motion / ray cast /
- *                             weights for the rank's slots
- *   (caller)                  all-gather the four arrays of mcl_exchange_buffers_dev in place
- *                             (x, y, theta, raw weight; slice [lo, lo+count) is this rank's)
- *   mcl_update_finish_dev     global weight sum, normalisation and expected pose on every rank
- * Resampling is the reference's exact global multinomial draw: with the same injected noise
- * the gathered result equals the single-filter update bit for bit. */
-int mcl_set_shard(mcl_ctx* ctx, int64_t lo, int64_t count);
-int mcl_update_local_dev(mcl_ctx* ctx, const double* action_dev, const float* obs_dev, int num_beams,
-                         const double* u_dev /*nullable, N*/, const double* z_dev /*nullable, 3N*/);
-int mcl_exchange_buffers_dev(mcl_ctx* ctx, void* ptrs_out[4], int64_t* n_total, int64_t* lo, int64_t* count);
-int mcl_update_finish_dev(mcl_ctx* ctx);
+/* ---- particle-sharded filter: one rank per GPU, ONE global filter ---------------------------
+ * The reference has no multi-process path; the coupling points of its update are the weight sum
+ * (:679), the CDF of std::discrete_distribution + the source gather (:658-665) and the pose sums
+ * (:702-710).  A sharded context holds ONLY its own slot range [rank * n, (rank + 1) * n) of every
+ * per-particle array (n = max_particles / world; mcl_params.max_particles is the particle count of
+ * the WHOLE filter) and keeps the reference's exact global multinomial resampling:
+ *   - the three sequentially rounded reductions (weight sum, the distribution's own sum, the CDF) run
+ *     per rank; each exchanges one < 2 KB summary per rank (step maps of csrc/exact_sum.cuh + the few
+ *     chunks that cross a binade), after which every rank evaluates the same short serial chain;
+ *   - resampling is sender-driven: every rank evaluates all draws, serves those that fall into its own
+ *     CDF range and PUSHES the source poses to the slots' owners over NVLink (k_route);
+ *   - no rank reads peer memory on the hot path; every exchange is stores + a system-scope release
+ *     flag written by the kernels themselves (csrc/shard.cuh), so an update has no host call between
+ *     its launches and replays as one CUDA graph.
+ * With the same injected noise the ranks' slices equal the single-filter update bit for bit.
+ * mcl_update / mcl_update_dev / mcl_read_pose / mcl_init_* / mcl_set_particles / mcl_get_* work on a
+ * sharded context and address the rank's own slice; injected noise (mcl_noise) covers the WHOLE
+ * filter and is indexed by the global slot.  Every rank must issue the same sequence of updates. */
 
-/* Peer-to-peer variant of the exchange: instead of all-gathering the poses (24 B/particle),
- * every rank maps the other ranks' state arrays (CUDA IPC) and the resampling kernel reads
- * each slot's source pose straight from its owner over NVLink; only the raw weights
- * (8 B/particle) and four pose partial sums per rank are all-gathered.  Set-up, once:
- *   mcl_ipc_export on every rank -> exchange the 512-byte blobs -> mcl_ipc_import(world, rank,
- *   blobs in rank order).  Per update: mcl_update_local_dev -> all-gather in place the two
- *   buffers of mcl_p2p_buffers_dev (w_raw: slice [lo, lo+count); partials: 4 doubles at
- *   [4*rank]) -> mcl_update_finish_dev.  After set-up only a rank's own slice of the state is
- *   current in its arrays.  mcl_set_peer_pointers does the same wiring from raw device
- *   pointers (several contexts in one process; mcl_state_pointers_dev lists them: x, y, theta of
- *   both state buffers, then the packed 32-byte (x, y, theta, 0) copies of both buffers, which is
- *   what the resampling kernel reads from a peer -- one NVLink transaction per source pose). */
-int mcl_ipc_export(mcl_ctx* ctx, void* handles_out, size_t capacity);
-int mcl_ipc_import(mcl_ctx* ctx, int world, int rank, const void* handles);
-int mcl_set_peer_pointers(mcl_ctx* ctx, int world, int rank, const void* const* ptrs /* world x 8 */);
-int mcl_state_pointers_dev(mcl_ctx* ctx, void* ptrs_out[8]);
-int mcl_p2p_buffers_dev(mcl_ctx* ctx, void** w_raw_dev, void** partials_dev);
+/* Creation without NCCL (the caller moves the 512-byte blobs): mcl_shard_create on every rank ->
+ * mcl_shard_export -> exchange -> mcl_shard_connect(blobs of all ranks in rank order).  Ranks that
+ * live in ONE process (one host thread per GPU, or test ranks emulated on one GPU) connect with
+ * mcl_shard_connect_local instead. */
+#define MCL_SHARD_BLOB_BYTES 512
+int mcl_shard_create(const mcl_params* p, int device, int world, int rank, mcl_ctx** out);
+int mcl_shard_export(mcl_ctx* ctx, void* blob, size_t capacity);
+int mcl_shard_connect(mcl_ctx* ctx, const void* blobs /* world x MCL_SHARD_BLOB_BYTES */);
+int mcl_shard_connect_local(mcl_ctx* ctx, mcl_ctx* const* ranks /* world contexts, rank order */);
+int mcl_shard_info(const mcl_ctx* ctx, int* world, int* rank, int64_t* n_local, int64_t* n_global);
+
+/* How the ranks meet at an exchange.  fused = 1 (default): the publishing kernel's last block waits for
+ * the peers' flags itself -- one rank per GPU only.  fused = 0: host-ordered; the library calls `hook`
+ * (after synchronising its stream) wherever every rank must have published before any rank consumes --
+ * for ranks emulated on one GPU, whose kernels must never spin on each other -- or, with hook == NULL on
+ * a context made by mcl_create_sharded, enqueues a one-word ncclAllGather as the barrier. */
+typedef int (*mcl_barrier_fn)(void* user);
+int mcl_shard_set_exchange(mcl_ctx* ctx, int fused, mcl_barrier_fn hook, void* user);
+
+/* The same with the library owning the NCCL communicator (bound at run time from libnccl.so.2):
+ * rank 0 obtains an id (mcl_nccl_unique_id, 128 bytes) and hands it to the other ranks by any means;
+ * mcl_create_sharded = mcl_shard_create + ncclCommInitRank + ncclAllGather of the blobs on the
+ * library's stream + mcl_shard_connect.  mcl_sharded_gather all-gathers the whole filter's particles
+ * (NG x 3 column-major) and normalised weights to the host of every rank (either may be NULL). */
+int mcl_nccl_unique_id(void* id_out, size_t capacity);
+int mcl_create_sharded(const mcl_params* p, int device, int world, int rank, const void* nccl_unique_id, mcl_ctx** out);
+int mcl_sharded_gather(mcl_ctx* ctx, double* particles_colmajor, double* weights);
 
 #ifdef __cplusplus
 }

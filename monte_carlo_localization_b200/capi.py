@@ -90,17 +90,22 @@ SIGNATURES = {
     "mcl_ray_stage_info": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_int)] * 4),
     "mcl_get_dir_map": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_uint8), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "mcl_microbench_gather": (C.c_int, [C.c_int, C.c_int, C.c_size_t, C.c_int, c_double_p]),
-    "mcl_set_shard": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64]),
-    "mcl_update_local_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
-    "mcl_exchange_buffers_dev": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
-                                           C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
-    "mcl_update_finish_dev": (C.c_int, [C.c_void_p]),
-    "mcl_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
-    "mcl_ipc_import": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
-    "mcl_set_peer_pointers": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
-    "mcl_state_pointers_dev": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
-    "mcl_p2p_buffers_dev": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "mcl_update_dev_noise": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "mcl_sample_particles_u": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p, c_double_p, c_int32_p]),
+    "mcl_get_kernel_ms": (C.c_int, [C.c_void_p, C.c_char_p, c_float_p, C.c_int, C.POINTER(C.c_int)]),
+    "mcl_debug_pass_cycles": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]),
+    "mcl_shard_create": (C.c_int, [C.POINTER(MclParams), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "mcl_shard_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "mcl_shard_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mcl_shard_connect_local": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "mcl_shard_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "mcl_shard_set_exchange": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "mcl_nccl_unique_id": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "mcl_create_sharded": (C.c_int, [C.POINTER(MclParams), C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "mcl_sharded_gather": (C.c_int, [C.c_void_p, c_double_p, c_double_p]),
 }
+
+BARRIER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p)
 
 _lib = None
 
@@ -153,6 +158,16 @@ def default_params(**kw) -> MclParams:
     return p
 
 
+def nccl_unique_id() -> bytes:
+    """ncclGetUniqueId through the library (rank 0 calls it and hands the 128 bytes to the others)."""
+    L = load_library()
+    buf = C.create_string_buffer(128)
+    rc = L.mcl_nccl_unique_id(buf, 128)
+    if rc != MCL_OK:
+        raise MclError(rc, "mcl_nccl_unique_id", L.mcl_last_error().decode(errors="replace"))
+    return bytes(buf.raw)
+
+
 def microbench_gather(shared: bool, array_bytes: int = 4 << 20, iters: int = 4096, device: int = 0) -> float:
     """Random single-byte gathers per second from shared memory or an L2-resident array."""
     L = load_library()
@@ -166,13 +181,27 @@ def microbench_gather(shared: bool, array_bytes: int = 4 << 20, iters: int = 409
 class MclContext:
     """One ``mcl_ctx``: a ParticleFilter's device state (or a batch of independent ones)."""
 
-    def __init__(self, device: int = 0, **params):
+    def __init__(self, device: int = 0, shard=None, nccl_id: bytes | None = None, **params):
+        """shard = (world, rank): one rank of a particle-sharded filter (``max_particles`` = particles of
+        the WHOLE filter); with ``nccl_id`` (mcl_nccl_unique_id of rank 0) the library owns the NCCL
+        communicator and connects the ranks itself, otherwise connect with ``shard_connect*``."""
         self._L = load_library()
         self.params = default_params(**params)
         h = C.c_void_p()
-        self._check(self._L.mcl_create(C.byref(self.params), device, C.byref(h)), "mcl_create")
+        self.world, self.rank = (1, 0) if shard is None else (int(shard[0]), int(shard[1]))
+        if shard is None:
+            self._check(self._L.mcl_create(C.byref(self.params), device, C.byref(h)), "mcl_create")
+        elif nccl_id is not None:
+            self._check(self._L.mcl_create_sharded(C.byref(self.params), device, self.world, self.rank,
+                                                   C.c_char_p(nccl_id), C.byref(h)), "mcl_create_sharded")
+        else:
+            self._check(self._L.mcl_shard_create(C.byref(self.params), device, self.world, self.rank, C.byref(h)),
+                        "mcl_shard_create")
         self._h = h
-        self.N = int(self.params.max_particles)
+        self.NG = int(self.params.max_particles)            # particles of the whole filter
+        self.N = self.NG // self.world                      # particles this context holds
+        self.glo = self.N * self.rank
+        self._hook = None
         self.F = int(self.params.num_filters)
         self.R = 0
         self.M = 0
@@ -255,8 +284,9 @@ class MclContext:
         keep = []
         if u is not None or z3n is not None:
             arr = (MclNoise * self.F)()
-            uu = None if u is None else np.ascontiguousarray(u, dtype=np.float64).reshape(self.F, self.N)
-            zz = None if z3n is None else np.ascontiguousarray(z3n, dtype=np.float64).reshape(self.F, 3 * self.N)
+            # injected noise covers the WHOLE filter (a sharded rank indexes it by the global slot)
+            uu = None if u is None else np.ascontiguousarray(u, dtype=np.float64).reshape(self.F, self.NG)
+            zz = None if z3n is None else np.ascontiguousarray(z3n, dtype=np.float64).reshape(self.F, 3 * self.NG)
             keep = [uu, zz]
             for f in range(self.F):
                 arr[f].u_resample = None if uu is None else uu[f].ctypes.data_as(c_double_p)
@@ -270,6 +300,11 @@ class MclContext:
     def update_dev(self, action_dev_ptr: int, obs_dev_ptr: int):
         self._check(self._L.mcl_update_dev(self._h, C.c_void_p(action_dev_ptr), C.c_void_p(obs_dev_ptr), self.R),
                     "mcl_update_dev")
+
+    def update_dev_noise(self, action_dev_ptr: int, obs_dev_ptr: int, u_dev_ptr: int = 0, z_dev_ptr: int = 0):
+        self._check(self._L.mcl_update_dev_noise(self._h, C.c_void_p(action_dev_ptr), C.c_void_p(obs_dev_ptr), self.R,
+                                                 C.c_void_p(u_dev_ptr or None), C.c_void_p(z_dev_ptr or None)),
+                    "mcl_update_dev_noise")
 
     def read_pose(self) -> np.ndarray:
         pose = np.empty(3 * self.F, dtype=np.float64)
@@ -322,10 +357,15 @@ class MclContext:
         self._check(self._L.mcl_get_cdf(self._h, filter, _dp(out)), "mcl_get_cdf")
         return out
 
-    def sample_particles(self, k: int, filter: int = 0) -> np.ndarray:
+    def sample_particles(self, k: int, filter: int = 0, u=None, return_indices: bool = False):
+        """visualize()'s weighted sub-sample (:946-958).  u: injected canonical uniforms (k of them)."""
         out = np.empty(3 * k, dtype=np.float64)
-        self._check(self._L.mcl_sample_particles(self._h, filter, k, _dp(out)), "mcl_sample_particles")
-        return out.reshape(3, k)
+        idx = np.empty(k, dtype=np.int32)
+        uu = None if u is None else np.ascontiguousarray(u, dtype=np.float64)
+        if uu is not None and uu.size != k:
+            raise ValueError("need %d uniforms" % k)
+        self._check(self._L.mcl_sample_particles_u(self._h, filter, k, _dp(uu), _dp(out), _ip(idx)), "mcl_sample_particles_u")
+        return (out.reshape(3, k), idx) if return_indices else out.reshape(3, k)
 
     # ---- options ----------------------------------------------------------------------
     def set_profiling(self, on: bool):
@@ -335,6 +375,20 @@ class MclContext:
         s = MclStageMs()
         self._check(self._L.mcl_get_stage_ms(self._h, C.byref(s)), "mcl_get_stage_ms")
         return {k: getattr(s, k) for k, _ in MclStageMs._fields_}
+
+    def kernel_ms(self) -> list:
+        """[(kernel name, device ms)] of the last profiled update, in launch order."""
+        cap = 64
+        names = C.create_string_buffer(48 * cap)
+        ms = np.zeros(cap, dtype=np.float32)
+        n = C.c_int(0)
+        self._check(self._L.mcl_get_kernel_ms(self._h, names, _fp(ms), cap, C.byref(n)), "mcl_get_kernel_ms")
+        return [(names.raw[48 * i:48 * i + 48].split(b"\0", 1)[0].decode(), float(ms[i])) for i in range(min(n.value, cap))]
+
+    def debug_pass_cycles(self, pass_kind: int, read: bool = False):
+        out = (C.c_uint64 * 8)() if read else None
+        self._check(self._L.mcl_debug_pass_cycles(self._h, pass_kind, out), "mcl_debug_pass_cycles")
+        return [int(v) for v in out] if read else None
 
     def set_keep_ranges(self, on: bool):
         self._check(self._L.mcl_set_keep_ranges(self._h, int(on)), "mcl_set_keep_ranges")
@@ -366,50 +420,39 @@ class MclContext:
         return int(n.value)
 
     # ---- particle sharding -------------------------------------------------------------
-    def set_shard(self, lo: int, count: int):
-        self._check(self._L.mcl_set_shard(self._h, lo, count), "mcl_set_shard")
+    SHARD_BLOB = 512
 
-    def update_local_dev(self, action_dev_ptr: int, obs_dev_ptr: int, u_dev_ptr: int = 0, z_dev_ptr: int = 0):
-        self._check(self._L.mcl_update_local_dev(self._h, C.c_void_p(action_dev_ptr), C.c_void_p(obs_dev_ptr), self.R,
-                                                 C.c_void_p(u_dev_ptr or None), C.c_void_p(z_dev_ptr or None)),
-                    "mcl_update_local_dev")
-
-    def exchange_buffers_dev(self):
-        """(ptrs[4], n_total, lo, count): device addresses of x, y, theta, raw weight."""
-        ptrs = (C.c_void_p * 4)()
-        n, lo, cnt = C.c_int64(0), C.c_int64(0), C.c_int64(0)
-        self._check(self._L.mcl_exchange_buffers_dev(self._h, ptrs, C.byref(n), C.byref(lo), C.byref(cnt)),
-                    "mcl_exchange_buffers_dev")
-        return [int(p) for p in ptrs], int(n.value), int(lo.value), int(cnt.value)
-
-    def update_finish_dev(self):
-        self._check(self._L.mcl_update_finish_dev(self._h), "mcl_update_finish_dev")
-
-    IPC_BLOB = 8 * 64   # eight cudaIpcMemHandle_t: x, y, theta of both state buffers + their packed copies
-
-    def ipc_export(self) -> bytes:
-        buf = C.create_string_buffer(self.IPC_BLOB)
-        self._check(self._L.mcl_ipc_export(self._h, buf, self.IPC_BLOB), "mcl_ipc_export")
+    def shard_export(self) -> bytes:
+        buf = C.create_string_buffer(self.SHARD_BLOB)
+        self._check(self._L.mcl_shard_export(self._h, buf, self.SHARD_BLOB), "mcl_shard_export")
         return bytes(buf.raw)
 
-    def ipc_import(self, world: int, rank: int, blobs: bytes):
-        if len(blobs) != world * self.IPC_BLOB:
-            raise ValueError("expected %d bytes of IPC handles" % (world * self.IPC_BLOB))
-        self._check(self._L.mcl_ipc_import(self._h, world, rank, C.c_char_p(blobs)), "mcl_ipc_import")
+    def shard_connect(self, blobs: bytes):
+        if len(blobs) != self.world * self.SHARD_BLOB:
+            raise ValueError("expected %d bytes of exchange-arena handles" % (self.world * self.SHARD_BLOB))
+        self._check(self._L.mcl_shard_connect(self._h, C.c_char_p(blobs)), "mcl_shard_connect")
 
-    def state_pointers_dev(self):
-        ptrs = (C.c_void_p * 8)()
-        self._check(self._L.mcl_state_pointers_dev(self._h, ptrs), "mcl_state_pointers_dev")
-        return [int(p) for p in ptrs]
+    def shard_connect_local(self, ranks):
+        """ranks: the `world` MclContext objects of this process, in rank order."""
+        arr = (C.c_void_p * len(ranks))(*[r._h for r in ranks])
+        self._check(self._L.mcl_shard_connect_local(self._h, arr), "mcl_shard_connect_local")
 
-    def set_peer_pointers(self, world: int, rank: int, ptrs):
-        arr = (C.c_void_p * (8 * world))(*[C.c_void_p(p) for p in ptrs])
-        self._check(self._L.mcl_set_peer_pointers(self._h, world, rank, arr), "mcl_set_peer_pointers")
+    def shard_set_exchange(self, fused: bool, hook=None):
+        """fused: the kernels wait for their peers themselves (one rank per GPU).  Otherwise the library
+        calls hook() -> int wherever all ranks must have published (hook None: NCCL barrier)."""
+        cb = None
+        if hook is not None:
+            cb = BARRIER_FN(lambda _user: int(hook() or 0))
+        self._hook = cb   # keep the trampoline alive
+        self._check(self._L.mcl_shard_set_exchange(self._h, int(fused), C.cast(cb, C.c_void_p) if cb else None, None),
+                    "mcl_shard_set_exchange")
 
-    def p2p_buffers_dev(self):
-        w, part = C.c_void_p(), C.c_void_p()
-        self._check(self._L.mcl_p2p_buffers_dev(self._h, C.byref(w), C.byref(part)), "mcl_p2p_buffers_dev")
-        return int(w.value), int(part.value)
+    def sharded_gather(self):
+        """(particles [3, NG], weights [NG]) of the whole filter, on every rank (NCCL, collective)."""
+        p = np.empty(3 * self.NG, dtype=np.float64)
+        w = np.empty(self.NG, dtype=np.float64)
+        self._check(self._L.mcl_sharded_gather(self._h, _dp(p), _dp(w)), "mcl_sharded_gather")
+        return p.reshape(3, self.NG), w
 
     def set_stream(self, cuda_stream_ptr: int):
         self._check(self._L.mcl_set_stream(self._h, C.c_void_p(cuda_stream_ptr)), "mcl_set_stream")

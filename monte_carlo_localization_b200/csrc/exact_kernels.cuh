@@ -5,7 +5,7 @@
 //   S2  = accumulate(weights / S1)                discrete_distribution's own sum (random.tcc:2666)
 //   cdf = partial_sum((weights / S1) / S2)        its _M_cp           (random.tcc:2672-2677)
 // Each is one PASS over the particles:
-//   k_tile_sums     approximate sums of 4096-element tiles (binade oracle of the exact pass)
+//   k_tile_sums     approximate sums of 4096-element tiles (they tell the exact pass which binade a running sum is in)
 //   k_exact_pass    one CTA per tile: 8-addend chunk step maps, their block scan, the tile's
 //                   opaque chunks compacted.  The LAST CTA to finish then (a) orders the filter's
 //                   opaque chunks with their incoming maps, (b) -- sharded filter -- publishes that
@@ -75,6 +75,7 @@ struct ExactArgs {
     double* pose_out;        // [F][3]
     double* pose_host;       // mapped pinned twin (nullable)
     unsigned long long* update_no;   // bumped when the pose of the update is written (nullable)
+    unsigned long long* dbg;         // diagnostics (nullable): clock64 stamps of the pass's phases, see mcl_debug_pass_cycles
     ShardDev sh;
 };
 
@@ -217,7 +218,9 @@ struct FinishShared {
     int cinc[kTileChunks];
     unsigned long long pay[kHdrWords + kOpqCap * kItemWords];
     unsigned long long items[kEvalBatch][kItemWords];
+    double item_v[kEvalBatch];              // running sum after each item of the batch
     int item_q[kEvalBatch], item_r[kEvalBatch];
+    int pay_chunk[kOpqCap];                 // chunk index of this rank's first kOpqCap opaque chunks
     int start[kMaxWorld + 1], kq[kMaxWorld];
     double vin, vcur;
     double pose[4];
@@ -267,37 +270,54 @@ __device__ __forceinline__ TileScan scan_tiles(const ExactArgs& a, int f, Finish
 // (a) the slice's opaque chunks in order, each with the step map that leads to it from the previous
 // anchor (or from the slice start), into the epoch-parity lists and -- the first kOpqCap -- into the
 // payload; header = count, tail map, pose partial sums
-__device__ __forceinline__ void finish_local(const ExactArgs& a, int f, FinishShared& S, unsigned long long epoch, bool pose) {
-    const TileScan ts = scan_tiles(a, f, S);
+__device__ __forceinline__ void finish_local(const ExactArgs& a, int f, FinishShared& S, const TileScan& ts, unsigned long long epoch,
+                                             bool pose) {
     const int par = static_cast<int>(epoch & 1ull);
     const int64_t* tile_elem = a.tile_elem + static_cast<int64_t>(f) * a.T * 3;
     const int* tile_opq = a.tile_opq + static_cast<int64_t>(f) * a.T;
     const int64_t fc = static_cast<int64_t>(f) * a.C;
     const int64_t lc = (static_cast<int64_t>(par) * gridDim.y + f) * a.C;
-    RFn run = ts.exc;
-    int rank = ts.cexc;
-    for (int t = ts.t0; t < ts.t1; ++t) {
-        const int n = tile_opq[t];
-        for (int q = 0; q < n; ++q) {
-            const int64_t slot = fc + static_cast<int64_t>(t) * kTileChunks + q;
-            const StepFn pre = a.opq_pre[slot];
-            const StepFn fn = q == 0 ? fn_compose(run.f, pre) : pre;   // the tile's first opaque chunk continues the run that entered the tile
-            a.list_chunk[fc + rank] = t * kTileChunks + a.opq_idx[slot];
-            a.list_fn[lc + rank] = fn;
-            unsigned long long* pw = rank < kOpqCap ? S.pay + kHdrWords + rank * kItemWords : nullptr;
-            if (pw) {
-                pw[0] = static_cast<unsigned long long>(fn.a0);
-                pw[1] = static_cast<unsigned long long>(fn.a1);
-            }
-#pragma unroll
-            for (int e = 0; e < kChunk; ++e) {
-                const double x = a.opq_add[slot * kChunk + e];
-                a.list_add[(lc + rank) * kChunk + e] = x;
-                if (pw) pw[2 + e] = static_cast<unsigned long long>(__double_as_longlong(x));
-            }
-            ++rank;
+    // one thread per opaque chunk (they are few, and mostly in the filter's first tiles: a loop of the tiles'
+    // owners would serialise on one thread): entry e belongs to the thread range whose inclusive count exceeds e
+    const int tpt = (a.T + kTileChunks - 1) / kTileChunks;
+    for (int e = threadIdx.x; e < ts.K; e += kTileChunks) {
+        int lo = 0, hi = kTileChunks - 1;
+        while (lo < hi) {   // first thread range th with cinc[th] > e
+            const int mid = (lo + hi) >> 1;
+            if (S.cinc[mid] > e)
+                hi = mid;
+            else
+                lo = mid + 1;
         }
-        run = RFnOp()(run, tile_rfn(tile_elem, t));
+        const int th = lo;
+        int local = e - (th ? S.cinc[th - 1] : 0);
+        RFn run = th ? S.inc[th - 1] : RFn{fn_identity(), 0};   // state entering the range's first tile
+        int t = th * tpt;
+        while (local >= tile_opq[t]) {
+            local -= tile_opq[t];
+            run = RFnOp()(run, tile_rfn(tile_elem, t));
+            ++t;
+        }
+        const int64_t slot = fc + static_cast<int64_t>(t) * kTileChunks + local;
+        const StepFn pre = a.opq_pre[slot];
+        const StepFn fn = local == 0 ? fn_compose(run.f, pre) : pre;   // the tile's first opaque chunk continues the run that entered the tile
+        const int chunk = t * kTileChunks + a.opq_idx[slot];
+        a.list_chunk[fc + e] = chunk;
+        a.list_fn[lc + e] = fn;
+        unsigned long long* pw = e < kOpqCap ? S.pay + kHdrWords + e * kItemWords : nullptr;
+        if (pw) {
+            S.pay_chunk[e] = chunk;
+            pw[0] = static_cast<unsigned long long>(fn.a0);
+            pw[1] = static_cast<unsigned long long>(fn.a1);
+        }
+        double add[kChunk];
+#pragma unroll
+        for (int q = 0; q < kChunk; ++q) add[q] = a.opq_add[slot * kChunk + q];
+#pragma unroll
+        for (int q = 0; q < kChunk; ++q) {
+            a.list_add[(lc + e) * kChunk + q] = add[q];
+            if (pw) pw[2 + q] = static_cast<unsigned long long>(__double_as_longlong(add[q]));
+        }
     }
     if (threadIdx.x < kHdrWords) S.pay[threadIdx.x] = 0ull;
     __syncthreads();
@@ -312,11 +332,12 @@ __device__ __forceinline__ void finish_local(const ExactArgs& a, int f, FinishSh
 }
 
 // (c) + (d): sequential evaluation of every rank's opaque chunks and tails, tile starts, total, pose
-__device__ __forceinline__ void finish_global(const ExactArgs& a, int f, FinishShared& S, unsigned long long epoch, bool pose) {
+// own_in_smem: S.pay / S.pay_chunk hold this rank's payload (the block that ran finish_local)
+__device__ __forceinline__ void finish_global(const ExactArgs& a, int f, FinishShared& S, const TileScan& ts, unsigned long long epoch,
+                                              bool pose, bool own_in_smem) {
     const int tid = threadIdx.x;
     const int world = a.sh.world > 1 ? a.sh.world : 1, me = a.sh.world > 1 ? a.sh.rank : 0;
     const int par = static_cast<int>(epoch & 1ull);
-    const TileScan ts = scan_tiles(a, f, S);
     const int64_t fc = static_cast<int64_t>(f) * a.C;
     const int64_t lc = (static_cast<int64_t>(par) * gridDim.y + f) * a.C;
     // per-rank counts: own from the scan, the others from their headers
@@ -355,6 +376,8 @@ __device__ __forceinline__ void finish_global(const ExactArgs& a, int f, FinishS
                     x = static_cast<unsigned long long>(k == 0 ? ts.all.f.a0 : ts.all.f.a1);
                 else
                     x = ld_sys_u64(mbox_slot(a.sh, me, epoch, q) + 1 + k);
+            } else if (q == me && own_in_smem && r < kOpqCap) {
+                x = S.pay[kHdrWords + r * kItemWords + k];
             } else if (q == me) {
                 x = k == 0   ? static_cast<unsigned long long>(a.list_fn[lc + r].a0)
                     : k == 1 ? static_cast<unsigned long long>(a.list_fn[lc + r].a1)
@@ -377,16 +400,22 @@ __device__ __forceinline__ void finish_global(const ExactArgs& a, int f, FinishS
 #pragma unroll
                 for (int e = 0; e < kChunk; ++e) s = __dadd_rn(s, __longlong_as_double(static_cast<long long>(S.items[it][2 + e])));
                 V = s;
-                const int q = S.item_q[it], r = S.item_r[it];
-                if (r == S.kq[q]) {
-                    if (a.rank_end) a.rank_end[q] = V;
-                    if (q + 1 == me) S.vin = V;
-                } else if (q == me) {
-                    a.anchors[fc + r] = V;
-                    a.anchor_val[fc + a.list_chunk[fc + r]] = V;
-                }
+                S.item_v[it] = V;   // (no global access inside this dependent chain)
             }
             S.vcur = V;
+        }
+        __syncthreads();
+        if (tid < nb) {   // what each item's value is: a rank's end, this rank's incoming sum, or an anchor of this rank
+            const int q = S.item_q[tid], r = S.item_r[tid];
+            const double V = S.item_v[tid];
+            if (r == S.kq[q]) {
+                if (a.rank_end) a.rank_end[q] = V;
+                if (q + 1 == me) S.vin = V;
+            } else if (q == me) {
+                a.anchors[fc + r] = V;
+                const int chunk = (own_in_smem && r < kOpqCap) ? S.pay_chunk[r] : a.list_chunk[fc + r];
+                a.anchor_val[fc + chunk] = V;
+            }
         }
         __syncthreads();
     }
@@ -446,6 +475,7 @@ __global__ void __launch_bounds__(kTileChunks) k_exact_pass(ExactArgs a) {
     __shared__ int wcnt[kTileChunks / 32];
     __shared__ bool is_last;
     const int f = blockIdx.y, t = blockIdx.x, tid = threadIdx.x;
+    const long long c_begin = clock64();
     const double* src = a.src + static_cast<int64_t>(f) * a.N;
     const double nrm = a.norm ? a.norm[f] : 0.0;
     const bool use_norm = a.norm != nullptr && nrm > 0.0;
@@ -486,17 +516,21 @@ __global__ void __launch_bounds__(kTileChunks) k_exact_pass(ExactArgs a) {
         // expected_pose (:696-716) over the weights just normalised
         const int64_t fo = static_cast<int64_t>(f) * a.N;
         double ax = 0.0, ay = 0.0, as = 0.0, ac = 0.0;
+        double q[kChunk];   // slots beyond N load 0 and carry weight 0
+        load_raw_chunk(q, a.pt + fo, base, a.N);
 #pragma unroll
         for (int i = 0; i < kChunk; ++i) {
-            if (base + i < a.N) {
-                double s, c;
-                sincos(a.pt[fo + base + i], &s, &c);
-                ax += v[i] * a.px[fo + base + i];
-                ay += v[i] * a.py[fo + base + i];
-                as += v[i] * s;
-                ac += v[i] * c;
-            }
+            double s, c;
+            sincos(q[i], &s, &c);
+            as += v[i] * s;
+            ac += v[i] * c;
         }
+        load_raw_chunk(q, a.px + fo, base, a.N);
+#pragma unroll
+        for (int i = 0; i < kChunk; ++i) ax += v[i] * q[i];
+        load_raw_chunk(q, a.py + fo, base, a.N);
+#pragma unroll
+        for (int i = 0; i < kChunk; ++i) ay += v[i] * q[i];
         ax = block_sum<kTileChunks>(ax, S.sd);
         ay = block_sum<kTileChunks>(ay, S.sd);
         as = block_sum<kTileChunks>(as, S.sd);
@@ -568,22 +602,39 @@ __global__ void __launch_bounds__(kTileChunks) k_exact_pass(ExactArgs a) {
     // ---- the last CTA of the filter finishes the pass ----
     __threadfence();
     __syncthreads();
+    if (a.dbg && tid == 0) atomicMax(a.dbg + 0, static_cast<unsigned long long>(clock64() - c_begin));   // slowest CTA's tile phase
     if (tid == 0) is_last = atomicAdd(a.done + f, 1u) == gridDim.x - 1u;
     __syncthreads();
     if (!is_last) return;
     __threadfence();
+    const long long c0 = clock64();
     if (tid == 0) a.done[f] = 0;
     if (POSE) fold_pose_partials(a, f, S);
     const bool sharded = a.sh.world > 1;
     const unsigned long long epoch = sharded ? *a.sh.xseq + 1ull : 0ull;
-    finish_local(a, f, S, epoch, POSE);
+    const long long c1 = clock64();
+    const TileScan ts = scan_tiles(a, f, S);
+    const long long c2 = clock64();
+    finish_local(a, f, S, ts, epoch, POSE);
+    const long long c3 = clock64();
     if (sharded) {
         const int nw = kHdrWords + min(static_cast<int>(S.pay[0]), kOpqCap) * kItemWords;
         shard_publish(a.sh, epoch, S.pay, nw);
         if (!a.sh.fused) return;
         if (!shard_wait(a.sh, epoch)) return;
     }
-    finish_global(a, f, S, epoch, POSE);
+    const long long c4 = clock64();
+    finish_global(a, f, S, ts, epoch, POSE, true);
+    if (a.dbg && tid == 0) {
+        const long long c5 = clock64();
+        a.dbg[1] = static_cast<unsigned long long>(c0 - c_begin);   // last CTA: its own tile phase + waiting to be last
+        a.dbg[2] = static_cast<unsigned long long>(c1 - c0);        // pose fold
+        a.dbg[3] = static_cast<unsigned long long>(c2 - c1);        // tile scan
+        a.dbg[4] = static_cast<unsigned long long>(c3 - c2);        // ordered opaque list
+        a.dbg[5] = static_cast<unsigned long long>(c4 - c3);        // exchange
+        a.dbg[6] = static_cast<unsigned long long>(c5 - c4);        // serial evaluation + tile starts
+        a.dbg[7] = S.pay[0];                                        // opaque chunks of this rank
+    }
 }
 
 // host-ordered ranks: the consume half of an exact pass (one CTA)
@@ -596,7 +647,8 @@ __global__ void __launch_bounds__(kTileChunks) k_exact_finish(ExactArgs a) {
         if (threadIdx.x < 4) S.pose[threadIdx.x] = ld_sys_f64(reinterpret_cast<const double*>(mbox_slot(a.sh, a.sh.rank, epoch, a.sh.rank) + 3 + threadIdx.x));
         __syncthreads();
     }
-    finish_global(a, 0, S, epoch, POSE);
+    const TileScan ts = scan_tiles(a, 0, S);
+    finish_global(a, 0, S, ts, epoch, POSE, false);
 }
 
 __global__ void __launch_bounds__(kTileChunks) k_exact_emit(ExactArgs a) {

@@ -20,6 +20,7 @@
 #include "exact_sum.cuh"
 #include "map_prep.h"
 #include "march.cuh"
+#include "shard.cuh"
 
 namespace mclb200 {
 
@@ -92,453 +93,16 @@ struct BeamDev {
 }  // namespace mclb200
 
 #include "dir_kernels.cuh"
+#include "exact_kernels.cuh"
 
 namespace mclb200 {
-
-// ------------------------------------------------------------------------------------------
-// exact sequential sums
-// ------------------------------------------------------------------------------------------
-struct ExactArgs {
-    const double* src;       // [F][N] addends (before the optional division)
-    const double* div;       // [F] divisor or nullptr
-    const double* approx_div;  // [F] or nullptr: tile_sum holds sums of src * approx_div (the weights
-                               // before normalisation); only the approximate prefix is rescaled
-    int64_t N;
-    int T;                   // tiles per filter
-    int C;                   // chunks per filter = T * kTileChunks
-    double* tile_sum;        // [F][T] approximate tile sums of src
-    StepFn* chunk_fn;        // [F][C]
-    StepFn* opq_pre;         // [F][C]  tile-compacted: step map from the previous anchor in the tile (or the
-                             //         tile start for the tile's first opaque chunk) to each opaque chunk
-    int* opq_idx;            // [F][C]  tile-compacted: index of the opaque chunk inside its tile
-    int* tile_opq;           // [F][T]  opaque chunks per tile
-    int64_t* tile_elem;      // [F][T][3]  (a0, a1, reset)
-    int* list_chunk;         // [F][C]  opaque chunks in order
-    StepFn* list_fn;         // [F][C]
-    double* anchors;         // [F][C]  exact running sum after each opaque chunk, by rank
-    double* anchor_val;      // [F][C]  same, by chunk index
-    double* tile_start;      // [F][T]  exact running sum before each tile
-    double* total;           // [F]     exact sequential sum
-    double* out;             // [F][N]  prefix sums (emit) or nullptr
-    int force_last_one;      // discrete_distribution sets _M_cp.back() = 1.0 (random.tcc:2677)
-    // coarse level of the CDF search (k_resample_motion): coarse[f][k] = out[(k+1)*8*coarse_m - 1],
-    // written by the emit step next to the prefix sums; coarse_m = 0: none
-    double* coarse;
-    int coarse_m, coarse_n;  // chunks per coarse entry (power of two), entries per filter
-};
-
-// emit step: the thread that holds the last chunk of a coarse segment publishes its final prefix sum
-__device__ __forceinline__ void emit_coarse(const ExactArgs& a, int f, int64_t chunk_in_filter, int64_t base, double last) {
-    if (a.coarse_m > 0 && ((chunk_in_filter + 1) & (a.coarse_m - 1)) == 0 && base + kChunk <= a.N) {
-        const int64_t k = (chunk_in_filter + 1) / a.coarse_m - 1;
-        if (k < a.coarse_n) a.coarse[static_cast<int64_t>(f) * a.coarse_n + k] = last;
-    }
-}
-
-struct RFn {
-    StepFn f;
-    int64_t reset;
-};
-struct RFnOp {
-    __device__ __forceinline__ RFn operator()(const RFn& l, const RFn& r) const {
-        if (r.reset) return r;
-        return RFn{fn_compose(l.f, r.f), l.reset};
-    }
-};
-struct SEOp {
-    __device__ __forceinline__ ScanElem operator()(const ScanElem& l, const ScanElem& r) const { return se_combine(l, r); }
-};
-struct AddOp {
-    __device__ __forceinline__ double operator()(double a, double b) const { return a + b; }
-};
-
-__device__ __forceinline__ void load_chunk(double (&v)[kChunk], const double* __restrict__ src, int64_t base,
-                                           int64_t N, bool use_div, double div) {
-    if (base + kChunk <= N) {
-        const double2* p = reinterpret_cast<const double2*>(src + base);
-#pragma unroll
-        for (int i = 0; i < kChunk / 2; ++i) {
-            const double2 t = __ldg(p + i);
-            v[2 * i] = t.x;
-            v[2 * i + 1] = t.y;
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < kChunk; ++i) v[i] = (base + i < N) ? __ldg(src + base + i) : 0.0;
-    }
-    if (use_div) {
-#pragma unroll
-        for (int i = 0; i < kChunk; ++i) v[i] = __ddiv_rn(v[i], div);
-    }
-}
-
-// approximate per-tile sums of src (no division)
-__global__ void __launch_bounds__(kTileChunks) k_tile_sums(ExactArgs a) {
-    __shared__ double sm[kTileChunks / 32];
-    const int f = blockIdx.y, t = blockIdx.x;
-    const double* src = a.src + static_cast<int64_t>(f) * a.N;
-    const int64_t base = (static_cast<int64_t>(t) * kTileChunks + threadIdx.x) * kChunk;
-    double v[kChunk];
-    load_chunk(v, src, base, a.N, false, 1.0);
-    double c = 0.0;
-#pragma unroll
-    for (int i = 0; i < kChunk; ++i) c += v[i];
-    const double s = block_sum<kTileChunks>(c, sm);
-    if (threadIdx.x == 0) a.tile_sum[static_cast<int64_t>(f) * a.T + t] = s;
-}
-
-__global__ void __launch_bounds__(kTileChunks) k_exact_chunks(ExactArgs a) {
-    __shared__ double smd[kTileChunks / 32];
-    __shared__ RFn smr[kTileChunks / 32];
-    __shared__ RFn sm_inc[kTileChunks];
-    const int f = blockIdx.y, t = blockIdx.x, tid = threadIdx.x;
-    const double* src = a.src + static_cast<int64_t>(f) * a.N;
-    const bool use_div = a.div != nullptr;
-    const double div = use_div ? a.div[f] : 1.0;
-
-    // approximate running sum before this tile
-    double pre = 0.0;
-    for (int tt = tid; tt < t; tt += kTileChunks) pre += a.tile_sum[static_cast<int64_t>(f) * a.T + tt];
-    pre = block_sum<kTileChunks>(pre, smd);
-    if (a.approx_div) {
-        const double ad = a.approx_div[f];
-        if (ad > 0.0) pre = pre / ad;   // `if (sum_weights > 0)`: otherwise the weights were left as they were
-    }
-    if (use_div) pre = pre / div;
-
-    const int64_t base = (static_cast<int64_t>(t) * kTileChunks + tid) * kChunk;
-    double v[kChunk];
-    load_chunk(v, src, base, a.N, use_div, div);
-    double c = 0.0;
-#pragma unroll
-    for (int i = 0; i < kChunk; ++i) c += v[i];
-    const double incl = block_scan_inclusive<kTileChunks>(c, AddOp(), smd, 0.0);
-    const double s_in = pre + (incl - c);
-    const double s_out = s_in + c;
-
-    StepFn fn = fn_identity();
-    int opaque = 0;
-    if (base < a.N) {
-        const int64_t cnt = (base + kChunk < a.N) ? base + kChunk : a.N;
-        const int e = chunk_safe_binade(s_in, s_out, cnt);
-        if (e < 0) {
-            fn = fn_opaque();
-            opaque = 1;
-        } else {
-            fn = chunk_step_fn(v, kChunk, e);
-        }
-    }
-    const int64_t cidx = static_cast<int64_t>(f) * a.C + static_cast<int64_t>(t) * kTileChunks + tid;
-    a.chunk_fn[cidx] = fn;
-
-    const RFn ident{fn_identity(), 0};
-    RFn el = opaque ? RFn{fn_identity(), 1} : RFn{fn, 0};
-    const RFn inc = block_scan_inclusive<kTileChunks>(el, RFnOp(), smr, ident);
-    sm_inc[tid] = inc;
-    __syncthreads();
-    const RFn exc = tid ? sm_inc[tid - 1] : ident;
-    // compact the tile's opaque chunks (in order) so the walk kernel never scans chunk records
-    __shared__ int wcnt[kTileChunks / 32];
-    const unsigned bal = __ballot_sync(kFullMask, opaque);
-    if ((tid & 31) == 0) wcnt[tid >> 5] = __popc(bal);
-    __syncthreads();
-    int orank = __popc(bal & ((1u << (tid & 31)) - 1u));
-    int nopq = 0;
-#pragma unroll
-    for (int w = 0; w < kTileChunks / 32; ++w) {
-        if (w < (tid >> 5)) orank += wcnt[w];
-        nopq += wcnt[w];
-    }
-    if (opaque) {
-        const int64_t slot = static_cast<int64_t>(f) * a.C + static_cast<int64_t>(t) * kTileChunks + orank;
-        a.opq_pre[slot] = exc.f;
-        a.opq_idx[slot] = tid;
-    }
-    if (tid == kTileChunks - 1) {
-        int64_t* te = a.tile_elem + (static_cast<int64_t>(f) * a.T + t) * 3;
-        te[0] = inc.f.a0;
-        te[1] = inc.f.a1;
-        te[2] = inc.reset;
-        a.tile_opq[static_cast<int64_t>(f) * a.T + t] = nopq;
-    }
-}
-
-constexpr int kWalkThreads = 512;
-constexpr int kWalkBatch = 128;
-
-__global__ void __launch_bounds__(kWalkThreads) k_exact_walk(ExactArgs a) {
-    __shared__ RFn smr[kWalkThreads / 32];
-    __shared__ RFn sm_inc[kWalkThreads];
-    __shared__ int smi[kWalkThreads / 32];
-    __shared__ int sm_cinc[kWalkThreads];
-    __shared__ double sm_add[kWalkBatch][kChunk];
-    __shared__ StepFn sm_fn[kWalkBatch];
-    __shared__ double sm_v;
-
-    const int f = blockIdx.y, tid = threadIdx.x;
-    const int T = a.T;
-    const int tpt = (T + kWalkThreads - 1) / kWalkThreads;
-    const int t0 = min(T, tid * tpt), t1 = min(T, t0 + tpt);
-    const int64_t* tile_elem = a.tile_elem + static_cast<int64_t>(f) * T * 3;
-    const int* tile_opq = a.tile_opq + static_cast<int64_t>(f) * T;
-    const int* opq_idx = a.opq_idx + static_cast<int64_t>(f) * a.C;
-    const StepFn* opq_pre = a.opq_pre + static_cast<int64_t>(f) * a.C;
-    int* list_chunk = a.list_chunk + static_cast<int64_t>(f) * a.C;
-    StepFn* list_fn = a.list_fn + static_cast<int64_t>(f) * a.C;
-    double* anchors = a.anchors + static_cast<int64_t>(f) * a.C;
-    double* anchor_val = a.anchor_val + static_cast<int64_t>(f) * a.C;
-    const double* src = a.src + static_cast<int64_t>(f) * a.N;
-    const bool use_div = a.div != nullptr;
-    const double div = use_div ? a.div[f] : 1.0;
-
-    const RFn ident{fn_identity(), 0};
-    RFn loc = ident;
-    int cnt = 0;
-    for (int t = t0; t < t1; ++t) {
-        loc = RFnOp()(loc, RFn{StepFn{tile_elem[3 * t], tile_elem[3 * t + 1]}, tile_elem[3 * t + 2]});
-        cnt += tile_opq[t];
-    }
-    const RFn inc = block_scan_inclusive<kWalkThreads>(loc, RFnOp(), smr, ident);
-    sm_inc[tid] = inc;
-    // integer inclusive scan of the counts
-    {
-        int v = cnt;
-        const int lane = tid & 31, warp = tid >> 5;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int o = __shfl_up_sync(kFullMask, v, d);
-            if (lane >= d) v += o;
-        }
-        if (lane == 31) smi[warp] = v;
-        __syncthreads();
-        if (warp == 0) {
-            int w = lane < kWalkThreads / 32 ? smi[lane] : 0;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int o = __shfl_up_sync(kFullMask, w, d);
-                if (lane >= d) w += o;
-            }
-            if (lane < kWalkThreads / 32) smi[lane] = w;
-        }
-        __syncthreads();
-        if (warp > 0) v += smi[warp - 1];
-        sm_cinc[tid] = v;
-    }
-    __syncthreads();
-    const RFn exc = tid ? sm_inc[tid - 1] : ident;
-    const int cexc = tid ? sm_cinc[tid - 1] : 0;
-    const int K = sm_cinc[kWalkThreads - 1];
-
-    // emit the ordered list of opaque chunks with their incoming step maps
-    {
-        RFn run = exc;
-        int rank = cexc;
-        for (int t = t0; t < t1; ++t) {
-            const int n = tile_opq[t];
-            for (int q = 0; q < n; ++q) {
-                const StepFn pre = opq_pre[t * kTileChunks + q];
-                list_chunk[rank] = t * kTileChunks + opq_idx[t * kTileChunks + q];
-                // the tile's first opaque chunk continues the run that entered the tile
-                list_fn[rank] = q == 0 ? fn_compose(run.f, pre) : pre;
-                ++rank;
-            }
-            run = RFnOp()(run, RFn{StepFn{tile_elem[3 * t], tile_elem[3 * t + 1]}, tile_elem[3 * t + 2]});
-        }
-    }
-    if (tid == 0) sm_v = 0.0;
-    __syncthreads();
-
-    // serial pass over the opaque chunks, batches staged through shared memory
-    for (int b0 = 0; b0 < K; b0 += kWalkBatch) {
-        const int nb = min(kWalkBatch, K - b0);
-        for (int i = tid; i < nb * kChunk; i += kWalkThreads) {
-            const int r = i / kChunk, e = i % kChunk;
-            const int64_t k = static_cast<int64_t>(list_chunk[b0 + r]) * kChunk + e;
-            double x = (k < a.N) ? src[k] : 0.0;
-            if (use_div) x = __ddiv_rn(x, div);
-            sm_add[r][e] = x;
-        }
-        for (int i = tid; i < nb; i += kWalkThreads) sm_fn[i] = list_fn[b0 + i];
-        __syncthreads();
-        if (tid == 0) {
-            double V = sm_v;
-            for (int r = 0; r < nb; ++r) {
-                const double vin = fn_apply(sm_fn[r], V);
-                V = chunk_seq_eval(sm_add[r], kChunk, vin);
-                anchors[b0 + r] = V;
-                anchor_val[list_chunk[b0 + r]] = V;
-            }
-            sm_v = V;
-        }
-        __syncthreads();
-    }
-
-    // exact running sum at every tile start, and the total
-    {
-        RFn run = exc;
-        int rank = cexc;
-        for (int t = t0; t < t1; ++t) {
-            a.tile_start[static_cast<int64_t>(f) * T + t] = fn_apply(run.f, run.reset ? anchors[rank - 1] : 0.0);
-            rank += tile_opq[t];
-            run = RFnOp()(run, RFn{StepFn{tile_elem[3 * t], tile_elem[3 * t + 1]}, tile_elem[3 * t + 2]});
-        }
-        if (t1 == T && t0 < t1) a.total[f] = fn_apply(run.f, run.reset ? anchors[rank - 1] : 0.0);
-    }
-}
-
-__global__ void __launch_bounds__(kTileChunks) k_exact_emit(ExactArgs a) {
-    __shared__ ScanElem sms[kTileChunks / 32];
-    __shared__ ScanElem sm_inc[kTileChunks];
-    const int f = blockIdx.y, t = blockIdx.x, tid = threadIdx.x;
-    const double* src = a.src + static_cast<int64_t>(f) * a.N;
-    const bool use_div = a.div != nullptr;
-    const double div = use_div ? a.div[f] : 1.0;
-    const int64_t cidx = static_cast<int64_t>(f) * a.C + static_cast<int64_t>(t) * kTileChunks + tid;
-    const double tstart = a.tile_start[static_cast<int64_t>(f) * a.T + t];
-
-    const StepFn cf = a.chunk_fn[cidx];
-    ScanElem el = fn_is_opaque(cf) ? se_abs(a.anchor_val[cidx]) : se_fn(cf);
-    if (tid == 0) el = se_combine(se_abs(tstart), el);
-    const ScanElem ident = se_fn(fn_identity());
-    const ScanElem inc = block_scan_inclusive<kTileChunks>(el, SEOp(), sms, ident);
-    sm_inc[tid] = inc;
-    __syncthreads();
-    double s = tid ? bits_dbl(sm_inc[tid - 1].a0) : tstart;
-
-    const int64_t base = (static_cast<int64_t>(t) * kTileChunks + tid) * kChunk;
-    if (base >= a.N) return;
-    double v[kChunk];
-    load_chunk(v, src, base, a.N, use_div, div);
-    double* out = a.out + static_cast<int64_t>(f) * a.N;
-#pragma unroll
-    for (int i = 0; i < kChunk; ++i) {
-        s = __dadd_rn(s, v[i]);
-        v[i] = s;
-    }
-    if (a.force_last_one && a.N - 1 >= base && a.N - 1 < base + kChunk) v[a.N - 1 - base] = 1.0;
-    emit_coarse(a, f, static_cast<int64_t>(t) * kTileChunks + tid, base, v[kChunk - 1]);
-    if (base + kChunk <= a.N) {
-        double2* p = reinterpret_cast<double2*>(out + base);
-#pragma unroll
-        for (int i = 0; i < kChunk / 2; ++i) p[i] = make_double2(v[2 * i], v[2 * i + 1]);
-    } else {
-#pragma unroll
-        for (int i = 0; i < kChunk; ++i)
-            if (base + i < a.N) out[base + i] = v[i];
-    }
-}
-
-// T == 1 (a filter of at most kTile = 4096 particles is ONE tile): chunks, walk and emit of the
-// exact sequential sum in a single CTA per filter -- one launch per pass instead of two or three,
-// which is what a small filter's update time is made of.  Same arithmetic as the three kernels
-// above with the tile prefix fixed at 0: chunk step maps, the ordered serial pass over the opaque
-// chunks (their addends re-read from global memory by thread 0: they are rare), the total, and
-// the prefix sums.
-__global__ void __launch_bounds__(kTileChunks) k_exact_single(ExactArgs a) {
-    __shared__ double smd[kTileChunks / 32];
-    __shared__ RFn smr[kTileChunks / 32];
-    __shared__ RFn sm_inc[kTileChunks];
-    __shared__ ScanElem sms[kTileChunks / 32];
-    __shared__ ScanElem sm_se[kTileChunks];
-    __shared__ double sm_anchor[kTileChunks];   // exact running sum after an opaque chunk, by chunk index
-    __shared__ StepFn sm_pre[kTileChunks];      // step map from the previous anchor (or 0) to each opaque chunk, by rank
-    __shared__ int sm_opq[kTileChunks];         // opaque chunk indices in order
-    __shared__ int wcnt[kTileChunks / 32];
-    const int f = blockIdx.y, tid = threadIdx.x;
-    const double* src = a.src + static_cast<int64_t>(f) * a.N;
-    const bool use_div = a.div != nullptr;
-    const double div = use_div ? a.div[f] : 1.0;
-
-    const int64_t base = static_cast<int64_t>(tid) * kChunk;
-    double v[kChunk];
-    load_chunk(v, src, base, a.N, use_div, div);
-    double c = 0.0;
-#pragma unroll
-    for (int i = 0; i < kChunk; ++i) c += v[i];
-    const double incl = block_scan_inclusive<kTileChunks>(c, AddOp(), smd, 0.0);
-    const double s_in = 0.0 + (incl - c);
-    const double s_out = s_in + c;
-    StepFn fn = fn_identity();
-    int opaque = 0;
-    if (base < a.N) {
-        const int64_t cnt = (base + kChunk < a.N) ? base + kChunk : a.N;
-        const int e = chunk_safe_binade(s_in, s_out, cnt);
-        if (e < 0) {
-            fn = fn_opaque();
-            opaque = 1;
-        } else {
-            fn = chunk_step_fn(v, kChunk, e);
-        }
-    }
-    const RFn ident{fn_identity(), 0};
-    const RFn el = opaque ? RFn{fn_identity(), 1} : RFn{fn, 0};
-    const RFn inc = block_scan_inclusive<kTileChunks>(el, RFnOp(), smr, ident);
-    sm_inc[tid] = inc;
-    const unsigned bal = __ballot_sync(kFullMask, opaque);
-    if ((tid & 31) == 0) wcnt[tid >> 5] = __popc(bal);
-    __syncthreads();
-    const RFn exc = tid ? sm_inc[tid - 1] : ident;
-    int orank = __popc(bal & ((1u << (tid & 31)) - 1u));
-    int nopq = 0;
-#pragma unroll
-    for (int w = 0; w < kTileChunks / 32; ++w) {
-        if (w < (tid >> 5)) orank += wcnt[w];
-        nopq += wcnt[w];
-    }
-    if (opaque) {
-        sm_opq[orank] = tid;
-        sm_pre[orank] = exc.f;
-    }
-    __syncthreads();
-    // serial pass over the opaque chunks in order, each from its exact input
-    if (tid == 0) {
-        double V = 0.0;
-        for (int r = 0; r < nopq; ++r) {
-            const int ch = sm_opq[r];
-            double w8[kChunk];
-            load_chunk(w8, src, static_cast<int64_t>(ch) * kChunk, a.N, use_div, div);
-            V = chunk_seq_eval(w8, kChunk, fn_apply(sm_pre[r], V));
-            sm_anchor[ch] = V;
-        }
-        const RFn run = sm_inc[kTileChunks - 1];
-        a.total[f] = fn_apply(run.f, run.reset ? V : 0.0);
-    }
-    if (!a.out) return;
-    __syncthreads();
-    // prefix sums: every chunk's exact input from a scan of step maps and anchors, then 8 adds
-    ScanElem se = opaque ? se_abs(sm_anchor[tid]) : se_fn(fn);
-    if (tid == 0) se = se_combine(se_abs(0.0), se);
-    const ScanElem seid = se_fn(fn_identity());
-    const ScanElem sinc = block_scan_inclusive<kTileChunks>(se, SEOp(), sms, seid);
-    sm_se[tid] = sinc;
-    __syncthreads();
-    double s = tid ? bits_dbl(sm_se[tid - 1].a0) : 0.0;
-    if (base >= a.N) return;
-    double* out = a.out + static_cast<int64_t>(f) * a.N;
-#pragma unroll
-    for (int i = 0; i < kChunk; ++i) {
-        s = __dadd_rn(s, v[i]);
-        v[i] = s;
-    }
-    if (a.force_last_one && a.N - 1 >= base && a.N - 1 < base + kChunk) v[a.N - 1 - base] = 1.0;
-    emit_coarse(a, f, tid, base, v[kChunk - 1]);
-    if (base + kChunk <= a.N) {
-        double2* p = reinterpret_cast<double2*>(out + base);
-#pragma unroll
-        for (int i = 0; i < kChunk / 2; ++i) p[i] = make_double2(v[2 * i], v[2 * i + 1]);
-    } else {
-#pragma unroll
-        for (int i = 0; i < kChunk; ++i)
-            if (base + i < a.N) out[base + i] = v[i];
-    }
-}
 
 // ------------------------------------------------------------------------------------------
 // resample (:658-665) + motion model (:449-503)
 // ------------------------------------------------------------------------------------------
 struct MotionArgs {
-    int64_t N;                // particles of the whole filter (CDF length)
-    int64_t lo, cnt;          // output slots [lo, lo+cnt) computed by this launch (shard)
+    int64_t N;                // particles of this rank's slice (CDF length, array length)
+    int64_t glo;              // global index of local slot 0: noise and RNG counters are keyed by the global slot
     const double* cdf;        // [F][N]
     const double* sx;         // source state [F][N] each
     const double* sy;
@@ -547,21 +111,16 @@ struct MotionArgs {
     double* dy;
     double* dt;
     int32_t* idx_out;         // [F][N]
-    const double* u;          // [F][N] injected or nullptr
-    const double* z;          // [F][3N] injected or nullptr
-    // peer-to-peer sharding: source poses are read from the owning rank's buffer over NVLink.
-    // peer_x/y/t[q] = rank q's state arrays (addressed by GLOBAL index); nullptr = local arrays
-    const double* const* peer_x;
-    const double* const* peer_y;
-    const double* const* peer_t;
-    int64_t n_local;
+    const double* u;          // [F][NG] injected or nullptr (indexed by the global slot)
+    const double* z;          // [F][3 NG] injected or nullptr
     // packed copy of the state, one 32-byte (x, y, theta, 0) entry per particle: the source-pose
-    // gather of the resampling touches one memory sector (one NVLink transaction from a peer)
-    // instead of three.  spose4 / peer_pose4 = source buffer (nullptr: not valid, use the SoA
-    // arrays), dpose4 = destination buffer, always written.
+    // gather of the resampling touches one memory sector instead of three.  spose4 = source buffer
+    // (nullptr: not valid, use the SoA arrays), dpose4 = destination buffer, always written.
     const double4* spose4;
-    const double4* const* peer_pose4;
     double4* dpose4;
+    // sharded filter: the source pose (and index) of every own slot, pushed here by the rank that
+    // owns the source (k_route); nullptr = search and gather locally (k_resample_motion)
+    const double4* routed;
     // coarse level of the CDF search, staged in shared memory: coarse[f][k] = cdf[(k+1) << cshift) - 1]
     const double* coarse;     // [F][nc] or nullptr
     int nc, cshift;
@@ -571,7 +130,7 @@ struct MotionArgs {
     const unsigned long long* update_no;   // device counter of completed updates (keys the Philox stream)
     double* centre;           // [F][2] accumulators (sum x, sum y)
     // directional ray stage (dir_kernels.cuh): ray-start records in slot order, or nullptr;
-    // the heading sort's scatter pass moves them to their sorted slots
+    // k_dir_gather moves them to their heading-sorted slots
     DirRec* rec;
     MapDev map;
     int B;                    // heading buckets of the directional stage's sector arithmetic
@@ -611,19 +170,114 @@ __device__ __forceinline__ double wrap_angle_dev(double a) {  // src/utils.cpp:4
     return a;
 }
 
+// Device noise streams (production mode; the parity tests inject the reference's own draws).
+// Philox4x32-10 keyed by (seed, update) and counted by the GLOBAL slot, so a sharded filter draws
+// what the same filter draws on one GPU.  One call yields the resampling uniforms of TWO slots
+// (stream 0, counter = slot / 2) or the three motion normals of one slot (stream 1).
+__device__ __forceinline__ Philox4 noise_words(uint64_t counter, int f, uint32_t stream, uint64_t seed, uint64_t update_no) {
+    return philox4x32_10(static_cast<uint32_t>(counter), static_cast<uint32_t>(counter >> 32), static_cast<uint32_t>(f), stream,
+                         static_cast<uint32_t>(seed) ^ static_cast<uint32_t>(update_no),
+                         static_cast<uint32_t>(seed >> 32) ^ static_cast<uint32_t>(update_no >> 32) ^ 0x5bd1e995u);
+}
+__device__ __forceinline__ double resample_uniform(int64_t i, int f, uint64_t seed, uint64_t update_no) {
+    const Philox4 r = noise_words(static_cast<uint64_t>(i) >> 1, f, 0u, seed, update_no);
+    return (i & 1) ? canonical_from_words(r.v[2], r.v[3]) : canonical_from_words(r.v[0], r.v[1]);
+}
+
+// lower_bound(cp.begin(), cp.end(), u)  (random.tcc:2709-2713) in two levels: the coarse entries
+// (shared memory) are the exact CDF values at the ends of 2^cshift-element segments, so the first
+// segment whose end value is >= u contains the answer; the fine steps go to L2.
+__device__ __forceinline__ int64_t cdf_lower_bound(const double* __restrict__ cp, int64_t N, const double* ts, int nc, int cshift,
+                                                   double u) {
+    int64_t lo = 0, hi = N;
+    if (nc > 0) {
+        int kl = 0, kh = nc;
+        while (kl < kh) {
+            const int km = (kl + kh) >> 1;
+            if (ts[km] < u)
+                kl = km + 1;
+            else
+                kh = km;
+        }
+        lo = static_cast<int64_t>(kl) << cshift;
+        hi = min(N, lo + (int64_t{1} << cshift));
+    }
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (__ldg(cp + mid) < u)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    if (lo >= N) lo = N - 1;  // unreachable for u < 1 == cp[N-1]; keeps reads in range
+    return lo;
+}
+
+// motion_model for one particle (:474-502) + the stores of the proposal: SoA state, packed copy,
+// ray-start record; returns the (finite) position for the cloud-centre sums
+__device__ __forceinline__ void motion_store(const MotionArgs& a, const MotionScalars& m, uint64_t update_no, int f, int64_t li,
+                                             double x, double y, double th, double* sum_x, double* sum_y) {
+    const int64_t fo = static_cast<int64_t>(f) * a.N;
+    const int64_t i = a.glo + li;
+    double z0, z1, z2;
+    if (a.z) {
+        const double* zp = a.z + 3 * (fo + i);   // [F][3 N]; a sharded filter is one filter (fo == 0), indexed by the global slot
+        z0 = zp[0];
+        z1 = zp[1];
+        z2 = zp[2];
+    } else {
+        const Philox4 r = noise_words(static_cast<uint64_t>(i), f, 1u, a.seed, update_no);
+        double t;
+        normal_pair(r.v[0], r.v[1], &z0, &z1);
+        normal_pair(r.v[2], r.v[3], &z2, &t);
+    }
+    double nx, ny, nt;
+    if (m.straight) {
+        double s, c;
+        sincos(th, &s, &c);
+        nx = __dadd_rn(x, __dmul_rn(m.vdt, c));
+        ny = __dadd_rn(y, __dmul_rn(m.vdt, s));
+        nt = th;
+    } else {
+        double s0, c0, s1, c1;
+        sincos(th, &s0, &c0);
+        sincos(__dadd_rn(th, m.dtheta), &s1, &c1);
+        nx = __dadd_rn(x, __dmul_rn(m.radius, __dsub_rn(s1, s0)));
+        ny = __dsub_rn(y, __dmul_rn(m.radius, __dsub_rn(c1, c0)));
+        nt = __dadd_rn(th, m.dtheta);
+    }
+    nx = __dadd_rn(nx, __dmul_rn(z0, a.disp_x));
+    ny = __dadd_rn(ny, __dmul_rn(z1, a.disp_y));
+    nt = __dadd_rn(nt, __dmul_rn(z2, a.disp_t));
+    nt = wrap_angle_dev(nt);
+    a.dx[fo + li] = nx;
+    a.dy[fo + li] = ny;
+    a.dt[fo + li] = nt;
+    {
+        double2* d4 = reinterpret_cast<double2*>(a.dpose4 + fo + li);
+        d4[0] = make_double2(nx, ny);
+        d4[1] = make_double2(nt, 0.0);
+    }
+    if (a.rec) dir_write_record(a.map, a.rec, fo + li, nx, ny, nt, theta_bucket(nt, a.B));
+    if (!(fabs(nx) < 1e12) || !(fabs(ny) < 1e12)) nx = ny = 0.0;  // keep the window centre finite
+    *sum_x += nx;
+    *sum_y += ny;
+}
+
 constexpr int kMotionThreads = 1024;
 
 // One thread per output slot, persistent blocks when the coarse CDF level is large (one staging of
-// the table per SM).  The search is lower_bound(cp, u) in two levels: the coarse entries are the
-// exact CDF values at the ends of 2^cshift-element segments, so the first segment whose end value
-// is >= u contains the answer.
+// the table per SM).  a.routed == nullptr: search the CDF and gather the source pose here (whole
+// filter on this GPU).  a.routed != nullptr (sharded filter): the source pose of every slot was
+// pushed into `routed` by k_route on the rank that owns the source; only the motion runs here.
 __global__ void __launch_bounds__(kMotionThreads) k_resample_motion(MotionArgs a) {
     __shared__ double sm[kMotionThreads / 32];
     extern __shared__ double ts[];   // a.nc doubles when the coarse level is used
     const int f = blockIdx.y;
-    const bool two_level = a.coarse != nullptr && a.nc > 0;
-    if (two_level) {
-        for (int t = threadIdx.x; t < a.nc; t += kMotionThreads) ts[t] = a.coarse[static_cast<int64_t>(f) * a.nc + t];
+    const bool search = a.routed == nullptr;
+    const int nc = (search && a.coarse != nullptr) ? a.nc : 0;
+    if (nc > 0) {
+        for (int t = threadIdx.x; t < nc; t += kMotionThreads) ts[t] = a.coarse[static_cast<int64_t>(f) * a.nc + t];
         __syncthreads();
     }
     const int64_t N = a.N;
@@ -631,120 +285,35 @@ __global__ void __launch_bounds__(kMotionThreads) k_resample_motion(MotionArgs a
     const MotionScalars m = motion_scalars(a.action[3 * f + 0], a.action[3 * f + 2]);
     const uint64_t update_no = *a.update_no;
     double sum_x = 0.0, sum_y = 0.0;
-    for (int64_t li = static_cast<int64_t>(blockIdx.x) * kMotionThreads + threadIdx.x; li < a.cnt;
+    for (int64_t li = static_cast<int64_t>(blockIdx.x) * kMotionThreads + threadIdx.x; li < N;
          li += static_cast<int64_t>(gridDim.x) * kMotionThreads) {
-        const int64_t i = a.lo + li;   // global slot: noise and RNG counters do not depend on the sharding
-        double nx, ny;
-        // noise: injected arrays in the reference's draw order, else Philox keyed by
-        // (seed, update) and counted by (filter, particle)
-        double u, z0, z1, z2;
-        Philox4 r0{}, r1{};
-        const bool need_rng = (a.u == nullptr) || (a.z == nullptr);
-        if (need_rng) {
-            r0 = philox4x32_10(static_cast<uint32_t>(i), static_cast<uint32_t>(i >> 32), static_cast<uint32_t>(f), 0u,
-                               static_cast<uint32_t>(a.seed) ^ static_cast<uint32_t>(update_no),
-                               static_cast<uint32_t>(a.seed >> 32) ^ static_cast<uint32_t>(update_no >> 32) ^ 0x5bd1e995u);
-            r1 = philox4x32_10(static_cast<uint32_t>(i), static_cast<uint32_t>(i >> 32), static_cast<uint32_t>(f), 1u,
-                               static_cast<uint32_t>(a.seed) ^ static_cast<uint32_t>(update_no),
-                               static_cast<uint32_t>(a.seed >> 32) ^ static_cast<uint32_t>(update_no >> 32) ^ 0x5bd1e995u);
-        }
-        u = a.u ? a.u[fo + i] : canonical_from_words(r0.v[0], r0.v[1]);
-        if (a.z) {
-            z0 = a.z[3 * (fo + i) + 0];
-            z1 = a.z[3 * (fo + i) + 1];
-            z2 = a.z[3 * (fo + i) + 2];
-        } else {
-            double t;
-            normal_pair(r0.v[2], r0.v[3], &z0, &z1);
-            normal_pair(r1.v[0], r1.v[1], &z2, &t);
-        }
-        // lower_bound(cp.begin(), cp.end(), u)  (random.tcc:2709-2713)
-        const double* cp = a.cdf + fo;
-        int64_t lo = 0, hi = N;
-        if (two_level) {
-            // k* = first segment whose end value ts[k] = cp[((k+1) << cshift) - 1] is >= u (nc if none):
-            // everything before segment k* is < u, so the answer lies in it (or in the tail past the table)
-            int kl = 0, kh = a.nc;
-            while (kl < kh) {
-                const int km = (kl + kh) >> 1;
-                if (ts[km] < u)
-                    kl = km + 1;
-                else
-                    kh = km;
-            }
-            lo = static_cast<int64_t>(kl) << a.cshift;
-            hi = min(N, lo + (int64_t{1} << a.cshift));
-        }
-        while (lo < hi) {
-            const int64_t mid = (lo + hi) >> 1;
-            if (__ldg(cp + mid) < u)
-                lo = mid + 1;
-            else
-                hi = mid;
-        }
-        if (lo >= N) lo = N - 1;  // unreachable for u < 1 == cp[N-1]; keeps reads in range
-        if (N < 2) lo = 0;        // libstdc++ clears the table for fewer than 2 weights
-        a.idx_out[fo + i] = static_cast<int32_t>(lo);
         double x, y, th;
-        if (a.peer_pose4) {
-            // the slot's source lives on rank q; its arrays are mapped into this address space
-            // (CUDA IPC), so this is a plain 32-byte load that travels over NVLink
-            const int q = static_cast<int>(lo / a.n_local);
-            const double2* p4 = reinterpret_cast<const double2*>(a.peer_pose4[q] + lo);
-            // cache-volatile loads: the owner rewrites this buffer every other update, and a line kept in
-            // this GPU's caches from two updates ago must not be served (measured: plain 128-bit loads
-            // returned stale poses on a real 2-GPU run; scripts/check_sharded_equals_single.py)
-            const double2 xy = __ldcv(p4), tz = __ldcv(p4 + 1);
-            x = xy.x;
-            y = xy.y;
-            th = tz.x;
-        } else if (a.peer_x) {
-            const int q = static_cast<int>(lo / a.n_local);
-            x = __ldcv(a.peer_x[q] + lo);   // cache-volatile like the packed path: a peer rewrites these arrays every other update
-            y = __ldcv(a.peer_y[q] + lo);
-            th = __ldcv(a.peer_t[q] + lo);
-        } else if (a.spose4) {
-            const double2* p4 = reinterpret_cast<const double2*>(a.spose4 + fo + lo);
-            const double2 xy = __ldg(p4), tz = __ldg(p4 + 1);
-            x = xy.x;
-            y = xy.y;
-            th = tz.x;
+        if (search) {
+            const int64_t i = a.glo + li;
+            const double u = a.u ? a.u[fo + i] : resample_uniform(i, f, a.seed, update_no);
+            int64_t lo = cdf_lower_bound(a.cdf + fo, N, ts, nc, a.cshift, u);
+            if (N < 2) lo = 0;        // libstdc++ clears the table for fewer than 2 weights
+            a.idx_out[fo + li] = static_cast<int32_t>(lo);
+            if (a.spose4) {
+                const double2* p4 = reinterpret_cast<const double2*>(a.spose4 + fo + lo);
+                const double2 xy = __ldg(p4), tz = __ldg(p4 + 1);
+                x = xy.x;
+                y = xy.y;
+                th = tz.x;
+            } else {
+                x = a.sx[fo + lo];
+                y = a.sy[fo + lo];
+                th = a.st[fo + lo];
+            }
         } else {
-            x = a.sx[fo + lo];
-            y = a.sy[fo + lo];
-            th = a.st[fo + lo];
+            // written by other GPUs over NVLink during k_route: system-scope loads (never a line of this SM's L1)
+            const double* r = reinterpret_cast<const double*>(a.routed + li);
+            x = ld_sys_f64(r);
+            y = ld_sys_f64(r + 1);
+            th = ld_sys_f64(r + 2);
+            a.idx_out[li] = static_cast<int32_t>(__double_as_longlong(ld_sys_f64(r + 3)));
         }
-        double nt;
-        if (m.straight) {
-            double s, c;
-            sincos(th, &s, &c);
-            nx = __dadd_rn(x, __dmul_rn(m.vdt, c));
-            ny = __dadd_rn(y, __dmul_rn(m.vdt, s));
-            nt = th;
-        } else {
-            double s0, c0, s1, c1;
-            sincos(th, &s0, &c0);
-            sincos(__dadd_rn(th, m.dtheta), &s1, &c1);
-            nx = __dadd_rn(x, __dmul_rn(m.radius, __dsub_rn(s1, s0)));
-            ny = __dsub_rn(y, __dmul_rn(m.radius, __dsub_rn(c1, c0)));
-            nt = __dadd_rn(th, m.dtheta);
-        }
-        nx = __dadd_rn(nx, __dmul_rn(z0, a.disp_x));
-        ny = __dadd_rn(ny, __dmul_rn(z1, a.disp_y));
-        nt = __dadd_rn(nt, __dmul_rn(z2, a.disp_t));
-        nt = wrap_angle_dev(nt);
-        a.dx[fo + i] = nx;
-        a.dy[fo + i] = ny;
-        a.dt[fo + i] = nt;
-        {
-            double2* d4 = reinterpret_cast<double2*>(a.dpose4 + fo + i);
-            d4[0] = make_double2(nx, ny);
-            d4[1] = make_double2(nt, 0.0);
-        }
-        if (a.rec) dir_write_record(a.map, a.rec, fo + li, nx, ny, nt, theta_bucket(nt, a.B));
-        if (!(fabs(nx) < 1e12) || !(fabs(ny) < 1e12)) nx = ny = 0.0;  // keep the window centre finite
-        sum_x += nx;
-        sum_y += ny;
+        motion_store(a, m, update_no, f, li, x, y, th, &sum_x, &sum_y);
     }
     // cloud centre for the shared-memory window of the ray kernel
     const double bx = block_sum<kMotionThreads>(sum_x, sm);
@@ -753,6 +322,143 @@ __global__ void __launch_bounds__(kMotionThreads) k_resample_motion(MotionArgs a
         atomicAdd(a.centre + 2 * f + 0, bx);
         atomicAdd(a.centre + 2 * f + 1, by);
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// sharded filter: sender-driven resampling
+// ------------------------------------------------------------------------------------------
+// Every rank owns a slice of the global CDF.  The draw u_i of EVERY global slot i is a pure function
+// of (seed, update, i), so each rank evaluates all of them, keeps the draws that fall into its own
+// CDF range (rank_end[rank-1], rank_end[rank]] -- exactly one rank claims each slot --, finds the
+// source particle in its local CDF slice and PUSHES the source pose (x, y, theta, global index) over
+// NVLink into slot i of the owner's `routed` array.  Nothing is ever read from a peer.  A warp tests
+// 64 slots per round (one Philox call per lane) and queues the claimed ones in shared memory, so the
+// searches run with full warps although only 1 / world of the slots are claimed.
+struct RouteArgs {
+    int64_t NG;               // global slots
+    int64_t N;                // particles of this rank (== slots per rank)
+    const double* cdf;        // [N] this rank's slice of the global CDF
+    const double* coarse;     // [nc] coarse level of the local slice
+    int nc, cshift;
+    const double* rank_end;   // [world] exact CDF value at the end of every rank's slice
+    const double4* spose4;    // [N] local source state, packed (nullptr: use the SoA arrays)
+    const double* sx;
+    const double* sy;
+    const double* st;
+    double4* routed[kMaxWorld];   // every rank's `routed` array (own included)
+    const double* u;          // [NG] injected uniforms or nullptr
+    uint64_t seed;
+    const unsigned long long* update_no;
+    unsigned int* done;
+    ShardDev sh;
+};
+constexpr int kRouteThreads = 1024;
+constexpr int kRouteQueue = 128;   // claimed slots a warp can hold (<= 31 left over + 64 new)
+
+__device__ __forceinline__ void route_finish(const ShardDev& sh, unsigned long long epoch) {
+    if (threadIdx.x == 0) *sh.xseq = epoch;
+}
+
+__global__ void __launch_bounds__(kRouteThreads) k_route(RouteArgs a) {
+    extern __shared__ double ts[];   // nc doubles of the coarse level, then the warps' queues
+    __shared__ bool is_last;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int t = tid; t < a.nc; t += kRouteThreads) ts[t] = a.coarse[t];
+    double* qu = ts + a.nc + warp * kRouteQueue;                                           // queued draws
+    int* qi = reinterpret_cast<int*>(ts + a.nc + (kRouteThreads / 32) * kRouteQueue) + warp * kRouteQueue;   // queued slots
+    __syncthreads();
+    const int me = a.sh.rank, world = a.sh.world;
+    const double lo_u = me > 0 ? a.rank_end[me - 1] : -1.0;          // claim u in (lo_u, hi_u]
+    const double hi_u = me + 1 < world ? a.rank_end[me] : 2.0;
+    const uint64_t update_no = *a.update_no;
+    const int64_t glo = static_cast<int64_t>(me) * a.N;
+    int qn = 0;   // entries in this warp's queue (warp-uniform)
+
+    auto serve = [&](int k) {   // lane k < count serves queue entry k
+        const double u = qu[k];
+        const int64_t i = qi[k];
+        const int64_t j = cdf_lower_bound(a.cdf, a.N, ts, a.nc, a.cshift, u);
+        double x, y, th;
+        if (a.spose4) {
+            const double2* p4 = reinterpret_cast<const double2*>(a.spose4 + j);
+            const double2 xy = __ldg(p4), tz = __ldg(p4 + 1);
+            x = xy.x;
+            y = xy.y;
+            th = tz.x;
+        } else {
+            x = a.sx[j];
+            y = a.sy[j];
+            th = a.st[j];
+        }
+        const int owner = static_cast<int>(i / a.N);
+        double* dst = reinterpret_cast<double*>(a.routed[owner] + (i - static_cast<int64_t>(owner) * a.N));
+        // one 32-byte store: one NVLink write transaction per routed particle
+        asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "d"(x), "d"(y), "d"(th),
+                     "d"(__longlong_as_double(glo + j))
+                     : "memory");
+    };
+
+    const int64_t warps_total = static_cast<int64_t>(gridDim.x) * (kRouteThreads / 32);
+    const int64_t gw = static_cast<int64_t>(blockIdx.x) * (kRouteThreads / 32) + warp;
+    for (int64_t base = gw * 64; base < a.NG; base += warps_total * 64) {
+        const int64_t i0 = base + 2 * lane;   // this lane's two slots: one Philox call
+        double u0 = 2.0, u1 = 2.0;
+        if (i0 < a.NG) {
+            if (a.u) {
+                u0 = a.u[i0];
+                if (i0 + 1 < a.NG) u1 = a.u[i0 + 1];
+            } else {
+                const Philox4 r = noise_words(static_cast<uint64_t>(i0) >> 1, 0, 0u, a.seed, update_no);
+                u0 = canonical_from_words(r.v[0], r.v[1]);
+                if (i0 + 1 < a.NG) u1 = canonical_from_words(r.v[2], r.v[3]);
+            }
+        }
+        const bool c0 = u0 > lo_u && u0 <= hi_u && u0 < 1.5, c1 = u1 > lo_u && u1 <= hi_u && u1 < 1.5;
+        const unsigned b0 = __ballot_sync(kFullMask, c0), b1 = __ballot_sync(kFullMask, c1);
+        const unsigned below = (1u << lane) - 1u;
+        if (c0) {
+            const int p = qn + __popc(b0 & below);
+            qu[p] = u0;
+            qi[p] = static_cast<int>(i0);
+        }
+        if (c1) {
+            const int p = qn + __popc(b0) + __popc(b1 & below);
+            qu[p] = u1;
+            qi[p] = static_cast<int>(i0 + 1);
+        }
+        qn += __popc(b0) + __popc(b1);
+        __syncwarp();
+        while (qn >= 32) {   // full warps of claimed slots, taken from the tail of the queue
+            qn -= 32;
+            serve(qn + lane);
+            __syncwarp();
+        }
+    }
+    if (lane < qn) serve(lane);
+    // every store of this CTA is performed at system scope before the CTA counts itself done
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        is_last = atomicAdd(a.done, 1u) == gridDim.x - 1u;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (tid == 0) *a.done = 0;
+    __syncthreads();
+    const unsigned long long epoch = *a.sh.xseq + 1ull;
+    shard_publish(a.sh, epoch, nullptr, 0);
+    if (!a.sh.fused) return;
+    if (!shard_wait(a.sh, epoch)) return;
+    route_finish(a.sh, epoch);
+}
+
+// host-ordered ranks: checks that every rank's k_route has published
+__global__ void __launch_bounds__(32) k_route_check(ShardDev sh) {
+    const unsigned long long epoch = *sh.xseq + 1ull;
+    if (!shard_wait(sh, epoch)) return;
+    route_finish(sh, epoch);
 }
 
 // Counting sort of the particles by heading bucket, in two kernels of fat blocks so that the
@@ -1123,51 +829,6 @@ __global__ void __launch_bounds__(kNormThreads) k_normalize_pose(NormArgs a) {
     }
 }
 
-// P2P sharding: fold the per-block pose partial sums of the rank's own slots (written by
-// k_normalize_pose run over the slice with raw weights) into four doubles, in block order
-__global__ void __launch_bounds__(256) k_sum_partials(const double* partial, int nblk, double* out4) {
-    __shared__ double sm[8];
-    double v[4] = {0, 0, 0, 0};
-    for (int b = threadIdx.x; b < nblk; b += 256) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) v[q] += partial[static_cast<int64_t>(b) * 4 + q];
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) v[q] = block_sum<256>(v[q], sm);
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) out4[q] = v[q];
-    }
-}
-
-__global__ void k_normalize_only(const double* w_raw, const double* total, double* wn, int64_t n) {
-    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const double tot = total[0];
-    const double w = w_raw[i];
-    wn[i] = tot > 0.0 ? __ddiv_rn(w, tot) : w;   // `if (sum_weights > 0)` (:680)
-}
-
-// pose from the gathered per-rank partial sums (rank order => identical on every rank)
-__global__ void k_pose_from_partials(const double* partials, int world, const double* total, double* pose_out, double* pose_host,
-                                     unsigned long long* update_no) {
-    if (threadIdx.x || blockIdx.x) return;
-    double v[4] = {0, 0, 0, 0};
-    for (int q = 0; q < world; ++q)
-        for (int k = 0; k < 4; ++k) v[k] += partials[4 * q + k];
-    const double tot = total[0];
-    const double s = tot > 0.0 ? tot : 1.0;
-    pose_out[0] = v[0] / s;
-    pose_out[1] = v[1] / s;
-    pose_out[2] = atan2(v[2], v[3]);
-    if (pose_host) {
-        pose_host[0] = pose_out[0];
-        pose_host[1] = pose_out[1];
-        pose_host[2] = pose_out[2];
-    }
-    *update_no += 1ull;
-}
-
 // ------------------------------------------------------------------------------------------
 // initialisers (:382-446), batch ray queries (:586-609), weighted sub-sampling (:946-958)
 // ------------------------------------------------------------------------------------------
@@ -1184,8 +845,10 @@ struct InitArgs {
     const int32_t* free_cells;
     int n_free, W;
     double res, ox, oy;
+    double w0;                 // initial weight 1 / max_particles (:107, :397, :444)
     uint64_t seed, stream_no;
     int filter0;               // first filter this launch applies to
+    int64_t glo;               // global index of local particle 0 (sharded filter): keys the device RNG; injected arrays are local
 };
 
 __global__ void k_init_pose(InitArgs a) {
@@ -1200,7 +863,8 @@ __global__ void k_init_pose(InitArgs a) {
         z1 = z[1];
         z2 = z[2];
     } else {
-        const Philox4 r = philox4x32_10(static_cast<uint32_t>(i), static_cast<uint32_t>(i >> 32), static_cast<uint32_t>(f), 7u,
+        const int64_t gi = a.glo + i;
+        const Philox4 r = philox4x32_10(static_cast<uint32_t>(gi), static_cast<uint32_t>(gi >> 32), static_cast<uint32_t>(f), 7u,
                                         static_cast<uint32_t>(a.seed) ^ static_cast<uint32_t>(a.stream_no),
                                         static_cast<uint32_t>(a.seed >> 32) ^ 0x9e3779b9u);
         double t;
@@ -1211,7 +875,7 @@ __global__ void k_init_pose(InitArgs a) {
     a.px[fo + i] = __dadd_rn(pose[0], __dmul_rn(z0, 0.5));
     a.py[fo + i] = __dadd_rn(pose[1], __dmul_rn(z1, 0.5));
     a.pt[fo + i] = wrap_angle_dev(__dadd_rn(pose[2], __dmul_rn(z2, 0.4)));
-    a.wn[fo + i] = 1.0 / static_cast<double>(a.N);
+    a.wn[fo + i] = a.w0;
 }
 
 __global__ void k_init_global(InitArgs a) {
@@ -1225,7 +889,8 @@ __global__ void k_init_global(InitArgs a) {
         ord = a.cell[static_cast<int64_t>(blockIdx.y) * a.N + i];
         th = a.theta[static_cast<int64_t>(blockIdx.y) * a.N + i];
     } else {
-        const Philox4 r = philox4x32_10(static_cast<uint32_t>(i), static_cast<uint32_t>(i >> 32), static_cast<uint32_t>(f), 11u,
+        const int64_t gi = a.glo + i;
+        const Philox4 r = philox4x32_10(static_cast<uint32_t>(gi), static_cast<uint32_t>(gi >> 32), static_cast<uint32_t>(f), 11u,
                                         static_cast<uint32_t>(a.seed) ^ static_cast<uint32_t>(a.stream_no),
                                         static_cast<uint32_t>(a.seed >> 32) ^ 0x85ebca6bu);
         ord = static_cast<int32_t>(__umulhi(r.v[0], static_cast<uint32_t>(a.n_free)));
@@ -1237,7 +902,7 @@ __global__ void k_init_global(InitArgs a) {
     a.px[fo + i] = __dadd_rn(__dmul_rn(static_cast<double>(col), a.res), a.ox);   // :438
     a.py[fo + i] = __dadd_rn(__dmul_rn(static_cast<double>(row), a.res), a.oy);   // :439
     a.pt[fo + i] = th;
-    a.wn[fo + i] = 1.0 / static_cast<double>(a.N);
+    a.wn[fo + i] = a.w0;
 }
 
 struct QueryArgs {
@@ -1280,13 +945,20 @@ __global__ void k_steps_to_ranges(const uint8_t* steps, int64_t n, int M, double
 }
 
 // weighted sub-sample for visualisation: k draws from the CDF of the current weights
+// (visualize() :946-958: discrete_distribution(weights_) drawn max_viz_particles times; u_in = the
+// canonical uniforms it would draw, or nullptr for the device RNG)
 __global__ void k_sample_particles(const double* cdf, int64_t N, const double* px, const double* py, const double* pt,
-                                   int k, uint64_t seed, uint64_t stream_no, double* out) {
+                                   int k, uint64_t seed, uint64_t stream_no, const double* u_in, double* out, int32_t* idx_out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= k) return;
-    const Philox4 r = philox4x32_10(static_cast<uint32_t>(i), 0u, 0u, 13u, static_cast<uint32_t>(seed) ^ static_cast<uint32_t>(stream_no),
-                                    static_cast<uint32_t>(seed >> 32) ^ 0xc2b2ae35u);
-    const double u = canonical_from_words(r.v[0], r.v[1]);
+    double u;
+    if (u_in) {
+        u = u_in[i];
+    } else {
+        const Philox4 r = philox4x32_10(static_cast<uint32_t>(i), 0u, 0u, 13u, static_cast<uint32_t>(seed) ^ static_cast<uint32_t>(stream_no),
+                                        static_cast<uint32_t>(seed >> 32) ^ 0xc2b2ae35u);
+        u = canonical_from_words(r.v[0], r.v[1]);
+    }
     int64_t lo = 0, hi = N;
     while (lo < hi) {
         const int64_t mid = (lo + hi) >> 1;
@@ -1296,9 +968,11 @@ __global__ void k_sample_particles(const double* cdf, int64_t N, const double* p
             hi = mid;
     }
     if (lo >= N) lo = N - 1;
+    if (N < 2) lo = 0;        // libstdc++ clears the table for fewer than 2 weights
     out[i] = px[lo];
     out[k + i] = py[lo];
     out[2 * k + i] = pt[lo];
+    if (idx_out) idx_out[i] = static_cast<int32_t>(lo);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -1,10 +1,13 @@
 // csrc/mcl_b200.cu -- C ABI (include/mcl_b200.h) over the sm_100a kernels in kernels.cuh.
 //
 // Host side of the drop-in boundary: owns the device buffers of one ParticleFilter (or a
-// batch of independent ones), uploads map / table / beams, and sequences the kernels of one
-// MCL update on a CUDA stream.  There is deliberately no CPU implementation behind these
-// entry points: without a CUDA device mcl_create fails.
+// batch of independent ones, or one rank's slice of a particle-sharded one), uploads map /
+// table / beams, and sequences the kernels of one MCL update on a CUDA stream.  There is
+// deliberately no CPU implementation behind these entry points: without a CUDA device
+// mcl_create fails.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include <algorithm>
 #include <cmath>
@@ -47,6 +50,46 @@ cudaError_t dalloc(T** p, size_t n) {
 }
 
 constexpr size_t kWindowBudget = 226 * 1024;   // shared memory for the skip-map window (227 KB/CTA - 1 KB reserved)
+constexpr int kMaxMarks = 64;
+
+// NCCL is bound at run time (dlopen) and only by sharded contexts: the single-GPU library has no
+// link-time dependency on it, and a process that already loaded an NCCL (torch) shares that copy.
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+
+int load_nccl() {
+    if (g_nccl.handle) return MCL_OK;
+    void* h = nullptr;
+    for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+        h = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) return fail(MCL_ERR_UNSUPPORTED, "libnccl.so.2 not found: %s", dlerror());
+    NcclApi a;
+    a.handle = h;
+    a.GetUniqueId = reinterpret_cast<decltype(a.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
+    a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
+    a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+    a.AllGather = reinterpret_cast<decltype(a.AllGather)>(dlsym(h, "ncclAllGather"));
+    a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+    if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.AllGather || !a.GetErrorString)
+        return fail(MCL_ERR_UNSUPPORTED, "libnccl.so.2 lacks a required symbol");
+    g_nccl = a;
+    return MCL_OK;
+}
+
+#define NK(call)                                                                                          \
+    do {                                                                                                  \
+        ncclResult_t r_ = (call);                                                                         \
+        if (r_ != ncclSuccess) return fail(MCL_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, g_nccl.GetErrorString(r_)); \
+    } while (0)
 
 }  // namespace
 
@@ -57,7 +100,7 @@ struct mcl_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
     int F = 1;
-    int64_t N = 0;
+    int64_t N = 0;                   // particles held by this context (a sharded rank: its slice)
     int R = 0, M = 0;
     bool have_map = false, have_beams = false;
     double res = 0, ox = 0, oy = 0, oyaw = 0;
@@ -90,16 +133,18 @@ struct mcl_ctx {
     float* d_obs = nullptr;
     double* d_slice = nullptr;
     size_t slice_elems = 0;
-    // exact-sum workspaces
+    // exact-sum workspaces (exact_kernels.cuh)
     int T = 0, C = 0;
     double* d_tile_sum = nullptr;
     StepFn* d_chunk_fn = nullptr;
     StepFn* d_opq_pre = nullptr;
     int* d_opq_idx = nullptr;
+    double* d_opq_add = nullptr;
     int* d_tile_opq = nullptr;
     int64_t* d_tile_elem = nullptr;
     int* d_list_chunk = nullptr;
-    StepFn* d_list_fn = nullptr;
+    StepFn* d_list_fn = nullptr;       // [2][F][C]
+    double* d_list_add = nullptr;      // [2][F][C][8]
     double* d_anchors = nullptr;
     double* d_anchor_val = nullptr;
     double* d_tile_start = nullptr;
@@ -108,6 +153,8 @@ struct mcl_ctx {
     double* d_S1 = nullptr;
     double* d_S2 = nullptr;
     double* d_scratch_total = nullptr;
+    double* d_slice_sum = nullptr;   // [kMaxWorld] approximate slice sums of all ranks
+    double* d_rank_end = nullptr;    // [kMaxWorld] exact CDF value at the end of every rank's slice
     // pose
     int norm_blocks = 1;
     double* d_partial = nullptr;
@@ -136,20 +183,32 @@ struct mcl_ctx {
     int64_t dir_stride = 0;
     int dir_box = 0;
     size_t dir_smem = 0;
-    // particle shard: this context computes output slots [lo, lo+cnt) of the filter
-    int64_t lo = 0, cnt = 0;
-    bool local_pending = false;
-    // peer-to-peer sharding
-    bool p2p = false;
+    // particle-sharded filter: this context holds slots [glo, glo + N) of a filter of NG particles
     int world = 1, rank = 0;
-    const double** d_peer_tab = nullptr;     // device: [buf 2][array 3][world] pointers
+    int64_t NG = 0, glo = 0;
+    bool connected = false;           // the peers' exchange buffers are mapped
+    int xmode = 1;                    // 1: kernels exchange and wait on their own (one rank per GPU); 0: host-ordered
+    mcl_barrier_fn hook = nullptr;    // host-ordered exchange: called where every rank must have published
+    void* hook_user = nullptr;
+    uint8_t* d_mbox = nullptr;        // [2][world][kMboxSlot]
+    unsigned long long* d_flag = nullptr;   // [kMaxWorld]
+    unsigned long long* d_xseq = nullptr;
+    double4* d_routed = nullptr;      // [N] source pose + index of every own slot, pushed by the sources' owners
+    int* h_err = nullptr;             // mapped pinned: first device-side exchange error
+    int* d_err = nullptr;
+    ShardDev sh{};                    // device view (peer pointers), by value in kernel arguments
+    double4* routed_peers[kMaxWorld] = {};
+    const StepFn* peer_list_fn[kMaxWorld] = {};
+    const double* peer_list_add[kMaxWorld] = {};
     std::vector<void*> ipc_opened;
-    double* d_partials = nullptr;            // [world][4] pose partial sums (rank's own at [rank])
-    unsigned int* d_done = nullptr;          // [F] block-completion counters of k_normalize_pose
-    // what d_tile_sum currently holds: 0 nothing usable, 1 tile sums of w_norm, 2 tile sums of
-    // w_raw with w_norm = w_raw / S1 (rescaled on the fly for the approximate prefix)
+    char* arena = nullptr;            // ONE allocation for everything a peer touches: mailbox | flags | routed | overflow lists
+    ncclComm_t comm = nullptr;        // mcl_create_sharded: bootstrap, state gathers, optional barrier transport
+    unsigned long long* d_nccl_tok = nullptr;   // [world] tokens of the NCCL barrier
+    unsigned int* d_done = nullptr;          // [F] block-completion counters
+    unsigned int* d_route_done = nullptr;
+    // what d_tile_sum currently holds: 0 nothing usable, 1 tile sums of w_norm (S2 valid), 2 tile sums of
+    // w_raw with w_norm = w_raw / S1 (S1, S2 valid; rescaled on the fly for the approximate prefix)
     int tile_state = 0;
-    // pinned staging for the host-facing update
     // pinned staging of the host-facing update: [F][3] doubles of action followed by [F][R] floats of
     // scan in ONE buffer (one H2D copy per update); d_action / d_obs alias the device twin
     double* h_action = nullptr;
@@ -158,7 +217,10 @@ struct mcl_ctx {
     double* d_pose_mapped = nullptr;   // device alias of h_pose (mapped pinned memory): the pose kernel writes it directly
     uint64_t update_no = 0, init_no = 0;
     unsigned long long* d_update_no = nullptr;   // device twin of update_no, read by k_resample_motion
-    // CUDA graphs of the steady-state host-facing update, one per state-buffer parity
+    // scratch for the occasional calls (initialisers, range queries, viz sampling): grown on demand, never per call
+    void* d_tmp = nullptr;
+    size_t tmp_bytes = 0;
+    // CUDA graphs of the steady-state update, one per state-buffer parity
     bool graphs_enabled = true;
     cudaGraphExec_t gexec[2] = {nullptr, nullptr};
     int64_t graph_launches = 0;
@@ -167,7 +229,14 @@ struct mcl_ctx {
     bool ev_valid = false;            // the stage events of a whole update have been recorded
     cudaEvent_t ev[7] = {};
     mcl_stage_ms last_ms{};
-    bool cdf_valid = false;
+    // per-kernel events of the last profiled update
+    cudaEvent_t mark_ev[kMaxMarks + 1] = {};
+    const char* mark_name[kMaxMarks] = {};
+    int nmarks = 0;
+    unsigned long long* d_dbg = nullptr;   // diagnostics: phase cycle counts of the exact passes (mcl_debug_pass_cycles)
+    int dbg_pass = -1;                // which pass kind records them (-1: none)
+    bool cdf_valid = false;           // d_cdf is the CDF of the CURRENT weights
+    bool cdf_any = false;             // d_cdf holds the CDF the last update drew from
 };
 
 namespace {
@@ -181,58 +250,193 @@ void drop_graphs(mcl_ctx* c) {
     }
 }
 
-ExactArgs exact_args(mcl_ctx* c, const double* src, const double* div, const double* approx_div, double* total,
-                     double* out, int force_one) {
+// scratch buffer of the occasional calls
+int ensure_tmp(mcl_ctx* c, size_t bytes) {
+    if (bytes <= c->tmp_bytes) return MCL_OK;
+    CK(cudaStreamSynchronize(c->stream));
+    if (c->d_tmp) cudaFree(c->d_tmp);
+    c->d_tmp = nullptr;
+    c->tmp_bytes = 0;
+    const size_t want = std::max<size_t>(bytes, 1 << 16);
+    CK(cudaMalloc(&c->d_tmp, want));
+    c->tmp_bytes = want;
+    return MCL_OK;
+}
+
+// profiling: one event after every kernel of the update (mcl_get_kernel_ms)
+void mark(mcl_ctx* c, const char* name) {
+    c->launches++;
+    if (!c->profiling || c->nmarks >= kMaxMarks) return;
+    if (!c->mark_ev[c->nmarks + 1] && cudaEventCreate(&c->mark_ev[c->nmarks + 1]) != cudaSuccess) return;
+    cudaEventRecord(c->mark_ev[c->nmarks + 1], c->stream);
+    c->mark_name[c->nmarks++] = name;
+}
+void marks_begin(mcl_ctx* c) {
+    c->nmarks = 0;
+    if (!c->profiling) return;
+    if (!c->mark_ev[0] && cudaEventCreate(&c->mark_ev[0]) != cudaSuccess) return;
+    cudaEventRecord(c->mark_ev[0], c->stream);
+}
+
+bool sharded(const mcl_ctx* c) { return c->world > 1; }
+// T == 1 on one GPU: the one-CTA-per-pass kernels (small filters, batches)
+bool single_tile(const mcl_ctx* c) { return c->T == 1 && !sharded(c); }
+
+ExactArgs exact_base(mcl_ctx* c) {
     ExactArgs a{};
-    a.src = src;
-    a.div = div;
-    a.approx_div = approx_div;
     a.N = c->N;
+    a.glo = c->glo;
     a.T = c->T;
     a.C = c->C;
     a.tile_sum = c->d_tile_sum;
+    a.slice_sum = c->d_slice_sum;
     a.chunk_fn = c->d_chunk_fn;
     a.opq_pre = c->d_opq_pre;
     a.opq_idx = c->d_opq_idx;
+    a.opq_add = c->d_opq_add;
     a.tile_opq = c->d_tile_opq;
     a.tile_elem = c->d_tile_elem;
     a.list_chunk = c->d_list_chunk;
     a.list_fn = c->d_list_fn;
+    a.list_add = c->d_list_add;
+    for (int q = 0; q < kMaxWorld; ++q) {
+        a.peer_list_fn[q] = c->peer_list_fn[q];
+        a.peer_list_add[q] = c->peer_list_add[q];
+    }
     a.anchors = c->d_anchors;
     a.anchor_val = c->d_anchor_val;
     a.tile_start = c->d_tile_start;
-    a.total = total;
-    a.out = out;
-    a.force_last_one = force_one;
-    // the pass that emits the CDF also publishes the coarse level of its search
-    a.coarse = (out && c->coarse_n > 0) ? c->d_coarse : nullptr;
-    a.coarse_m = a.coarse ? (1 << c->coarse_shift) / kChunk : 0;
-    a.coarse_n = c->coarse_n;
+    a.done = c->d_done;
+    a.partial = c->d_partial;
+    a.sh = c->sh;
+    a.sh.fused = c->xmode;
     return a;
 }
 
-// sequential-order sum (and optionally prefix sums) of src[k] (/ div), see exact_sum.cuh
-int run_exact(mcl_ctx* c, const double* src, const double* div, double* total, double* out, int force_one,
-              bool need_tile_sums, const double* approx_div = nullptr) {
-    ExactArgs a = exact_args(c, src, div, approx_div, total, out, force_one);
-    const dim3 gt(c->T, c->F);
-    if (c->T == 1) {   // a filter of one tile: the whole pass is one CTA per filter
-        k_exact_single<<<gt, kTileChunks, 0, c->stream>>>(a);
-        c->launches++;
-        CK(cudaGetLastError());
+// host-ordered exchange: every rank must have launched (and finished) its publishing kernel before any
+// rank's consuming kernel runs.  Either the caller's hook (ranks emulated on one GPU: the hook
+// synchronises them) or a stream-ordered NCCL all-gather of one word per rank.
+int exchange_barrier(mcl_ctx* c) {
+    if (c->hook) {
+        CK(cudaStreamSynchronize(c->stream));
+        const int rc = c->hook(c->hook_user);
+        if (rc != 0) return fail(MCL_ERR_INVALID, "barrier hook failed (%d)", rc);
         return MCL_OK;
     }
-    if (need_tile_sums) {
-        k_tile_sums<<<gt, kTileChunks, 0, c->stream>>>(a);
-        c->launches++;
+    if (c->comm) {
+        NK(g_nccl.AllGather(c->d_nccl_tok + c->rank, c->d_nccl_tok, 1, ncclUint64, c->comm, c->stream));
+        return MCL_OK;
     }
-    k_exact_chunks<<<gt, kTileChunks, 0, c->stream>>>(a);
-    k_exact_walk<<<dim3(1, c->F), kWalkThreads, 0, c->stream>>>(a);
-    c->launches += 2;
-    if (out) {
-        k_exact_emit<<<gt, kTileChunks, 0, c->stream>>>(a);
-        c->launches++;
+    return fail(MCL_ERR_INVALID, "host-ordered exchange needs a barrier hook or an NCCL communicator");
+}
+
+// approximate tile sums of src (+ the slice sums of all ranks of a sharded filter)
+int launch_tile_sums(mcl_ctx* c, const double* src) {
+    ExactArgs a = exact_base(c);
+    a.src = src;
+    k_tile_sums<<<dim3(c->T, c->F), kTileChunks, 0, c->stream>>>(a);
+    mark(c, "k_tile_sums");
+    if (sharded(c) && !c->xmode) {
+        const int rc = exchange_barrier(c);
+        if (rc) return rc;
+        k_slice_sums_collect<<<1, kTileChunks, 0, c->stream>>>(a);
+        mark(c, "k_slice_sums_collect");
     }
+    CK(cudaGetLastError());
+    return MCL_OK;
+}
+
+enum PassKind { kPassRaw, kPassNormalise, kPassStored, kPassCdf };
+
+// one exact pass (exact_kernels.cuh):
+//   kPassRaw        S1 = sum w_raw                                    (:679)
+//   kPassNormalise  w_norm = w_raw / S1 stored, pose, S2 = sum w_norm  (:680-686, :696-716, random.tcc:2666)
+//   kPassStored     S2 = sum w_norm of weights set from outside
+//   kPassCdf        running sums of w_norm / S2 at the tile starts     (random.tcc:2672)
+int launch_pass(mcl_ctx* c, PassKind kind, int pose_buf) {
+    ExactArgs a = exact_base(c);
+    bool pose = false;
+    switch (kind) {
+        case kPassRaw:
+            a.src = c->d_wraw;
+            a.total = c->d_S1;
+            break;
+        case kPassNormalise:
+            a.src = c->d_wraw;
+            a.norm = c->d_S1;
+            a.pre_norm = c->d_S1;
+            a.store = c->d_wn;
+            a.total = c->d_S2;
+            a.px = c->d_px[pose_buf];
+            a.py = c->d_py[pose_buf];
+            a.pt = c->d_pt[pose_buf];
+            a.pose_out = c->d_pose;
+            a.pose_host = c->d_pose_mapped;
+            a.update_no = c->d_update_no;
+            pose = true;
+            break;
+        case kPassStored:
+            a.src = c->d_wn;
+            a.total = c->d_S2;
+            break;
+        case kPassCdf:
+            a.src = c->d_wn;
+            a.div = c->d_S2;
+            a.pre_norm = c->tile_state == 2 ? c->d_S1 : nullptr;
+            a.total = c->d_scratch_total;
+            a.rank_end = sharded(c) ? c->d_rank_end : nullptr;
+            break;
+    }
+    a.dbg = (c->d_dbg && c->dbg_pass == static_cast<int>(kind)) ? c->d_dbg : nullptr;
+    const dim3 g(c->T, c->F);
+    if (pose)
+        k_exact_pass<true><<<g, kTileChunks, 0, c->stream>>>(a);
+    else
+        k_exact_pass<false><<<g, kTileChunks, 0, c->stream>>>(a);
+    mark(c, kind == kPassRaw ? "k_exact_pass(S1)" : kind == kPassNormalise ? "k_exact_pass(normalise+pose+S2)"
+                                                : kind == kPassStored      ? "k_exact_pass(S2)"
+                                                                           : "k_exact_pass(cdf)");
+    if (sharded(c) && !c->xmode) {
+        const int rc = exchange_barrier(c);
+        if (rc) return rc;
+        if (pose)
+            k_exact_finish<true><<<1, kTileChunks, 0, c->stream>>>(a);
+        else
+            k_exact_finish<false><<<1, kTileChunks, 0, c->stream>>>(a);
+        mark(c, "k_exact_finish");
+    }
+    CK(cudaGetLastError());
+    return MCL_OK;
+}
+
+int launch_emit(mcl_ctx* c) {
+    ExactArgs a = exact_base(c);
+    a.src = c->d_wn;
+    a.div = c->d_S2;
+    a.out = c->d_cdf;
+    a.force_last_one = c->rank == c->world - 1 ? 1 : 0;   // _M_cp.back() = 1.0 is the LAST particle of the whole filter
+    a.coarse = c->coarse_n > 0 ? c->d_coarse : nullptr;
+    a.coarse_m = a.coarse ? (1 << c->coarse_shift) / kChunk : 0;
+    a.coarse_n = c->coarse_n;
+    k_exact_emit<<<dim3(c->T, c->F), kTileChunks, 0, c->stream>>>(a);
+    mark(c, "k_exact_emit");
+    CK(cudaGetLastError());
+    return MCL_OK;
+}
+
+// one-tile filters: a whole pass in one CTA per filter
+int launch_single(mcl_ctx* c, const double* src, const double* div, double* total, double* out, int force_one) {
+    ExactArgs a = exact_base(c);
+    a.src = src;
+    a.div = div;
+    a.total = total;
+    a.out = out;
+    a.force_last_one = force_one;
+    a.coarse = (out && c->coarse_n > 0) ? c->d_coarse : nullptr;
+    a.coarse_m = a.coarse ? (1 << c->coarse_shift) / kChunk : 0;
+    a.coarse_n = c->coarse_n;
+    k_exact_single<<<dim3(1, c->F), kTileChunks, 0, c->stream>>>(a);
+    mark(c, "k_exact_single");
     CK(cudaGetLastError());
     return MCL_OK;
 }
@@ -329,8 +533,8 @@ int upload_replay_ctx(mcl_ctx* c) {
         h[b].px = c->d_px[b];
         h[b].py = c->d_py[b];
         h[b].pt = c->d_pt[b];
-        h[b].perm = c->d_perm + c->lo;
-        h[b].lo = c->lo;
+        h[b].perm = c->d_perm;
+        h[b].lo = 0;
         h[b].nfil = c->dir_pool ? c->N : (int64_t{1} << 40);
         for (int j = 0; j < kMaxBeams; ++j) h[b].angle[j] = j < c->R ? c->beams.angle[j] : 0.0f;
     }
@@ -368,6 +572,12 @@ int ensure_dir(mcl_ctx* c, bool map_changed) {
         std::vector<float> gap;
         build_gap_map(c->skip, gap);
         float* d_gap = nullptr;
+        struct GapGuard {
+            float*& p;
+            ~GapGuard() {
+                if (p) cudaFree(p);
+            }
+        } gap_guard{d_gap};
         CK(dalloc(&d_gap, ncell));
         CK(cudaMemcpy(d_gap, gap.data(), ncell * sizeof(float), cudaMemcpyHostToDevice));
         CK(dalloc(&c->d_sectors, static_cast<size_t>(kDirSectors)));
@@ -378,7 +588,6 @@ int ensure_dir(mcl_ctx* c, bool map_changed) {
         c->launches++;
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(c->stream));
-        cudaFree(d_gap);
         CK(dalloc(&c->d_plan, static_cast<size_t>(kPlanInts)));
         CK(cudaMemset(c->d_plan, 0, sizeof(int) * kPlanInts));
         CK(dalloc(&c->d_rec, static_cast<size_t>(2 * pool_n)));
@@ -432,27 +641,49 @@ int launch_pose(mcl_ctx* c, const double* w, const double* total, double* wn_out
 }
 
 // discrete_distribution(weights_): sum, normalise, partial_sum (random.tcc:2657-2678) of the
-// current normalised weights.  The approximate tile sums the exact kernels need are reused from
-// the last weight-sum pass whenever the weights have not been touched since.
-int build_cdf(mcl_ctx* c) {
-    const double* approx = c->tile_state == 2 ? c->d_S1 : nullptr;
-    int rc = run_exact(c, c->d_wn, nullptr, c->d_S2, nullptr, 0, c->tile_state == 0, approx);
-    if (rc) return rc;
-    if (c->tile_state == 0) c->tile_state = 1;
-    rc = run_exact(c, c->d_wn, c->d_S2, c->d_scratch_total, c->d_cdf, 1, false, approx);
-    if (rc) return rc;
+// current normalised weights.  After an update S2 = sum(w_norm) is already known (the normalising
+// pass computed it) and the tile sums of w_raw tell the binades of the running sums, so only the CDF pass and
+// the emit run; after weights were set from outside, tile sums and S2 are rebuilt first.
+int ensure_cdf(mcl_ctx* c) {
+    if (c->cdf_valid) return MCL_OK;
+    int rc;
+    if (single_tile(c)) {
+        if (c->tile_state == 0) {
+            rc = launch_single(c, c->d_wn, nullptr, c->d_S2, nullptr, 0);
+            if (rc) return rc;
+            c->tile_state = 1;
+        }
+        rc = launch_single(c, c->d_wn, c->d_S2, c->d_scratch_total, c->d_cdf, 1);
+        if (rc) return rc;
+    } else {
+        if (c->tile_state == 0) {
+            rc = launch_tile_sums(c, c->d_wn);
+            if (rc) return rc;
+            rc = launch_pass(c, kPassStored, c->cur);
+            if (rc) return rc;
+            c->tile_state = 1;
+        }
+        rc = launch_pass(c, kPassCdf, c->cur);
+        if (rc) return rc;
+        rc = launch_emit(c);
+        if (rc) return rc;
+    }
     c->cdf_valid = true;
+    c->cdf_any = true;
     return MCL_OK;
 }
 
-// First half of MCL(): CDF of the current weights, then resample / motion / ray cast / weight
-// for this context's slots [lo, lo+cnt) into the destination buffers.
-int update_local(mcl_ctx* c, const double* action_dev, const float* obs_dev, const double* u_dev, const double* z_dev) {
+// MCL() (:652-694) + expected_pose() (:696-716) for this context's particles:
+//   CDF of the current weights -> resample + motion -> heading sort -> ray cast -> weights ->
+//   exact weight sum -> normalise + pose (+ the sum the next CDF needs).
+// u_dev / z_dev: injected noise indexed by the GLOBAL slot (nullptr: device Philox).
+int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, const double* u_dev, const double* z_dev) {
     if (!c->have_map) return fail(MCL_ERR_NO_MAP, "mcl_set_map has not been called");
     if (!c->have_beams) return fail(MCL_ERR_INVALID, "mcl_set_beam_angles has not been called");
-    if (c->local_pending) return fail(MCL_ERR_INVALID, "mcl_update_finish must follow mcl_update_local");
+    if (sharded(c) && !c->connected) return fail(MCL_ERR_INVALID, "sharded context: mcl_shard_connect* has not been called");
     const int src = c->cur, dst = c->cur ^ 1;
     cudaStream_t s = c->stream;
+    marks_begin(c);
     if (c->profiling) CK(cudaEventRecord(c->ev[0], s));
 
     ObsArgs oa{};
@@ -468,21 +699,57 @@ int update_local(mcl_ctx* c, const double* action_dev, const float* obs_dev, con
     oa.hist = c->sort_enabled ? c->d_hist : nullptr;
     oa.nhist = 2 * c->B * c->F;
     k_prepare_obs<<<dim3(c->R, c->F), 256, 0, s>>>(oa);
-    c->launches++;
+    mark(c, "k_prepare_obs");
 
-    int rc = build_cdf(c);
+    int rc = ensure_cdf(c);
     if (rc) return rc;
     if (c->profiling) CK(cudaEventRecord(c->ev[1], s));
 
     // a batch's pool mode is opt-in (ray mode 2): measured slower than the isotropic kernel on small maps
     const bool dir = c->dir_ready && c->sort_enabled && c->ray_mode != 1 && (!c->dir_pool || c->ray_mode == 2);
+    static const bool no_packed = std::getenv("MCL_NO_PACKED") != nullptr;   // debugging knob
+    const bool packed = !no_packed && c->pose4_ok[src];   // the packed source copy was written by the last update (no set_particles / init since)
+    if (sharded(c)) {
+        // sender-driven resampling: every rank tests all NG draws, serves those that fall into its
+        // CDF range and pushes the source poses to the slots' owners (k_route)
+        RouteArgs ra{};
+        ra.NG = c->NG;
+        ra.N = c->N;
+        ra.cdf = c->d_cdf;
+        ra.coarse = c->coarse_n > 0 ? c->d_coarse : nullptr;
+        ra.nc = c->coarse_n;
+        ra.cshift = c->coarse_shift;
+        ra.rank_end = c->d_rank_end;
+        ra.spose4 = packed ? c->d_pose4[src] : nullptr;
+        ra.sx = c->d_px[src];
+        ra.sy = c->d_py[src];
+        ra.st = c->d_pt[src];
+        for (int q = 0; q < kMaxWorld; ++q) ra.routed[q] = c->routed_peers[q];
+        ra.u = u_dev;
+        ra.seed = c->prm.seed;
+        ra.update_no = c->d_update_no;
+        ra.done = c->d_route_done;
+        ra.sh = c->sh;
+        ra.sh.fused = c->xmode;
+        const size_t rsmem = sizeof(double) * static_cast<size_t>(c->coarse_n) + (kRouteThreads / 32) * kRouteQueue * (sizeof(double) + sizeof(int));
+        const int rblocks = static_cast<int>(std::min<int64_t>(c->num_sms, (c->NG + 2 * kRouteThreads - 1) / (2 * kRouteThreads)));
+        k_route<<<rblocks, kRouteThreads, rsmem, s>>>(ra);
+        mark(c, "k_route");
+        if (!c->xmode) {
+            rc = exchange_barrier(c);
+            if (rc) return rc;
+            ShardDev sd = c->sh;
+            sd.fused = 0;
+            k_route_check<<<1, 32, 0, s>>>(sd);
+            mark(c, "k_route_check");
+        }
+    }
     MotionArgs ma{};
     ma.rec = dir ? c->d_rec : nullptr;
     ma.map = c->map;
     ma.B = c->dir_B;
     ma.N = c->N;
-    ma.lo = c->lo;
-    ma.cnt = c->cnt;
+    ma.glo = c->glo;
     ma.cdf = c->d_cdf;
     ma.sx = c->d_px[src];
     ma.sy = c->d_py[src];
@@ -493,25 +760,9 @@ int update_local(mcl_ctx* c, const double* action_dev, const float* obs_dev, con
     ma.idx_out = c->d_idx;
     ma.u = u_dev;
     ma.z = z_dev;
-    // the packed source copy is usable if k_resample_motion wrote it (no set_particles / init since) and,
-    // for a shard, if the other ranks' slices are reachable too (p2p; the all-gather mode only moves the SoA arrays)
-    // Only the unsharded filter reads the packed copy.  For p2p shards the packed PEER reads measured
-    // 20 % faster than three SoA reads (one NVLink transaction per pose) but were not bit-exact against
-    // one GPU for a 1 M-particle filter on real 2- and 4-GPU runs (exact for 512 k particles;
-    // scripts/check_sharded_equals_single.py), so they stay off until that is understood; the SoA peer
-    // reads are verified exact at 2 and 4 GPUs.
-    static const bool no_packed = std::getenv("MCL_NO_PACKED") != nullptr;   // debugging knob
-    static const bool packed_peers = std::getenv("MCL_PACKED_PEERS") != nullptr;   // experiment
-    const bool packed = !no_packed && c->pose4_ok[src] && ((c->p2p && packed_peers) || (!c->p2p && c->cnt == c->N));
     ma.spose4 = packed ? c->d_pose4[src] : nullptr;
     ma.dpose4 = c->d_pose4[dst];
-    if (c->p2p) {
-        ma.peer_pose4 = packed ? reinterpret_cast<const double4* const*>(c->d_peer_tab + static_cast<size_t>(6 + src) * c->world) : nullptr;
-        ma.peer_x = c->d_peer_tab + static_cast<size_t>(src * 3 + 0) * c->world;
-        ma.peer_y = c->d_peer_tab + static_cast<size_t>(src * 3 + 1) * c->world;
-        ma.peer_t = c->d_peer_tab + static_cast<size_t>(src * 3 + 2) * c->world;
-        ma.n_local = c->N / c->world;
-    }
+    ma.routed = sharded(c) ? c->d_routed : nullptr;
     ma.coarse = c->coarse_n > 0 ? c->d_coarse : nullptr;
     ma.nc = c->coarse_n;
     ma.cshift = c->coarse_shift;
@@ -522,18 +773,18 @@ int update_local(mcl_ctx* c, const double* action_dev, const float* obs_dev, con
     ma.seed = c->prm.seed;
     ma.update_no = c->d_update_no;
     ma.centre = c->d_centre;
-    int mblocks = static_cast<int>((c->cnt + kMotionThreads - 1) / kMotionThreads);
-    const size_t msmem = sizeof(double) * static_cast<size_t>(c->coarse_n);
+    int mblocks = static_cast<int>((c->N + kMotionThreads - 1) / kMotionThreads);
+    const size_t msmem = sharded(c) ? 0 : sizeof(double) * static_cast<size_t>(c->coarse_n);
     // a large table is staged once per SM by persistent blocks; a small one by every block
     if (msmem > 16 * 1024) mblocks = std::min(mblocks, std::max(1, c->num_sms / std::min(c->F, c->num_sms)));
     k_resample_motion<<<dim3(mblocks, c->F), kMotionThreads, msmem, s>>>(ma);
-    c->launches++;
+    mark(c, sharded(c) ? "k_resample_motion(routed)" : "k_resample_motion");
     c->pose4_ok[dst] = true;
     if (c->sort_enabled) {
         SortArgs sa{};
         sa.N = c->N;
-        sa.lo = c->lo;
-        sa.cnt = c->cnt;
+        sa.lo = 0;
+        sa.cnt = c->N;
         sa.pt = c->d_pt[dst];
         sa.hist = c->d_hist;
         sa.cursor = c->d_hist + static_cast<size_t>(c->B) * c->F;
@@ -541,28 +792,30 @@ int update_local(mcl_ctx* c, const double* action_dev, const float* obs_dev, con
         sa.B = c->B;
         // a few fat blocks per filter: ~one per SM for a single big filter
         const int64_t per_filter = std::max<int64_t>(1, c->num_sms / std::min(c->F, c->num_sms));
-        int64_t chunk = (c->cnt + per_filter - 1) / per_filter;
+        int64_t chunk = (c->N + per_filter - 1) / per_filter;
         chunk = std::max<int64_t>(kSortThreads, (chunk + kSortThreads - 1) / kSortThreads * kSortThreads);
         sa.chunk = chunk;
-        const dim3 gs(static_cast<unsigned>((c->cnt + chunk - 1) / chunk), c->F);
+        const dim3 gs(static_cast<unsigned>((c->N + chunk - 1) / chunk), c->F);
         k_sort_hist<<<gs, kSortThreads, 0, s>>>(sa);
+        mark(c, "k_sort_hist");
         k_sort_scatter<<<gs, kSortThreads, 0, s>>>(sa);
-        c->launches += 2;
+        mark(c, "k_sort_scatter");
     }
+    const int64_t slots = static_cast<int64_t>(c->F) * c->N;   // slots of the directional stage (== N for one filter)
     if (dir) {
         DirPrepArgs pa{};
         pa.map = c->map;
         pa.centre = c->d_centre;
-        const int64_t slots = c->dir_pool ? static_cast<int64_t>(c->F) * c->N : c->cnt;
         pa.rec_in = c->d_rec;
-        pa.rec = c->d_rec + static_cast<int64_t>(c->F) * c->N;
-        pa.perm = c->d_perm + c->lo;
+        pa.rec = c->d_rec + slots;
+        pa.perm = c->d_perm;
         pa.plan = c->d_plan;
         pa.cnt = slots;
         pa.nfil = c->dir_pool ? c->N : (int64_t{1} << 40);
         pa.box = c->dir_box;
         pa.whole = c->dir_pool ? 1 : 0;
         k_dir_gather<<<static_cast<unsigned>((slots + 255) / 256), 256, 0, s>>>(pa);
+        mark(c, "k_dir_gather");
         DirPlanArgs la{};
         la.hist = c->d_hist;
         std::memcpy(la.io, c->beam_io, sizeof(la.io));
@@ -574,7 +827,7 @@ int update_local(mcl_ctx* c, const double* action_dev, const float* obs_dev, con
         la.force = c->dir_pool ? 2 : c->ray_mode;   // the pool has no cloud box to be outside of
         la.all_chunks = c->dir_pool ? 1 : 0;
         k_dir_plan<<<1, kPlanThreads, 0, s>>>(la);
-        c->launches += 2;
+        mark(c, "k_dir_plan");
     }
     if (c->profiling) CK(cudaEventRecord(c->ev[2], s));
 
@@ -583,8 +836,8 @@ int update_local(mcl_ctx* c, const double* action_dev, const float* obs_dev, con
         ra.map = c->map;
         ra.beams = c->beams;
         ra.N = c->N;
-        ra.lo = c->lo;
-        ra.cnt = c->cnt;
+        ra.lo = 0;
+        ra.cnt = c->N;
         ra.px = c->d_px[dst];
         ra.py = c->d_py[dst];
         ra.pt = c->d_pt[dst];
@@ -600,7 +853,7 @@ int update_local(mcl_ctx* c, const double* action_dev, const float* obs_dev, con
         // persistent blocks: one per SM when the window fills shared memory, a few otherwise
         const int per_sm = smem > 100 * 1024 ? 1 : 2;
         const int budget = std::max(1, (c->num_sms * per_sm) / std::min(c->F, c->num_sms * per_sm));
-        const int rblocks = static_cast<int>(std::min<int64_t>((c->cnt + kRayThreads - 1) / kRayThreads, budget));
+        const int rblocks = static_cast<int>(std::min<int64_t>((c->N + kRayThreads - 1) / kRayThreads, budget));
         // MAX_RANGE_PX of the usual map resolutions is baked into specialised instances
         // (0.05 m -> 239, 0.0504 m -> 238, 0.05796 m -> 207); anything else takes the generic one
         const dim3 rgrid(rblocks, c->F);
@@ -621,7 +874,7 @@ int update_local(mcl_ctx* c, const double* action_dev, const float* obs_dev, con
             }
         }
 #undef MCL_LAUNCH_RAY
-        c->launches++;
+        mark(c, "k_raycast_weight");
     }
     if (dir) {
         DirRayArgs da{};
@@ -630,8 +883,7 @@ int update_local(mcl_ctx* c, const double* action_dev, const float* obs_dev, con
         std::memcpy(da.io, c->beam_io, sizeof(da.io));
         da.sectors = c->d_sectors;
         da.dirmaps = c->d_dirmaps;
-        const int64_t slots = c->dir_pool ? static_cast<int64_t>(c->F) * c->N : c->cnt;
-        da.rec = c->d_rec + static_cast<int64_t>(c->F) * c->N;
+        da.rec = c->d_rec + slots;
         da.sec_tab = c->d_sec_tab;
         da.replay = c->d_replay_ctx + dst;
         da.plan = c->d_plan;
@@ -654,6 +906,7 @@ int update_local(mcl_ctx* c, const double* action_dev, const float* obs_dev, con
             case 239: k_raycast_dir<239><<<dblocks, kDirThreads, dsmem, s>>>(da); break;
             default: k_raycast_dir<0><<<dblocks, kDirThreads, dsmem, s>>>(da); break;
         }
+        mark(c, "k_raycast_dir");
         if (c->profiling) CK(cudaEventRecord(c->ev[5], s));
         WeightStepsArgs wa{};
         wa.plan = c->d_plan;
@@ -662,7 +915,7 @@ int update_local(mcl_ctx* c, const double* action_dev, const float* obs_dev, con
         wa.slice = c->d_slice;
         wa.w_raw = c->d_wraw;
         wa.steps = c->keep_ranges ? c->d_steps : nullptr;
-        wa.lo = c->lo;
+        wa.lo = 0;
         wa.cnt = slots;
         wa.nfil = c->dir_pool ? c->N : (int64_t{1} << 40);
         wa.stride = c->dir_stride;
@@ -674,65 +927,41 @@ int update_local(mcl_ctx* c, const double* action_dev, const float* obs_dev, con
             k_weight_steps<true><<<wblocks, kWeightThreads, 0, s>>>(wa);
         else
             k_weight_steps<false><<<wblocks, kWeightThreads, 0, s>>>(wa);
-        c->launches += 2;
+        mark(c, "k_weight_steps");
     }
     if (!dir && c->profiling) CK(cudaEventRecord(c->ev[5], s));
-    if (c->p2p) {
-        // unnormalised pose sums of the rank's own slots (deterministic two-stage reduction)
-        NormArgs na{};
-        na.N = c->cnt;
-        na.w_raw = c->d_wraw + c->lo;
-        na.total = nullptr;
-        na.wn = nullptr;
-        na.px = c->d_px[dst] + c->lo;
-        na.py = c->d_py[dst] + c->lo;
-        na.pt = c->d_pt[dst] + c->lo;
-        na.partial = c->d_partial;
-        na.nblk = c->norm_blocks;
-        k_normalize_pose<<<dim3(c->norm_blocks, 1), kNormThreads, 0, s>>>(na);
-        k_sum_partials<<<1, 256, 0, s>>>(c->d_partial, c->norm_blocks, c->d_partials + 4 * c->rank);
-        c->launches += 2;
+    if (c->profiling) {
+        CK(cudaEventRecord(c->ev[3], s));
+        CK(cudaEventRecord(c->ev[6], s));
     }
-    if (c->profiling) CK(cudaEventRecord(c->ev[3], s));
     CK(cudaGetLastError());
-    c->local_pending = true;
-    return MCL_OK;
-}
 
-// Second half: sum_weights = accumulate(weights_); w /= sum (:679-686); particles_ = proposal
-// (:689); expected_pose (:696-716) -- over ALL particles of the filter.
-int update_finish(mcl_ctx* c) {
-    if (!c->local_pending) return fail(MCL_ERR_INVALID, "mcl_update_finish without mcl_update_local");
-    const int dst = c->cur ^ 1;
-    if (c->profiling) CK(cudaEventRecord(c->ev[6], c->stream));
-    int rc = run_exact(c, c->d_wraw, nullptr, c->d_S1, nullptr, 0, true);
-    if (rc) return rc;
-    c->tile_state = 2;   // d_tile_sum = tile sums of w_raw; w_norm = w_raw / S1 follows
-    if (c->p2p) {
-        // poses of other ranks are not local: normalise all weights, pose from the gathered partials
-        const int64_t n = c->N;
-        k_normalize_only<<<static_cast<unsigned>((n + 255) / 256), 256, 0, c->stream>>>(c->d_wraw, c->d_S1, c->d_wn, n);
-        k_pose_from_partials<<<1, 32, 0, c->stream>>>(c->d_partials, c->world, c->d_S1, c->d_pose, c->d_pose_mapped, c->d_update_no);
-        c->launches += 2;
-    } else {
+    // sum_weights = accumulate(weights_); w /= sum (:679-686); particles_ = proposal (:689);
+    // expected_pose (:696-716)
+    if (single_tile(c)) {
+        rc = launch_single(c, c->d_wraw, nullptr, c->d_S1, nullptr, 0);
+        if (rc) return rc;
         rc = launch_pose(c, c->d_wraw, c->d_S1, c->d_wn, dst, true);
         if (rc) return rc;
+        c->tile_state = 0;   // the one-CTA passes need no tile sums; S2 is rebuilt by ensure_cdf
+    } else {
+        rc = launch_tile_sums(c, c->d_wraw);
+        if (rc) return rc;
+        rc = launch_pass(c, kPassRaw, dst);
+        if (rc) return rc;
+        rc = launch_pass(c, kPassNormalise, dst);
+        if (rc) return rc;
+        c->tile_state = 2;   // d_tile_sum = tile sums of w_raw; w_norm = w_raw / S1; S2 = sum w_norm
     }
     if (c->profiling) {
-        CK(cudaEventRecord(c->ev[4], c->stream));
+        CK(cudaEventRecord(c->ev[4], s));
         c->ev_valid = true;
     }
     CK(cudaGetLastError());
+    c->cdf_valid = false;
     c->cur = dst;
     c->update_no++;
-    c->local_pending = false;
     return MCL_OK;
-}
-
-int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, const double* u_dev, const double* z_dev) {
-    int rc = update_local(c, action_dev, obs_dev, u_dev, z_dev);
-    if (rc) return rc;
-    return update_finish(c);
 }
 
 // per-stage device times of the last profiled update, from its CUDA events (the stream must have
@@ -756,14 +985,16 @@ void read_stage_times(mcl_ctx* c) {
 }
 
 // One update from device-resident inputs, replayed as a CUDA graph when the update is in its steady
-// state (no diagnostics, whole filter on this GPU, weights untouched since the last update): the
-// ~18 launches become one.  The graph reads action and scan from the context's own staging
-// buffers, so foreign device pointers are first copied there (264 bytes, device to device).
+// state (no diagnostics, weights untouched since the previous update): the ~18 launches become one.
+// The graph reads action and scan from the context's own staging buffers, so foreign device pointers
+// are first copied there (264 bytes, device to device).  A sharded filter replays a graph too when its
+// kernels exchange on their own (xmode 1): there is no host call between its launches.
 int update_steady(mcl_ctx* c, const double* action_dev, const float* obs_dev) {
     cudaStream_t s = c->stream;
     // (a captured graph reads the packed copy of the state: an update whose packed source is stale runs directly)
-    const bool graph_ok = c->graphs_enabled && !c->profiling && !c->keep_ranges && !c->p2p && c->lo == 0 && c->cnt == c->N &&
-                          c->tile_state == 2 && !c->local_pending && c->pose4_ok[c->cur];
+    const bool steady = single_tile(c) ? true : c->tile_state == 2;
+    const bool graph_ok = c->graphs_enabled && !c->profiling && !c->keep_ranges && (!sharded(c) || (c->xmode == 1 && c->connected)) &&
+                          steady && !c->cdf_valid && c->pose4_ok[c->cur] && c->update_no > 0;
     if (!graph_ok) return update_device(c, action_dev, obs_dev, nullptr, nullptr);
     if (action_dev != c->d_action)
         CK(cudaMemcpyAsync(c->d_action, action_dev, sizeof(double) * 3 * c->F, cudaMemcpyDeviceToDevice, s));
@@ -783,6 +1014,8 @@ int update_steady(mcl_ctx* c, const double* action_dev, const float* obs_dev) {
     }
     const int parity = c->cur;
     const int64_t before = c->launches;
+    const int tile_state0 = c->tile_state;
+    const bool p4[2] = {c->pose4_ok[0], c->pose4_ok[1]};
     int rc = update_device(c, c->d_action, c->d_obs, nullptr, nullptr);
     cudaGraph_t g = nullptr;
     const cudaError_t e = cudaStreamEndCapture(s, &g);
@@ -792,16 +1025,33 @@ int update_steady(mcl_ctx* c, const double* action_dev, const float* obs_dev) {
         CK(cudaGraphLaunch(c->gexec[parity], s));
         return MCL_OK;
     }
-    // capture refused (e.g. an enclosing capture): run this update directly and stop trying
+    // capture refused (e.g. an enclosing capture): nothing of the captured update has executed.  Undo its
+    // host-side bookkeeping, stop trying, and run this update directly.
     if (g) cudaGraphDestroy(g);
     cudaGetLastError();
     c->gexec[parity] = nullptr;
     c->graphs_enabled = false;
-    if (rc != MCL_OK) return rc;
-    c->cur ^= 1;                 // undo the host-side bookkeeping of the captured (never executed) update
-    c->update_no--;
     c->launches = before;
+    c->tile_state = tile_state0;
+    c->pose4_ok[0] = p4[0];
+    c->pose4_ok[1] = p4[1];
+    c->cdf_valid = false;
+    if (rc == MCL_OK) {
+        c->cur ^= 1;
+        c->update_no--;
+    }
     return update_device(c, c->d_action, c->d_obs, nullptr, nullptr);
+}
+
+// device-side exchange errors of a sharded filter (a peer that never published, a missing barrier)
+int check_shard_error(mcl_ctx* c) {
+    if (!c->h_err || *c->h_err == 0) return MCL_OK;
+    const int e = *c->h_err;
+    *c->h_err = 0;
+    return fail(MCL_ERR_CUDA, "sharded exchange failed on rank %d: %s", c->rank,
+                e == kShardTimeout ? "a peer did not publish within the time limit"
+                : e == kShardMissing ? "a peer's payload was not there when the host-ordered consumer ran"
+                                     : "unexpected error code");
 }
 
 }  // namespace
@@ -856,12 +1106,41 @@ int mcl_device_count(void) {
 
 int mcl_destroy(mcl_ctx* c);
 
-static int create_buffers(mcl_ctx* c, const mcl_params* p, int device) {
+namespace {
+
+struct ArenaLayout {
+    size_t mbox, flag, routed, list_fn, list_add, bytes;
+};
+ArenaLayout arena_layout(int world, int64_t n_local) {
+    const size_t C = static_cast<size_t>((n_local + kTile - 1) / kTile) * kTileChunks;
+    auto up = [](size_t v) { return (v + 255) & ~size_t{255}; };
+    ArenaLayout L{};
+    size_t o = 0;
+    L.mbox = o;
+    o = up(o + static_cast<size_t>(2) * world * kMboxSlot);
+    L.flag = o;
+    o = up(o + sizeof(unsigned long long) * kMaxWorld);
+    L.routed = o;
+    o = up(o + sizeof(double4) * static_cast<size_t>(n_local));
+    L.list_fn = o;
+    o = up(o + sizeof(StepFn) * 2 * C);
+    L.list_add = o;
+    o = up(o + sizeof(double) * 2 * C * kChunk);
+    L.bytes = o;
+    return L;
+}
+
+}  // namespace
+
+static int create_buffers(mcl_ctx* c, const mcl_params* p, int device, int world, int rank) {
     c->prm = *p;
     c->device = device;
     c->F = p->num_filters;
-    c->N = p->max_particles;
-    c->cnt = c->N;
+    c->world = world;
+    c->rank = rank;
+    c->NG = p->max_particles;
+    c->N = c->NG / world;
+    c->glo = c->N * rank;
     cudaDeviceProp prop{};
     CK(cudaGetDeviceProperties(&prop, device));
     c->num_sms = prop.multiProcessorCount;
@@ -887,24 +1166,31 @@ static int create_buffers(mcl_ctx* c, const mcl_params* p, int device) {
     CK(cudaMemset(c->d_idx, 0, FN * sizeof(int32_t)));
     {   // weights_ = 1/N (:107)
         const int64_t n = static_cast<int64_t>(FN);
-        k_fill<<<static_cast<unsigned>((n + 255) / 256), 256>>>(c->d_wn, n, 1.0 / static_cast<double>(c->N));
-        k_fill<<<static_cast<unsigned>((n + 255) / 256), 256>>>(c->d_wraw, n, 1.0 / static_cast<double>(c->N));
+        k_fill<<<static_cast<unsigned>((n + 255) / 256), 256>>>(c->d_wn, n, 1.0 / static_cast<double>(c->NG));
+        k_fill<<<static_cast<unsigned>((n + 255) / 256), 256>>>(c->d_wraw, n, 1.0 / static_cast<double>(c->NG));
         c->launches += 2;
     }
     c->T = static_cast<int>((c->N + kTile - 1) / kTile);
     c->C = c->T * kTileChunks;
     const size_t FT = static_cast<size_t>(c->F) * c->T, FC = static_cast<size_t>(c->F) * c->C;
     CK(dalloc(&c->d_tile_sum, FT));
-    CK(dalloc(&c->d_chunk_fn, FC));
-    CK(dalloc(&c->d_opq_pre, FC));
-    CK(dalloc(&c->d_opq_idx, FC));
-    CK(dalloc(&c->d_tile_opq, FT));
-    CK(dalloc(&c->d_tile_elem, FT * 3));
-    CK(dalloc(&c->d_list_chunk, FC));
-    CK(dalloc(&c->d_list_fn, FC));
-    CK(dalloc(&c->d_anchors, FC));
-    CK(dalloc(&c->d_anchor_val, FC));
-    CK(dalloc(&c->d_tile_start, FT));
+    if (!single_tile(c)) {   // (one-tile filters run k_exact_single, which keeps everything in shared memory)
+        CK(dalloc(&c->d_chunk_fn, FC));
+        CK(dalloc(&c->d_opq_pre, FC));
+        CK(dalloc(&c->d_opq_idx, FC));
+        CK(dalloc(&c->d_opq_add, FC * kChunk));
+        CK(dalloc(&c->d_tile_opq, FT));
+        CK(dalloc(&c->d_tile_elem, FT * 3));
+        CK(dalloc(&c->d_list_chunk, FC));
+        if (world == 1) {   // (a sharded rank keeps them in its exchange arena)
+            CK(dalloc(&c->d_list_fn, 2 * FC));
+            CK(dalloc(&c->d_list_add, 2 * FC * kChunk));
+        }
+        CK(dalloc(&c->d_anchors, FC));
+        CK(dalloc(&c->d_anchor_val, FC));
+        CK(dalloc(&c->d_tile_start, FT));
+        CK(dalloc(&c->d_partial, FT * 4));
+    }
     {   // coarse CDF level: segments of 64 particles, doubled until at most 16384 entries (128 KB of shared memory)
         c->coarse_shift = 6;
         while ((c->N >> c->coarse_shift) > 16384) ++c->coarse_shift;
@@ -914,14 +1200,26 @@ static int create_buffers(mcl_ctx* c, const mcl_params* p, int device) {
     CK(dalloc(&c->d_S1, static_cast<size_t>(c->F)));
     CK(dalloc(&c->d_S2, static_cast<size_t>(c->F)));
     CK(dalloc(&c->d_scratch_total, static_cast<size_t>(c->F)));
-    c->norm_blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((c->N + kNormThreads * 4 - 1) / (kNormThreads * 4),
-                                                                               std::max(1, 4 * c->num_sms / std::min(c->F, 4 * c->num_sms)))));
-    CK(dalloc(&c->d_partial, static_cast<size_t>(c->F) * c->norm_blocks * 4));
+    CK(dalloc(&c->d_slice_sum, static_cast<size_t>(kMaxWorld)));
+    CK(dalloc(&c->d_rank_end, static_cast<size_t>(kMaxWorld)));
+    CK(cudaMemset(c->d_slice_sum, 0, sizeof(double) * kMaxWorld));
+    CK(cudaMemset(c->d_rank_end, 0, sizeof(double) * kMaxWorld));
+    if (single_tile(c)) {
+        c->norm_blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((c->N + kNormThreads * 4 - 1) / (kNormThreads * 4),
+                                                                                   std::max(1, 4 * c->num_sms / std::min(c->F, 4 * c->num_sms)))));
+        CK(dalloc(&c->d_partial, static_cast<size_t>(c->F) * c->norm_blocks * 4));
+    } else {
+        c->norm_blocks = static_cast<int>(std::min<int64_t>(4 * c->num_sms, (c->N + kNormThreads * 4 - 1) / (kNormThreads * 4)));   // mcl_expected_pose only
+        if (static_cast<size_t>(c->norm_blocks) > static_cast<size_t>(c->T)) c->norm_blocks = c->T;   // d_partial is [F][T][4]
+        if (c->norm_blocks < 1) c->norm_blocks = 1;
+    }
     CK(dalloc(&c->d_pose, static_cast<size_t>(c->F) * 3));
     CK(cudaMemset(c->d_pose, 0, sizeof(double) * 3 * c->F));
     CK(dalloc(&c->d_centre, static_cast<size_t>(c->F) * 2));
     CK(dalloc(&c->d_done, static_cast<size_t>(c->F)));
     CK(cudaMemset(c->d_done, 0, sizeof(unsigned int) * c->F));
+    CK(dalloc(&c->d_route_done, size_t{1}));
+    CK(cudaMemset(c->d_route_done, 0, sizeof(unsigned int)));
     {   // heading buckets: ~16 particles per bucket, power of two in [32, 4096]
         int B = 32;
         while (B < kMaxBuckets && static_cast<int64_t>(B) * 16 < c->N) B <<= 1;
@@ -947,6 +1245,31 @@ static int create_buffers(mcl_ctx* c, const mcl_params* p, int device) {
         CK(cudaHostAlloc(reinterpret_cast<void**>(&c->h_pose), sizeof(double) * 3 * c->F, cudaHostAllocMapped));
         std::memset(c->h_pose, 0, sizeof(double) * 3 * c->F);
         CK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->d_pose_mapped), c->h_pose, 0));
+        CK(cudaHostAlloc(reinterpret_cast<void**>(&c->h_err), sizeof(int), cudaHostAllocMapped));
+        *c->h_err = 0;
+        CK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->d_err), c->h_err, 0));
+    }
+    // exchange state: a single context is "rank 0 of 1" and never publishes
+    c->sh.world = world;
+    c->sh.rank = rank;
+    c->sh.fused = 1;
+    c->sh.err = c->d_err;
+    if (world > 1) {
+        // everything a peer writes (mailbox, flags, routed poses) or may read (overflow lists) lives in ONE
+        // allocation, so that one IPC handle maps it
+        const ArenaLayout L = arena_layout(world, c->N);
+        CK(cudaMalloc(reinterpret_cast<void**>(&c->arena), L.bytes));
+        CK(cudaMemset(c->arena, 0, L.bytes));
+        c->d_mbox = reinterpret_cast<uint8_t*>(c->arena + L.mbox);
+        c->d_flag = reinterpret_cast<unsigned long long*>(c->arena + L.flag);
+        c->d_routed = reinterpret_cast<double4*>(c->arena + L.routed);
+        c->d_list_fn = reinterpret_cast<StepFn*>(c->arena + L.list_fn);
+        c->d_list_add = reinterpret_cast<double*>(c->arena + L.list_add);
+        CK(dalloc(&c->d_xseq, size_t{1}));
+        CK(cudaMemset(c->d_xseq, 0, sizeof(unsigned long long)));
+        CK(dalloc(&c->d_nccl_tok, static_cast<size_t>(kMaxWorld)));
+        CK(cudaMemset(c->d_nccl_tok, 0, sizeof(unsigned long long) * kMaxWorld));
+        c->sh.xseq = c->d_xseq;
     }
 #define MCL_RAY_SMEM(WB, MCV) \
     CK(cudaFuncSetAttribute(k_raycast_weight<WB, MCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kWindowBudget)))
@@ -960,6 +1283,8 @@ static int create_buffers(mcl_ctx* c, const mcl_params* p, int device) {
     MCL_RAY_SMEM(4, 239);
 #undef MCL_RAY_SMEM
     CK(cudaFuncSetAttribute(k_resample_motion, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * static_cast<int>(sizeof(double))));
+    CK(cudaFuncSetAttribute(k_route, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            16384 * static_cast<int>(sizeof(double)) + (kRouteThreads / 32) * kRouteQueue * 12));
     CK(cudaFuncSetAttribute(k_raycast_dir<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kWindowBudget)));
     CK(cudaFuncSetAttribute(k_raycast_dir<207>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kWindowBudget)));
     CK(cudaFuncSetAttribute(k_raycast_dir<238>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kWindowBudget)));
@@ -968,12 +1293,16 @@ static int create_buffers(mcl_ctx* c, const mcl_params* p, int device) {
     return MCL_OK;
 }
 
-int mcl_create(const mcl_params* p, int device, mcl_ctx** out) {
+static int create_any(const mcl_params* p, int device, int world, int rank, mcl_ctx** out) {
     if (!p || !out) return fail(MCL_ERR_INVALID, "null argument");
     *out = nullptr;
     if (p->max_particles < 1) return fail(MCL_ERR_INVALID, "max_particles must be >= 1");
     if (p->num_filters < 1) return fail(MCL_ERR_INVALID, "num_filters must be >= 1");
     if (!(p->squash_factor > 0) || !(p->max_range > 0)) return fail(MCL_ERR_INVALID, "squash_factor / max_range must be positive");
+    if (world < 1 || world > kMaxWorld || rank < 0 || rank >= world) return fail(MCL_ERR_INVALID, "rank %d / world %d outside [1,%d]", rank, world, kMaxWorld);
+    if (world > 1 && p->num_filters != 1) return fail(MCL_ERR_INVALID, "particle sharding applies to a single filter, not a batch");
+    if (world > 1 && (p->max_particles % world) != 0)
+        return fail(MCL_ERR_INVALID, "max_particles (%d) must be a multiple of the number of ranks (%d)", p->max_particles, world);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();
@@ -982,7 +1311,7 @@ int mcl_create(const mcl_params* p, int device, mcl_ctx** out) {
     if (device < 0 || device >= ndev) return fail(MCL_ERR_INVALID, "device %d not in [0,%d)", device, ndev);
     CK(cudaSetDevice(device));
     auto* c = new mcl_ctx();
-    const int rc = create_buffers(c, p, device);
+    const int rc = create_buffers(c, p, device, world, rank);
     if (rc != MCL_OK) {
         const std::string keep = g_err;   // mcl_destroy must not clobber the reason
         mcl_destroy(c);
@@ -993,34 +1322,38 @@ int mcl_create(const mcl_params* p, int device, mcl_ctx** out) {
     return MCL_OK;
 }
 
+int mcl_create(const mcl_params* p, int device, mcl_ctx** out) { return create_any(p, device, 1, 0, out); }
+
 int mcl_destroy(mcl_ctx* c) {
     if (!c) return MCL_OK;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     void* ptrs[] = {c->d_pose4[0], c->d_pose4[1],
                     c->d_grid, c->d_v8, c->d_v4, c->d_free, c->d_tabT, c->d_step2idx, c->d_px[0], c->d_px[1], c->d_py[0],
                     c->d_py[1], c->d_pt[0], c->d_pt[1], c->d_wraw, c->d_wn, c->d_cdf, c->d_idx, c->d_steps, c->d_u, c->d_z,
-                    c->d_action, c->d_slice, c->d_tile_sum, c->d_chunk_fn, c->d_opq_pre, c->d_opq_idx,
-                    c->d_tile_opq, c->d_tile_elem, c->d_list_chunk, c->d_list_fn, c->d_anchors, c->d_anchor_val,
-                    c->d_tile_start, c->d_coarse, c->d_S1, c->d_S2, c->d_scratch_total, c->d_partial, c->d_pose, c->d_centre, c->d_replays,
-                    c->d_hist, c->d_perm, c->d_done};
+                    c->d_action, c->d_slice, c->d_tile_sum, c->d_chunk_fn, c->d_opq_pre, c->d_opq_idx, c->d_opq_add,
+                    c->d_tile_opq, c->d_tile_elem, c->d_list_chunk, c->arena ? nullptr : c->d_list_fn, c->arena ? nullptr : c->d_list_add,
+                    c->arena, c->d_anchors, c->d_anchor_val,
+                    c->d_tile_start, c->d_coarse, c->d_S1, c->d_S2, c->d_scratch_total, c->d_slice_sum, c->d_rank_end,
+                    c->d_partial, c->d_pose, c->d_centre, c->d_replays, c->d_hist, c->d_perm, c->d_done, c->d_route_done,
+                    c->d_xseq, c->d_nccl_tok, c->d_tmp, c->d_update_no, c->d_dbg};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     free_dir(c);
     drop_graphs(c);
-    if (c->d_update_no) cudaFree(c->d_update_no);
     for (void* p : c->ipc_opened) cudaIpcCloseMemHandle(p);
-    if (c->d_peer_tab) cudaFree(c->d_peer_tab);
-    if (c->d_partials) cudaFree(c->d_partials);
     if (c->h_action) cudaFreeHost(c->h_action);
     if (c->h_pose) cudaFreeHost(c->h_pose);
+    if (c->h_err) cudaFreeHost(c->h_err);
     for (auto& e : c->ev)
+        if (e) cudaEventDestroy(e);
+    for (auto& e : c->mark_ev)
         if (e) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
     return MCL_OK;
 }
-
 int mcl_set_map(mcl_ctx* c, const int8_t* data, int width, int height, float resolution, double ox, double oy,
                 double oyaw) {
     if (!c || !data) return fail(MCL_ERR_INVALID, "null argument");
@@ -1152,26 +1485,31 @@ int mcl_set_beam_angles(mcl_ctx* c, const float* angles, int n) {
 
 int mcl_num_free_cells(const mcl_ctx* c) { return c ? static_cast<int>(c->skip.free_cells.size()) : 0; }
 
+// initialize_particles_pose :382-399.  normals_3n: the context's own particles (a sharded rank: its slice).
 int mcl_init_pose(mcl_ctx* c, int filter, const double pose[3], const double* normals) {
     int rc = check_filter(c, filter, true);
     if (rc) return rc;
     if (!pose) return fail(MCL_ERR_INVALID, "null pose");
     CK(cudaSetDevice(c->device));
     const int f0 = filter < 0 ? 0 : filter, nf = filter < 0 ? c->F : 1;
-    double* d_pose = nullptr;
-    double* d_norm = nullptr;
+    const size_t pose_bytes = sizeof(double) * 3 * nf;
+    const size_t norm_bytes = normals ? sizeof(double) * 3 * c->N * nf : 0;
+    rc = ensure_tmp(c, 256 + pose_bytes + norm_bytes);
+    if (rc) return rc;
+    double* d_pose = static_cast<double*>(c->d_tmp);
+    double* d_norm = normals ? reinterpret_cast<double*>(static_cast<char*>(c->d_tmp) + ((pose_bytes + 255) & ~size_t{255})) : nullptr;
     std::vector<double> hp(static_cast<size_t>(3) * nf);
     for (int k = 0; k < nf; ++k) std::memcpy(&hp[3 * k], pose, 3 * sizeof(double));
-    CK(dalloc(&d_pose, hp.size()));
-    CK(cudaMemcpyAsync(d_pose, hp.data(), hp.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d_pose, hp.data(), pose_bytes, cudaMemcpyHostToDevice, c->stream));
     if (normals) {
-        CK(dalloc(&d_norm, static_cast<size_t>(3) * c->N * nf));
         for (int k = 0; k < nf; ++k)   // the same injected stream for every addressed filter
             CK(cudaMemcpyAsync(d_norm + static_cast<size_t>(3) * c->N * k, normals, sizeof(double) * 3 * c->N,
                                cudaMemcpyHostToDevice, c->stream));
     }
     InitArgs a{};
     a.N = c->N;
+    a.glo = c->glo;
+    a.w0 = 1.0 / static_cast<double>(c->NG);
     a.px = c->d_px[c->cur];
     a.py = c->d_py[c->cur];
     a.pt = c->d_pt[c->cur];
@@ -1184,15 +1522,15 @@ int mcl_init_pose(mcl_ctx* c, int filter, const double pose[3], const double* no
     k_init_pose<<<dim3(static_cast<unsigned>((c->N + 255) / 256), nf), 256, 0, c->stream>>>(a);
     c->launches++;
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(c->stream));
-    cudaFree(d_pose);
-    if (d_norm) cudaFree(d_norm);
+    CK(cudaStreamSynchronize(c->stream));   // hp is read by the copy above
     c->cdf_valid = false;
+    c->cdf_any = false;
     c->tile_state = 0;
     c->pose4_ok[c->cur] = false;   // the packed copy no longer matches the state arrays
     return MCL_OK;
 }
 
+// initialize_global :401-446.  Injected draws: the context's own particles.
 int mcl_init_global(mcl_ctx* c, int filter, const int32_t* cell, const double* theta) {
     int rc = check_filter(c, filter, true);
     if (rc) return rc;
@@ -1204,8 +1542,11 @@ int mcl_init_global(mcl_ctx* c, int filter, const int32_t* cell, const double* t
     int32_t* d_cell = nullptr;
     double* d_theta = nullptr;
     if (cell) {
-        CK(dalloc(&d_cell, static_cast<size_t>(c->N) * nf));
-        CK(dalloc(&d_theta, static_cast<size_t>(c->N) * nf));
+        const size_t n = static_cast<size_t>(c->N) * nf;
+        rc = ensure_tmp(c, n * (sizeof(double) + sizeof(int32_t)) + 256);
+        if (rc) return rc;
+        d_theta = static_cast<double*>(c->d_tmp);
+        d_cell = reinterpret_cast<int32_t*>(d_theta + n);
         for (int k = 0; k < nf; ++k) {
             CK(cudaMemcpyAsync(d_cell + static_cast<size_t>(c->N) * k, cell, sizeof(int32_t) * c->N, cudaMemcpyHostToDevice, c->stream));
             CK(cudaMemcpyAsync(d_theta + static_cast<size_t>(c->N) * k, theta, sizeof(double) * c->N, cudaMemcpyHostToDevice, c->stream));
@@ -1213,6 +1554,8 @@ int mcl_init_global(mcl_ctx* c, int filter, const int32_t* cell, const double* t
     }
     InitArgs a{};
     a.N = c->N;
+    a.glo = c->glo;
+    a.w0 = 1.0 / static_cast<double>(c->NG);
     a.px = c->d_px[c->cur];
     a.py = c->d_py[c->cur];
     a.pt = c->d_pt[c->cur];
@@ -1232,9 +1575,8 @@ int mcl_init_global(mcl_ctx* c, int filter, const int32_t* cell, const double* t
     c->launches++;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->stream));
-    if (d_cell) cudaFree(d_cell);
-    if (d_theta) cudaFree(d_theta);
     c->cdf_valid = false;
+    c->cdf_any = false;
     c->tile_state = 0;
     c->pose4_ok[c->cur] = false;   // the packed copy no longer matches the state arrays
     return MCL_OK;
@@ -1257,6 +1599,7 @@ int mcl_set_particles(mcl_ctx* c, int filter, const double* P, const double* w) 
         c->tile_state = 0;
     }
     c->cdf_valid = false;
+    c->cdf_any = false;
     return MCL_OK;
 }
 
@@ -1291,8 +1634,10 @@ int mcl_get_raw_weights(mcl_ctx* c, int filter, double* w) {
     return get_array(c, filter, c ? c->d_wraw : nullptr, sizeof(double), c ? c->N : 0, w);
 }
 int mcl_get_cdf(mcl_ctx* c, int filter, double* out) {
-    if (c && !c->cdf_valid) return fail(MCL_ERR_INVALID, "no CDF yet: call mcl_update first");
-    return get_array(c, filter, c ? c->d_cdf : nullptr, sizeof(double), c ? c->N : 0, out);
+    if (!c) return fail(MCL_ERR_INVALID, "null context");
+    CK(cudaSetDevice(c->device));
+    if (!c->cdf_any) return fail(MCL_ERR_INVALID, "no CDF yet: call mcl_update first");
+    return get_array(c, filter, c->d_cdf, sizeof(double), c->N, out);   // the _M_cp the last update drew from
 }
 int mcl_get_resample_indices(mcl_ctx* c, int filter, int32_t* out) {
     return get_array(c, filter, c ? c->d_idx : nullptr, sizeof(int32_t), c ? c->N : 0, out);
@@ -1308,15 +1653,15 @@ int mcl_get_ranges(mcl_ctx* c, int filter, float* out) {
     if (!c->d_steps) return fail(MCL_ERR_INVALID, "ranges are not kept: call mcl_set_keep_ranges(ctx, 1) before the update");
     CK(cudaSetDevice(c->device));
     const int64_t n = c->N * c->R;
-    float* d_out = nullptr;
-    CK(dalloc(&d_out, static_cast<size_t>(n)));
+    rc = ensure_tmp(c, sizeof(float) * static_cast<size_t>(n));
+    if (rc) return rc;
+    float* d_out = static_cast<float*>(c->d_tmp);
     k_steps_to_ranges<<<static_cast<unsigned>((n + 255) / 256), 256, 0, c->stream>>>(c->d_steps + n * filter, n, c->M, c->res,
                                                                                        c->prm.max_range, d_out);
     c->launches++;
     CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, d_out, sizeof(float) * n, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    CK(cudaMemcpy(out, d_out, sizeof(float) * n, cudaMemcpyDeviceToHost));
-    cudaFree(d_out);
     return MCL_OK;
 }
 
@@ -1327,20 +1672,28 @@ int mcl_update_dev(mcl_ctx* c, const double* action_dev, const float* obs_dev, i
     return update_steady(c, action_dev, obs_dev);
 }
 
+int mcl_update_dev_noise(mcl_ctx* c, const double* action_dev, const float* obs_dev, int num_beams, const double* u_dev,
+                         const double* z_dev) {
+    if (!c || !action_dev || !obs_dev) return fail(MCL_ERR_INVALID, "null argument");
+    if (num_beams != c->R) return fail(MCL_ERR_INVALID, "num_beams %d != configured %d", num_beams, c->R);
+    CK(cudaSetDevice(c->device));
+    return update_device(c, action_dev, obs_dev, u_dev, z_dev);
+}
+
 int mcl_read_pose(mcl_ctx* c, double* pose_out) {
     if (!c || !pose_out) return fail(MCL_ERR_INVALID, "null argument");
     CK(cudaSetDevice(c->device));
     CK(cudaMemcpyAsync(c->h_pose, c->d_pose, sizeof(double) * 3 * c->F, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     std::memcpy(pose_out, c->h_pose, sizeof(double) * 3 * c->F);
-    return MCL_OK;
+    return check_shard_error(c);
 }
 
 int mcl_synchronize(mcl_ctx* c) {
     if (!c) return fail(MCL_ERR_INVALID, "null context");
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
-    return MCL_OK;
+    return check_shard_error(c);
 }
 
 int mcl_update(mcl_ctx* c, const double* action, const float* obs, int num_beams, const mcl_noise* noise, double* pose_out) {
@@ -1364,17 +1717,18 @@ int mcl_update(mcl_ctx* c, const double* action, const float* obs, int num_beams
             all_z &= noise[f].z_motion != nullptr;
         }
         if (any_u != all_u || any_z != all_z) return fail(MCL_ERR_INVALID, "noise must be injected for all filters of a batch or none");
-        const size_t N = static_cast<size_t>(c->N);
+        // injected noise covers the WHOLE filter (a sharded rank indexes it by the global slot)
+        const size_t NG = static_cast<size_t>(sharded(c) ? c->NG : c->N);
         if (any_u) {
-            if (!c->d_u) CK(dalloc(&c->d_u, N * c->F));
+            if (!c->d_u) CK(dalloc(&c->d_u, NG * c->F));
             for (int f = 0; f < c->F; ++f)
-                CK(cudaMemcpyAsync(c->d_u + N * f, noise[f].u_resample, N * sizeof(double), cudaMemcpyHostToDevice, s));
+                CK(cudaMemcpyAsync(c->d_u + NG * f, noise[f].u_resample, NG * sizeof(double), cudaMemcpyHostToDevice, s));
             u_dev = c->d_u;
         }
         if (any_z) {
-            if (!c->d_z) CK(dalloc(&c->d_z, 3 * N * c->F));
+            if (!c->d_z) CK(dalloc(&c->d_z, 3 * NG * c->F));
             for (int f = 0; f < c->F; ++f)
-                CK(cudaMemcpyAsync(c->d_z + 3 * N * f, noise[f].z_motion, 3 * N * sizeof(double), cudaMemcpyHostToDevice, s));
+                CK(cudaMemcpyAsync(c->d_z + 3 * NG * f, noise[f].z_motion, 3 * NG * sizeof(double), cudaMemcpyHostToDevice, s));
             z_dev = c->d_z;
         }
     }
@@ -1382,6 +1736,8 @@ int mcl_update(mcl_ctx* c, const double* action, const float* obs, int num_beams
     if (rc) return rc;
     // the pose kernel has written the pose into h_pose (mapped pinned memory): no D2H copy call
     CK(cudaStreamSynchronize(s));
+    rc = check_shard_error(c);
+    if (rc) return rc;
     if (pose_out) std::memcpy(pose_out, c->h_pose, sizeof(double) * 3 * c->F);
     if (c->profiling && c->ev_valid) read_stage_times(c);
     return MCL_OK;
@@ -1391,6 +1747,7 @@ int mcl_expected_pose(mcl_ctx* c, int filter, double pose_out[3]) {
     int rc = check_filter(c, filter, false);
     if (rc) return rc;
     if (!pose_out) return fail(MCL_ERR_INVALID, "null output");
+    if (sharded(c)) return fail(MCL_ERR_UNSUPPORTED, "mcl_expected_pose on a sharded context: the pose of the whole filter is the update's result (mcl_read_pose)");
     CK(cudaSetDevice(c->device));
     rc = launch_pose(c, c->d_wn, nullptr, nullptr, c->cur, false);
     if (rc) return rc;
@@ -1406,10 +1763,11 @@ int mcl_calc_range_many(mcl_ctx* c, const double* q, int64_t n, float* out) {
     if (!c->have_map) return fail(MCL_ERR_NO_MAP, "map not set");   // reference returns MAX_RANGE here (:613)
     if (n == 0) return MCL_OK;
     CK(cudaSetDevice(c->device));
-    double* d_q = nullptr;
-    float* d_o = nullptr;
-    CK(dalloc(&d_q, static_cast<size_t>(3 * n)));
-    CK(dalloc(&d_o, static_cast<size_t>(n)));
+    const size_t qbytes = (sizeof(double) * 3 * static_cast<size_t>(n) + 255) & ~size_t{255};
+    const int rc = ensure_tmp(c, qbytes + sizeof(float) * static_cast<size_t>(n));
+    if (rc) return rc;
+    double* d_q = static_cast<double*>(c->d_tmp);
+    float* d_o = reinterpret_cast<float*>(static_cast<char*>(c->d_tmp) + qbytes);
     CK(cudaMemcpyAsync(d_q, q, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, c->stream));
     QueryArgs a{};
     a.map = c->map;
@@ -1422,8 +1780,6 @@ int mcl_calc_range_many(mcl_ctx* c, const double* q, int64_t n, float* out) {
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out, d_o, sizeof(float) * n, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    cudaFree(d_q);
-    cudaFree(d_o);
     return MCL_OK;
 }
 
@@ -1432,43 +1788,96 @@ int mcl_cast_ray(mcl_ctx* c, double x, double y, double angle, float* out) {
     return mcl_calc_range_many(c, q, 1, out);
 }
 
-int mcl_sample_particles(mcl_ctx* c, int filter, int k, double* out) {
+// visualize() :946-958: k draws from discrete_distribution(weights_) over the current particles.
+// u: the canonical uniforms the reference's generator would produce (NULL: device RNG);
+// idx_out (nullable): the drawn particle indices.
+int mcl_sample_particles_u(mcl_ctx* c, int filter, int k, const double* u, double* out, int32_t* idx_out) {
     int rc = check_filter(c, filter, false);
     if (rc) return rc;
     if (!out || k < 1) return fail(MCL_ERR_INVALID, "bad arguments");
+    if (sharded(c)) return fail(MCL_ERR_UNSUPPORTED, "viz sampling of a sharded filter: gather the state first (mcl_sharded_gather)");
     CK(cudaSetDevice(c->device));
-    // CDF of the current weights, as visualize() builds it (:949)
-    rc = build_cdf(c);
+    rc = ensure_cdf(c);   // the CDF of the current weights, as visualize() builds it (:949); reused by the next update
     if (rc) return rc;
-    double* d_o = nullptr;
-    CK(dalloc(&d_o, static_cast<size_t>(3) * k));
+    const size_t obytes = (sizeof(double) * 3 * k + 255) & ~size_t{255}, ubytes = (sizeof(double) * k + 255) & ~size_t{255};
+    rc = ensure_tmp(c, obytes + ubytes + sizeof(int32_t) * k);
+    if (rc) return rc;
+    double* d_o = static_cast<double*>(c->d_tmp);
+    double* d_u = reinterpret_cast<double*>(static_cast<char*>(c->d_tmp) + obytes);
+    int32_t* d_i = reinterpret_cast<int32_t*>(static_cast<char*>(c->d_tmp) + obytes + ubytes);
+    if (u) CK(cudaMemcpyAsync(d_u, u, sizeof(double) * k, cudaMemcpyHostToDevice, c->stream));
     const size_t fo = static_cast<size_t>(c->N) * filter;
     k_sample_particles<<<(k + 127) / 128, 128, 0, c->stream>>>(c->d_cdf + fo, c->N, c->d_px[c->cur] + fo, c->d_py[c->cur] + fo,
-                                                               c->d_pt[c->cur] + fo, k, c->prm.seed, ++c->init_no, d_o);
+                                                               c->d_pt[c->cur] + fo, k, c->prm.seed, ++c->init_no, u ? d_u : nullptr,
+                                                               d_o, d_i);
     c->launches++;
     CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, d_o, sizeof(double) * 3 * k, cudaMemcpyDeviceToHost, c->stream));
+    if (idx_out) CK(cudaMemcpyAsync(idx_out, d_i, sizeof(int32_t) * k, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    CK(cudaMemcpy(out, d_o, sizeof(double) * 3 * k, cudaMemcpyDeviceToHost));
-    cudaFree(d_o);
     return MCL_OK;
 }
+
+int mcl_sample_particles(mcl_ctx* c, int filter, int k, double* out) { return mcl_sample_particles_u(c, filter, k, nullptr, out, nullptr); }
 
 int mcl_set_profiling(mcl_ctx* c, int enabled) {
     if (!c) return fail(MCL_ERR_INVALID, "null context");
     c->profiling = enabled != 0;
     c->ev_valid = false;
+    c->nmarks = 0;
     return MCL_OK;
 }
 
 int mcl_get_stage_ms(mcl_ctx* c, mcl_stage_ms* out) {
     if (!c || !out) return fail(MCL_ERR_INVALID, "null argument");
-    if (c->profiling && c->ev_valid && !c->local_pending) {
-        // the device-resident and sharded entry points do not synchronise: wait for the last event here
+    if (c->profiling && c->ev_valid) {
+        // the device-resident entry points do not synchronise: wait for the last event here
         CK(cudaSetDevice(c->device));
         CK(cudaEventSynchronize(c->ev[4]));
         read_stage_times(c);
     }
     *out = c->last_ms;
+    return MCL_OK;
+}
+
+// Device time of every kernel of the last profiled update, in launch order.  names_out: capacity x 48
+// bytes (NUL-terminated); ms_out: capacity floats; *count = kernels of the update.
+int mcl_get_kernel_ms(mcl_ctx* c, char* names_out, float* ms_out, int capacity, int* count) {
+    if (!c || !count) return fail(MCL_ERR_INVALID, "null argument");
+    *count = c->nmarks;
+    if (!c->profiling || c->nmarks == 0) return MCL_OK;
+    CK(cudaSetDevice(c->device));
+    CK(cudaEventSynchronize(c->mark_ev[c->nmarks]));
+    for (int i = 0; i < c->nmarks && i < capacity; ++i) {
+        float t = 0;
+        cudaEventElapsedTime(&t, c->mark_ev[i], c->mark_ev[i + 1]);
+        if (ms_out) ms_out[i] = t;
+        if (names_out) {
+            std::strncpy(names_out + static_cast<size_t>(i) * 48, c->mark_name[i], 47);
+            names_out[static_cast<size_t>(i) * 48 + 47] = 0;
+        }
+    }
+    return MCL_OK;
+}
+
+// Diagnostics: SM cycle counts of the phases of ONE kind of exact pass (0 S1, 1 normalise+pose+S2, 2 S2 of stored
+// weights, 3 cdf) in the updates that follow; pass_kind < 0 switches it off.  out[8]: slowest CTA's tile phase |
+// last CTA until it knows it is last | pose fold | tile scan | ordered opaque list | exchange | serial evaluation +
+// tile starts | opaque chunks.  Call with out != NULL after an update to read (and clear) them.
+int mcl_debug_pass_cycles(mcl_ctx* c, int pass_kind, unsigned long long* out) {
+    if (!c) return fail(MCL_ERR_INVALID, "null context");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    if (!c->d_dbg) {
+        CK(dalloc(&c->d_dbg, size_t{8}));
+        CK(cudaMemset(c->d_dbg, 0, 8 * sizeof(unsigned long long)));
+    }
+    if (out) {
+        CK(cudaMemcpy(out, c->d_dbg, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        CK(cudaMemset(c->d_dbg, 0, 8 * sizeof(unsigned long long)));
+    }
+    c->dbg_pass = pass_kind;
+    drop_graphs(c);
     return MCL_OK;
 }
 
@@ -1485,139 +1894,6 @@ int mcl_kernel_launches(mcl_ctx* c, int64_t* count) {
     *count = c->launches;
     return MCL_OK;
 }
-
-int mcl_set_shard(mcl_ctx* c, int64_t lo, int64_t count) {
-    if (!c) return fail(MCL_ERR_INVALID, "null context");
-    if (c->F != 1) return fail(MCL_ERR_INVALID, "particle sharding applies to a single filter, not a batch");
-    if (lo < 0 || count < 1 || lo + count > c->N) return fail(MCL_ERR_INVALID, "shard [%lld,+%lld) outside [0,%lld)",
-                                                               (long long)lo, (long long)count, (long long)c->N);
-    if (c->local_pending) return fail(MCL_ERR_INVALID, "update in flight");
-    c->lo = lo;
-    c->cnt = count;
-    c->pose4_ok[0] = c->pose4_ok[1] = false;
-    drop_graphs(c);
-    CK(cudaSetDevice(c->device));
-    CK(cudaStreamSynchronize(c->stream));
-    return upload_replay_ctx(c);
-}
-
-int mcl_update_local_dev(mcl_ctx* c, const double* action_dev, const float* obs_dev, int num_beams, const double* u_dev,
-                         const double* z_dev) {
-    if (!c || !action_dev || !obs_dev) return fail(MCL_ERR_INVALID, "null argument");
-    if (num_beams != c->R) return fail(MCL_ERR_INVALID, "num_beams %d != configured %d", num_beams, c->R);
-    CK(cudaSetDevice(c->device));
-    return update_local(c, action_dev, obs_dev, u_dev, z_dev);
-}
-
-int mcl_exchange_buffers_dev(mcl_ctx* c, void* ptrs_out[4], int64_t* n_total, int64_t* lo, int64_t* count) {
-    if (!c || !ptrs_out) return fail(MCL_ERR_INVALID, "null argument");
-    if (!c->local_pending) return fail(MCL_ERR_INVALID, "call mcl_update_local_dev first");
-    const int dst = c->cur ^ 1;
-    ptrs_out[0] = c->d_px[dst];
-    ptrs_out[1] = c->d_py[dst];
-    ptrs_out[2] = c->d_pt[dst];
-    ptrs_out[3] = c->d_wraw;
-    if (n_total) *n_total = c->N;
-    if (lo) *lo = c->lo;
-    if (count) *count = c->cnt;
-    return MCL_OK;
-}
-
-static int install_peers(mcl_ctx* c, int world, int rank, const std::vector<const double*>& tab) {
-    if (c->F != 1) return fail(MCL_ERR_INVALID, "peer-to-peer sharding applies to a single filter");
-    if (world < 1 || rank < 0 || rank >= world || c->N % world) return fail(MCL_ERR_INVALID, "bad world/rank %d/%d for %lld particles", world, rank, (long long)c->N);
-    if (c->d_peer_tab) cudaFree(c->d_peer_tab);
-    if (c->d_partials) cudaFree(c->d_partials);
-    c->d_peer_tab = nullptr;
-    c->d_partials = nullptr;
-    CK(cudaMalloc(reinterpret_cast<void**>(&c->d_peer_tab), sizeof(double*) * tab.size()));
-    CK(cudaMemcpy(c->d_peer_tab, tab.data(), sizeof(double*) * tab.size(), cudaMemcpyHostToDevice));
-    CK(dalloc(&c->d_partials, static_cast<size_t>(4) * world));
-    CK(cudaMemset(c->d_partials, 0, sizeof(double) * 4 * world));
-    c->world = world;
-    c->rank = rank;
-    c->lo = (c->N / world) * rank;
-    c->cnt = c->N / world;
-    c->p2p = true;
-    c->pose4_ok[0] = c->pose4_ok[1] = false;
-    drop_graphs(c);
-    return upload_replay_ctx(c);   // the shard moved: the exact-replay context of the directional stage follows it
-}
-
-int mcl_ipc_export(mcl_ctx* c, void* handles_out, size_t capacity) {
-    if (!c || !handles_out) return fail(MCL_ERR_INVALID, "null argument");
-    if (capacity < 8 * sizeof(cudaIpcMemHandle_t)) return fail(MCL_ERR_INVALID, "need %zu bytes", 8 * sizeof(cudaIpcMemHandle_t));
-    CK(cudaSetDevice(c->device));
-    auto* h = static_cast<cudaIpcMemHandle_t*>(handles_out);
-    for (int b = 0; b < 2; ++b) {
-        CK(cudaIpcGetMemHandle(&h[b * 3 + 0], c->d_px[b]));
-        CK(cudaIpcGetMemHandle(&h[b * 3 + 1], c->d_py[b]));
-        CK(cudaIpcGetMemHandle(&h[b * 3 + 2], c->d_pt[b]));
-        CK(cudaIpcGetMemHandle(&h[6 + b], c->d_pose4[b]));
-    }
-    return MCL_OK;
-}
-
-int mcl_ipc_import(mcl_ctx* c, int world, int rank, const void* handles) {
-    if (!c || !handles) return fail(MCL_ERR_INVALID, "null argument");
-    CK(cudaSetDevice(c->device));
-    CK(cudaStreamSynchronize(c->stream));
-    const auto* h = static_cast<const cudaIpcMemHandle_t*>(handles);
-    std::vector<const double*> tab(static_cast<size_t>(8) * world, nullptr);   // [x y t of buf 0 | of buf 1 | pose4 buf 0 | buf 1][world]
-    for (int q = 0; q < world; ++q) {
-        for (int k = 0; k < 8; ++k) {
-            const double* ptr;
-            if (q == rank) {
-                const int b = k / 3, a = k % 3;
-                ptr = k >= 6 ? reinterpret_cast<const double*>(c->d_pose4[k - 6])
-                             : (a == 0 ? c->d_px[b] : (a == 1 ? c->d_py[b] : c->d_pt[b]));
-            } else {
-                void* p = nullptr;
-                CK(cudaIpcOpenMemHandle(&p, h[q * 8 + k], cudaIpcMemLazyEnablePeerAccess));
-                c->ipc_opened.push_back(p);
-                ptr = static_cast<const double*>(p);
-            }
-            tab[static_cast<size_t>(k) * world + q] = ptr;
-        }
-    }
-    return install_peers(c, world, rank, tab);
-}
-
-int mcl_set_peer_pointers(mcl_ctx* c, int world, int rank, const void* const* ptrs) {
-    if (!c || !ptrs) return fail(MCL_ERR_INVALID, "null argument");
-    CK(cudaSetDevice(c->device));
-    CK(cudaStreamSynchronize(c->stream));
-    std::vector<const double*> tab(static_cast<size_t>(8) * world, nullptr);
-    for (int q = 0; q < world; ++q)
-        for (int k = 0; k < 8; ++k) tab[static_cast<size_t>(k) * world + q] = static_cast<const double*>(ptrs[q * 8 + k]);
-    return install_peers(c, world, rank, tab);
-}
-
-int mcl_state_pointers_dev(mcl_ctx* c, void* ptrs_out[8]) {
-    if (!c || !ptrs_out) return fail(MCL_ERR_INVALID, "null argument");
-    for (int b = 0; b < 2; ++b) {
-        ptrs_out[b * 3 + 0] = c->d_px[b];
-        ptrs_out[b * 3 + 1] = c->d_py[b];
-        ptrs_out[b * 3 + 2] = c->d_pt[b];
-        ptrs_out[6 + b] = c->d_pose4[b];
-    }
-    return MCL_OK;
-}
-
-int mcl_p2p_buffers_dev(mcl_ctx* c, void** w_raw_dev, void** partials_dev) {
-    if (!c || !w_raw_dev || !partials_dev) return fail(MCL_ERR_INVALID, "null argument");
-    if (!c->p2p) return fail(MCL_ERR_INVALID, "peer-to-peer sharding is not set up");
-    *w_raw_dev = c->d_wraw;
-    *partials_dev = c->d_partials;
-    return MCL_OK;
-}
-
-int mcl_update_finish_dev(mcl_ctx* c) {
-    if (!c) return fail(MCL_ERR_INVALID, "null context");
-    CK(cudaSetDevice(c->device));
-    return update_finish(c);
-}
-
 int mcl_microbench_gather(int device, int shared, size_t array_bytes, int iters_per_thread, double* gathers_per_second) {
     if (!gathers_per_second || iters_per_thread < 1) return fail(MCL_ERR_INVALID, "bad arguments");
     int ndev = 0;
@@ -1723,6 +1999,188 @@ int mcl_set_stream(mcl_ctx* c, void* stream) {
     c->stream = stream ? static_cast<cudaStream_t>(stream) : c->own_stream;
     drop_graphs(c);
     return MCL_OK;
+}
+
+/* ---- particle-sharded filter ------------------------------------------------------------- */
+
+namespace {
+
+// every rank's exchange arena (own included) -> the pointer tables the kernels take by value
+int install_arenas(mcl_ctx* c, void* const* bases) {
+    const ArenaLayout L = arena_layout(c->world, c->N);
+    for (int q = 0; q < c->world; ++q) {
+        char* b = static_cast<char*>(bases[q]);
+        c->sh.mbox[q] = reinterpret_cast<uint8_t*>(b + L.mbox);
+        c->sh.flag[q] = reinterpret_cast<unsigned long long*>(b + L.flag);
+        c->routed_peers[q] = reinterpret_cast<double4*>(b + L.routed);
+        c->peer_list_fn[q] = reinterpret_cast<const StepFn*>(b + L.list_fn);
+        c->peer_list_add[q] = reinterpret_cast<const double*>(b + L.list_add);
+    }
+    c->connected = true;
+    drop_graphs(c);
+    return MCL_OK;
+}
+
+}  // namespace
+
+int mcl_shard_create(const mcl_params* p, int device, int world, int rank, mcl_ctx** out) {
+    if (world < 2) return fail(MCL_ERR_INVALID, "a sharded filter has at least 2 ranks (use mcl_create for one GPU)");
+    return create_any(p, device, world, rank, out);
+}
+
+int mcl_shard_export(mcl_ctx* c, void* blob, size_t capacity) {
+    if (!c || !blob) return fail(MCL_ERR_INVALID, "null argument");
+    if (!c->arena) return fail(MCL_ERR_INVALID, "not a sharded context");
+    if (capacity < MCL_SHARD_BLOB_BYTES) return fail(MCL_ERR_INVALID, "need %d bytes", MCL_SHARD_BLOB_BYTES);
+    CK(cudaSetDevice(c->device));
+    std::memset(blob, 0, MCL_SHARD_BLOB_BYTES);
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, c->arena));
+    std::memcpy(blob, &h, sizeof h);
+    const int64_t meta[3] = {c->world, c->N, static_cast<int64_t>(arena_layout(c->world, c->N).bytes)};
+    std::memcpy(static_cast<char*>(blob) + sizeof h, meta, sizeof meta);
+    return MCL_OK;
+}
+
+int mcl_shard_connect(mcl_ctx* c, const void* blobs) {
+    if (!c || !blobs) return fail(MCL_ERR_INVALID, "null argument");
+    if (!c->arena) return fail(MCL_ERR_INVALID, "not a sharded context");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    void* bases[kMaxWorld] = {};
+    for (int q = 0; q < c->world; ++q) {
+        const char* b = static_cast<const char*>(blobs) + static_cast<size_t>(q) * MCL_SHARD_BLOB_BYTES;
+        int64_t meta[3];
+        std::memcpy(meta, b + sizeof(cudaIpcMemHandle_t), sizeof meta);
+        if (meta[0] != c->world || meta[1] != c->N)
+            return fail(MCL_ERR_INVALID, "rank %d was created with world %lld / %lld particles per rank, this rank with %d / %lld", q,
+                        (long long)meta[0], (long long)meta[1], c->world, (long long)c->N);
+        if (q == c->rank) {
+            bases[q] = c->arena;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, b, sizeof h);
+        void* p = nullptr;
+        CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        c->ipc_opened.push_back(p);
+        bases[q] = p;
+    }
+    return install_arenas(c, bases);
+}
+
+int mcl_shard_connect_local(mcl_ctx* c, mcl_ctx* const* ranks) {
+    if (!c || !ranks) return fail(MCL_ERR_INVALID, "null argument");
+    if (!c->arena) return fail(MCL_ERR_INVALID, "not a sharded context");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    void* bases[kMaxWorld] = {};
+    for (int q = 0; q < c->world; ++q) {
+        const mcl_ctx* r = ranks[q];
+        if (!r || !r->arena || r->world != c->world || r->N != c->N || r->rank != q)
+            return fail(MCL_ERR_INVALID, "ranks[%d] is not rank %d of the same sharded filter", q, q);
+        if (r->device != c->device) {
+            int can = 0;
+            CK(cudaDeviceCanAccessPeer(&can, c->device, r->device));
+            if (!can) return fail(MCL_ERR_UNSUPPORTED, "device %d cannot access device %d", c->device, r->device);
+            const cudaError_t e = cudaDeviceEnablePeerAccess(r->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
+            cudaGetLastError();
+        }
+        bases[q] = r->arena;
+    }
+    return install_arenas(c, bases);
+}
+
+int mcl_shard_set_exchange(mcl_ctx* c, int fused, mcl_barrier_fn hook, void* user) {
+    if (!c) return fail(MCL_ERR_INVALID, "null context");
+    if (!c->arena) return fail(MCL_ERR_INVALID, "not a sharded context");
+    if (!fused && !hook && !c->comm) return fail(MCL_ERR_INVALID, "host-ordered exchange needs a barrier hook or an NCCL communicator");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    c->xmode = fused ? 1 : 0;
+    c->hook = fused ? nullptr : hook;
+    c->hook_user = user;
+    drop_graphs(c);
+    return MCL_OK;
+}
+
+int mcl_shard_info(const mcl_ctx* c, int* world, int* rank, int64_t* n_local, int64_t* n_global) {
+    if (!c) return fail(MCL_ERR_INVALID, "null context");
+    if (world) *world = c->world;
+    if (rank) *rank = c->rank;
+    if (n_local) *n_local = c->N;
+    if (n_global) *n_global = c->NG;
+    return MCL_OK;
+}
+
+int mcl_nccl_unique_id(void* id_out, size_t capacity) {
+    if (!id_out || capacity < sizeof(ncclUniqueId)) return fail(MCL_ERR_INVALID, "need %zu bytes", sizeof(ncclUniqueId));
+    const int rc = load_nccl();
+    if (rc) return rc;
+    ncclUniqueId id;
+    NK(g_nccl.GetUniqueId(&id));
+    std::memcpy(id_out, &id, sizeof id);
+    return MCL_OK;
+}
+
+int mcl_create_sharded(const mcl_params* p, int device, int world, int rank, const void* nccl_unique_id, mcl_ctx** out) {
+    if (!nccl_unique_id) return fail(MCL_ERR_INVALID, "null NCCL id");
+    int rc = load_nccl();
+    if (rc) return rc;
+    rc = mcl_shard_create(p, device, world, rank, out);
+    if (rc) return rc;
+    mcl_ctx* c = *out;
+    auto bail = [&](int code) {
+        const std::string keep = g_err;
+        mcl_destroy(c);
+        *out = nullptr;
+        g_err = keep;
+        return code;
+    };
+    ncclUniqueId id;
+    std::memcpy(&id, nccl_unique_id, sizeof id);
+    if (g_nccl.CommInitRank(&c->comm, world, id, rank) != ncclSuccess) {
+        c->comm = nullptr;
+        fail(MCL_ERR_CUDA, "ncclCommInitRank failed for rank %d of %d", rank, world);
+        return bail(MCL_ERR_CUDA);
+    }
+    // all-gather the ranks' exchange-arena handles over the communicator it owns, then map them
+    std::vector<char> blobs(static_cast<size_t>(world) * MCL_SHARD_BLOB_BYTES);
+    rc = mcl_shard_export(c, blobs.data() + static_cast<size_t>(rank) * MCL_SHARD_BLOB_BYTES, MCL_SHARD_BLOB_BYTES);
+    if (rc) return bail(rc);
+    rc = ensure_tmp(c, blobs.size());
+    if (rc) return bail(rc);
+    char* d = static_cast<char*>(c->d_tmp);
+    if (cudaMemcpyAsync(d + static_cast<size_t>(rank) * MCL_SHARD_BLOB_BYTES, blobs.data() + static_cast<size_t>(rank) * MCL_SHARD_BLOB_BYTES,
+                        MCL_SHARD_BLOB_BYTES, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
+        g_nccl.AllGather(d + static_cast<size_t>(rank) * MCL_SHARD_BLOB_BYTES, d, MCL_SHARD_BLOB_BYTES, ncclChar, c->comm, c->stream) != ncclSuccess ||
+        cudaMemcpyAsync(blobs.data(), d, blobs.size(), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+        cudaStreamSynchronize(c->stream) != cudaSuccess) {
+        fail(MCL_ERR_CUDA, "exchanging the arena handles over NCCL failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return bail(MCL_ERR_CUDA);
+    }
+    rc = mcl_shard_connect(c, blobs.data());
+    if (rc) return bail(rc);
+    return MCL_OK;
+}
+
+// Whole-filter read-back on every rank (parity harness, visualize()): ncclAllGather of the four
+// per-particle arrays on the library's stream.  particles_colmajor: NG x 3; either may be NULL.
+int mcl_sharded_gather(mcl_ctx* c, double* particles_colmajor, double* weights) {
+    if (!c) return fail(MCL_ERR_INVALID, "null context");
+    if (!c->comm) return fail(MCL_ERR_INVALID, "mcl_sharded_gather needs the communicator of mcl_create_sharded");
+    CK(cudaSetDevice(c->device));
+    const size_t NG = static_cast<size_t>(c->NG), n = static_cast<size_t>(c->N);
+    const int rc = ensure_tmp(c, sizeof(double) * 4 * NG);
+    if (rc) return rc;
+    double* g = static_cast<double*>(c->d_tmp);
+    const double* srcs[4] = {c->d_px[c->cur], c->d_py[c->cur], c->d_pt[c->cur], c->d_wn};
+    for (int k = 0; k < 4; ++k) NK(g_nccl.AllGather(srcs[k], g + k * NG, n, ncclDouble, c->comm, c->stream));
+    if (particles_colmajor) CK(cudaMemcpyAsync(particles_colmajor, g, sizeof(double) * 3 * NG, cudaMemcpyDeviceToHost, c->stream));
+    if (weights) CK(cudaMemcpyAsync(weights, g + 3 * NG, sizeof(double) * NG, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return check_shard_error(c);
 }
 
 }  // extern "C"

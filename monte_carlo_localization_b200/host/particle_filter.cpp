@@ -88,6 +88,8 @@ bool Parameters::load_yaml(const std::string& path, std::string* err) {
 }
 
 ParticleFilter::ParticleFilter(const Parameters& params) : p_(params) {
+    shell_.delay_compensation_factor = p_.delay_compensation_factor;
+    shell_.max_pose_range = p_.max_pose_range;
     mcl_params mp;
     mcl_default_params(&mp);
     mp.max_particles = p_.max_particles;
@@ -171,18 +173,29 @@ void ParticleFilter::initialize_global() {
     if (rc != MCL_OK) log_error("initialize_global", rc);   // "No free space found in map!" (:425)
 }
 
-void ParticleFilter::MCL(const Vector3d& action, const std::vector<float>& observation) {
+// MCL(action, observation) followed by expected_pose(), as timer_update calls them (:777-778): ONE C-ABI call
+UpdateShell::MclResult ParticleFilter::run_mcl(const Vector3d& action, const std::vector<float>& observation) {
+    UpdateShell::MclResult r;
     const auto t0 = std::chrono::steady_clock::now();
     double pose[3];
     const int rc = mcl_update(ctx_, action.data(), observation.data(), static_cast<int>(observation.size()), nullptr, pose);
     if (rc != MCL_OK) {
-        log_error("MCL", rc);
-        return;
+        log_error("MCL", rc);   // e.g. a scan whose downsampled length differs from the first scan's
+        return r;               // ok == false: the caller leaves every piece of tracking state alone
     }
-    inferred_pose_ = {pose[0], pose[1], pose[2]};   // expected_pose() of the same update (:778)
-    last_update_ms_ = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    mcl_total_ms_ += last_update_ms_;   // timing_stats_.total_mcl_time / measurement_count (:692-693)
-    ++mcl_count_;
+    r.pose = {pose[0], pose[1], pose[2]};
+    r.elapsed_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    r.ok = true;
+    last_update_ms_ = r.elapsed_ms;
+    return r;
+}
+
+void ParticleFilter::MCL(const Vector3d& action, const std::vector<float>& observation) {
+    const UpdateShell::MclResult r = run_mcl(action, observation);
+    if (!r.ok) return;
+    shell_.inferred_pose_ = r.pose;           // expected_pose() of the same update (:778)
+    shell_.window_total_ms_ += r.elapsed_ms;  // timing_stats_.total_mcl_time / measurement_count (:692-693)
+    ++shell_.window_count_;
 }
 
 Vector3d ParticleFilter::expected_pose() {
@@ -213,7 +226,7 @@ bool ParticleFilter::update(double dt, double current_velocity, double current_a
     if (!map_initialized_) return false;                              // :722-724
     if (dt > 1.0) return false;                                        // :750-752
     if (!lidar_initialized_ || downsampled_ranges_.empty()) return false;   // :758
-    ++iters_;
+    ++shell_.iters_;
     Vector3d action{{0.0, 0.0, 0.0}};
     const bool apply_motion = dt >= 0.0001;                            // :754
     if (apply_motion && (std::abs(current_velocity) > 0.0001 || std::abs(current_angular_vel) > 0.0001)) {
@@ -226,10 +239,9 @@ bool ParticleFilter::update(double dt, double current_velocity, double current_a
     return true;
 }
 
-// ---- the node's update shell ----------------------------------------------------
+// ---- the node's update shell: logic in host/update_shell.hpp, hooks bound here ----
 
 namespace {
-double norm3(const Vector3d& v) { return std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
 // standard normal for the start-up jitter only (three draws per tick for the first 15 ticks);
 // the reference draws these from its mt19937 (:769-771), which is not reproducible either
 double jitter_normal(uint64_t& s) {
@@ -244,90 +256,33 @@ double jitter_normal(uint64_t& s) {
 }
 }  // namespace
 
-void ParticleFilter::initialize_odom_tracking(const Vector3d& initial_pose, bool from_rviz) {
-    odom_pose_ = initial_pose;
-    odom_reference_pose_ = initial_pose;
-    if (norm3(last_pose_) > 0) odom_reference_odom_ = last_pose_;
-    pose_initialized_from_rviz_ = from_rviz;
-    odom_tracking_active_ = true;
-}
-
-void ParticleFilter::update_odom_pose(const Vector3d& current_odom) {
-    if (!odom_tracking_active_) return;
-    for (int k = 0; k < 3; ++k) odom_pose_[k] = odom_reference_pose_[k] + (current_odom[k] - odom_reference_odom_[k]);
-}
-
 void ParticleFilter::odomCB(const Vector3d& odom_pose, double linear_velocity, double angular_velocity) {
-    current_velocity_ = linear_velocity;       // :328-329
-    current_angular_vel_ = angular_velocity;
-    const bool can_track = pose_initialized_from_rviz_ || (map_initialized_ && iters_ > 0 && is_pose_valid(inferred_pose_));
-    if (can_track && odom_tracking_active_) update_odom_pose(odom_pose);   // :332-337
-    last_pose_ = odom_pose;                    // :343-351
-    odom_initialized_ = true;
+    shell_.odomCB(odom_pose, linear_velocity, angular_velocity, map_initialized_);
 }
 
 void ParticleFilter::clicked_pose(const Vector3d& pose) {
-    initialize_particles_pose(pose);           // :361-367
-    initialize_odom_tracking(pose);
-    inferred_pose_ = pose;
+    shell_.clicked_pose(pose, [this](const Vector3d& p) { initialize_particles_pose(p); });
 }
 
 bool ParticleFilter::timer_update(double dt) {
-    if (!map_initialized_) return false;                                   // :722-724
-    const bool has_odom = odom_initialized_;
-    if (dt > 1.0) return false;                                            // :750-752
-    const bool apply_motion = dt >= 0.0001;                                // :754
-    if (!lidar_initialized_ || downsampled_ranges_.empty()) return false;  // :758
-    ++iters_;
-    Vector3d action{{0.0, 0.0, 0.0}};
-    if (has_odom && apply_motion && (std::abs(current_velocity_) > 0.0001 || std::abs(current_angular_vel_) > 0.0001)) {
-        action[0] = current_velocity_ * dt;                                // :764-766
-        action[1] = 0.0;
-        action[2] = current_angular_vel_ * dt;
-    } else if (!has_odom && !pose_initialized_from_rviz_ && iters_ < 15) {
-        const double noise_factor = std::max(0.1, 1.0 - (static_cast<double>(iters_) / 15.0));   // :768
-        action[0] = jitter_normal(jitter_state_) * 0.02 * noise_factor;
-        action[1] = jitter_normal(jitter_state_) * 0.01 * noise_factor;
-        action[2] = jitter_normal(jitter_state_) * 0.05 * noise_factor;
-    }
-    const std::vector<float> observation = downsampled_ranges_;            // :774
-    MCL(action, observation);                                              // :777-778
-    const bool can_track = has_odom && (pose_initialized_from_rviz_ ||
-                                        (map_initialized_ && iters_ > 0 && is_pose_valid(inferred_pose_)));   // :781-782
-    if (can_track) {
-        if (!odom_tracking_active_ && is_pose_valid(inferred_pose_)) initialize_odom_tracking(inferred_pose_, false);
-        Vector3d compensated = inferred_pose_;                             // :791-802
-        if (mcl_count_ > 0) {
-            const double delay = mcl_total_ms_ / mcl_count_ / 1000.0;
-            const double lon = current_velocity_ * delay * p_.delay_compensation_factor;
-            const double ang = current_angular_vel_ * delay * p_.delay_compensation_factor;
-            compensated[0] += lon * std::cos(inferred_pose_[2]);
-            compensated[1] += lon * std::sin(inferred_pose_[2]);
-            compensated[2] += ang;
-        }
-        odom_reference_pose_ = compensated;                                // :804-806
-        odom_reference_odom_ = last_pose_;
-        odom_pose_ = compensated;
-    }
-    return true;
+    return shell_.timer_update(
+        dt, map_initialized_, lidar_initialized_, downsampled_ranges_,
+        [this](const Vector3d& action, const std::vector<float>& obs) { return run_mcl(action, obs); },
+        [this]() { return jitter_normal(jitter_state_); });
 }
 
 Vector3d ParticleFilter::get_current_pose() {
-    if (odom_tracking_active_ && is_pose_valid(odom_pose_)) return odom_pose_;   // :895-896
-    if (is_pose_valid(inferred_pose_) && iters_ > 0) return inferred_pose_;      // :899-900
-    if (map_initialized_) {                                                      // :903-908
+    return shell_.get_current_pose(map_initialized_, [this](Vector3d* c) {   // particles_.colwise().mean() (:904)
         const std::vector<double> p = particles();
         const size_t n = static_cast<size_t>(p_.max_particles);
-        Vector3d c{{0, 0, 0}};
+        if (n == 0) return false;
         for (int k = 0; k < 3; ++k) {
             double s = 0.0;
             for (size_t i = 0; i < n; ++i) s += p[k * n + i];
-            c[k] = s / static_cast<double>(n);
+            (*c)[k] = s / static_cast<double>(n);
         }
-        if (is_pose_valid(c)) return c;
-    }
-    if (is_pose_valid(last_pose_)) return last_pose_;                            // :911-912
-    return Vector3d{{0, 0, 0}};
+        return true;
+    });
 }
 
 std::vector<double> ParticleFilter::particles() const {
@@ -349,11 +304,6 @@ std::vector<double> ParticleFilter::sample_particles(int k) const {
     const int rc = mcl_sample_particles(ctx_, 0, k, out.data());
     if (rc != MCL_OK) log_error("sample_particles", rc);
     return out;
-}
-
-bool ParticleFilter::is_pose_valid(const Vector3d& pose) const {   // src/utils.cpp:80-84
-    return std::isfinite(pose[0]) && std::isfinite(pose[1]) && std::isfinite(pose[2]) &&
-           std::abs(pose[0]) < p_.max_pose_range && std::abs(pose[1]) < p_.max_pose_range;
 }
 
 }  // namespace particle_filter_cpp

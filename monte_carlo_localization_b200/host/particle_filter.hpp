@@ -20,12 +20,11 @@
 #include <vector>
 
 #include "map_loader.hpp"
+#include "update_shell.hpp"
 
 struct mcl_ctx;
 
 namespace particle_filter_cpp {
-
-using Vector3d = std::array<double, 3>;
 
 // The declared ROS parameters (src/particle_filter.cpp:23-47), same names and defaults.
 struct Parameters {
@@ -97,17 +96,18 @@ class ParticleFilter {
     bool timer_update(double dt);
     // get_current_pose (:892-916): odometry tracking > filter estimate > particle mean > last odom
     Vector3d get_current_pose();
-    // mean MCL time the delay compensation uses (:792-795), milliseconds
-    double mean_mcl_ms() const { return mcl_count_ ? mcl_total_ms_ / mcl_count_ : 0.0; }
-    bool odom_tracking_active() const { return odom_tracking_active_; }
+    // mean MCL time the delay compensation uses (:792-795), milliseconds: the mean over the CURRENT
+    // 200-iteration TimingStats window (:814-827)
+    double mean_mcl_ms() const { return shell_.window_count_ ? shell_.window_total_ms_ / shell_.window_count_ : 0.0; }
+    bool odom_tracking_active() const { return shell_.odom_tracking_active_; }
 
     // --- state access (visualize() :944-963, get_current_pose :892-916) ---
     std::vector<double> particles() const;          // column-major N x 3
     std::vector<double> weights() const;
     std::vector<double> sample_particles(int k) const;   // weighted subsample, k x 3 column-major
-    Vector3d inferred_pose() const { return inferred_pose_; }
-    bool is_pose_valid(const Vector3d& pose) const;
-    int iterations() const { return iters_; }
+    Vector3d inferred_pose() const { return shell_.inferred_pose_; }
+    bool is_pose_valid(const Vector3d& pose) const { return shell_.is_pose_valid(pose); }
+    int iterations() const { return shell_.iters_; }
     int max_range_px() const { return MAX_RANGE_PX; }
     const std::vector<float>& downsampled_angles() const { return downsampled_angles_; }
     const std::vector<float>& downsampled_ranges() const { return downsampled_ranges_; }
@@ -120,17 +120,11 @@ class ParticleFilter {
     int MAX_RANGE_PX = 0;
     bool map_initialized_ = false, lidar_initialized_ = false;
     std::vector<float> laser_angles_, downsampled_angles_, downsampled_ranges_;
-    Vector3d inferred_pose_{{0, 0, 0}};
-    int iters_ = 0;
     double last_update_ms_ = 0.0;
-    // update-shell state (particle_filter.hpp:104-113, 170-178)
-    void initialize_odom_tracking(const Vector3d& initial_pose, bool from_rviz = true);   // :988-1002
-    void update_odom_pose(const Vector3d& current_odom);                                  // :1004-1013
-    Vector3d last_pose_{{0, 0, 0}}, odom_pose_{{0, 0, 0}}, odom_reference_pose_{{0, 0, 0}}, odom_reference_odom_{{0, 0, 0}};
-    bool odom_initialized_ = false, pose_initialized_from_rviz_ = false, odom_tracking_active_ = false;
-    double current_velocity_ = 0.0, current_angular_vel_ = 0.0;
-    double mcl_total_ms_ = 0.0;
-    int mcl_count_ = 0;
+    // the node's update shell (timer_update / odomCB / clicked_pose / get_current_pose): pure host state,
+    // host/update_shell.hpp; this class binds its MCL / mean / init hooks to the C ABI
+    UpdateShell shell_;
+    UpdateShell::MclResult run_mcl(const Vector3d& action, const std::vector<float>& observation);
     uint64_t jitter_state_ = 0x243F6A8885A308D3ull;   // start-up jitter noise (:769-771)
 };
 

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(L, name), "libmcl_b200.so does not export %s" % name
     # the ctypes table binds exactly the header's functions
     assert sorted(capi.SIGNATURES) == declared
-    assert L.mcl_abi_version() == 2
+    assert L.mcl_abi_version() == 3
 
 
 def test_params_defaults_match_reference_declarations():

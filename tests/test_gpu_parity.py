@@ -218,119 +218,6 @@ def test_device_rng_update_runs_and_tracks():
     c.close()
 
 
-def test_particle_shards_reproduce_single_filter():
-    """Two emulated ranks on one GPU (run one after the other, exchange by copying slices):
-    local slots -> exchange -> finish must equal the golden single-filter update exactly."""
-    import torch
-    from monte_carlo_localization_b200 import maps
-    from monte_carlo_localization_b200.sharded import ShardPlan, _DevArray
-    z = load_golden("update_sibal1_4000.npz")
-    g = maps.load_named_map("sibal1")
-    N, world = int(z["N"]), 2
-    plan = ShardPlan(N, world)
-    ranks = []
-    for r in range(world):
-        c = _ctx(g, z["angles"], N)
-        c.set_shard(*plan.slots(r))
-        ranks.append(c)
-    stream = torch.cuda.Stream()
-    torch.cuda.set_stream(stream)
-    for c in ranks:
-        c.set_stream(stream.cuda_stream)
-    prev_p, prev_w = z["init_particles"], z["init_weights"]
-    for t in range(len(z["u"])):
-        a = torch.from_numpy(z["actions"][t].copy()).cuda()
-        o = torch.from_numpy(z["obs"][t].copy()).cuda()
-        u = torch.from_numpy(z["u"][t].copy()).cuda()
-        zz = torch.from_numpy(z["z"][t].copy()).cuda()
-        bufs = []
-        for c in ranks:
-            c.set_particles(prev_p, prev_w)
-            c.update_local_dev(a.data_ptr(), o.data_ptr(), u.data_ptr(), zz.data_ptr())
-            ptrs, n, lo, cnt = c.exchange_buffers_dev()
-            bufs.append([torch.as_tensor(_DevArray(p, n), device="cuda") for p in ptrs])
-        for r, c in enumerate(ranks):          # the all-gather, emulated with copies
-            for q in range(world):
-                if q == r:
-                    continue
-                lo, cnt = plan.slots(q)
-                for k in range(4):
-                    bufs[r][k][lo:lo + cnt].copy_(bufs[q][k][lo:lo + cnt])
-        torch.cuda.synchronize()
-        for r, c in enumerate(ranks):
-            c.update_finish_dev()
-            pose = c.read_pose()
-            lo, cnt = plan.slots(r)
-            assert np.array_equal(c.resample_indices()[lo:lo + cnt], z["idx"][t][lo:lo + cnt])
-            assert_weights_close(c.get_weights(), z["weights"][t])
-            assert_pose_close(pose, z["pose"][t])
-        assert np.array_equal(ranks[0].get_weights(), ranks[1].get_weights())   # ranks bit-identical
-        assert np.array_equal(ranks[0].get_particles(), ranks[1].get_particles())
-        prev_p, prev_w = z["particles"][t], z["weights"][t]
-    for c in ranks:
-        c.close()
-
-
-def test_p2p_shards_reproduce_single_filter():
-    """Peer-to-peer sharding, two emulated ranks on one GPU: each rank reads its slots' source
-    poses from the owner's arrays (mcl_set_peer_pointers), only raw weights and pose partial
-    sums are exchanged.  Must equal the golden single-filter update."""
-    import torch
-    from monte_carlo_localization_b200 import maps
-    from monte_carlo_localization_b200.sharded import ShardPlan, _DevArray
-    z = load_golden("update_sibal1_4000.npz")
-    g = maps.load_named_map("sibal1")
-    N, world = int(z["N"]), 2
-    plan = ShardPlan(N, world)
-    ranks = [_ctx(g, z["angles"], N) for _ in range(world)]
-    stream = torch.cuda.Stream()
-    torch.cuda.set_stream(stream)
-    all_ptrs = []
-    for c in ranks:
-        c.set_stream(stream.cuda_stream)
-        all_ptrs += c.state_pointers_dev()
-    for r, c in enumerate(ranks):
-        c.set_peer_pointers(world, r, all_ptrs)
-    prev_p, prev_w = z["init_particles"], z["init_weights"]
-    for t in range(len(z["u"])):
-        a = torch.from_numpy(z["actions"][t].copy()).cuda()
-        o = torch.from_numpy(z["obs"][t].copy()).cuda()
-        u = torch.from_numpy(z["u"][t].copy()).cuda()
-        zz = torch.from_numpy(z["z"][t].copy()).cuda()
-        for r, c in enumerate(ranks):
-            # only the owner's slice has to be current: poison the rest to prove peers are used
-            lo, cnt = plan.slots(r)
-            p = np.full_like(prev_p, 1e6)
-            p[:, lo:lo + cnt] = prev_p[:, lo:lo + cnt]
-            c.set_particles(p, prev_w)
-        bufs = []
-        for c in ranks:
-            c.update_local_dev(a.data_ptr(), o.data_ptr(), u.data_ptr(), zz.data_ptr())
-            w_ptr, part_ptr = c.p2p_buffers_dev()
-            bufs.append((torch.as_tensor(_DevArray(w_ptr, N), device="cuda"),
-                         torch.as_tensor(_DevArray(part_ptr, 4 * world), device="cuda")))
-        for r in range(world):          # the two all-gathers, emulated with copies
-            for q in range(world):
-                if q != r:
-                    lo, cnt = plan.slots(q)
-                    bufs[r][0][lo:lo + cnt].copy_(bufs[q][0][lo:lo + cnt])
-                    bufs[r][1][4 * q:4 * q + 4].copy_(bufs[q][1][4 * q:4 * q + 4])
-        torch.cuda.synchronize()
-        for r, c in enumerate(ranks):
-            c.update_finish_dev()
-            pose = c.read_pose()
-            lo, cnt = plan.slots(r)
-            assert np.array_equal(c.resample_indices()[lo:lo + cnt], z["idx"][t][lo:lo + cnt])
-            assert_weights_close(c.get_weights(), z["weights"][t])
-            assert_pose_close(pose, z["pose"][t])
-            got = c.get_particles()[:, lo:lo + cnt]
-            assert np.abs(got - z["particles"][t][:, lo:lo + cnt]).max() < 1e-9
-        assert np.array_equal(ranks[0].get_weights(), ranks[1].get_weights())
-        prev_p, prev_w = z["particles"][t], z["weights"][t]
-    for c in ranks:
-        c.close()
-
-
 def test_full_size_update_1m_spielberg_vs_oracle():
     """BASELINE config 3 at full size: one update of 1,048,576 particles x 60 beams on
     Spielberg_map against the oracle (indices and range steps exact), plus the size-independent
@@ -617,58 +504,6 @@ def test_directional_stage_edge_cases_match_oracle():
     c.close()
 
 
-def test_directional_stage_in_particle_shards():
-    """Two emulated ranks on one GPU, each large enough for the directional stage: the sharded
-    update (local slots -> exchange -> finish) equals the single-filter update bit for bit."""
-    import torch
-    from monte_carlo_localization_b200.sharded import ShardPlan, _DevArray
-    N, world = 40000, 2
-    g, angles, orc, ns, action, obs = _tracking_case("sibal1", N, 3.0, 5)
-    p0, w0 = orc.get_state()
-    u, z = ns.update_noise(N)
-    single = _ctx(g, angles, N)
-    single.set_particles(p0, w0)
-    pose_single = single.update(action, obs, u, z)
-    assert single.ray_stage_info()["last_mode"] == 1
-    plan = ShardPlan(N, world)
-    ranks = []
-    stream = torch.cuda.Stream()
-    torch.cuda.set_stream(stream)
-    for r in range(world):
-        c = _ctx(g, angles, N)
-        c.set_shard(*plan.slots(r))
-        c.set_stream(stream.cuda_stream)
-        ranks.append(c)
-    a = torch.from_numpy(np.asarray(action, dtype=np.float64).copy()).cuda()
-    o = torch.from_numpy(obs.copy()).cuda()
-    ud = torch.from_numpy(u.copy()).cuda()
-    zd = torch.from_numpy(z.copy()).cuda()
-    bufs = []
-    for c in ranks:
-        c.set_particles(p0, w0)
-        c.update_local_dev(a.data_ptr(), o.data_ptr(), ud.data_ptr(), zd.data_ptr())
-        ptrs, n, lo, cnt = c.exchange_buffers_dev()
-        bufs.append([torch.as_tensor(_DevArray(p, n), device="cuda") for p in ptrs])
-    for r in range(world):              # the all-gather, emulated with copies
-        for q in range(world):
-            if q != r:
-                lo, cnt = plan.slots(q)
-                for k in range(4):
-                    bufs[r][k][lo:lo + cnt].copy_(bufs[q][k][lo:lo + cnt])
-    torch.cuda.synchronize()
-    for r, c in enumerate(ranks):
-        c.update_finish_dev()
-        pose = c.read_pose()
-        assert c.ray_stage_info()["last_mode"] == 1
-        assert np.array_equal(c.get_weights(), single.get_weights())
-        assert np.array_equal(c.get_particles(), single.get_particles())
-        assert np.array_equal(pose, pose_single)
-        lo, cnt = plan.slots(r)
-        assert np.array_equal(c.range_steps()[lo:lo + cnt], single.range_steps()[lo:lo + cnt])
-    for c in ranks + [single]:
-        c.close()
-
-
 @pytest.mark.parametrize("name,N", [("sibal1", 4000), ("sibal1", 30000)])
 def test_graph_replay_equals_direct_launches(name, N):
     """The host-facing update replays its steady state as a CUDA graph: particles, weights and
@@ -754,55 +589,95 @@ def test_batch_pool_directional_stage_equals_isotropic_kernel():
     assert_weights_close(out[0][0][2], orcs[0].get_state()[1])
 
 
-def test_p2p_shards_free_running_use_packed_peer_poses():
-    """Peer-to-peer sharding without teacher forcing: from the second update on, every slot's
-    source pose is ONE 32-byte read of the owner's packed (x, y, theta) copy.  Two emulated ranks
-    must stay bit-identical to the single filter over the whole run."""
-    import torch
+# ---- particle-sharded filter: ranks emulated on ONE GPU (helpers.EmuRanks) ------------------------
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_ranks_reproduce_golden_updates(world):
+    """Teacher-forced golden updates through `world` ranks: every rank holds only its slice; the
+    gathered indices, particles, weights and the pose equal the reference's single-filter update."""
+    from helpers import EmuRanks
     from monte_carlo_localization_b200 import maps
-    from monte_carlo_localization_b200.sharded import ShardPlan, _DevArray
     z = load_golden("update_sibal1_4000.npz")
     g = maps.load_named_map("sibal1")
-    N, world = int(z["N"]), 2
-    plan = ShardPlan(N, world)
-    single = _ctx(g, z["angles"], N)
-    single.set_particles(z["init_particles"], z["init_weights"])
-    ranks = [_ctx(g, z["angles"], N) for _ in range(world)]
-    stream = torch.cuda.Stream()
-    torch.cuda.set_stream(stream)
-    all_ptrs = []
-    for c in ranks:
-        c.set_stream(stream.cuda_stream)
-        all_ptrs += c.state_pointers_dev()
-    for r, c in enumerate(ranks):
-        c.set_peer_pointers(world, r, all_ptrs)
-        c.set_particles(z["init_particles"], z["init_weights"])
+    N = int(z["N"])
+    ranks = EmuRanks(g, z["angles"], N, world)
+    prev_p, prev_w = z["init_particles"], z["init_weights"]
     for t in range(len(z["u"])):
-        pose_single = single.update(z["actions"][t], z["obs"][t], z["u"][t], z["z"][t])
-        a = torch.from_numpy(z["actions"][t].copy()).cuda()
-        o = torch.from_numpy(z["obs"][t].copy()).cuda()
-        u = torch.from_numpy(z["u"][t].copy()).cuda()
-        zz = torch.from_numpy(z["z"][t].copy()).cuda()
-        bufs = []
-        for c in ranks:
-            c.update_local_dev(a.data_ptr(), o.data_ptr(), u.data_ptr(), zz.data_ptr())
-            w_ptr, part_ptr = c.p2p_buffers_dev()
-            bufs.append((torch.as_tensor(_DevArray(w_ptr, N), device="cuda"),
-                         torch.as_tensor(_DevArray(part_ptr, 4 * world), device="cuda")))
-        for r in range(world):          # the two all-gathers, emulated with copies
-            for q in range(world):
-                if q != r:
-                    lo, cnt = plan.slots(q)
-                    bufs[r][0][lo:lo + cnt].copy_(bufs[q][0][lo:lo + cnt])
-                    bufs[r][1][4 * q:4 * q + 4].copy_(bufs[q][1][4 * q:4 * q + 4])
-        torch.cuda.synchronize()
-        for r, c in enumerate(ranks):
-            c.update_finish_dev()
-            pose = c.read_pose()
-            lo, cnt = plan.slots(r)
-            assert np.array_equal(c.resample_indices()[lo:lo + cnt], single.resample_indices()[lo:lo + cnt]), "update %d" % t
-            assert np.array_equal(c.get_weights(), single.get_weights())
-            assert np.array_equal(c.get_particles()[:, lo:lo + cnt], single.get_particles()[:, lo:lo + cnt])
-            assert_pose_close(pose, pose_single)
-    for c in ranks + [single]:
-        c.close()
+        ranks.set_state(prev_p, prev_w)
+        poses = ranks.update(z["actions"][t], z["obs"][t], z["u"][t], z["z"][t])
+        assert np.array_equal(ranks.gather(lambda c: c.resample_indices()), z["idx"][t]), "resample indices differ at update %d" % t
+        assert np.array_equal(ranks.gather(lambda c: c.range_steps().T).T, z["steps"][t])
+        assert_weights_close(ranks.gather(lambda c: c.get_weights()), z["weights"][t])
+        p = ranks.gather(lambda c: c.get_particles())
+        assert np.abs(p - z["particles"][t]).max() < 1e-9
+        for pose in poses:
+            assert_pose_close(pose, z["pose"][t])
+            assert np.array_equal(pose, poses[0])      # every rank computes the same pose bits
+        prev_p, prev_w = z["particles"][t], z["weights"][t]
+    ranks.close()
+
+
+@pytest.mark.parametrize("world,N", [(2, 4000), (2, 40000), (4, 65536)])
+def test_sharded_ranks_free_running_equal_single_filter(world, N):
+    """No teacher forcing, device RNG: the sharded filter must stay BIT-identical to the same filter on
+    one GPU over several updates (noise is keyed by the global slot; sums are sequentially rounded)."""
+    from helpers import EmuRanks
+    g, angles, orc, ns, action, obs = _tracking_case("sibal1", N, 3.0, 11)
+    p0, w0 = orc.get_state()
+    single = _ctx(g, angles, N, seed=4242)
+    single.set_graphs(False)
+    single.set_particles(p0, w0)
+    ranks = EmuRanks(g, angles, N, world, seed=4242)
+    ranks.set_state(p0, w0)
+    for t in range(4):
+        pose_s = single.update(action, obs)
+        poses = ranks.update(action, obs)
+        assert np.array_equal(ranks.gather(lambda c: c.resample_indices()), single.resample_indices()), "update %d" % t
+        assert np.array_equal(ranks.gather(lambda c: c.get_particles()), single.get_particles()), "update %d" % t
+        assert np.array_equal(ranks.gather(lambda c: c.raw_weights()), single.raw_weights())
+        assert np.array_equal(ranks.gather(lambda c: c.get_weights()), single.get_weights()), "update %d" % t
+        assert np.array_equal(ranks.gather(lambda c: c.cdf()), single.cdf())
+        for pose in poses:
+            assert np.abs(pose - pose_s).max() < 1e-9
+    if N // world >= 1024:
+        assert all(c.ray_stage_info()["last_mode"] == 1 for c in ranks.ctxs)   # the directional stage ran on every rank
+    ranks.close()
+    single.close()
+
+
+def test_sharded_ranks_degenerate_weights_match_oracle():
+    """Weight vectors that defeat the step-map summary: one particle holds all the mass (the running
+    sum sits exactly on a power of two, every later chunk is opaque -- far more than the mailbox payload
+    carries, so the ranks read each other's overflow lists), all-equal weights, and a zero-weight rank."""
+    from helpers import EmuRanks
+    from monte_carlo_localization_b200 import maps
+    from oracle import bindings as ob
+    g = maps.load_named_map("sibal1")
+    angles = load_golden("update_sibal1_4000.npz")["angles"]
+    N, world = 16384, 2
+    rng = np.random.default_rng(3)
+    p = np.zeros((3, N))
+    p[0] = -3.3 + rng.normal(0, 0.05, N)
+    p[1] = 1.6 + rng.normal(0, 0.05, N)
+    p[2] = rng.uniform(-3, 3, N)
+    obs = np.full(len(angles), 2.0, dtype=np.float32)
+    cases = {}
+    w = np.zeros(N)
+    w[0] = 1.0
+    cases["one particle holds all the mass"] = w
+    w = np.zeros(N)
+    w[N // 2 + 5] = 0.5
+    w[N // 2 + 6000] = 0.5
+    cases["rank 0 has no mass"] = w
+    cases["uniform"] = np.full(N, 1.0 / N)
+    w = rng.random(N) ** 8 + 1e-300
+    cases["heavy-tailed"] = w / w.sum()
+    ranks = EmuRanks(g, angles, N, world, keep_ranges=False)
+    for name, w in cases.items():
+        ns = ob.NoiseStream(5)
+        u, z = ns.update_noise(N)
+        ranks.set_state(p, w)
+        ranks.update([0.05, 0, 0.01], obs, u, z)
+        idx_ref, cdf_ref = ob.resample_indices(w, u, want_cdf=True)
+        assert np.array_equal(ranks.gather(lambda c: c.cdf()), cdf_ref), name
+        assert np.array_equal(ranks.gather(lambda c: c.resample_indices()), idx_ref), name
+    ranks.close()

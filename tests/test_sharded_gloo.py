@@ -1,19 +1,19 @@
-"""world_size-2 gloo test (CPU) of the particle-sharding host logic: the slot plan and the
-in-place exchange that monte_carlo_localization_b200/sharded.py uses on NCCL.  The per-slice
-compute is done with the oracle here; the protocol (own slots -> exchange -> global finish)
-must reproduce the single-filter oracle update bit for bit."""
+"""world_size-2 gloo test (CPU) of the particle-sharding HOST logic in
+monte_carlo_localization_b200/sharded.py: the slot plan, the bootstrap that carries the NCCL id from
+rank 0 to the others, and the slicing / gathering of whole-filter arrays.  The per-slice compute is
+done with the oracle here; the protocol (own slice of the global multinomial draw -> motion -> weights
+-> global sequential sum) must reproduce the single-filter oracle update bit for bit."""
 import os
 import socket
 
 import numpy as np
 import pytest
-import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from helpers import load_golden
 from monte_carlo_localization_b200 import maps
-from monte_carlo_localization_b200.sharded import ShardPlan, exchange
+from monte_carlo_localization_b200.sharded import ShardPlan, bootstrap_id, gather_host, local_slice
 from oracle import bindings as ob
 
 
@@ -30,36 +30,33 @@ def _worker(rank, world, port, out_dir):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
+        # the id is made on rank 0 only and must arrive unchanged everywhere
+        made = bytes(range(128))
+        got = bootstrap_id(lambda: made, rank)
+        assert got == made
         z = load_golden("update_sibal1_4000.npz")
         g = maps.load_named_map("sibal1")
         N = int(z["N"])
         plan = ShardPlan(N, world)
         lo, cnt = plan.slots(rank)
-        # full state on every rank
-        x, y, th = (torch.from_numpy(z["init_particles"][k].copy()) for k in range(3))
-        w = torch.from_numpy(z["init_weights"].copy())
-        slice_orc = ob.Oracle(g, z["angles"], max_particles=cnt)   # per-slice compute stand-in
+        P, W = z["init_particles"].copy(), z["init_weights"].copy()   # whole filter, for the oracle's global CDF
+        slice_orc = ob.Oracle(g, z["angles"], max_particles=cnt)      # per-slice compute stand-in
         for t in range(len(z["u"])):
             u, zz = z["u"][t], z["z"][t]
-            # --- local: resample own slots from the GLOBAL cdf, motion, weights -------------
-            idx = ob.resample_indices(w.numpy(), u[lo:lo + cnt])
-            prop = np.stack([x.numpy()[idx], y.numpy()[idx], th.numpy()[idx]])
-            prop = slice_orc.motion_model(prop, z["actions"][t], zz[3 * lo:3 * (lo + cnt)])
+            # own slots of the GLOBAL multinomial draw, motion and weights of the own slice
+            idx = ob.resample_indices(W, u[lo:lo + cnt])
+            _, z_loc = local_slice(plan, rank, weights=zz, per_particle=3)
+            prop = slice_orc.motion_model(P[:, idx], z["actions"][t], z_loc)
             w_loc = slice_orc.sensor_weights(prop, z["obs"][t])
-            nx, ny, nth, nw = x.clone(), y.clone(), th.clone(), w.clone()
-            nx[lo:lo + cnt] = torch.from_numpy(prop[0])
-            ny[lo:lo + cnt] = torch.from_numpy(prop[1])
-            nth[lo:lo + cnt] = torch.from_numpy(prop[2])
-            nw[lo:lo + cnt] = torch.from_numpy(w_loc)
-            # --- exchange ---------------------------------------------------------------------
-            exchange([nx, ny, nth, nw], plan, rank)
-            # --- finish: sequential global sum, normalise --------------------------------------
-            s = np.add.accumulate(nw.numpy())[-1]
-            w = nw / s
-            x, y, th = nx, ny, nth
-            assert np.array_equal(np.stack([x.numpy(), y.numpy(), th.numpy()]), z["particles"][t]), "rank %d t %d" % (rank, t)
-            assert np.array_equal(w.numpy(), z["weights"][t]), "rank %d t %d weights" % (rank, t)
-        np.save(os.path.join(out_dir, "w_rank%d.npy" % rank), w.numpy())
+            # whole filter from the slices
+            P, w_raw = gather_host(plan, prop, w_loc)
+            s = np.add.accumulate(w_raw)[-1]       # the reference's sequential sum (:679)
+            W = w_raw / s
+            assert np.array_equal(P, z["particles"][t]), "rank %d t %d" % (rank, t)
+            assert np.array_equal(W, z["weights"][t]), "rank %d t %d weights" % (rank, t)
+            p_loc, w_sl = local_slice(plan, rank, P, W)
+            assert np.array_equal(p_loc, prop) and np.array_equal(w_sl, W[lo:lo + cnt])
+        np.save(os.path.join(out_dir, "w_rank%d.npy" % rank), W)
     finally:
         dist.destroy_process_group()
 
