@@ -334,8 +334,28 @@ def _reflib():
         L.ref_num_ranges.argtypes = [C.c_void_p]
         L.ref_get_timing.argtypes = [C.c_void_p, c_double_p, C.POINTER(C.c_int)]
         L.ref_reset_timing.argtypes = [C.c_void_p]
+        L.ref_clock_fake.argtypes = [C.c_int]
+        L.ref_clock_set_steady.argtypes = [C.c_double]
+        L.ref_clock_set_hr_quantum.argtypes = [C.c_double]
+        L.ref_odom.argtypes = [C.c_void_p] + [C.c_double] * 5
+        L.ref_clicked_pose.argtypes = [C.c_void_p] + [C.c_double] * 3
+        L.ref_timer_update.argtypes = [C.c_void_p]
+        L.ref_current_pose.argtypes = [C.c_void_p, c_double_p]
+        L.ref_set_inferred.argtypes = [C.c_void_p, c_double_p]
+        L.ref_shell_state.argtypes = [C.c_void_p, c_double_p]
+        L.ref_viz_sample.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int)]
         _ref = L
     return _ref
+
+
+def unpack_shell_state(v) -> dict:
+    """Layout shared by ref_shell_state (oracle/ref_harness.cpp) and pfhost_shell_state (host/host_capi.cpp)."""
+    v = np.asarray(v, dtype=np.float64)
+    d = {k: v[3 * i:3 * i + 3].copy() for i, k in enumerate(Reference.SHELL_KEYS)}
+    d.update(iters=int(v[15]), odom_initialized=bool(v[16]), pose_initialized_from_rviz=bool(v[17]),
+             odom_tracking_active=bool(v[18]), window_total_ms=float(v[19]), window_count=int(v[20]),
+             velocity=float(v[21]), angular_velocity=float(v[22]))
+    return d
 
 
 class Reference:
@@ -426,6 +446,52 @@ class Reference:
         out = np.empty(n, dtype=np.float32)
         self._L.ref_get_ranges(self._h, _fp(out))
         return out
+
+    # ---- the node's update shell (timer_update / odomCB / clicked_pose / get_current_pose) ----------
+    SHELL_KEYS = ("inferred", "odom_pose", "odom_reference_pose", "odom_reference_odom", "last_pose")
+
+    @staticmethod
+    def clock_fake(on: bool):
+        _reflib().ref_clock_fake(int(on))
+
+    @staticmethod
+    def clock_set_steady(seconds: float):
+        _reflib().ref_clock_set_steady(float(seconds))
+
+    @staticmethod
+    def clock_set_hr_quantum(ms: float):
+        _reflib().ref_clock_set_hr_quantum(float(ms))
+
+    def odom(self, pose, v: float, w: float):
+        self._L.ref_odom(self._h, float(pose[0]), float(pose[1]), float(pose[2]), float(v), float(w))
+
+    def clicked_pose(self, pose):
+        self._L.ref_clicked_pose(self._h, float(pose[0]), float(pose[1]), float(pose[2]))
+
+    def timer_update(self):
+        self._L.ref_timer_update(self._h)
+
+    def current_pose(self) -> np.ndarray:
+        out = np.empty(3, dtype=np.float64)
+        self._L.ref_current_pose(self._h, _dp(out))
+        return out
+
+    def set_inferred(self, pose):
+        self._L.ref_set_inferred(self._h, _dp(np.asarray(pose, dtype=np.float64)))
+
+    def shell_state(self) -> dict:
+        return unpack_shell_state(self._shell_raw())
+
+    def _shell_raw(self) -> np.ndarray:
+        out = np.empty(23, dtype=np.float64)
+        self._L.ref_shell_state(self._h, _dp(out))
+        return out
+
+    def viz_sample(self, k: int) -> np.ndarray:
+        """visualize()'s weighted sub-sample (:946-958): k draws of discrete_distribution(weights_) from rng_."""
+        out = (C.c_int * k)()
+        self._L.ref_viz_sample(self._h, k, out)
+        return np.asarray(list(out), dtype=np.int32)
 
     def timing(self) -> dict:
         buf = np.zeros(6, dtype=np.float64)

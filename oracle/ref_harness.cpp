@@ -18,6 +18,11 @@ struct ref_pf {
     std::unique_ptr<ParticleFilter> pf;
 };
 
+ref_clock::State& ref_clock::state() {
+    static State s;
+    return s;
+}
+
 extern "C" {
 
 void ref_clear_params() { rclcpp::ShimGlobals::get().overrides.clear(); }
@@ -131,5 +136,62 @@ void ref_get_timing(ref_pf* h, double out[6], int* count) {
     *count = t.measurement_count;
 }
 void ref_reset_timing(ref_pf* h) { h->pf->timing_stats_.reset(); }
+
+// ---- the node's update shell: the reference's own callbacks, with scripted clocks -------------------
+// (timer_update keeps its timer in function-local statics, :735-746: one timeline per process.  Scripted
+// steady time must therefore only move forward, in steps of at most 1 s -- a larger step makes the
+// reference return before it stores the new time (:750-752), and every later tick would do the same.)
+void ref_clock_fake(int on) { ref_clock::state().fake = on != 0; }
+void ref_clock_set_steady(double seconds) { ref_clock::state().steady_ns = static_cast<long long>(seconds * 1e9 + 0.5); }
+void ref_clock_set_hr_quantum(double ms) { ref_clock::state().hr_quantum_ns = static_cast<long long>(ms * 1e6 + 0.5); }
+
+void ref_odom(ref_pf* h, double x, double y, double yaw, double v, double w) {
+    auto msg = std::make_shared<nav_msgs::msg::Odometry>();
+    msg->pose.pose.position.x = x;
+    msg->pose.pose.position.y = y;
+    msg->pose.pose.orientation = particle_filter_cpp::utils::geometry::yaw_to_quaternion(yaw);
+    msg->twist.twist.linear.x = v;
+    msg->twist.twist.angular.z = w;
+    msg->header.stamp.sec = 1;
+    h->pf->odomCB(msg);
+}
+void ref_clicked_pose(ref_pf* h, double x, double y, double yaw) {
+    auto msg = std::make_shared<geometry_msgs::msg::PoseWithCovarianceStamped>();
+    msg->pose.pose.position.x = x;
+    msg->pose.pose.position.y = y;
+    msg->pose.pose.orientation = particle_filter_cpp::utils::geometry::yaw_to_quaternion(yaw);
+    h->pf->clicked_pose(msg);
+}
+void ref_timer_update(ref_pf* h) { h->pf->timer_update(); }
+void ref_current_pose(ref_pf* h, double out[3]) {
+    const Eigen::Vector3d p = h->pf->get_current_pose();
+    for (int k = 0; k < 3; ++k) out[k] = p[k];
+}
+void ref_set_inferred(ref_pf* h, const double pose[3]) { h->pf->inferred_pose_ = Eigen::Vector3d(pose[0], pose[1], pose[2]); }
+// same layout as pfhost_shell_state (monte_carlo_localization_b200/host/host_capi.cpp)
+void ref_shell_state(ref_pf* h, double out[23]) {
+    const auto& p = *h->pf;
+    for (int k = 0; k < 3; ++k) {
+        out[k] = p.inferred_pose_[k];
+        out[3 + k] = p.odom_pose_[k];
+        out[6 + k] = p.odom_reference_pose_[k];
+        out[9 + k] = p.odom_reference_odom_[k];
+        out[12 + k] = p.last_pose_[k];
+    }
+    out[15] = p.iters_;
+    out[16] = p.odom_initialized_;
+    out[17] = p.pose_initialized_from_rviz_;
+    out[18] = p.odom_tracking_active_;
+    out[19] = p.timing_stats_.total_mcl_time;
+    out[20] = p.timing_stats_.measurement_count;
+    out[21] = p.current_velocity_;
+    out[22] = p.current_angular_vel_;
+}
+// visualize()'s weighted sub-sample (:946-958) with the reference's own generator: k draws of
+// discrete_distribution(weights_) -> indices
+void ref_viz_sample(ref_pf* h, int k, int* idx_out) {
+    std::discrete_distribution<int> dist(h->pf->weights_.begin(), h->pf->weights_.end());
+    for (int i = 0; i < k; ++i) idx_out[i] = dist(h->pf->rng_);
+}
 
 }  // extern "C"

@@ -681,3 +681,38 @@ def test_sharded_ranks_degenerate_weights_match_oracle():
         assert np.array_equal(ranks.gather(lambda c: c.cdf()), cdf_ref), name
         assert np.array_equal(ranks.gather(lambda c: c.resample_indices()), idx_ref), name
     ranks.close()
+
+
+def test_viz_weighted_subsample_matches_reference_draws():
+    """visualize()'s weighted sub-sample (:946-958): k draws of discrete_distribution(weights_).  With the
+    reference generator's canonical uniforms injected, mcl_sample_particles_u returns the same particle indices
+    as the reference's own sampling (oracle/_ref) and as lower_bound on the oracle's CDF; without injection
+    the device RNG draws particles in proportion to their weights."""
+    from monte_carlo_localization_b200 import maps
+    from oracle import bindings as ob
+    g = maps.load_named_map("sibal1")
+    angles = load_golden("update_sibal1_4000.npz")["angles"]
+    for N, k in ((4000, 60), (100000, 200)):
+        rng = np.random.default_rng(N)
+        w = rng.random(N) ** 5 + 1e-9
+        w /= w.sum()
+        p = np.stack([rng.uniform(-4, -2, N), rng.uniform(1, 2, N), rng.uniform(-3, 3, N)])
+        c = _ctx(g, angles, N)
+        c.set_particles(p, w)
+        u = ob.NoiseStream(31 + N).canonical(k)
+        got, idx = c.sample_particles(k, u=u, return_indices=True)
+        idx_ref = ob.resample_indices(w, u)
+        assert np.array_equal(idx, idx_ref)
+        assert np.array_equal(got, p[:, idx_ref])
+        if ob.have_reference():
+            ref = ob.Reference(g, 31 + N, max_particles=N, num_threads=2)
+            ref.set_state(p, w)
+            ref.seed(31 + N)
+            assert np.array_equal(idx, ref.viz_sample(k)), "indices differ from the reference's own visualize() sampling"
+        # device RNG: heavy particles dominate the draws
+        _, idx_dev = c.sample_particles(4000, return_indices=True)
+        heavy = w > np.quantile(w, 0.9)
+        assert abs(heavy[idx_dev].mean() - w[heavy].sum()) < 0.05
+        # sampling leaves the filter usable: the next update draws from the same CDF
+        assert np.array_equal(c.get_weights(), w)
+        c.close()

@@ -139,3 +139,7 @@ def test_cpp_particle_filter_replay_tracks(tmp_path):
                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
     assert res.returncode == 0, res.stdout
     assert "MAX_RANGE_PX 239" in res.stdout and "iter  15" in res.stdout
+    # the estimate must TRACK the ground truth, not merely exist: every tick's position error, as printed
+    import re
+    errs = [float(m) for m in re.findall(r"err ([0-9.]+) m", res.stdout)]
+    assert len(errs) == 15 and max(errs[3:]) < 0.3, errs

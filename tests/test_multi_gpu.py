@@ -47,17 +47,30 @@ def test_sharded_filter_equals_single_gpu_bit_for_bit(exchange):
     assert r["degenerate_particles_bit_identical"] and r["degenerate_weights_bit_identical"], r
 
 
-def test_cpp_sharded_host_binary():
+def test_cpp_sharded_host_binary(tmp_path):
     """host/mcl_sharded: the C++ caller of mcl_create_sharded (one process per GPU, forked by the binary
-    itself, the NCCL id handed over through a pipe) tracks the ground truth and its ranks agree."""
+    itself, the NCCL id handed over through pipes) tracks the ground truth and its ranks agree bit for bit."""
+    import numpy as np
+    from PIL import Image
+
+    from monte_carlo_localization_b200 import maps
     if _device_count() < 2:
         pytest.skip("needs 2 GPUs")
+    g = maps.load_named_map("sibal1")
+    img = np.where(g.data[::-1] == 100, 0, np.where(g.data[::-1] == 0, 254, 205)).astype(np.uint8)
+    Image.fromarray(img, "L").save(str(tmp_path / "sibal1.png"))
+    y = str(tmp_path / "sibal1.yaml")
+    with open(y, "w") as f:
+        f.write("image: sibal1.png\nresolution: %r\norigin: [%r, %r, %r]\nnegate: 0\noccupied_thresh: 0.65\nfree_thresh: 0.1\n"
+                % ((float(g.resolution),) + tuple(g.origin)))
     exe = os.path.join(ROOT, "monte_carlo_localization_b200", "host", "mcl_sharded")
     if not os.path.exists(exe):
         subprocess.check_call(["make", "-s", "-C", os.path.dirname(exe)])
-    res = subprocess.run([exe, "--world", "2", "--particles", "262144", "--steps", "20"], stdout=subprocess.PIPE,
-                         stderr=subprocess.STDOUT, text=True, timeout=300, cwd=ROOT)
-    assert res.returncode == 0, res.stdout[-3000:]
-    lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
-    r = json.loads(lines[-1])
-    assert r["ranks_agree"] and r["pose_error_m"] < 0.3, r
+    for extra in ([], ["--nccl-barrier"]):
+        res = subprocess.run([exe, y, "--world", "2", "--particles", "65536", "--steps", "20", "--x", "-3.3", "--y", "1.6",
+                              "--theta", "0.3"] + extra, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                             timeout=300, cwd=ROOT)
+        lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+        assert res.returncode == 0 and lines, res.stdout[-3000:]
+        r = json.loads(lines[-1])
+        assert r["ranks_agree"] and r["failed_ranks"] == 0 and r["pose_error_m"] < 0.3, r

@@ -139,3 +139,23 @@ def test_noise_stream_is_deterministic_and_stateful():
     assert np.array_equal(x, y)
     u = a.canonical(1000)
     assert (u >= 0).all() and (u < 1).all()
+
+
+def test_oracle_resampling_equals_reference_viz_sampling():
+    """visualize()'s weighted sub-sample (:946-958) draws discrete_distribution(weights_) from rng_: the oracle's
+    lower_bound over its CDF with the twin generator's canonical uniforms picks the same particles."""
+    if not ob.have_reference():
+        pytest.skip("oracle/_ref absent")
+    from monte_carlo_localization_b200 import maps
+    g = maps.load_named_map("sibal1")
+    N, k = 3000, 60
+    rng = np.random.default_rng(2)
+    w = rng.random(N) ** 4 + 1e-12
+    w /= w.sum()
+    p = rng.normal(size=(3, N))
+    ref = ob.Reference(g, 77, max_particles=N, num_threads=2)
+    ref.set_state(p, w)
+    ref.seed(77)
+    idx_ref = ref.viz_sample(k)
+    u = ob.NoiseStream(77).canonical(k)
+    assert np.array_equal(ob.resample_indices(w, u), idx_ref)
