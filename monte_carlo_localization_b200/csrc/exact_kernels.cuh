@@ -234,8 +234,12 @@ struct TileScan {
     RFn all;
 };
 
+// (tile records, opaque-chunk records and partial sums are written by OTHER CTAs -- in the fused kernel several
+// times per launch -- so the last CTA reads them past its L1: __ldcg)
 __device__ __forceinline__ RFn tile_rfn(const int64_t* tile_elem, int t) {
-    return RFn{StepFn{tile_elem[3 * t], tile_elem[3 * t + 1]}, tile_elem[3 * t + 2]};
+    return RFn{StepFn{static_cast<int64_t>(__ldcg(reinterpret_cast<const long long*>(tile_elem + 3 * t))),
+                      static_cast<int64_t>(__ldcg(reinterpret_cast<const long long*>(tile_elem + 3 * t + 1)))},
+               static_cast<int64_t>(__ldcg(reinterpret_cast<const long long*>(tile_elem + 3 * t + 2)))};
 }
 
 // every thread folds its range of tiles; block scans give the state entering the range
@@ -252,7 +256,7 @@ __device__ __forceinline__ TileScan scan_tiles(const ExactArgs& a, int f, Finish
     int cnt = 0;
     for (int t = r.t0; t < r.t1; ++t) {
         loc = RFnOp()(loc, tile_rfn(tile_elem, t));
-        cnt += tile_opq[t];
+        cnt += __ldcg(tile_opq + t);
     }
     const RFn inc = block_scan_inclusive<kTileChunks>(loc, RFnOp(), S.smr, ident);
     S.inc[tid] = inc;
@@ -293,15 +297,18 @@ __device__ __forceinline__ void finish_local(const ExactArgs& a, int f, FinishSh
         int local = e - (th ? S.cinc[th - 1] : 0);
         RFn run = th ? S.inc[th - 1] : RFn{fn_identity(), 0};   // state entering the range's first tile
         int t = th * tpt;
-        while (local >= tile_opq[t]) {
-            local -= tile_opq[t];
+        for (;;) {
+            const int n_t = __ldcg(tile_opq + t);
+            if (local < n_t) break;
+            local -= n_t;
             run = RFnOp()(run, tile_rfn(tile_elem, t));
             ++t;
         }
         const int64_t slot = fc + static_cast<int64_t>(t) * kTileChunks + local;
-        const StepFn pre = a.opq_pre[slot];
+        const StepFn pre{static_cast<int64_t>(__ldcg(reinterpret_cast<const long long*>(&a.opq_pre[slot].a0))),
+                         static_cast<int64_t>(__ldcg(reinterpret_cast<const long long*>(&a.opq_pre[slot].a1)))};
         const StepFn fn = local == 0 ? fn_compose(run.f, pre) : pre;   // the tile's first opaque chunk continues the run that entered the tile
-        const int chunk = t * kTileChunks + a.opq_idx[slot];
+        const int chunk = t * kTileChunks + __ldcg(a.opq_idx + slot);
         a.list_chunk[fc + e] = chunk;
         a.list_fn[lc + e] = fn;
         unsigned long long* pw = e < kOpqCap ? S.pay + kHdrWords + e * kItemWords : nullptr;
@@ -312,7 +319,7 @@ __device__ __forceinline__ void finish_local(const ExactArgs& a, int f, FinishSh
         }
         double add[kChunk];
 #pragma unroll
-        for (int q = 0; q < kChunk; ++q) add[q] = a.opq_add[slot * kChunk + q];
+        for (int q = 0; q < kChunk; ++q) add[q] = __ldcg(a.opq_add + slot * kChunk + q);
 #pragma unroll
         for (int q = 0; q < kChunk; ++q) {
             a.list_add[(lc + e) * kChunk + q] = add[q];
@@ -428,7 +435,7 @@ __device__ __forceinline__ void finish_global(const ExactArgs& a, int f, FinishS
         int rank = ts.cexc;
         for (int t = ts.t0; t < ts.t1; ++t) {
             a.tile_start[static_cast<int64_t>(f) * a.T + t] = fn_apply(run.f, run.reset ? a.anchors[fc + rank - 1] : vin);
-            rank += tile_opq[t];
+            rank += __ldcg(tile_opq + t);
             run = RFnOp()(run, tile_rfn(tile_elem, t));
         }
         if (tid == 0) a.total[f] = S.vcur;
@@ -469,33 +476,34 @@ __device__ __forceinline__ void fold_pose_partials(const ExactArgs& a, int f, Fi
     __syncthreads();
 }
 
+// One tile of an exact pass: the 8-addend chunk step maps of tile t, their block scan, the tile's summary
+// (tile_elem) and its opaque chunks compacted; optionally the normalised weights stored and the tile's
+// expected-pose partial sums.  All threads of the CTA call; ends with the CTA's global writes issued.
 template <bool POSE>
-__global__ void __launch_bounds__(kTileChunks) k_exact_pass(ExactArgs a) {
-    __shared__ FinishShared S;
-    __shared__ int wcnt[kTileChunks / 32];
-    __shared__ bool is_last;
-    const int f = blockIdx.y, t = blockIdx.x, tid = threadIdx.x;
-    const long long c_begin = clock64();
+__device__ __forceinline__ void tile_phase(const ExactArgs& a, FinishShared& S, int* wcnt, int f, int t) {
+    const int tid = threadIdx.x;
     const double* src = a.src + static_cast<int64_t>(f) * a.N;
-    const double nrm = a.norm ? a.norm[f] : 0.0;
+    // (sums and tile sums may have been written by another CTA earlier in the SAME launch -- the fused kernel --
+    // so they are read past this SM's L1)
+    const double nrm = a.norm ? __ldcg(a.norm + f) : 0.0;
     const bool use_norm = a.norm != nullptr && nrm > 0.0;
     const bool use_div = a.div != nullptr;
-    const double div = use_div ? a.div[f] : 1.0;
+    const double div = use_div ? __ldcg(a.div + f) : 1.0;
 
     // approximate running sum before this tile: the lower ranks' slices + this rank's earlier tiles
     double pre = 0.0;
-    for (int tt = tid; tt < t; tt += kTileChunks) pre += a.tile_sum[static_cast<int64_t>(f) * a.T + tt];
-    if (a.sh.world > 1 && tid < a.sh.rank) pre += a.slice_sum[tid];
+    for (int tt = tid; tt < t; tt += kTileChunks) pre += __ldcg(a.tile_sum + static_cast<int64_t>(f) * a.T + tt);
+    if (a.sh.world > 1 && tid < a.sh.rank) pre += __ldcg(a.slice_sum + tid);
     pre = block_sum<kTileChunks>(pre, S.sd);
     if (a.pre_norm) {
-        const double pn = a.pre_norm[f];
+        const double pn = __ldcg(a.pre_norm + f);
         if (pn > 0.0) pre = pre / pn;   // `if (sum_weights > 0)`: otherwise the weights were left as they were
     }
     if (use_div) pre = pre / div;
 
     const int64_t base = (static_cast<int64_t>(t) * kTileChunks + tid) * kChunk;
     double v[kChunk];
-    load_raw_chunk(v, src, base, a.N);
+    load_raw_chunk(v, src, base, a.N);   // (read-only for the whole launch: the non-coherent path is fine)
     if (use_norm) {
 #pragma unroll
         for (int i = 0; i < kChunk; ++i) v[i] = __ddiv_rn(v[i], nrm);
@@ -599,16 +607,14 @@ __global__ void __launch_bounds__(kTileChunks) k_exact_pass(ExactArgs a) {
         te[2] = inc.reset;
         a.tile_opq[static_cast<int64_t>(f) * a.T + t] = nopq;
     }
-    // ---- the last CTA of the filter finishes the pass ----
-    __threadfence();
-    __syncthreads();
-    if (a.dbg && tid == 0) atomicMax(a.dbg + 0, static_cast<unsigned long long>(clock64() - c_begin));   // slowest CTA's tile phase
-    if (tid == 0) is_last = atomicAdd(a.done + f, 1u) == gridDim.x - 1u;
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
+}
+
+// The last CTA of a pass: order the opaque chunks, exchange with the other ranks, evaluate, tile starts.
+// Returns false when the pass continues in another kernel (host-ordered exchange) or a peer went missing.
+template <bool POSE>
+__device__ __forceinline__ bool pass_finish(const ExactArgs& a, FinishShared& S, int f, long long c_begin) {
+    const int tid = threadIdx.x;
     const long long c0 = clock64();
-    if (tid == 0) a.done[f] = 0;
     if (POSE) fold_pose_partials(a, f, S);
     const bool sharded = a.sh.world > 1;
     const unsigned long long epoch = sharded ? *a.sh.xseq + 1ull : 0ull;
@@ -620,8 +626,8 @@ __global__ void __launch_bounds__(kTileChunks) k_exact_pass(ExactArgs a) {
     if (sharded) {
         const int nw = kHdrWords + min(static_cast<int>(S.pay[0]), kOpqCap) * kItemWords;
         shard_publish(a.sh, epoch, S.pay, nw);
-        if (!a.sh.fused) return;
-        if (!shard_wait(a.sh, epoch)) return;
+        if (!a.sh.fused) return false;
+        if (!shard_wait(a.sh, epoch)) return false;
     }
     const long long c4 = clock64();
     finish_global(a, f, S, ts, epoch, POSE, true);
@@ -635,6 +641,27 @@ __global__ void __launch_bounds__(kTileChunks) k_exact_pass(ExactArgs a) {
         a.dbg[6] = static_cast<unsigned long long>(c5 - c4);        // serial evaluation + tile starts
         a.dbg[7] = S.pay[0];                                        // opaque chunks of this rank
     }
+    return true;
+}
+
+template <bool POSE>
+__global__ void __launch_bounds__(kTileChunks) k_exact_pass(ExactArgs a) {
+    __shared__ FinishShared S;
+    __shared__ int wcnt[kTileChunks / 32];
+    __shared__ bool is_last;
+    const int f = blockIdx.y, t = blockIdx.x, tid = threadIdx.x;
+    const long long c_begin = clock64();
+    tile_phase<POSE>(a, S, wcnt, f, t);
+    // ---- the last CTA of the filter finishes the pass ----
+    __threadfence();
+    __syncthreads();
+    if (a.dbg && tid == 0) atomicMax(a.dbg + 0, static_cast<unsigned long long>(clock64() - c_begin));   // slowest CTA's tile phase
+    if (tid == 0) is_last = atomicAdd(a.done + f, 1u) == gridDim.x - 1u;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (tid == 0) a.done[f] = 0;
+    pass_finish<POSE>(a, S, f, c_begin);
 }
 
 // host-ordered ranks: the consume half of an exact pass (one CTA)
@@ -651,18 +678,20 @@ __global__ void __launch_bounds__(kTileChunks) k_exact_finish(ExactArgs a) {
     finish_global(a, 0, S, ts, epoch, POSE, false);
 }
 
-__global__ void __launch_bounds__(kTileChunks) k_exact_emit(ExactArgs a) {
-    __shared__ ScanElem sms[kTileChunks / 32];
-    __shared__ ScanElem sm_inc[kTileChunks];
-    const int f = blockIdx.y, t = blockIdx.x, tid = threadIdx.x;
+// prefix sums of one tile from its exact start value: a scan of the chunks' step maps and anchors gives every
+// chunk's exact input, then 8 sequential adds per thread
+__device__ __forceinline__ void emit_tile(const ExactArgs& a, ScanElem* sms, ScanElem* sm_inc, int f, int t) {
+    const int tid = threadIdx.x;
     const double* src = a.src + static_cast<int64_t>(f) * a.N;
+    const double nrm = a.norm ? __ldcg(a.norm + f) : 0.0;
+    const bool use_norm = a.norm != nullptr && nrm > 0.0;
     const bool use_div = a.div != nullptr;
-    const double div = use_div ? a.div[f] : 1.0;
+    const double div = use_div ? __ldcg(a.div + f) : 1.0;
     const int64_t cidx = static_cast<int64_t>(f) * a.C + static_cast<int64_t>(t) * kTileChunks + tid;
-    const double tstart = a.tile_start[static_cast<int64_t>(f) * a.T + t];
+    const double tstart = __ldcg(a.tile_start + static_cast<int64_t>(f) * a.T + t);
 
     const StepFn cf = a.chunk_fn[cidx];
-    ScanElem el = fn_is_opaque(cf) ? se_abs(a.anchor_val[cidx]) : se_fn(cf);
+    ScanElem el = fn_is_opaque(cf) ? se_abs(__ldcg(a.anchor_val + cidx)) : se_fn(cf);
     if (tid == 0) el = se_combine(se_abs(tstart), el);
     const ScanElem ident = se_fn(fn_identity());
     const ScanElem inc = block_scan_inclusive<kTileChunks>(el, SEOp(), sms, ident);
@@ -673,7 +702,15 @@ __global__ void __launch_bounds__(kTileChunks) k_exact_emit(ExactArgs a) {
     const int64_t base = (static_cast<int64_t>(t) * kTileChunks + tid) * kChunk;
     if (base >= a.N) return;
     double v[kChunk];
-    load_chunk(v, src, base, a.N, use_div, div);
+    load_raw_chunk(v, src, base, a.N);
+    if (use_norm) {
+#pragma unroll
+        for (int i = 0; i < kChunk; ++i) v[i] = __ddiv_rn(v[i], nrm);
+    }
+    if (use_div) {
+#pragma unroll
+        for (int i = 0; i < kChunk; ++i) v[i] = __ddiv_rn(v[i], div);
+    }
     double* out = a.out + static_cast<int64_t>(f) * a.N;
 #pragma unroll
     for (int i = 0; i < kChunk; ++i) {
@@ -691,6 +728,12 @@ __global__ void __launch_bounds__(kTileChunks) k_exact_emit(ExactArgs a) {
         for (int i = 0; i < kChunk; ++i)
             if (base + i < a.N) out[base + i] = v[i];
     }
+}
+
+__global__ void __launch_bounds__(kTileChunks) k_exact_emit(ExactArgs a) {
+    __shared__ ScanElem sms[kTileChunks / 32];
+    __shared__ ScanElem sm_inc[kTileChunks];
+    emit_tile(a, sms, sm_inc, blockIdx.y, blockIdx.x);
 }
 
 // T == 1 (a filter of at most kTile = 4096 particles is ONE tile): chunks, walk and emit of the

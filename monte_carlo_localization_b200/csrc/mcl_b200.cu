@@ -123,7 +123,8 @@ struct mcl_ctx {
     int cur = 0;
     double* d_wraw = nullptr;
     double* d_wn = nullptr;
-    double* d_cdf = nullptr;
+    double* d_cdf2[2] = {nullptr, nullptr};   // discrete_distribution's _M_cp for the update that resamples FROM state buffer b
+    int cdf_last = 0;                         // which of them the last update drew from
     int32_t* d_idx = nullptr;
     uint8_t* d_steps = nullptr;
     bool keep_ranges = false;
@@ -148,13 +149,14 @@ struct mcl_ctx {
     double* d_anchors = nullptr;
     double* d_anchor_val = nullptr;
     double* d_tile_start = nullptr;
-    double* d_coarse = nullptr;      // [F][coarse_n] coarse level of the CDF search (exact values at segment ends)
+    double* d_coarse2[2] = {nullptr, nullptr};   // [F][coarse_n] coarse level of the CDF search (exact values at segment ends), per CDF
     int coarse_n = 0, coarse_shift = 0;
     double* d_S1 = nullptr;
     double* d_S2 = nullptr;
     double* d_scratch_total = nullptr;
     double* d_slice_sum = nullptr;   // [kMaxWorld] approximate slice sums of all ranks
-    double* d_rank_end = nullptr;    // [kMaxWorld] exact CDF value at the end of every rank's slice
+    double* d_rank_end2[2] = {nullptr, nullptr};   // [kMaxWorld] exact CDF value at the end of every rank's slice, per CDF
+
     // pose
     int norm_blocks = 1;
     double* d_partial = nullptr;
@@ -353,7 +355,7 @@ enum PassKind { kPassRaw, kPassNormalise, kPassStored, kPassCdf };
 //   kPassNormalise  w_norm = w_raw / S1 stored, pose, S2 = sum w_norm  (:680-686, :696-716, random.tcc:2666)
 //   kPassStored     S2 = sum w_norm of weights set from outside
 //   kPassCdf        running sums of w_norm / S2 at the tile starts     (random.tcc:2672)
-int launch_pass(mcl_ctx* c, PassKind kind, int pose_buf) {
+int launch_pass(mcl_ctx* c, PassKind kind, int pose_buf, int cdf_idx) {
     ExactArgs a = exact_base(c);
     bool pose = false;
     switch (kind) {
@@ -384,7 +386,7 @@ int launch_pass(mcl_ctx* c, PassKind kind, int pose_buf) {
             a.div = c->d_S2;
             a.pre_norm = c->tile_state == 2 ? c->d_S1 : nullptr;
             a.total = c->d_scratch_total;
-            a.rank_end = sharded(c) ? c->d_rank_end : nullptr;
+            a.rank_end = sharded(c) ? c->d_rank_end2[cdf_idx] : nullptr;
             break;
     }
     a.dbg = (c->d_dbg && c->dbg_pass == static_cast<int>(kind)) ? c->d_dbg : nullptr;
@@ -409,13 +411,13 @@ int launch_pass(mcl_ctx* c, PassKind kind, int pose_buf) {
     return MCL_OK;
 }
 
-int launch_emit(mcl_ctx* c) {
+int launch_emit(mcl_ctx* c, int cdf_idx) {
     ExactArgs a = exact_base(c);
     a.src = c->d_wn;
     a.div = c->d_S2;
-    a.out = c->d_cdf;
+    a.out = c->d_cdf2[cdf_idx];
     a.force_last_one = c->rank == c->world - 1 ? 1 : 0;   // _M_cp.back() = 1.0 is the LAST particle of the whole filter
-    a.coarse = c->coarse_n > 0 ? c->d_coarse : nullptr;
+    a.coarse = c->coarse_n > 0 ? c->d_coarse2[cdf_idx] : nullptr;
     a.coarse_m = a.coarse ? (1 << c->coarse_shift) / kChunk : 0;
     a.coarse_n = c->coarse_n;
     k_exact_emit<<<dim3(c->T, c->F), kTileChunks, 0, c->stream>>>(a);
@@ -425,14 +427,14 @@ int launch_emit(mcl_ctx* c) {
 }
 
 // one-tile filters: a whole pass in one CTA per filter
-int launch_single(mcl_ctx* c, const double* src, const double* div, double* total, double* out, int force_one) {
+int launch_single(mcl_ctx* c, const double* src, const double* div, double* total, double* out, int force_one, int cdf_idx) {
     ExactArgs a = exact_base(c);
     a.src = src;
     a.div = div;
     a.total = total;
     a.out = out;
     a.force_last_one = force_one;
-    a.coarse = (out && c->coarse_n > 0) ? c->d_coarse : nullptr;
+    a.coarse = (out && c->coarse_n > 0) ? c->d_coarse2[cdf_idx] : nullptr;
     a.coarse_m = a.coarse ? (1 << c->coarse_shift) / kChunk : 0;
     a.coarse_n = c->coarse_n;
     k_exact_single<<<dim3(1, c->F), kTileChunks, 0, c->stream>>>(a);
@@ -646,30 +648,30 @@ int launch_pose(mcl_ctx* c, const double* w, const double* total, double* wn_out
 // the emit run; after weights were set from outside, tile sums and S2 are rebuilt first.
 int ensure_cdf(mcl_ctx* c) {
     if (c->cdf_valid) return MCL_OK;
+    const int ci = c->cur;   // the CDF the next update (which resamples from state buffer `cur`) draws from
     int rc;
     if (single_tile(c)) {
         if (c->tile_state == 0) {
-            rc = launch_single(c, c->d_wn, nullptr, c->d_S2, nullptr, 0);
+            rc = launch_single(c, c->d_wn, nullptr, c->d_S2, nullptr, 0, ci);
             if (rc) return rc;
             c->tile_state = 1;
         }
-        rc = launch_single(c, c->d_wn, c->d_S2, c->d_scratch_total, c->d_cdf, 1);
+        rc = launch_single(c, c->d_wn, c->d_S2, c->d_scratch_total, c->d_cdf2[ci], 1, ci);
         if (rc) return rc;
     } else {
         if (c->tile_state == 0) {
             rc = launch_tile_sums(c, c->d_wn);
             if (rc) return rc;
-            rc = launch_pass(c, kPassStored, c->cur);
+            rc = launch_pass(c, kPassStored, c->cur, ci);
             if (rc) return rc;
             c->tile_state = 1;
         }
-        rc = launch_pass(c, kPassCdf, c->cur);
+        rc = launch_pass(c, kPassCdf, c->cur, ci);
         if (rc) return rc;
-        rc = launch_emit(c);
+        rc = launch_emit(c, ci);
         if (rc) return rc;
     }
     c->cdf_valid = true;
-    c->cdf_any = true;
     return MCL_OK;
 }
 
@@ -715,11 +717,11 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
         RouteArgs ra{};
         ra.NG = c->NG;
         ra.N = c->N;
-        ra.cdf = c->d_cdf;
-        ra.coarse = c->coarse_n > 0 ? c->d_coarse : nullptr;
+        ra.cdf = c->d_cdf2[src];
+        ra.coarse = c->coarse_n > 0 ? c->d_coarse2[src] : nullptr;
         ra.nc = c->coarse_n;
         ra.cshift = c->coarse_shift;
-        ra.rank_end = c->d_rank_end;
+        ra.rank_end = c->d_rank_end2[src];
         ra.spose4 = packed ? c->d_pose4[src] : nullptr;
         ra.sx = c->d_px[src];
         ra.sy = c->d_py[src];
@@ -750,7 +752,7 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
     ma.B = c->dir_B;
     ma.N = c->N;
     ma.glo = c->glo;
-    ma.cdf = c->d_cdf;
+    ma.cdf = c->d_cdf2[src];
     ma.sx = c->d_px[src];
     ma.sy = c->d_py[src];
     ma.st = c->d_pt[src];
@@ -763,7 +765,7 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
     ma.spose4 = packed ? c->d_pose4[src] : nullptr;
     ma.dpose4 = c->d_pose4[dst];
     ma.routed = sharded(c) ? c->d_routed : nullptr;
-    ma.coarse = c->coarse_n > 0 ? c->d_coarse : nullptr;
+    ma.coarse = c->coarse_n > 0 ? c->d_coarse2[src] : nullptr;
     ma.nc = c->coarse_n;
     ma.cshift = c->coarse_shift;
     ma.action = action_dev;
@@ -938,8 +940,9 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
 
     // sum_weights = accumulate(weights_); w /= sum (:679-686); particles_ = proposal (:689);
     // expected_pose (:696-716)
+    bool next_cdf_built = false;
     if (single_tile(c)) {
-        rc = launch_single(c, c->d_wraw, nullptr, c->d_S1, nullptr, 0);
+        rc = launch_single(c, c->d_wraw, nullptr, c->d_S1, nullptr, 0, dst);
         if (rc) return rc;
         rc = launch_pose(c, c->d_wraw, c->d_S1, c->d_wn, dst, true);
         if (rc) return rc;
@@ -947,9 +950,9 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
     } else {
         rc = launch_tile_sums(c, c->d_wraw);
         if (rc) return rc;
-        rc = launch_pass(c, kPassRaw, dst);
+        rc = launch_pass(c, kPassRaw, dst, dst);
         if (rc) return rc;
-        rc = launch_pass(c, kPassNormalise, dst);
+        rc = launch_pass(c, kPassNormalise, dst, dst);
         if (rc) return rc;
         c->tile_state = 2;   // d_tile_sum = tile sums of w_raw; w_norm = w_raw / S1; S2 = sum w_norm
     }
@@ -958,7 +961,9 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
         c->ev_valid = true;
     }
     CK(cudaGetLastError());
-    c->cdf_valid = false;
+    c->cdf_last = src;
+    c->cdf_any = true;
+    c->cdf_valid = next_cdf_built;
     c->cur = dst;
     c->update_no++;
     return MCL_OK;
@@ -992,9 +997,10 @@ void read_stage_times(mcl_ctx* c) {
 int update_steady(mcl_ctx* c, const double* action_dev, const float* obs_dev) {
     cudaStream_t s = c->stream;
     // (a captured graph reads the packed copy of the state: an update whose packed source is stale runs directly)
-    const bool steady = single_tile(c) ? true : c->tile_state == 2;
+    // steady state: what the captured update finds is what it leaves behind (weights from the last update, no CDF yet)
+    const bool steady = (single_tile(c) || c->tile_state == 2) && !c->cdf_valid;
     const bool graph_ok = c->graphs_enabled && !c->profiling && !c->keep_ranges && (!sharded(c) || (c->xmode == 1 && c->connected)) &&
-                          steady && !c->cdf_valid && c->pose4_ok[c->cur] && c->update_no > 0;
+                          steady && c->pose4_ok[c->cur];
     if (!graph_ok) return update_device(c, action_dev, obs_dev, nullptr, nullptr);
     if (action_dev != c->d_action)
         CK(cudaMemcpyAsync(c->d_action, action_dev, sizeof(double) * 3 * c->F, cudaMemcpyDeviceToDevice, s));
@@ -1002,7 +1008,9 @@ int update_steady(mcl_ctx* c, const double* action_dev, const float* obs_dev) {
         CK(cudaMemcpyAsync(c->d_obs, obs_dev, sizeof(float) * c->R * c->F, cudaMemcpyDeviceToDevice, s));
     if (c->gexec[c->cur]) {
         CK(cudaGraphLaunch(c->gexec[c->cur], s));
-        c->cur ^= 1;             // what update_device does on the host side
+        c->cdf_last = c->cur;    // what update_device does on the host side
+        c->cdf_any = true;
+        c->cur ^= 1;
         c->update_no++;
         c->launches += c->graph_launches;
         return MCL_OK;
@@ -1014,8 +1022,8 @@ int update_steady(mcl_ctx* c, const double* action_dev, const float* obs_dev) {
     }
     const int parity = c->cur;
     const int64_t before = c->launches;
-    const int tile_state0 = c->tile_state;
-    const bool p4[2] = {c->pose4_ok[0], c->pose4_ok[1]};
+    const int tile_state0 = c->tile_state, cdf_last0 = c->cdf_last;
+    const bool p4[2] = {c->pose4_ok[0], c->pose4_ok[1]}, cdf_valid0 = c->cdf_valid, cdf_any0 = c->cdf_any;
     int rc = update_device(c, c->d_action, c->d_obs, nullptr, nullptr);
     cudaGraph_t g = nullptr;
     const cudaError_t e = cudaStreamEndCapture(s, &g);
@@ -1035,7 +1043,9 @@ int update_steady(mcl_ctx* c, const double* action_dev, const float* obs_dev) {
     c->tile_state = tile_state0;
     c->pose4_ok[0] = p4[0];
     c->pose4_ok[1] = p4[1];
-    c->cdf_valid = false;
+    c->cdf_valid = cdf_valid0;
+    c->cdf_any = cdf_any0;
+    c->cdf_last = cdf_last0;
     if (rc == MCL_OK) {
         c->cur ^= 1;
         c->update_no--;
@@ -1161,7 +1171,7 @@ static int create_buffers(mcl_ctx* c, const mcl_params* p, int device, int world
     }
     CK(dalloc(&c->d_wraw, FN));
     CK(dalloc(&c->d_wn, FN));
-    CK(dalloc(&c->d_cdf, FN));
+    for (int b = 0; b < 2; ++b) CK(dalloc(&c->d_cdf2[b], FN));
     CK(dalloc(&c->d_idx, FN));
     CK(cudaMemset(c->d_idx, 0, FN * sizeof(int32_t)));
     {   // weights_ = 1/N (:107)
@@ -1195,15 +1205,17 @@ static int create_buffers(mcl_ctx* c, const mcl_params* p, int device, int world
         c->coarse_shift = 6;
         while ((c->N >> c->coarse_shift) > 16384) ++c->coarse_shift;
         c->coarse_n = static_cast<int>(c->N >> c->coarse_shift);
-        CK(dalloc(&c->d_coarse, static_cast<size_t>(c->F) * std::max(c->coarse_n, 1)));
+        for (int b = 0; b < 2; ++b) CK(dalloc(&c->d_coarse2[b], static_cast<size_t>(c->F) * std::max(c->coarse_n, 1)));
     }
     CK(dalloc(&c->d_S1, static_cast<size_t>(c->F)));
     CK(dalloc(&c->d_S2, static_cast<size_t>(c->F)));
     CK(dalloc(&c->d_scratch_total, static_cast<size_t>(c->F)));
     CK(dalloc(&c->d_slice_sum, static_cast<size_t>(kMaxWorld)));
-    CK(dalloc(&c->d_rank_end, static_cast<size_t>(kMaxWorld)));
     CK(cudaMemset(c->d_slice_sum, 0, sizeof(double) * kMaxWorld));
-    CK(cudaMemset(c->d_rank_end, 0, sizeof(double) * kMaxWorld));
+    for (int b = 0; b < 2; ++b) {
+        CK(dalloc(&c->d_rank_end2[b], static_cast<size_t>(kMaxWorld)));
+        CK(cudaMemset(c->d_rank_end2[b], 0, sizeof(double) * kMaxWorld));
+    }
     if (single_tile(c)) {
         c->norm_blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((c->N + kNormThreads * 4 - 1) / (kNormThreads * 4),
                                                                                    std::max(1, 4 * c->num_sms / std::min(c->F, 4 * c->num_sms)))));
@@ -1331,11 +1343,12 @@ int mcl_destroy(mcl_ctx* c) {
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     void* ptrs[] = {c->d_pose4[0], c->d_pose4[1],
                     c->d_grid, c->d_v8, c->d_v4, c->d_free, c->d_tabT, c->d_step2idx, c->d_px[0], c->d_px[1], c->d_py[0],
-                    c->d_py[1], c->d_pt[0], c->d_pt[1], c->d_wraw, c->d_wn, c->d_cdf, c->d_idx, c->d_steps, c->d_u, c->d_z,
+                    c->d_py[1], c->d_pt[0], c->d_pt[1], c->d_wraw, c->d_wn, c->d_cdf2[0], c->d_cdf2[1], c->d_idx, c->d_steps, c->d_u, c->d_z,
                     c->d_action, c->d_slice, c->d_tile_sum, c->d_chunk_fn, c->d_opq_pre, c->d_opq_idx, c->d_opq_add,
                     c->d_tile_opq, c->d_tile_elem, c->d_list_chunk, c->arena ? nullptr : c->d_list_fn, c->arena ? nullptr : c->d_list_add,
                     c->arena, c->d_anchors, c->d_anchor_val,
-                    c->d_tile_start, c->d_coarse, c->d_S1, c->d_S2, c->d_scratch_total, c->d_slice_sum, c->d_rank_end,
+                    c->d_tile_start, c->d_coarse2[0], c->d_coarse2[1], c->d_S1, c->d_S2, c->d_scratch_total, c->d_slice_sum, c->d_rank_end2[0],
+                    c->d_rank_end2[1],
                     c->d_partial, c->d_pose, c->d_centre, c->d_replays, c->d_hist, c->d_perm, c->d_done, c->d_route_done,
                     c->d_xseq, c->d_nccl_tok, c->d_tmp, c->d_update_no, c->d_dbg};
     for (void* p : ptrs)
@@ -1637,7 +1650,7 @@ int mcl_get_cdf(mcl_ctx* c, int filter, double* out) {
     if (!c) return fail(MCL_ERR_INVALID, "null context");
     CK(cudaSetDevice(c->device));
     if (!c->cdf_any) return fail(MCL_ERR_INVALID, "no CDF yet: call mcl_update first");
-    return get_array(c, filter, c->d_cdf, sizeof(double), c->N, out);   // the _M_cp the last update drew from
+    return get_array(c, filter, c->d_cdf2[c->cdf_last], sizeof(double), c->N, out);   // the _M_cp the last update drew from
 }
 int mcl_get_resample_indices(mcl_ctx* c, int filter, int32_t* out) {
     return get_array(c, filter, c ? c->d_idx : nullptr, sizeof(int32_t), c ? c->N : 0, out);
@@ -1807,7 +1820,7 @@ int mcl_sample_particles_u(mcl_ctx* c, int filter, int k, const double* u, doubl
     int32_t* d_i = reinterpret_cast<int32_t*>(static_cast<char*>(c->d_tmp) + obytes + ubytes);
     if (u) CK(cudaMemcpyAsync(d_u, u, sizeof(double) * k, cudaMemcpyHostToDevice, c->stream));
     const size_t fo = static_cast<size_t>(c->N) * filter;
-    k_sample_particles<<<(k + 127) / 128, 128, 0, c->stream>>>(c->d_cdf + fo, c->N, c->d_px[c->cur] + fo, c->d_py[c->cur] + fo,
+    k_sample_particles<<<(k + 127) / 128, 128, 0, c->stream>>>(c->d_cdf2[c->cur] + fo, c->N, c->d_px[c->cur] + fo, c->d_py[c->cur] + fo,
                                                                c->d_pt[c->cur] + fo, k, c->prm.seed, ++c->init_no, u ? d_u : nullptr,
                                                                d_o, d_i);
     c->launches++;

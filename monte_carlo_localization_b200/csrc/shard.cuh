@@ -88,12 +88,13 @@ __device__ __forceinline__ bool shard_wait(const ShardDev& s, unsigned long long
     __syncthreads();
     if (static_cast<int>(threadIdx.x) < s.world) {
         const unsigned long long* f = s.flag[s.rank] + threadIdx.x;
-        if (ld_acquire_sys(f) < epoch) {
+        // relaxed polls, then ONE acquire: an acquire load invalidates the SM's L1 every time it is issued
+        if (ld_sys_u64(f) < epoch) {
             if (!s.fused) {
                 s_bad = kShardMissing;
             } else {
                 const unsigned long long t0 = global_timer_ns();
-                while (ld_acquire_sys(f) < epoch) {
+                while (ld_sys_u64(f) < epoch) {
                     if (global_timer_ns() - t0 > kSpinTimeoutNs) {
                         s_bad = kShardTimeout;
                         break;
@@ -102,6 +103,7 @@ __device__ __forceinline__ bool shard_wait(const ShardDev& s, unsigned long long
                 }
             }
         }
+        (void)ld_acquire_sys(f);
     }
     __syncthreads();
     const int bad = s_bad;
