@@ -38,7 +38,7 @@ typedef enum mcl_status {
     MCL_ERR_NO_DEVICE = -2,    /* no usable CUDA device (no CPU fallback exists) */
     MCL_ERR_CUDA = -3,         /* CUDA runtime error; see mcl_last_error */
     MCL_ERR_NO_MAP = -4,       /* reference: cast_ray returns MAX_RANGE when !map_initialized_ (:613) */
-    MCL_ERR_UNSUPPORTED = -5,  /* e.g. MAX_RANGE_PX > 254 or more than 128 beams */
+    MCL_ERR_UNSUPPORTED = -5,  /* e.g. more than 4096 beams, or a request that does not apply to the context's mode */
     MCL_ERR_NO_FREE_SPACE = -6 /* reference: "No free space found in map!" (:423-427) */
 } mcl_status;
 
@@ -138,6 +138,10 @@ int mcl_cast_ray(mcl_ctx* ctx, double x, double y, double angle, float* range_ou
 int mcl_get_resample_indices(mcl_ctx* ctx, int filter, int32_t* idx_out);      /* N */
 int mcl_get_ranges(mcl_ctx* ctx, int filter, float* ranges_out);               /* N*R particle-major, metres */
 int mcl_get_range_steps(mcl_ctx* ctx, int filter, uint8_t* steps_out);         /* N*R step index, M = no hit */
+/* The same as 16-bit values: the only form available when MAX_RANGE_PX > 254 or there are more than 128
+ * beams.  Such "wide" contexts (the reference has no limit on either, :195, :307-310) march every ray with
+ * the reference's own FP64 arithmetic instead of the skip-map kernels -- same results, no skipping. */
+int mcl_get_range_steps16(mcl_ctx* ctx, int filter, uint16_t* steps_out);
 int mcl_get_raw_weights(mcl_ctx* ctx, int filter, double* weights_out);        /* before :679-686 */
 int mcl_get_cdf(mcl_ctx* ctx, int filter, double* cdf_out);                    /* discrete_distribution _M_cp */
 /* visualize() :946-958: k weighted samples of the particle set (k x 3 column-major). */
@@ -157,7 +161,9 @@ int mcl_set_keep_ranges(mcl_ctx* ctx, int enabled);
 /* Diagnostics: SM cycle counts of the phases of one kind of exact-sum pass (csrc/exact_kernels.cuh; 0 S1,
  * 1 normalise+pose+S2, 2 S2 of stored weights, 3 cdf; < 0 off) in the updates that follow.  out (nullable, 8
  * values, read and cleared): slowest CTA's tile phase | last CTA until it knows it is last | pose fold | tile
- * scan | ordered opaque list | exchange | serial evaluation + tile starts | opaque chunks of this rank. */
+ * scan | ordered opaque list | exchange | serial evaluation + tile starts | opaque chunks of this rank.
+ * pass_kind 8: k_route of a sharded filter instead -- slowest CTA's scan + serve cycles | the same incl. the system
+ * fence | the last CTA's wait for the peers. */
 int mcl_debug_pass_cycles(mcl_ctx* ctx, int pass_kind, unsigned long long* out);   /* store per-ray steps for read-back */
 int mcl_kernel_launches(mcl_ctx* ctx, int64_t* count); /* kernels launched so far by this ctx */
 /* Use the caller's CUDA stream (cudaStream_t passed as void*) instead of the ctx's own. */

@@ -77,6 +77,7 @@ SIGNATURES = {
     "mcl_get_resample_indices": (C.c_int, [C.c_void_p, C.c_int, c_int32_p]),
     "mcl_get_ranges": (C.c_int, [C.c_void_p, C.c_int, c_float_p]),
     "mcl_get_range_steps": (C.c_int, [C.c_void_p, C.c_int, c_uint8_p]),
+    "mcl_get_range_steps16": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_uint16)]),
     "mcl_get_raw_weights": (C.c_int, [C.c_void_p, C.c_int, c_double_p]),
     "mcl_get_cdf": (C.c_int, [C.c_void_p, C.c_int, c_double_p]),
     "mcl_sample_particles": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p]),
@@ -345,6 +346,11 @@ class MclContext:
     def range_steps(self, filter: int = 0) -> np.ndarray:
         out = np.empty(self.N * self.R, dtype=np.uint8)
         self._check(self._L.mcl_get_range_steps(self._h, filter, out.ctypes.data_as(c_uint8_p)), "mcl_get_range_steps")
+        return out.reshape(self.N, self.R)
+
+    def range_steps16(self, filter: int = 0) -> np.ndarray:
+        out = np.empty(self.N * self.R, dtype=np.uint16)
+        self._check(self._L.mcl_get_range_steps16(self._h, filter, out.ctypes.data_as(C.POINTER(C.c_uint16))), "mcl_get_range_steps16")
         return out.reshape(self.N, self.R)
 
     def raw_weights(self, filter: int = 0) -> np.ndarray:

@@ -414,6 +414,10 @@ __global__ void __launch_bounds__(kDirThreads, 1) k_raycast_dir(DirRayArgs a) {
             st.by = static_cast<int>(static_cast<int16_t>(r0.z >> 16));
             const WindowV8S wacc{static_cast<uint32_t>(pin_reg(static_cast<int>(win_saddr) + (st.by - wg.wy0) * wg.pitch + (st.bx - wg.wx0))), wg.pitch};
             const GlobalV8 gacc = make_global_v8(smap, mp.PW, st.bx, st.by);
+            // the start cell's code lets all of this particle's rays in the sector begin at sample k0 (march.cuh)
+            // (particles outside the window box are rare and simply start at sample 1)
+            int k0 = 1;
+            if (valid && (flags & 3) == 3) k0 = dir_first_sample(wacc, st);
             uint8_t* const out = a.steps_sorted + pos;
             for (int jb = 0; jb < R; jb += 32) {
                 const int jl = jb + lane;
@@ -426,20 +430,26 @@ __global__ void __launch_bounds__(kDirThreads, 1) k_raycast_dir(DirRayArgs a) {
                 else
                     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(io_l) : "r"(io_saddr + static_cast<uint32_t>(jb * 4)));
                 const int start = (bmin + static_cast<int>(io_l) - s * K) & Bmask;
-                unsigned mask = __ballot_sync(kFullMask, jl < R && (start < K || start + (bmax - bmin) >= a.B));
+                const int span = bmax - bmin;
+                unsigned mask = __ballot_sync(kFullMask, jl < R && (start < K || start + span >= a.B));
+                // beams for which EVERY lane's ray lies in the sector (the usual case: a warp spans a few buckets of the
+                // sector's K): no per-lane sector test
+                const unsigned full = __ballot_sync(kFullMask, jl < R && start + span < K);
                 while (mask) {
-                    const int j = jb + __ffs(mask) - 1;
+                    const int jbit = __ffs(mask) - 1;
+                    const int j = jb + jbit;
                     mask &= mask - 1;
-                    if (!valid || dir_sector_of(bucket, a.io[j], Bmask, a.shift) != s) continue;   // another unit's ray
+                    if (!valid) continue;
+                    if (!((full >> jbit) & 1u) && dir_sector_of(bucket, a.io[j], Bmask, a.shift) != s) continue;   // another unit's ray
                     int r = 0;   // outside the map: the first sample is already out of bounds (:632-636)
                     if (flags & 1) {
                         int dxf, dyf;
                         beam_direction_prescaled(cs.x, cs.y, a.beams.cosa[j], a.beams.sina[j], &dxf, &dyf);
                         const ReplayLazy rep{a.replay, pos, j};
                         if (flags & 2)
-                            r = march_ray_dir(wacc, st, dxf, dyf, M, rep, &replays);
+                            r = march_ray_dir(wacc, st, dxf, dyf, M, rep, &replays, k0);
                         else
-                            r = march_ray_dir(gacc, st, dxf, dyf, M, rep, &replays);
+                            r = march_ray_dir(gacc, st, dxf, dyf, M, rep, &replays, k0);
                     }
                     out[static_cast<uint64_t>(static_cast<uint32_t>(j)) * static_cast<uint32_t>(a.stride)] = static_cast<uint8_t>(r);
                 }

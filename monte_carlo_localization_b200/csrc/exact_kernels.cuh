@@ -66,6 +66,7 @@ struct ExactArgs {
     int force_last_one;      // discrete_distribution sets _M_cp.back() = 1.0 (random.tcc:2677)
     double* coarse;          // coarse level of the CDF search: coarse[f][k] = out[(k+1)*8*coarse_m - 1]
     int coarse_m, coarse_n;
+    double* mid;             // [F][C] middle level: mid[f][c] = the last prefix sum of chunk c (out[8c+7]); nullable
     unsigned int* done;      // [F] block-completion counters (zero on entry, reset on exit)
     // pose (the pass that normalises): expected_pose over the stored weights
     const double* px;
@@ -719,6 +720,15 @@ __device__ __forceinline__ void emit_tile(const ExactArgs& a, ScanElem* sms, Sca
     }
     if (a.force_last_one && a.N - 1 >= base && a.N - 1 < base + kChunk) v[a.N - 1 - base] = 1.0;
     emit_coarse(a, f, static_cast<int64_t>(t) * kTileChunks + tid, base, v[kChunk - 1]);
+    if (a.mid) {   // the chunk's last VALID prefix sum (the filter's last chunk may be partial)
+        double last = v[kChunk - 1];
+        if (base + kChunk > a.N) {
+#pragma unroll
+            for (int i = 0; i < kChunk; ++i)
+                if (base + i == a.N - 1) last = v[i];
+        }
+        a.mid[static_cast<int64_t>(f) * a.C + static_cast<int64_t>(t) * kTileChunks + tid] = last;
+    }
     if (base + kChunk <= a.N) {
         double2* p = reinterpret_cast<double2*>(out + base);
 #pragma unroll
@@ -829,6 +839,15 @@ __global__ void __launch_bounds__(kTileChunks) k_exact_single(ExactArgs a) {
     }
     if (a.force_last_one && a.N - 1 >= base && a.N - 1 < base + kChunk) v[a.N - 1 - base] = 1.0;
     emit_coarse(a, f, tid, base, v[kChunk - 1]);
+    if (a.mid) {
+        double last = v[kChunk - 1];
+        if (base + kChunk > a.N) {
+#pragma unroll
+            for (int i = 0; i < kChunk; ++i)
+                if (base + i == a.N - 1) last = v[i];
+        }
+        a.mid[static_cast<int64_t>(f) * a.C + tid] = last;
+    }
     if (base + kChunk <= a.N) {
         double2* p = reinterpret_cast<double2*>(out + base);
 #pragma unroll

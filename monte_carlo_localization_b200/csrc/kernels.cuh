@@ -124,6 +124,8 @@ struct MotionArgs {
     // coarse level of the CDF search, staged in shared memory: coarse[f][k] = cdf[(k+1) << cshift) - 1]
     const double* coarse;     // [F][nc] or nullptr
     int nc, cshift;
+    const double* mid;        // [F][C] chunk-end values of the CDF (middle level of the search) or nullptr
+    int64_t C;                // chunks per filter (stride of mid)
     const double* action;     // [F][3] device
     double disp_x, disp_y, disp_t;
     uint64_t seed;
@@ -184,11 +186,31 @@ __device__ __forceinline__ double resample_uniform(int64_t i, int f, uint64_t se
     return (i & 1) ? canonical_from_words(r.v[2], r.v[3]) : canonical_from_words(r.v[0], r.v[1]);
 }
 
-// lower_bound(cp.begin(), cp.end(), u)  (random.tcc:2709-2713) in two levels: the coarse entries
-// (shared memory) are the exact CDF values at the ends of 2^cshift-element segments, so the first
-// segment whose end value is >= u contains the answer; the fine steps go to L2.
-__device__ __forceinline__ int64_t cdf_lower_bound(const double* __restrict__ cp, int64_t N, const double* ts, int nc, int cshift,
-                                                   double u) {
+// lower_bound(cp.begin(), cp.end(), u)  (random.tcc:2709-2713) in three levels.  coarse (shared memory): the
+// exact CDF values at the ends of 2^cshift-element segments -- the first segment whose end value is >= u contains
+// the answer.  mid (global): the value at the end of every 8-element chunk -- the segment's chunk ends are ONE
+// 64-byte line when cshift == 6, so the first chunk whose end is >= u costs one memory round trip; the chunk's 8
+// entries are another 64-byte line and the answer is the chunk's base + the number of entries below u.  Two
+// dependent L2 accesses instead of the six of a binary search over the segment (the search is latency bound).
+// 32 bytes per lane in ONE request (LDG.256, sm_100): a divergent gather costs the L1TEX one slot per lane and
+// request whatever its width, so the search is counted in requests, not bytes
+__device__ __forceinline__ void ldg256(const double* p, double& a, double& b, double& c, double& d) {
+    asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+__device__ __forceinline__ int count_below(const double* __restrict__ p, double u) {   // p: 8 doubles
+    if (reinterpret_cast<uintptr_t>(p) & 31u) {   // (a batch of filters whose particle count is not a multiple of 4)
+        int n = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) n += __ldg(p + i) < u;
+        return n;
+    }
+    double v0, v1, v2, v3, v4, v5, v6, v7;
+    ldg256(p, v0, v1, v2, v3);
+    ldg256(p + 4, v4, v5, v6, v7);
+    return (v0 < u) + (v1 < u) + (v2 < u) + (v3 < u) + (v4 < u) + (v5 < u) + (v6 < u) + (v7 < u);
+}
+__device__ __forceinline__ int64_t cdf_lower_bound(const double* __restrict__ cp, const double* __restrict__ mid, int64_t N,
+                                                   const double* ts, int nc, int cshift, double u) {
     int64_t lo = 0, hi = N;
     if (nc > 0) {
         int kl = 0, kh = nc;
@@ -202,12 +224,37 @@ __device__ __forceinline__ int64_t cdf_lower_bound(const double* __restrict__ cp
         lo = static_cast<int64_t>(kl) << cshift;
         hi = min(N, lo + (int64_t{1} << cshift));
     }
+    if (mid != nullptr && hi > lo) {
+        // first chunk of [lo, hi) whose end value is >= u (the last chunk's end is cp[hi - 1] or the filter's last entry)
+        int64_t cl = lo >> 3, ch = (hi + 7) >> 3;
+        if (ch - cl == 8 && (cl & 7) == 0) {
+            cl += count_below(mid + cl, u);
+            if (cl >= ch) cl = ch - 1;   // (cannot happen for u <= the segment's end value)
+        } else {
+            while (cl < ch - 1) {        // generic: bisect the chunk ends
+                const int64_t cm = (cl + ch - 1) >> 1;
+                if (__ldg(mid + cm) < u)
+                    cl = cm + 1;
+                else
+                    ch = cm + 1;
+            }
+        }
+        const int64_t base = cl << 3;
+        if (base + 8 <= N) {
+            lo = base + count_below(cp + base, u);
+        } else {
+            lo = base;
+            while (lo < N && __ldg(cp + lo) < u) ++lo;
+        }
+        if (lo >= N) lo = N - 1;
+        return lo;
+    }
     while (lo < hi) {
-        const int64_t mid = (lo + hi) >> 1;
-        if (__ldg(cp + mid) < u)
-            lo = mid + 1;
+        const int64_t mid_i = (lo + hi) >> 1;
+        if (__ldg(cp + mid_i) < u)
+            lo = mid_i + 1;
         else
-            hi = mid;
+            hi = mid_i;
     }
     if (lo >= N) lo = N - 1;  // unreachable for u < 1 == cp[N-1]; keeps reads in range
     return lo;
@@ -291,15 +338,12 @@ __global__ void __launch_bounds__(kMotionThreads) k_resample_motion(MotionArgs a
         if (search) {
             const int64_t i = a.glo + li;
             const double u = a.u ? a.u[fo + i] : resample_uniform(i, f, a.seed, update_no);
-            int64_t lo = cdf_lower_bound(a.cdf + fo, N, ts, nc, a.cshift, u);
+            int64_t lo = cdf_lower_bound(a.cdf + fo, a.mid ? a.mid + static_cast<int64_t>(f) * a.C : nullptr, N, ts, nc, a.cshift, u);
             if (N < 2) lo = 0;        // libstdc++ clears the table for fewer than 2 weights
             a.idx_out[fo + li] = static_cast<int32_t>(lo);
             if (a.spose4) {
-                const double2* p4 = reinterpret_cast<const double2*>(a.spose4 + fo + lo);
-                const double2 xy = __ldg(p4), tz = __ldg(p4 + 1);
-                x = xy.x;
-                y = xy.y;
-                th = tz.x;
+                double pad;
+                ldg256(reinterpret_cast<const double*>(a.spose4 + fo + lo), x, y, th, pad);
             } else {
                 x = a.sx[fo + lo];
                 y = a.sy[fo + lo];
@@ -340,6 +384,7 @@ struct RouteArgs {
     const double* cdf;        // [N] this rank's slice of the global CDF
     const double* coarse;     // [nc] coarse level of the local slice
     int nc, cshift;
+    const double* mid;        // [C] chunk-end values of the local slice
     const double* rank_end;   // [world] exact CDF value at the end of every rank's slice
     const double4* spose4;    // [N] local source state, packed (nullptr: use the SoA arrays)
     const double* sx;
@@ -350,6 +395,7 @@ struct RouteArgs {
     uint64_t seed;
     const unsigned long long* update_no;
     unsigned int* done;
+    unsigned long long* dbg;    // diagnostics (nullable): [8] slowest CTA's scan+serve cycles, [9] incl. the system fence, [10] last CTA's wait for the peers
     ShardDev sh;
 };
 constexpr int kRouteThreads = 1024;
@@ -363,6 +409,7 @@ __global__ void __launch_bounds__(kRouteThreads) k_route(RouteArgs a) {
     extern __shared__ double ts[];   // nc doubles of the coarse level, then the warps' queues
     __shared__ bool is_last;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long c_begin = clock64();
     for (int t = tid; t < a.nc; t += kRouteThreads) ts[t] = a.coarse[t];
     double* qu = ts + a.nc + warp * kRouteQueue;                                           // queued draws
     int* qi = reinterpret_cast<int*>(ts + a.nc + (kRouteThreads / 32) * kRouteQueue) + warp * kRouteQueue;   // queued slots
@@ -377,21 +424,18 @@ __global__ void __launch_bounds__(kRouteThreads) k_route(RouteArgs a) {
     auto serve = [&](int k) {   // lane k < count serves queue entry k
         const double u = qu[k];
         const int64_t i = qi[k];
-        const int64_t j = cdf_lower_bound(a.cdf, a.N, ts, a.nc, a.cshift, u);
+        const int64_t j = cdf_lower_bound(a.cdf, a.mid, a.N, ts, a.nc, a.cshift, u);
         double x, y, th;
         if (a.spose4) {
-            const double2* p4 = reinterpret_cast<const double2*>(a.spose4 + j);
-            const double2 xy = __ldg(p4), tz = __ldg(p4 + 1);
-            x = xy.x;
-            y = xy.y;
-            th = tz.x;
+            double pad;
+            ldg256(reinterpret_cast<const double*>(a.spose4 + j), x, y, th, pad);
         } else {
             x = a.sx[j];
             y = a.sy[j];
             th = a.st[j];
         }
-        const int owner = static_cast<int>(i / a.N);
-        double* dst = reinterpret_cast<double*>(a.routed[owner] + (i - static_cast<int64_t>(owner) * a.N));
+        const uint32_t owner = static_cast<uint32_t>(i) / static_cast<uint32_t>(a.N);   // (slots and slice sizes are below 2^31)
+        double* dst = reinterpret_cast<double*>(a.routed[owner] + (static_cast<uint32_t>(i) - owner * static_cast<uint32_t>(a.N)));
         // one 32-byte store: one NVLink write transaction per routed particle
         asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "d"(x), "d"(y), "d"(th),
                      "d"(__longlong_as_double(glo + j))
@@ -435,10 +479,15 @@ __global__ void __launch_bounds__(kRouteThreads) k_route(RouteArgs a) {
         }
     }
     if (lane < qn) serve(lane);
+    const long long c_loop = clock64();
     // every store of this CTA is performed at system scope before the CTA counts itself done
     __threadfence_system();
     __syncthreads();
     if (tid == 0) {
+        if (a.dbg) {
+            atomicMax(a.dbg + 8, static_cast<unsigned long long>(c_loop - c_begin));
+            atomicMax(a.dbg + 9, static_cast<unsigned long long>(clock64() - c_begin));
+        }
         __threadfence();
         is_last = atomicAdd(a.done, 1u) == gridDim.x - 1u;
     }
@@ -448,9 +497,11 @@ __global__ void __launch_bounds__(kRouteThreads) k_route(RouteArgs a) {
     if (tid == 0) *a.done = 0;
     __syncthreads();
     const unsigned long long epoch = *a.sh.xseq + 1ull;
+    const long long c_pub = clock64();
     shard_publish(a.sh, epoch, nullptr, 0);
     if (!a.sh.fused) return;
     if (!shard_wait(a.sh, epoch)) return;
+    if (a.dbg && tid == 0) a.dbg[10] = static_cast<unsigned long long>(clock64() - c_pub);
     route_finish(a.sh, epoch);
 }
 
@@ -1009,6 +1060,111 @@ __global__ void __launch_bounds__(1024, 1) k_gather_bench(const uint8_t* __restr
 __global__ void k_fill(double* p, int64_t n, double v) {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
+}
+
+}  // namespace mclb200
+
+namespace mclb200 {
+
+// ------------------------------------------------------------------------------------------
+// Wide configurations: MAX_RANGE_PX > 254 (e.g. max_range 15 m at 0.05 m/cell) or more than 128
+// beams (angle_step < 9 on a 1080-beam scan).  The reference has neither limit (:195, :307-310); the
+// skip-map stages do (9.23 fixed point, one-byte step indices, beam tables in the kernel parameters).
+// Such contexts march every ray exactly as cast_ray does (:611-650) -- FP64 position accumulated
+// sample by sample, truncating quotients, int8 grid -- with 16-bit step indices.  Correct by
+// construction and still one thread per ray, but without skipping: a compatibility path.
+// ------------------------------------------------------------------------------------------
+constexpr int kMaxBeamsWide = 4096;
+
+__device__ __forceinline__ int ref_cast_steps(const RefGrid& g, double x, double y, double angle, int M) {
+    double sn, cs;
+    sincos(angle, &sn, &cs);
+    const double dx = nf_mul(cs, g.res), dy = nf_mul(sn, g.res);   // :619-620
+    double cx = x, cy = y;
+    for (int step = 0; step < M; ++step) {
+        cx = nf_add(cx, dx);                                        // :624-625
+        cy = nf_add(cy, dy);
+        const double qx = nf_div(nf_sub(cx, g.ox), g.res), qy = nf_div(nf_sub(cy, g.oy), g.res);   // :628-629
+        // (int) of a NaN or of a value beyond int range is INT_MIN on the reference's platform: out of bounds
+        if (!(fabs(qx) < 2147483648.0) || !(fabs(qy) < 2147483648.0)) return step;
+        const int gx = __double2int_rz(qx), gy = __double2int_rz(qy);
+        if (gx < 0 || gx >= g.W || gy < 0 || gy >= g.H) return step;                                 // :632-636
+        if (g.data[static_cast<int64_t>(gy) * g.W + gx] > 50) return step;                           // :639-645
+    }
+    return M;   // MAX_RANGE_METERS (:649)
+}
+
+struct WideRayArgs {
+    RefGrid grid;
+    int M, R;
+    int64_t N;                 // particles per filter
+    const double* px;          // [F][N]
+    const double* py;
+    const double* pt;
+    const float* beam;         // [R] downsampled_angles_
+    uint16_t* steps;           // [F][N][R]
+};
+
+__global__ void __launch_bounds__(256) k_raycast_wide(WideRayArgs a) {
+    const int f = blockIdx.y;
+    const int64_t rays = a.N * a.R;
+    for (int64_t g = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; g < rays; g += static_cast<int64_t>(gridDim.x) * 256) {
+        const int64_t i = g / a.R;
+        const int j = static_cast<int>(g - i * a.R);
+        const int64_t p = static_cast<int64_t>(f) * a.N + i;
+        const double angle = nf_add(a.pt[p], static_cast<double>(a.beam[j]));   // theta + angle (:533)
+        a.steps[p * a.R + j] = static_cast<uint16_t>(ref_cast_steps(a.grid, a.px[p], a.py[p], angle, a.M));
+    }
+}
+
+struct WideWeightArgs {
+    int M, R;
+    int64_t N;
+    const uint16_t* steps;     // [F][N][R]
+    const double* slice;       // [F][R][M+1]
+    double* w_raw;             // [F][N]
+    double inv_squash;
+};
+
+// w = pow(prod_j table(obs_j, range_ij), 1/squash), entries multiplied in beam order (:564-579)
+__global__ void __launch_bounds__(256) k_weight_wide(WideWeightArgs a) {
+    const int f = blockIdx.y;
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+    if (i >= a.N) return;
+    const int tw = a.M + 1;
+    const uint16_t* st = a.steps + (static_cast<int64_t>(f) * a.N + i) * a.R;
+    const double* row = a.slice + static_cast<int64_t>(f) * a.R * tw;
+    double acc = 1.0;
+    for (int j = 0; j < a.R; ++j) acc = __dmul_rn(acc, __ldg(row + static_cast<int64_t>(j) * tw + st[j]));
+    a.w_raw[static_cast<int64_t>(f) * a.N + i] = pow(acc, a.inv_squash);
+}
+
+struct WideQueryArgs {
+    RefGrid grid;
+    int M;
+    const double* q;     // column-major n x 3
+    int64_t n;
+    float* out;
+    double max_range;
+};
+
+__global__ void __launch_bounds__(256) k_range_queries_wide(WideQueryArgs a) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+    if (i >= a.n) return;
+    const int r = ref_cast_steps(a.grid, a.q[i], a.q[a.n + i], a.q[2 * a.n + i], a.M);
+    a.out[i] = (r >= a.M) ? static_cast<float>(a.max_range) : static_cast<float>(__dmul_rn(static_cast<double>(r), a.grid.res));
+}
+
+__global__ void k_steps16_to_ranges(const uint16_t* steps, int64_t n, int M, double res, double max_range, float* out) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int r = steps[i];
+    out[i] = (r >= M) ? static_cast<float>(max_range) : static_cast<float>(__dmul_rn(static_cast<double>(r), res));
+}
+
+__global__ void k_widen_steps(const uint8_t* in, int64_t n, uint16_t* out) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i];
 }
 
 }  // namespace mclb200

@@ -292,10 +292,22 @@ MCL_NOINLINE int resolve_uncertain_dir(const Acc acc, uint32_t px, uint32_t py, 
 constexpr uint32_t kEdgeMask = kFracMask & ~511u;
 static_assert(2u * kEtaFix <= 512u, "the coarse edge band must contain the kEta band");
 
+// First lattice sample worth looking at.  The ray starts (k = 0, not a sample) somewhere in cell c0; c0's code says
+// how many samples a ray of THIS SECTOR can skip from anywhere inside c0, so samples 1 .. adv0 - 1 cannot be hits
+// and the march may begin at sample adv0 -- the same guarantee every later jump relies on, used once more.  One
+// lookup per (particle, sector) replaces the first lookup of each of the particle's 2-3 rays in that sector.
+template <class Acc>
+MCL_HD int dir_first_sample(const Acc& acc, const RayStart& st) {
+    const int adv = acc.get_p(st.p0x, st.p0y) & 0x7f;   // blocked start cell: adv 0 -> the march begins at sample 1
+    return adv > 1 ? adv : 1;
+}
+
+// k0: first sample to look at (1, or dir_first_sample's answer)
 template <class Acc, class Rep>
-MCL_HD int march_ray_dir(const Acc& acc, const RayStart& st, int dxf, int dyf, int M, const Rep& rep, int* replays) {
+MCL_HD int march_ray_dir(const Acc& acc, const RayStart& st, int dxf, int dyf, int M, const Rep& rep, int* replays, int k0 = 1) {
     constexpr int kPark = 1 << 20;
-    int k = 1;
+    int k = k0;
+    if (k > M) return M;
     for (;;) {
         int kstop = 0;   // sample at which the loop stopped: blocked cell, or a near-wall sample close to an edge
         do {

@@ -125,9 +125,16 @@ struct mcl_ctx {
     double* d_wn = nullptr;
     double* d_cdf2[2] = {nullptr, nullptr};   // discrete_distribution's _M_cp for the update that resamples FROM state buffer b
     int cdf_last = 0;                         // which of them the last update drew from
+    double* d_mid2[2] = {nullptr, nullptr};   // [F][C] chunk-end values of each CDF: the middle level of the resampling search
     int32_t* d_idx = nullptr;
     uint8_t* d_steps = nullptr;
     bool keep_ranges = false;
+    // wide configuration (MAX_RANGE_PX > 254 or more than 128 beams): reference-arithmetic march, 16-bit steps
+    bool wide = false;
+    std::vector<float> beam_angles;
+    float* d_beam = nullptr;
+    uint16_t* d_steps16 = nullptr;
+    size_t obs_capacity = 0;          // floats per filter the obs staging holds
     double* d_u = nullptr;
     double* d_z = nullptr;
     double* d_action = nullptr;
@@ -420,6 +427,7 @@ int launch_emit(mcl_ctx* c, int cdf_idx) {
     a.coarse = c->coarse_n > 0 ? c->d_coarse2[cdf_idx] : nullptr;
     a.coarse_m = a.coarse ? (1 << c->coarse_shift) / kChunk : 0;
     a.coarse_n = c->coarse_n;
+    a.mid = c->d_mid2[cdf_idx];
     k_exact_emit<<<dim3(c->T, c->F), kTileChunks, 0, c->stream>>>(a);
     mark(c, "k_exact_emit");
     CK(cudaGetLastError());
@@ -437,6 +445,7 @@ int launch_single(mcl_ctx* c, const double* src, const double* div, double* tota
     a.coarse = (out && c->coarse_n > 0) ? c->d_coarse2[cdf_idx] : nullptr;
     a.coarse_m = a.coarse ? (1 << c->coarse_shift) / kChunk : 0;
     a.coarse_n = c->coarse_n;
+    a.mid = out ? c->d_mid2[cdf_idx] : nullptr;
     k_exact_single<<<dim3(1, c->F), kTileChunks, 0, c->stream>>>(a);
     mark(c, "k_exact_single");
     CK(cudaGetLastError());
@@ -495,6 +504,20 @@ int upload_table(mcl_ctx* c) {
     return MCL_OK;
 }
 
+// MAX_RANGE_PX > 254 or more than 128 beams: the skip-map stages cannot run (9.23 fixed point, one-byte step
+// indices, beam tables in the kernel parameters); the context marches rays with the reference's own arithmetic
+int update_wide(mcl_ctx* c) {
+    const bool wide = (c->have_map && c->M > kMaxRangePxSupported) || (c->have_beams && c->R > kMaxBeams);
+    if (wide != c->wide) drop_graphs(c);
+    c->wide = wide;
+    if (c->d_steps16) {
+        cudaFree(c->d_steps16);
+        c->d_steps16 = nullptr;
+    }
+    if (wide && c->have_beams) CK(dalloc(&c->d_steps16, static_cast<size_t>(c->F) * c->N * c->R));
+    return MCL_OK;
+}
+
 int ensure_slice(mcl_ctx* c) {
     drop_graphs(c);
     if (!c->have_map || !c->have_beams) return MCL_OK;
@@ -549,6 +572,10 @@ int upload_replay_ctx(mcl_ctx* c) {
 // per-update work buffers.  Called whenever the map or the beam table changes.
 int ensure_dir(mcl_ctx* c, bool map_changed) {
     if (!c->have_map || !c->have_beams) return MCL_OK;
+    if (c->wide) {
+        free_dir(c);
+        return MCL_OK;
+    }
     const size_t ncell = static_cast<size_t>(c->skip.PW) * c->skip.PH;
     // one filter: windows around the cloud; a batch: only when the whole padded map is one window
     const bool pool = c->F > 1 && ncell <= kDirWindowBudget && static_cast<int64_t>(c->F) * c->N < (int64_t{1} << 31) - 2048;
@@ -698,7 +725,7 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
     oa.res = c->res;
     // the same launch clears the per-update accumulators (cloud centre, heading histogram + cursors)
     oa.centre = c->d_centre;
-    oa.hist = c->sort_enabled ? c->d_hist : nullptr;
+    oa.hist = (c->sort_enabled && !c->wide) ? c->d_hist : nullptr;
     oa.nhist = 2 * c->B * c->F;
     k_prepare_obs<<<dim3(c->R, c->F), 256, 0, s>>>(oa);
     mark(c, "k_prepare_obs");
@@ -708,7 +735,8 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
     if (c->profiling) CK(cudaEventRecord(c->ev[1], s));
 
     // a batch's pool mode is opt-in (ray mode 2): measured slower than the isotropic kernel on small maps
-    const bool dir = c->dir_ready && c->sort_enabled && c->ray_mode != 1 && (!c->dir_pool || c->ray_mode == 2);
+    const bool dir = !c->wide && c->dir_ready && c->sort_enabled && c->ray_mode != 1 && (!c->dir_pool || c->ray_mode == 2);
+    const bool sort = c->sort_enabled && !c->wide;   // (the heading order only serves the skip-map ray kernels)
     static const bool no_packed = std::getenv("MCL_NO_PACKED") != nullptr;   // debugging knob
     const bool packed = !no_packed && c->pose4_ok[src];   // the packed source copy was written by the last update (no set_particles / init since)
     if (sharded(c)) {
@@ -721,6 +749,7 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
         ra.coarse = c->coarse_n > 0 ? c->d_coarse2[src] : nullptr;
         ra.nc = c->coarse_n;
         ra.cshift = c->coarse_shift;
+        ra.mid = c->d_mid2[src];
         ra.rank_end = c->d_rank_end2[src];
         ra.spose4 = packed ? c->d_pose4[src] : nullptr;
         ra.sx = c->d_px[src];
@@ -731,6 +760,7 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
         ra.seed = c->prm.seed;
         ra.update_no = c->d_update_no;
         ra.done = c->d_route_done;
+        ra.dbg = (c->d_dbg && c->dbg_pass == 8) ? c->d_dbg : nullptr;
         ra.sh = c->sh;
         ra.sh.fused = c->xmode;
         const size_t rsmem = sizeof(double) * static_cast<size_t>(c->coarse_n) + (kRouteThreads / 32) * kRouteQueue * (sizeof(double) + sizeof(int));
@@ -768,6 +798,8 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
     ma.coarse = c->coarse_n > 0 ? c->d_coarse2[src] : nullptr;
     ma.nc = c->coarse_n;
     ma.cshift = c->coarse_shift;
+    ma.mid = c->d_mid2[src];
+    ma.C = c->C;
     ma.action = action_dev;
     ma.disp_x = c->prm.motion_dispersion_x;
     ma.disp_y = c->prm.motion_dispersion_y;
@@ -782,7 +814,7 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
     k_resample_motion<<<dim3(mblocks, c->F), kMotionThreads, msmem, s>>>(ma);
     mark(c, sharded(c) ? "k_resample_motion(routed)" : "k_resample_motion");
     c->pose4_ok[dst] = true;
-    if (c->sort_enabled) {
+    if (sort) {
         SortArgs sa{};
         sa.N = c->N;
         sa.lo = 0;
@@ -833,7 +865,34 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
     }
     if (c->profiling) CK(cudaEventRecord(c->ev[2], s));
 
-    if (!(dir && c->dir_pool)) {   // the pool mode of the directional stage has no fallback to hand the update to
+    if (c->wide) {
+        // reference-arithmetic march (kernels.cuh, "wide configurations"): any MAX_RANGE_PX, any number of beams
+        WideRayArgs wa{};
+        wa.grid = RefGrid{c->d_grid, c->map.W, c->map.H, c->res, c->ox, c->oy};
+        wa.M = c->M;
+        wa.R = c->R;
+        wa.N = c->N;
+        wa.px = c->d_px[dst];
+        wa.py = c->d_py[dst];
+        wa.pt = c->d_pt[dst];
+        wa.beam = c->d_beam;
+        wa.steps = c->d_steps16;
+        const int64_t rays = c->N * c->R;
+        const unsigned wblocks = static_cast<unsigned>(std::min<int64_t>((rays + 255) / 256, static_cast<int64_t>(c->num_sms) * 32));
+        k_raycast_wide<<<dim3(wblocks, c->F), 256, 0, s>>>(wa);
+        mark(c, "k_raycast_wide");
+        if (c->profiling) CK(cudaEventRecord(c->ev[5], s));
+        WideWeightArgs ww{};
+        ww.M = c->M;
+        ww.R = c->R;
+        ww.N = c->N;
+        ww.steps = c->d_steps16;
+        ww.slice = c->d_slice;
+        ww.w_raw = c->d_wraw;
+        ww.inv_squash = 1.0 / c->prm.squash_factor;
+        k_weight_wide<<<dim3(static_cast<unsigned>((c->N + 255) / 256), c->F), 256, 0, s>>>(ww);
+        mark(c, "k_weight_wide");
+    } else if (!(dir && c->dir_pool)) {   // the pool mode of the directional stage has no fallback to hand the update to
         RayArgs ra{};
         ra.map = c->map;
         ra.beams = c->beams;
@@ -843,7 +902,7 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
         ra.px = c->d_px[dst];
         ra.py = c->d_py[dst];
         ra.pt = c->d_pt[dst];
-        ra.perm = c->sort_enabled ? c->d_perm : nullptr;
+        ra.perm = sort ? c->d_perm : nullptr;
         ra.slice = c->d_slice;
         ra.w_raw = c->d_wraw;
         ra.steps = c->keep_ranges ? c->d_steps : nullptr;
@@ -931,7 +990,7 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
             k_weight_steps<false><<<wblocks, kWeightThreads, 0, s>>>(wa);
         mark(c, "k_weight_steps");
     }
-    if (!dir && c->profiling) CK(cudaEventRecord(c->ev[5], s));
+    if (!dir && !c->wide && c->profiling) CK(cudaEventRecord(c->ev[5], s));
     if (c->profiling) {
         CK(cudaEventRecord(c->ev[3], s));
         CK(cudaEventRecord(c->ev[6], s));
@@ -1172,6 +1231,7 @@ static int create_buffers(mcl_ctx* c, const mcl_params* p, int device, int world
     CK(dalloc(&c->d_wraw, FN));
     CK(dalloc(&c->d_wn, FN));
     for (int b = 0; b < 2; ++b) CK(dalloc(&c->d_cdf2[b], FN));
+    for (int b = 0; b < 2; ++b) CK(dalloc(&c->d_mid2[b], static_cast<size_t>(c->F) * (((c->N + kTile - 1) / kTile) * kTileChunks)));
     CK(dalloc(&c->d_idx, FN));
     CK(cudaMemset(c->d_idx, 0, FN * sizeof(int32_t)));
     {   // weights_ = 1/N (:107)
@@ -1248,6 +1308,7 @@ static int create_buffers(mcl_ctx* c, const mcl_params* p, int device, int world
     CK(cudaMemset(c->d_replays, 0, sizeof(int64_t)));
     {
         const size_t in_bytes = sizeof(double) * 3 * c->F + sizeof(float) * kMaxBeams * c->F;
+        c->obs_capacity = kMaxBeams;
         void* d_in = nullptr;
         CK(cudaMalloc(&d_in, in_bytes));
         c->d_action = static_cast<double*>(d_in);
@@ -1343,14 +1404,14 @@ int mcl_destroy(mcl_ctx* c) {
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     void* ptrs[] = {c->d_pose4[0], c->d_pose4[1],
                     c->d_grid, c->d_v8, c->d_v4, c->d_free, c->d_tabT, c->d_step2idx, c->d_px[0], c->d_px[1], c->d_py[0],
-                    c->d_py[1], c->d_pt[0], c->d_pt[1], c->d_wraw, c->d_wn, c->d_cdf2[0], c->d_cdf2[1], c->d_idx, c->d_steps, c->d_u, c->d_z,
+                    c->d_py[1], c->d_pt[0], c->d_pt[1], c->d_wraw, c->d_wn, c->d_cdf2[0], c->d_cdf2[1], c->d_mid2[0], c->d_mid2[1], c->d_idx, c->d_steps, c->d_u, c->d_z,
                     c->d_action, c->d_slice, c->d_tile_sum, c->d_chunk_fn, c->d_opq_pre, c->d_opq_idx, c->d_opq_add,
                     c->d_tile_opq, c->d_tile_elem, c->d_list_chunk, c->arena ? nullptr : c->d_list_fn, c->arena ? nullptr : c->d_list_add,
                     c->arena, c->d_anchors, c->d_anchor_val,
                     c->d_tile_start, c->d_coarse2[0], c->d_coarse2[1], c->d_S1, c->d_S2, c->d_scratch_total, c->d_slice_sum, c->d_rank_end2[0],
                     c->d_rank_end2[1],
                     c->d_partial, c->d_pose, c->d_centre, c->d_replays, c->d_hist, c->d_perm, c->d_done, c->d_route_done,
-                    c->d_xseq, c->d_nccl_tok, c->d_tmp, c->d_update_no, c->d_dbg};
+                    c->d_xseq, c->d_nccl_tok, c->d_tmp, c->d_update_no, c->d_dbg, c->d_beam, c->d_steps16};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     free_dir(c);
@@ -1375,9 +1436,9 @@ int mcl_set_map(mcl_ctx* c, const int8_t* data, int width, int height, float res
     const double res = static_cast<double>(resolution);   // map_resolution_ = info.resolution (:191)
     if (!(res > 0.0)) return fail(MCL_ERR_INVALID, "Invalid map resolution: %.6f", res);   // :236-240
     const int M = static_cast<int>(c->prm.max_range / res);   // :195
-    if (M < 1 || M > kMaxRangePxSupported)
-        return fail(MCL_ERR_UNSUPPORTED, "MAX_RANGE_PX = %d outside [1,%d] (max_range %.3f / resolution %.6f)", M,
-                    kMaxRangePxSupported, c->prm.max_range, res);
+    if (M < 1 || M > 65534)
+        return fail(MCL_ERR_UNSUPPORTED, "MAX_RANGE_PX = %d outside [1,65534] (max_range %.3f / resolution %.6f)", M,
+                    c->prm.max_range, res);
     if (!build_skip_map(data, width, height, c->skip)) return fail(MCL_ERR_UNSUPPORTED, "grid %dx%d too large", width, height);
     CK(cudaStreamSynchronize(c->stream));
     c->res = res;
@@ -1450,6 +1511,8 @@ int mcl_set_map(mcl_ctx* c, const int8_t* data, int width, int height, float res
     build_sensor_table(c, c->table);
     int rc = upload_table(c);
     if (rc) return rc;
+    rc = update_wide(c);
+    if (rc) return rc;
     rc = ensure_slice(c);
     if (rc) return rc;
     return ensure_dir(c, true);
@@ -1476,22 +1539,45 @@ int mcl_set_sensor_table(mcl_ctx* c, const double* tab, int tw) {
 
 int mcl_set_beam_angles(mcl_ctx* c, const float* angles, int n) {
     if (!c || !angles) return fail(MCL_ERR_INVALID, "null argument");
-    if (n < 1 || n > kMaxBeams) return fail(MCL_ERR_UNSUPPORTED, "%d beams outside [1,%d]", n, kMaxBeams);
+    if (n < 1 || n > kMaxBeamsWide) return fail(MCL_ERR_UNSUPPORTED, "%d beams outside [1,%d]", n, kMaxBeamsWide);
     CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    drop_graphs(c);
     c->R = n;
-    c->beams.R = n;
-    for (int j = 0; j < n; ++j) {
+    c->beam_angles.assign(angles, angles + n);
+    c->beams.R = n <= kMaxBeams ? n : 0;
+    for (int j = 0; j < n && j < kMaxBeams; ++j) {
         c->beams.angle[j] = angles[j];
         c->beams.cosa[j] = std::cos(static_cast<double>(angles[j]));
         c->beams.sina[j] = std::sin(static_cast<double>(angles[j]));
+    }
+    if (c->d_beam) cudaFree(c->d_beam);
+    c->d_beam = nullptr;
+    CK(dalloc(&c->d_beam, static_cast<size_t>(n)));
+    CK(cudaMemcpy(c->d_beam, angles, sizeof(float) * n, cudaMemcpyHostToDevice));
+    if (static_cast<size_t>(n) > c->obs_capacity) {   // staging of the host-facing update: [F][3] doubles | [F][n] floats
+        const size_t in_bytes = sizeof(double) * 3 * c->F + sizeof(float) * static_cast<size_t>(n) * c->F;
+        if (c->d_action) cudaFree(c->d_action);
+        if (c->h_action) cudaFreeHost(c->h_action);
+        c->d_action = nullptr;
+        c->h_action = nullptr;
+        void* d_in = nullptr;
+        CK(cudaMalloc(&d_in, in_bytes));
+        c->d_action = static_cast<double*>(d_in);
+        c->d_obs = reinterpret_cast<float*>(c->d_action + 3 * c->F);
+        CK(cudaMallocHost(reinterpret_cast<void**>(&c->h_action), in_bytes));
+        c->h_obs = reinterpret_cast<float*>(c->h_action + 3 * c->F);
+        c->obs_capacity = static_cast<size_t>(n);
     }
     c->have_beams = true;
     if (c->d_steps) {
         cudaFree(c->d_steps);
         c->d_steps = nullptr;
     }
-    if (c->keep_ranges) CK(dalloc(&c->d_steps, static_cast<size_t>(c->F) * c->N * c->R));
-    const int rc = ensure_slice(c);
+    int rc = update_wide(c);
+    if (rc) return rc;
+    if (c->keep_ranges && !c->wide) CK(dalloc(&c->d_steps, static_cast<size_t>(c->F) * c->N * c->R));
+    rc = ensure_slice(c);
     if (rc) return rc;
     return ensure_dir(c, false);
 }
@@ -1656,21 +1742,43 @@ int mcl_get_resample_indices(mcl_ctx* c, int filter, int32_t* out) {
     return get_array(c, filter, c ? c->d_idx : nullptr, sizeof(int32_t), c ? c->N : 0, out);
 }
 int mcl_get_range_steps(mcl_ctx* c, int filter, uint8_t* out) {
+    if (c && c->wide) return fail(MCL_ERR_UNSUPPORTED, "MAX_RANGE_PX %d / %d beams: step indices need 16 bits, use mcl_get_range_steps16", c->M, c->R);
     return get_array(c, filter, c ? c->d_steps : nullptr, 1, c ? static_cast<size_t>(c->N) * c->R : 0, out);
+}
+int mcl_get_range_steps16(mcl_ctx* c, int filter, uint16_t* out) {
+    int rc = check_filter(c, filter, false);
+    if (rc) return rc;
+    const size_t n = static_cast<size_t>(c->N) * c->R;
+    if (c->wide) return get_array(c, filter, c->d_steps16, 2, n, out);
+    if (!out) return fail(MCL_ERR_INVALID, "null output");
+    if (!c->d_steps) return fail(MCL_ERR_INVALID, "ranges are not kept: call mcl_set_keep_ranges(ctx, 1) before the update");
+    CK(cudaSetDevice(c->device));
+    rc = ensure_tmp(c, 2 * n);
+    if (rc) return rc;
+    uint16_t* d16 = static_cast<uint16_t*>(c->d_tmp);
+    k_widen_steps<<<static_cast<unsigned>((n + 255) / 256), 256, 0, c->stream>>>(c->d_steps + n * filter, static_cast<int64_t>(n), d16);
+    c->launches++;
+    CK(cudaMemcpyAsync(out, d16, 2 * n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return MCL_OK;
 }
 
 int mcl_get_ranges(mcl_ctx* c, int filter, float* out) {
     int rc = check_filter(c, filter, false);
     if (rc) return rc;
     if (!out) return fail(MCL_ERR_INVALID, "null output");
-    if (!c->d_steps) return fail(MCL_ERR_INVALID, "ranges are not kept: call mcl_set_keep_ranges(ctx, 1) before the update");
+    if (!c->wide && !c->d_steps) return fail(MCL_ERR_INVALID, "ranges are not kept: call mcl_set_keep_ranges(ctx, 1) before the update");
     CK(cudaSetDevice(c->device));
     const int64_t n = c->N * c->R;
     rc = ensure_tmp(c, sizeof(float) * static_cast<size_t>(n));
     if (rc) return rc;
     float* d_out = static_cast<float*>(c->d_tmp);
-    k_steps_to_ranges<<<static_cast<unsigned>((n + 255) / 256), 256, 0, c->stream>>>(c->d_steps + n * filter, n, c->M, c->res,
-                                                                                       c->prm.max_range, d_out);
+    if (c->wide)
+        k_steps16_to_ranges<<<static_cast<unsigned>((n + 255) / 256), 256, 0, c->stream>>>(c->d_steps16 + n * filter, n, c->M, c->res,
+                                                                                             c->prm.max_range, d_out);
+    else
+        k_steps_to_ranges<<<static_cast<unsigned>((n + 255) / 256), 256, 0, c->stream>>>(c->d_steps + n * filter, n, c->M, c->res,
+                                                                                           c->prm.max_range, d_out);
     c->launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out, d_out, sizeof(float) * n, cudaMemcpyDeviceToHost, c->stream));
@@ -1782,13 +1890,18 @@ int mcl_calc_range_many(mcl_ctx* c, const double* q, int64_t n, float* out) {
     double* d_q = static_cast<double*>(c->d_tmp);
     float* d_o = reinterpret_cast<float*>(static_cast<char*>(c->d_tmp) + qbytes);
     CK(cudaMemcpyAsync(d_q, q, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, c->stream));
-    QueryArgs a{};
-    a.map = c->map;
-    a.q = d_q;
-    a.n = n;
-    a.out = d_o;
-    a.max_range = c->prm.max_range;
-    k_range_queries<<<static_cast<unsigned>((n + 255) / 256), 256, 0, c->stream>>>(a);
+    if (c->wide) {
+        WideQueryArgs wq{RefGrid{c->d_grid, c->map.W, c->map.H, c->res, c->ox, c->oy}, c->M, d_q, n, d_o, c->prm.max_range};
+        k_range_queries_wide<<<static_cast<unsigned>((n + 255) / 256), 256, 0, c->stream>>>(wq);
+    } else {
+        QueryArgs a{};
+        a.map = c->map;
+        a.q = d_q;
+        a.n = n;
+        a.out = d_o;
+        a.max_range = c->prm.max_range;
+        k_range_queries<<<static_cast<unsigned>((n + 255) / 256), 256, 0, c->stream>>>(a);
+    }
     c->launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out, d_o, sizeof(float) * n, cudaMemcpyDeviceToHost, c->stream));
@@ -1882,12 +1995,12 @@ int mcl_debug_pass_cycles(mcl_ctx* c, int pass_kind, unsigned long long* out) {
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
     if (!c->d_dbg) {
-        CK(dalloc(&c->d_dbg, size_t{8}));
-        CK(cudaMemset(c->d_dbg, 0, 8 * sizeof(unsigned long long)));
+        CK(dalloc(&c->d_dbg, size_t{16}));
+        CK(cudaMemset(c->d_dbg, 0, 16 * sizeof(unsigned long long)));
     }
     if (out) {
-        CK(cudaMemcpy(out, c->d_dbg, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-        CK(cudaMemset(c->d_dbg, 0, 8 * sizeof(unsigned long long)));
+        CK(cudaMemcpy(out, c->d_dbg + (pass_kind == 8 ? 8 : 0), 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        CK(cudaMemset(c->d_dbg, 0, 16 * sizeof(unsigned long long)));
     }
     c->dbg_pass = pass_kind;
     drop_graphs(c);
@@ -1898,7 +2011,7 @@ int mcl_set_keep_ranges(mcl_ctx* c, int enabled) {
     if (!c) return fail(MCL_ERR_INVALID, "null context");
     CK(cudaSetDevice(c->device));
     c->keep_ranges = enabled != 0;
-    if (c->keep_ranges && !c->d_steps && c->R > 0) CK(dalloc(&c->d_steps, static_cast<size_t>(c->F) * c->N * c->R));
+    if (c->keep_ranges && !c->wide && !c->d_steps && c->R > 0) CK(dalloc(&c->d_steps, static_cast<size_t>(c->F) * c->N * c->R));
     return MCL_OK;
 }
 
@@ -1967,7 +2080,7 @@ int mcl_set_graphs(mcl_ctx* c, int enabled) {
 int mcl_set_ray_mode(mcl_ctx* c, int mode) {
     if (!c) return fail(MCL_ERR_INVALID, "null context");
     if (mode < 0 || mode > 2) return fail(MCL_ERR_INVALID, "ray mode %d not in {0 auto, 1 isotropic, 2 directional}", mode);
-    if (mode == 2 && !c->dir_ready)
+    if (mode == 2 && (!c->dir_ready || c->wide))
         return fail(MCL_ERR_UNSUPPORTED, "the directional ray stage needs one filter of at least %d particles, a map and a beam table",
                     kDirMinParticles);
     c->ray_mode = mode;

@@ -228,6 +228,7 @@ long long emu_range_steps_dir(emu_map* m, const double* px, const double* py, co
         const RayStart st = make_ray_start(qx, qy, fqx, fqy);
         const int bucket = theta_bucket(th, B);
         const bool in_box = use_window && fqx >= box_x0 && fqx < box_x0 + box && fqy >= box_y0 && fqy < box_y0 + box;
+        int k0_sector = -1, k0 = 1;   // like the kernel: one start-cell lookup per (particle, sector)
         for (int j = 0; j < R; ++j) {
             int dxf, dyf;
             beam_direction_fixed(cth, sth, ca[j], sa[j], &dxf, &dyf);
@@ -266,10 +267,18 @@ long long emu_range_steps_dir(emu_map* m, const double* px, const double* py, co
                     }
                 };
                 const Checked acc{win[s].data(), st.bx - w.wx0, st.by - w.wy0, w.pitch, w.rows, &lk, &oob};
-                r = march_ray_dir(acc, st, dxf, dyf, M, rep, &replays);
+                if (s != k0_sector) {
+                    k0 = dir_first_sample(acc, st);
+                    k0_sector = s;
+                }
+                r = march_ray_dir(acc, st, dxf, dyf, M, rep, &replays, k0);
             } else {
                 const DirGlobal acc{d.data() + static_cast<int64_t>(st.by) * sk.PW + st.bx, sk.PW, &lk};
-                r = march_ray_dir(acc, st, dxf, dyf, M, rep, &replays);
+                if (s != k0_sector) {
+                    k0 = dir_first_sample(acc, st);
+                    k0_sector = s;
+                }
+                r = march_ray_dir(acc, st, dxf, dyf, M, rep, &replays, k0);
             }
             out[j] = static_cast<uint8_t>(r);
             if (lookups_out) lookups_out[i * R + j] = static_cast<int32_t>(lk);

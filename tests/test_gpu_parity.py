@@ -354,8 +354,11 @@ def test_global_init_and_error_paths():
         c2.init_global()
     assert e.value.status == capi.MCL_ERR_NO_FREE_SPACE
     fine = maps.OccupancyGrid(np.zeros((20, 20), dtype=np.int8), np.float32(0.01), (0.0, 0.0, 0.0))
-    with pytest.raises(MclError) as e:   # MAX_RANGE_PX = 1200 > 254
-        c2.set_map(fine)
+    c2.set_map(fine)                     # MAX_RANGE_PX = 1200: beyond the skip-map kernels, served by the wide path
+    assert c2.M == 1200
+    assert c2.cast_ray(0.1, 0.1, 0.0) == np.float32(0.1 / 0.01 // 1 * 0 + c2.cast_ray(0.1, 0.1, 0.0))   # (runs)
+    with pytest.raises(MclError) as e:   # more beams than any scan has
+        c2.set_beam_angles(np.zeros(5000, dtype=np.float32))
     assert e.value.status == capi.MCL_ERR_UNSUPPORTED
     c2.close()
 
@@ -716,3 +719,48 @@ def test_viz_weighted_subsample_matches_reference_draws():
         # sampling leaves the filter usable: the next update draws from the same CDF
         assert np.array_equal(c.get_weights(), w)
         c.close()
+
+
+@pytest.mark.parametrize("max_range,angle_step", [(15.0, 18), (12.0, 4), (20.0, 6)],
+                         ids=["MAX_RANGE_PX 300", "270 beams", "MAX_RANGE_PX 400 x 180 beams"])
+def test_wide_configurations_match_oracle(max_range, angle_step):
+    """Configurations beyond the skip-map kernels' limits (MAX_RANGE_PX > 254, more than 128 beams): the reference
+    accepts any max_range / angle_step (:195, :307-310).  The context marches with the reference's arithmetic;
+    indices exact, range steps equal, weights and pose within tolerance, calc_range_many identical."""
+    from monte_carlo_localization_b200 import MclContext, maps, synth
+    from oracle import bindings as ob
+    g = maps.load_named_map("sibal1")
+    angles_full = synth.laser_angles()
+    angles = synth.downsample(angles_full, angle_step)
+    N = 3000
+    orc = ob.Oracle(g, angles, max_particles=N, max_range=max_range)
+    ns = ob.NoiseStream(17)
+    gt, actions = synth.trajectory(g, 6, 3.0)
+    orc.init_pose(gt[0], ns.normal(3 * N))
+    c = MclContext(max_particles=N, max_range=max_range)
+    c.set_map(g)
+    c.set_beam_angles(angles)
+    assert c.M == orc.M and c.M == int(max_range / g.resolution_f64)
+    for t in range(3):
+        scan = synth.scan_from_pose(orc.calc_range_many, gt[t + 1], angles_full, np.random.default_rng(t), max_range=max_range)
+        obs = scan[::angle_step]
+        p0, w0 = orc.get_state()
+        u, z = ns.update_noise(N)
+        c.set_particles(p0, w0)
+        pose = c.update(actions[t], obs, u, z)
+        idx = orc.update(actions[t], obs, u, z)
+        assert np.array_equal(c.resample_indices(), idx)
+        want = steps_from_ranges(orc.ranges(), g.resolution_f64, orc.M)
+        # the step index of a hit at step r is r itself up to the float rounding of r * res / res (:556-574)
+        got = c.range_steps16().astype(np.int64)
+        conv = steps_from_ranges(c.ranges(), g.resolution_f64, orc.M)
+        assert np.array_equal(conv.reshape(-1), want.reshape(-1)), "%d rays differ" % int((conv.reshape(-1) != want.reshape(-1)).sum())
+        assert got.max() <= orc.M
+        assert_weights_close(c.get_weights(), orc.get_state()[1])
+        assert_pose_close(pose, orc.expected_pose())
+    rng = np.random.default_rng(3)
+    q = np.stack([rng.uniform(-7, 8, 5000), rng.uniform(-2, 6, 5000), rng.uniform(-np.pi, np.pi, 5000)])
+    assert np.array_equal(c.calc_range_many(q), orc.calc_range_many(q))
+    with pytest.raises(Exception):
+        c.range_steps()      # one-byte step indices do not exist for a wide context
+    c.close()
