@@ -209,14 +209,22 @@ __device__ __forceinline__ int count_below(const double* __restrict__ p, double 
     ldg256(p + 4, v4, v5, v6, v7);
     return (v0 < u) + (v1 < u) + (v2 < u) + (v3 < u) + (v4 < u) + (v5 < u) + (v6 < u) + (v7 < u);
 }
+// The coarse level is searched on 32-bit keys: for non-negative doubles the order of the values is the order of
+// their bit patterns, so the high word decides unless it ties (then the exact double from global memory does).
+// Random 4-byte shared-memory reads cost a third of the bank-conflict replays of 8-byte ones, and the table is
+// half the size.
 __device__ __forceinline__ int64_t cdf_lower_bound(const double* __restrict__ cp, const double* __restrict__ mid, int64_t N,
-                                                   const double* ts, int nc, int cshift, double u) {
+                                                   const uint32_t* ts, const double* __restrict__ coarse, int nc, int cshift, double u) {
     int64_t lo = 0, hi = N;
     if (nc > 0) {
+        const uint32_t uh = static_cast<uint32_t>(__double2hiint(u));
         int kl = 0, kh = nc;
         while (kl < kh) {
             const int km = (kl + kh) >> 1;
-            if (ts[km] < u)
+            const uint32_t t = ts[km];
+            bool below = t < uh;
+            if (t == uh) below = __ldg(coarse + km) < u;   // rare: same 32 leading bits
+            if (below)
                 kl = km + 1;
             else
                 kh = km;
@@ -319,12 +327,13 @@ constexpr int kMotionThreads = 1024;
 // pushed into `routed` by k_route on the rank that owns the source; only the motion runs here.
 __global__ void __launch_bounds__(kMotionThreads) k_resample_motion(MotionArgs a) {
     __shared__ double sm[kMotionThreads / 32];
-    extern __shared__ double ts[];   // a.nc doubles when the coarse level is used
+    extern __shared__ uint32_t ts[];   // a.nc keys (high words of the coarse level) when it is used
     const int f = blockIdx.y;
     const bool search = a.routed == nullptr;
     const int nc = (search && a.coarse != nullptr) ? a.nc : 0;
+    const double* coarse = nc > 0 ? a.coarse + static_cast<int64_t>(f) * a.nc : nullptr;
     if (nc > 0) {
-        for (int t = threadIdx.x; t < nc; t += kMotionThreads) ts[t] = a.coarse[static_cast<int64_t>(f) * a.nc + t];
+        for (int t = threadIdx.x; t < nc; t += kMotionThreads) ts[t] = static_cast<uint32_t>(__double2hiint(coarse[t]));
         __syncthreads();
     }
     const int64_t N = a.N;
@@ -338,7 +347,7 @@ __global__ void __launch_bounds__(kMotionThreads) k_resample_motion(MotionArgs a
         if (search) {
             const int64_t i = a.glo + li;
             const double u = a.u ? a.u[fo + i] : resample_uniform(i, f, a.seed, update_no);
-            int64_t lo = cdf_lower_bound(a.cdf + fo, a.mid ? a.mid + static_cast<int64_t>(f) * a.C : nullptr, N, ts, nc, a.cshift, u);
+            int64_t lo = cdf_lower_bound(a.cdf + fo, a.mid ? a.mid + static_cast<int64_t>(f) * a.C : nullptr, N, ts, coarse, nc, a.cshift, u);
             if (N < 2) lo = 0;        // libstdc++ clears the table for fewer than 2 weights
             a.idx_out[fo + li] = static_cast<int32_t>(lo);
             if (a.spose4) {
@@ -406,13 +415,14 @@ __device__ __forceinline__ void route_finish(const ShardDev& sh, unsigned long l
 }
 
 __global__ void __launch_bounds__(kRouteThreads) k_route(RouteArgs a) {
-    extern __shared__ double ts[];   // nc doubles of the coarse level, then the warps' queues
+    extern __shared__ __align__(8) uint32_t ts[];   // nc keys of the coarse level (padded to even), then the warps' queues
     __shared__ bool is_last;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long c_begin = clock64();
-    for (int t = tid; t < a.nc; t += kRouteThreads) ts[t] = a.coarse[t];
-    double* qu = ts + a.nc + warp * kRouteQueue;                                           // queued draws
-    int* qi = reinterpret_cast<int*>(ts + a.nc + (kRouteThreads / 32) * kRouteQueue) + warp * kRouteQueue;   // queued slots
+    for (int t = tid; t < a.nc; t += kRouteThreads) ts[t] = static_cast<uint32_t>(__double2hiint(a.coarse[t]));
+    double* qbase = reinterpret_cast<double*>(ts + ((a.nc + 1) & ~1));
+    double* qu = qbase + warp * kRouteQueue;                                               // queued draws
+    int* qi = reinterpret_cast<int*>(qbase + (kRouteThreads / 32) * kRouteQueue) + warp * kRouteQueue;   // queued slots
     __syncthreads();
     const int me = a.sh.rank, world = a.sh.world;
     const double lo_u = me > 0 ? a.rank_end[me - 1] : -1.0;          // claim u in (lo_u, hi_u]
@@ -424,7 +434,7 @@ __global__ void __launch_bounds__(kRouteThreads) k_route(RouteArgs a) {
     auto serve = [&](int k) {   // lane k < count serves queue entry k
         const double u = qu[k];
         const int64_t i = qi[k];
-        const int64_t j = cdf_lower_bound(a.cdf, a.mid, a.N, ts, a.nc, a.cshift, u);
+        const int64_t j = cdf_lower_bound(a.cdf, a.mid, a.N, ts, a.coarse, a.nc, a.cshift, u);
         double x, y, th;
         if (a.spose4) {
             double pad;

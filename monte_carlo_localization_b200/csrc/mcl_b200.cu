@@ -763,7 +763,7 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
         ra.dbg = (c->d_dbg && c->dbg_pass == 8) ? c->d_dbg : nullptr;
         ra.sh = c->sh;
         ra.sh.fused = c->xmode;
-        const size_t rsmem = sizeof(double) * static_cast<size_t>(c->coarse_n) + (kRouteThreads / 32) * kRouteQueue * (sizeof(double) + sizeof(int));
+        const size_t rsmem = sizeof(uint32_t) * static_cast<size_t>((c->coarse_n + 1) & ~1) + (kRouteThreads / 32) * kRouteQueue * (sizeof(double) + sizeof(int));
         const int rblocks = static_cast<int>(std::min<int64_t>(c->num_sms, (c->NG + 2 * kRouteThreads - 1) / (2 * kRouteThreads)));
         k_route<<<rblocks, kRouteThreads, rsmem, s>>>(ra);
         mark(c, "k_route");
@@ -808,9 +808,9 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
     ma.update_no = c->d_update_no;
     ma.centre = c->d_centre;
     int mblocks = static_cast<int>((c->N + kMotionThreads - 1) / kMotionThreads);
-    const size_t msmem = sharded(c) ? 0 : sizeof(double) * static_cast<size_t>(c->coarse_n);
+    const size_t msmem = sharded(c) ? 0 : sizeof(uint32_t) * static_cast<size_t>(c->coarse_n);
     // a large table is staged once per SM by persistent blocks; a small one by every block
-    if (msmem > 16 * 1024) mblocks = std::min(mblocks, std::max(1, c->num_sms / std::min(c->F, c->num_sms)));
+    if (msmem > 8 * 1024) mblocks = std::min(mblocks, std::max(1, c->num_sms / std::min(c->F, c->num_sms)));
     k_resample_motion<<<dim3(mblocks, c->F), kMotionThreads, msmem, s>>>(ma);
     mark(c, sharded(c) ? "k_resample_motion(routed)" : "k_resample_motion");
     c->pose4_ok[dst] = true;

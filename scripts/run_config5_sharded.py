@@ -23,7 +23,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--particles-per-gpu", type=int, default=2097152)
     ap.add_argument("--updates", type=int, default=60)
-    ap.add_argument("--shard-mode", default="p2p")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"])
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -38,7 +38,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         flt = ShardedFilter(g, angles, n_local=a.particles_per_gpu, rank=rank, world=world, device=local_rank,
-                            seed=20255, mode=a.shard_mode)
+                            seed=20255, exchange=a.exchange)
         ctx = flt.ctx
     else:
         flt = None
@@ -72,7 +72,7 @@ def main():
         print(json.dumps({
             "config": 5, "map": "basement_fixed (levine stand-in: levine.pgm is missing from the reference checkout)",
             "n_gpus": world, "particles": n_global, "beams": len(angles), "free_cells": ctx.num_free_cells(),
-            "sharding": "single GPU" if world == 1 else "particle-sharded x%d (%s)" % (world, flt.mode),
+            "sharding": "single GPU" if world == 1 else "particle-sharded x%d, slice-local state, %s exchange" % (world, flt.exchange),
             "updates_run": a.updates, "converged_at_update": conv,
             "ms_per_update_first5": 1e3 * float(np.mean(times[:5])), "ms_per_update_last5": 1e3 * float(np.mean(times[-5:])),
             "time_to_converge_s": None if conv is None else float(np.sum(times[:conv + 9])),
