@@ -984,10 +984,19 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
         wa.tw = c->M + 1;
         wa.inv_squash = 1.0 / c->prm.squash_factor;
         const unsigned wblocks = static_cast<unsigned>((slots + 4 * kWeightThreads - 1) / (4 * kWeightThreads));
-        if (c->dir_pool)
+        const size_t tab_bytes = sizeof(double) * static_cast<size_t>(c->R) * (c->M + 1);
+        static const bool no_sm_table = std::getenv("MCL_NO_SMEM_TABLE") != nullptr;   // debugging knob
+        if (c->dir_pool) {
             k_weight_steps<true><<<wblocks, kWeightThreads, 0, s>>>(wa);
-        else
+        } else if (!no_sm_table && tab_bytes <= 110 * 1024) {   // two persistent 512-thread CTAs per SM share the SM's shared memory
+            const unsigned g = static_cast<unsigned>(std::min<int64_t>(2 * c->num_sms, (slots + 4 * 512 - 1) / (4 * 512)));
+            k_weight_steps_sm<512><<<g, 512, tab_bytes, s>>>(wa);
+        } else if (!no_sm_table && tab_bytes <= 220 * 1024) {
+            const unsigned g = static_cast<unsigned>(std::min<int64_t>(c->num_sms, (slots + 4 * 1024 - 1) / (4 * 1024)));
+            k_weight_steps_sm<1024><<<g, 1024, tab_bytes, s>>>(wa);
+        } else {
             k_weight_steps<false><<<wblocks, kWeightThreads, 0, s>>>(wa);
+        }
         mark(c, "k_weight_steps");
     }
     if (!dir && !c->wide && c->profiling) CK(cudaEventRecord(c->ev[5], s));
@@ -1358,6 +1367,8 @@ static int create_buffers(mcl_ctx* c, const mcl_params* p, int device, int world
     CK(cudaFuncSetAttribute(k_resample_motion, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * static_cast<int>(sizeof(double))));
     CK(cudaFuncSetAttribute(k_route, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             16384 * static_cast<int>(sizeof(double)) + (kRouteThreads / 32) * kRouteQueue * 12));
+    CK(cudaFuncSetAttribute(k_weight_steps_sm<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+    CK(cudaFuncSetAttribute(k_weight_steps_sm<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     CK(cudaFuncSetAttribute(k_raycast_dir<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kWindowBudget)));
     CK(cudaFuncSetAttribute(k_raycast_dir<207>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kWindowBudget)));
     CK(cudaFuncSetAttribute(k_raycast_dir<238>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kWindowBudget)));
