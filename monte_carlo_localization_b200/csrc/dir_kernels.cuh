@@ -280,6 +280,8 @@ struct DirRayArgs {
     int B, shift, box;
     int win_bytes;              // shared-memory bytes reserved for the sector window
     int whole;                  // pool mode: the window of every sector is its whole map
+    int beam_ranges;            // 1: the beam offsets io[] are cyclically non-decreasing (any real scan): the beams of a
+                                // (warp, sector) are one or two INDEX RANGES read from a table; 0: found by ballots
 };
 
 // dynamic shared memory of k_raycast_dir: window | rec0 prefetch [2][1024] | rec1 prefetch [2][1024]
@@ -295,6 +297,7 @@ __global__ void __launch_bounds__(kDirThreads, 1) k_raycast_dir(DirRayArgs a) {
     __shared__ uint32_t s_units[kDirGrab];    // chunk << 6 | sector
     __shared__ int s_sec[2 * kDirSectors + 2];
     __shared__ int s_io[kMaxBeams];
+    __shared__ uint16_t s_cnt[kMaxBuckets + 1];   // s_cnt[x] = number of beams whose offset, counted from beam 0's, is below x
     if (a.plan[kPlanMode] != 1) return;
     const unsigned n_units = static_cast<unsigned>(a.plan[kPlanUnits]);
     const MapDev& mp = a.map;
@@ -313,6 +316,21 @@ __global__ void __launch_bounds__(kDirThreads, 1) k_raycast_dir(DirRayArgs a) {
     const uint32_t io_saddr = static_cast<uint32_t>(__cvta_generic_to_shared(s_io)) + static_cast<uint32_t>(lane) * 4u;
     if (tid < 2 * kDirSectors + 1) s_sec[tid] = a.sec_tab[tid];
     if (tid < kMaxBeams) s_io[tid] = tid < R ? a.io[tid] : 0;
+    if (a.beam_ranges) {
+        __syncthreads();
+        const int io0 = s_io[0];
+        for (int x = tid; x <= a.B; x += kDirThreads) {   // beams with ((io_j - io_0) mod B) < x: a binary search, the offsets are sorted
+            int lo = 0, hi = R;
+            while (lo < hi) {
+                const int m = (lo + hi) >> 1;
+                if (((s_io[m] - io0) & (a.B - 1)) < x)
+                    lo = m + 1;
+                else
+                    hi = m;
+            }
+            s_cnt[x] = static_cast<uint16_t>(lo);
+        }
+    }
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -419,6 +437,42 @@ __global__ void __launch_bounds__(kDirThreads, 1) k_raycast_dir(DirRayArgs a) {
             int k0 = 1;
             if (valid && (flags & 3) == 3) k0 = dir_first_sample(wacc, st);
             uint8_t* const out = a.steps_sorted + pos;
+            // one ray: beam j of this lane's particle, if it lies in sector s (`inside`: it does for every lane of the warp)
+            auto cast = [&](int j, bool inside) {
+                if (!valid) return;
+                if (!inside && dir_sector_of(bucket, a.io[j], Bmask, a.shift) != s) return;   // another unit's ray
+                int r = 0;   // outside the map: the first sample is already out of bounds (:632-636)
+                if (flags & 1) {
+                    int dxf, dyf;
+                    beam_direction_prescaled(cs.x, cs.y, a.beams.cosa[j], a.beams.sina[j], &dxf, &dyf);
+                    const ReplayLazy rep{a.replay, pos, j};
+                    if (flags & 2)
+                        r = march_ray_dir(wacc, st, dxf, dyf, M, rep, &replays, k0);
+                    else
+                        r = march_ray_dir(gacc, st, dxf, dyf, M, rep, &replays, k0);
+                }
+                out[static_cast<uint64_t>(static_cast<uint32_t>(j)) * static_cast<uint32_t>(a.stride)] = static_cast<uint8_t>(r);
+            };
+            const int span = bmax - bmin;
+            if (a.beam_ranges) {
+                // Beam j has rays in sector s for some bucket of [bmin, bmax] iff io_j lies in the cyclic interval
+                // [s K - bmax, s K - bmin + K) of length K + span.  The offsets are sorted from beam 0 on, so that is
+                // one index range of the table, or two when the interval wraps past beam 0's offset.
+                const int L = K + span;
+                int j0 = 0, j1 = R, j2 = 0, j3 = 0;
+                if (L < a.B) {
+                    const int aU = (s * K - bmax - s_io[0]) & Bmask;
+                    j0 = s_cnt[aU];
+                    if (aU + L <= a.B) {
+                        j1 = s_cnt[aU + L];
+                    } else {
+                        j3 = s_cnt[aU + L - a.B];
+                    }
+                }
+                for (int j = j0; j < j1; ++j) cast(j, ((bmin + s_io[j] - s * K) & Bmask) + span < K);
+                for (int j = j2; j < j3; ++j) cast(j, ((bmin + s_io[j] - s * K) & Bmask) + span < K);
+                continue;
+            }
             for (int jb = 0; jb < R; jb += 32) {
                 const int jl = jb + lane;
                 // the warp's buckets shifted by the beam's offset: [start, start + len) cyclically; sector s = [0, K)
@@ -430,28 +484,14 @@ __global__ void __launch_bounds__(kDirThreads, 1) k_raycast_dir(DirRayArgs a) {
                 else
                     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(io_l) : "r"(io_saddr + static_cast<uint32_t>(jb * 4)));
                 const int start = (bmin + static_cast<int>(io_l) - s * K) & Bmask;
-                const int span = bmax - bmin;
                 unsigned mask = __ballot_sync(kFullMask, jl < R && (start < K || start + span >= a.B));
                 // beams for which EVERY lane's ray lies in the sector (the usual case: a warp spans a few buckets of the
                 // sector's K): no per-lane sector test
                 const unsigned full = __ballot_sync(kFullMask, jl < R && start + span < K);
                 while (mask) {
                     const int jbit = __ffs(mask) - 1;
-                    const int j = jb + jbit;
                     mask &= mask - 1;
-                    if (!valid) continue;
-                    if (!((full >> jbit) & 1u) && dir_sector_of(bucket, a.io[j], Bmask, a.shift) != s) continue;   // another unit's ray
-                    int r = 0;   // outside the map: the first sample is already out of bounds (:632-636)
-                    if (flags & 1) {
-                        int dxf, dyf;
-                        beam_direction_prescaled(cs.x, cs.y, a.beams.cosa[j], a.beams.sina[j], &dxf, &dyf);
-                        const ReplayLazy rep{a.replay, pos, j};
-                        if (flags & 2)
-                            r = march_ray_dir(wacc, st, dxf, dyf, M, rep, &replays, k0);
-                        else
-                            r = march_ray_dir(gacc, st, dxf, dyf, M, rep, &replays, k0);
-                    }
-                    out[static_cast<uint64_t>(static_cast<uint32_t>(j)) * static_cast<uint32_t>(a.stride)] = static_cast<uint8_t>(r);
+                    cast(jb + jbit, ((full >> jbit) & 1u) != 0);
                 }
             }
         }

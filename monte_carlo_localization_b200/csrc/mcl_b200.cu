@@ -184,6 +184,7 @@ struct mcl_ctx {
     uint8_t* d_dirmaps = nullptr;     // [S][PH*PW]
     DirSector* d_sectors = nullptr;
     int beam_io[kMaxBeams] = {};
+    bool beam_ranges = false;         // beam offsets sorted from beam 0 on (cyclically): the ray kernel reads beam index ranges from a table
     int* d_sec_tab = nullptr;         // [S+1] first unit | [S] first chunk, per sector
     DirReplayCtx* d_replay_ctx = nullptr;   // [2]: one per state buffer
     DirRec* d_rec = nullptr;          // [2][N]: slot order | heading-sorted order
@@ -630,13 +631,16 @@ int ensure_dir(mcl_ctx* c, bool map_changed) {
     c->d_steps_sorted = nullptr;
     c->d_replay_ctx = nullptr;
     for (int j = 0; j < c->R; ++j) c->beam_io[j] = dir_beam_offset(c->beams.angle[j], c->dir_B);
+    c->beam_ranges = true;   // any real scan: angles increase with the beam index and span less than a turn
+    for (int j = 1; j < c->R; ++j)
+        if (((c->beam_io[j] - c->beam_io[0]) & (c->dir_B - 1)) < ((c->beam_io[j - 1] - c->beam_io[0]) & (c->dir_B - 1))) c->beam_ranges = false;
     CK(dalloc(&c->d_sec_tab, static_cast<size_t>(2 * kDirSectors + 2)));
     CK(dalloc(&c->d_replay_ctx, size_t{2}));
     const int64_t nchunks = (pool_n + kDirThreads - 1) / kDirThreads;
     c->dir_stride = nchunks * kDirThreads;
     CK(dalloc(&c->d_steps_sorted, static_cast<size_t>(c->R) * c->dir_stride));
     CK(cudaMemset(c->d_steps_sorted, 0, static_cast<size_t>(c->R) * c->dir_stride));   // slots beyond the shard stay valid steps
-    if (dir_ray_smem(static_cast<int>((c->dir_smem + 15) & ~size_t{15})) > kWindowBudget) return MCL_OK;   // stays on the isotropic kernel
+    if (dir_ray_smem(static_cast<int>((c->dir_smem + 15) & ~size_t{15})) > kWindowBudget - 10 * 1024) return MCL_OK;   // stays on the isotropic kernel (the kernel has 9 KB of static shared memory)
     c->dir_ready = true;
     return upload_replay_ctx(c);
 }
@@ -959,6 +963,7 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
         da.box = c->dir_box;
         da.whole = c->dir_pool ? 1 : 0;
         da.win_bytes = static_cast<int>((c->dir_smem + 15) & ~size_t{15});
+        da.beam_ranges = c->beam_ranges ? 1 : 0;
         const size_t dsmem = dir_ray_smem(da.win_bytes);
         const int dblocks = static_cast<int>(std::min<int64_t>(c->num_sms, (slots * c->R + kDirThreads - 1) / kDirThreads));
         switch (c->M) {
@@ -1369,10 +1374,10 @@ static int create_buffers(mcl_ctx* c, const mcl_params* p, int device, int world
                             16384 * static_cast<int>(sizeof(double)) + (kRouteThreads / 32) * kRouteQueue * 12));
     CK(cudaFuncSetAttribute(k_weight_steps_sm<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
     CK(cudaFuncSetAttribute(k_weight_steps_sm<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    CK(cudaFuncSetAttribute(k_raycast_dir<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kWindowBudget)));
-    CK(cudaFuncSetAttribute(k_raycast_dir<207>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kWindowBudget)));
-    CK(cudaFuncSetAttribute(k_raycast_dir<238>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kWindowBudget)));
-    CK(cudaFuncSetAttribute(k_raycast_dir<239>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kWindowBudget)));
+    CK(cudaFuncSetAttribute(k_raycast_dir<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kWindowBudget) - 10 * 1024));
+    CK(cudaFuncSetAttribute(k_raycast_dir<207>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kWindowBudget) - 10 * 1024));
+    CK(cudaFuncSetAttribute(k_raycast_dir<238>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kWindowBudget) - 10 * 1024));
+    CK(cudaFuncSetAttribute(k_raycast_dir<239>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kWindowBudget) - 10 * 1024));
     CK(cudaDeviceSynchronize());
     return MCL_OK;
 }
