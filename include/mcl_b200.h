@@ -192,7 +192,8 @@ int mcl_set_ray_mode(mcl_ctx* ctx, int mode);
 int mcl_ray_stage_info(mcl_ctx* ctx, int* directional_ready, int* last_mode, int* box_cells, int* units);
 
 /* Diagnostics: one sector's directional skip map (padded grid, *pw x *ph bytes, see
- * csrc/dirmap.cuh for the code).  out may be NULL to query the size. */
+ * csrc/dirmap.cuh for the code); sector -1: the isotropic skip codes (csrc/map_prep.h), as built on the
+ * device by mcl_set_map.  out may be NULL to query the size. */
 int mcl_get_dir_map(mcl_ctx* ctx, int sector, uint8_t* out, int* pw, int* ph);
 
 /* Gather micro-benchmark (measurement aid): random single-byte reads per second from

@@ -15,7 +15,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libmcl_b200.so")
 SOURCES = [os.path.join(CSRC, "mcl_b200.cu"), os.path.join(CSRC, "map_prep.cpp")]
 HEADERS = [os.path.join(CSRC, h) for h in
-           ("kernels.cuh", "dir_kernels.cuh", "exact_kernels.cuh", "shard.cuh", "march.cuh", "dirmap.cuh", "exact_sum.cuh",
+           ("kernels.cuh", "map_kernels.cuh", "dir_kernels.cuh", "exact_kernels.cuh", "shard.cuh", "march.cuh", "dirmap.cuh", "exact_sum.cuh",
             "device_utils.cuh", "map_prep.h")] + [
     os.path.join(os.path.dirname(_HERE), "include", "mcl_b200.h")]
 

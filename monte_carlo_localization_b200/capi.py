@@ -122,7 +122,8 @@ def load_library(path: str | None = None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or _build.LIB_PATH
+    # MCL_B200_LIB: development aid (A/B builds of the same library, scripts/build_variant.sh); still CUDA-only
+    p = path or os.environ.get("MCL_B200_LIB") or _build.LIB_PATH
     if not os.path.exists(p):
         raise FileNotFoundError(
             "%s is missing: build it with `python -m monte_carlo_localization_b200.build` "

@@ -26,6 +26,23 @@ namespace mclb200 {
 constexpr int kDirThreads = 1024;     // threads of a ray CTA == sorted slots of one unit
 constexpr int kDirGrab = 16;          // units a CTA takes per visit to the global counter
 
+// 1: rows of the shared-memory window are padded to an odd multiple of 16 bytes, so that the rows a warp's lanes
+// touch (heading-neighbours: a few cells apart in x and y) fall into different bank groups whatever the window width
+#ifndef MCL_DIR_PAD
+#define MCL_DIR_PAD 1
+#endif
+
+constexpr int kDirMaxRanges = 256;    // CTAs of the ray kernel (diagnostics array)
+
+// Development builds only (-DMCL_DIR_DIAG=1, scripts/build_variant.sh): per-CTA counters of the last k_raycast_dir launch
+// [cycles, units, pieces, windows staged, cycles in the scheduler, cycles staging windows, SM clock at start, at end]
+#ifndef MCL_DIR_DIAG
+#define MCL_DIR_DIAG 0
+#endif
+#if MCL_DIR_DIAG
+__device__ unsigned long long g_dir_diag[kDirMaxRanges][8];
+#endif
+
 // ints of the plan buffer
 enum { kPlanMode = 0, kPlanUnits = 1, kPlanCounter = 2, kPlanInBox = 3, kPlanBoxX = 4, kPlanBoxY = 5, kPlanInts = 8 };
 
@@ -296,9 +313,14 @@ __global__ void __launch_bounds__(kDirThreads, 1) k_raycast_dir(DirRayArgs a) {
     __shared__ unsigned s_u0;
     __shared__ uint32_t s_units[kDirGrab];    // chunk << 6 | sector
     __shared__ int s_sec[2 * kDirSectors + 2];
-    __shared__ int s_io[kMaxBeams];
+    __shared__ int s_io[kMaxBeams + 32];          // padded: a warp reads 32 consecutive entries from any beam
     __shared__ uint16_t s_cnt[kMaxBuckets + 1];   // s_cnt[x] = number of beams whose offset, counted from beam 0's, is below x
     if (a.plan[kPlanMode] != 1) return;
+#if MCL_DIR_DIAG
+    unsigned long long dg_t0 = clock64(), dg_units = 0, dg_pieces = 0, dg_wins = 0, dg_sched = 0, dg_stage = 0;
+    unsigned long long dg_g0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dg_g0));
+#endif
     const unsigned n_units = static_cast<unsigned>(a.plan[kPlanUnits]);
     const MapDev& mp = a.map;
     const int M = MC > 0 ? MC : pin_reg(mp.M);
@@ -313,9 +335,9 @@ __global__ void __launch_bounds__(kDirThreads, 1) k_raycast_dir(DirRayArgs a) {
     // thread-private prefetch slots of the ray-start records (two buffers)
     const uint32_t rec0_s = win_saddr + static_cast<uint32_t>(a.win_bytes) + static_cast<uint32_t>(tid) * 16u;
     const uint32_t rec1_s = rec0_s + 2u * kDirThreads * 16u;
-    const uint32_t io_saddr = static_cast<uint32_t>(__cvta_generic_to_shared(s_io)) + static_cast<uint32_t>(lane) * 4u;
+    const uint32_t io_base = static_cast<uint32_t>(__cvta_generic_to_shared(s_io));
     if (tid < 2 * kDirSectors + 1) s_sec[tid] = a.sec_tab[tid];
-    if (tid < kMaxBeams) s_io[tid] = tid < R ? a.io[tid] : 0;
+    if (tid < kMaxBeams + 32) s_io[tid] = tid < R ? a.io[tid] : 0;
     if (a.beam_ranges) {
         __syncthreads();
         const int io0 = s_io[0];
@@ -337,21 +359,20 @@ __global__ void __launch_bounds__(kDirThreads, 1) k_raycast_dir(DirRayArgs a) {
     }
     const int64_t ncell = static_cast<int64_t>(mp.PW) * mp.PH;
     const int K = a.B >> 5, Bmask = a.B - 1;
-    const uint32_t io_r0 = static_cast<uint32_t>(pin_reg(lane < R ? a.io[lane] : 0));
-    const uint32_t io_r1 = static_cast<uint32_t>(pin_reg(lane + 32 < R ? a.io[lane + 32] : 0));
     uint32_t phase = 0;
     unsigned seen = 0;
     int cur_s = -1, replays = 0;
+    int spitch = 0;                     // row pitch of the window in shared memory (dir_smem_pitch)
     DirWindow wg{0, 0, 0, 0};
     const uint8_t* smap = a.dirmaps;
 
     // asynchronous copy of this thread's records of a unit into prefetch buffer `buf`
     auto prefetch = [&](uint32_t unit, uint32_t buf) {
-        const int pos = static_cast<int>(unit >> 6) * kDirThreads + tid;
-        if (pos < cnt) {
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(rec0_s + buf * (kDirThreads * 16u)), "l"(&a.rec[pos].a) : "memory");
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(rec1_s + buf * (kDirThreads * 16u)), "l"(&a.rec[pos].b) : "memory");
-        }
+        // slots beyond the last particle repeat it: every lane always holds a real record (the duplicates recompute
+        // and rewrite the last particle's steps), so nothing below needs a validity test
+        const int pos = min(static_cast<int>(unit >> 6) * kDirThreads + tid, cnt - 1);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(rec0_s + buf * (kDirThreads * 16u)), "l"(&a.rec[pos].a) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(rec1_s + buf * (kDirThreads * 16u)), "l"(&a.rec[pos].b) : "memory");
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
@@ -366,6 +387,10 @@ __global__ void __launch_bounds__(kDirThreads, 1) k_raycast_dir(DirRayArgs a) {
         if (u0 >= n_units) break;
         seen = u0 + grab;
         const unsigned nu = min(grab, n_units - u0);
+#if MCL_DIR_DIAG
+        dg_units += nu;
+        dg_pieces += 1;
+#endif
         if (tid < static_cast<int>(nu)) {
             // sector of unit u: the last sector whose first unit is <= u (empty sectors share offsets)
             const int u = static_cast<int>(u0) + tid;
@@ -382,9 +407,14 @@ __global__ void __launch_bounds__(kDirThreads, 1) k_raycast_dir(DirRayArgs a) {
             const int s = static_cast<int>(unit & 63u);
             if (s != cur_s) {
                 // ---- stage sector s's window: one bulk copy per row, bytes counted on the mbarrier
+#if MCL_DIR_DIAG
+                const unsigned long long dg_w0 = clock64();
+                dg_wins++;
+#endif
                 __syncthreads();            // every warp has left the old window
                 wg = a.whole ? DirWindow{0, 0, mp.PW, mp.PH} : dir_window(a.sectors[s], bx0, by0, a.box, mp.PW, mp.PH);
                 smap = a.dirmaps + static_cast<int64_t>(s) * ncell;
+                spitch = (MCL_DIR_PAD && !a.whole) ? dir_smem_pitch(wg.pitch) : wg.pitch;
                 if (tid == 0) {
                     const uint32_t total = static_cast<uint32_t>(wg.pitch) * static_cast<uint32_t>(wg.rows);
                     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(total) : "memory");
@@ -393,7 +423,7 @@ __global__ void __launch_bounds__(kDirThreads, 1) k_raycast_dir(DirRayArgs a) {
                 const uint8_t* gsrc = smap + static_cast<int64_t>(wg.wy0) * mp.PW + wg.wx0;
                 for (int row = tid; row < wg.rows; row += kDirThreads) {
                     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                                     win_saddr + static_cast<uint32_t>(row * wg.pitch)),
+                                     win_saddr + static_cast<uint32_t>(row * spitch)),
                                  "l"(gsrc + static_cast<int64_t>(row) * mp.PW), "r"(static_cast<uint32_t>(wg.pitch)), "r"(bar)
                                  : "memory");
                 }
@@ -409,6 +439,9 @@ __global__ void __launch_bounds__(kDirThreads, 1) k_raycast_dir(DirRayArgs a) {
                 }
                 phase ^= 1u;
                 cur_s = s;
+#if MCL_DIR_DIAG
+                dg_stage += clock64() - dg_w0;
+#endif
             }
             // this unit's records have landed; start the copy of the next unit's
             asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -418,85 +451,97 @@ __global__ void __launch_bounds__(kDirThreads, 1) k_raycast_dir(DirRayArgs a) {
             asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r0.x), "=r"(r0.y), "=r"(r0.z), "=r"(r0.w) : "r"(rec0_s + buf * (kDirThreads * 16u)));
             asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(cs.x), "=d"(cs.y) : "r"(rec1_s + buf * (kDirThreads * 16u)));
             if (k + 1 < nu) prefetch(s_units[k + 1], buf ^ 1u);
-            const int pos = static_cast<int>(unit >> 6) * kDirThreads + tid;
-            const bool valid = pos < cnt;
+            const int pos = min(static_cast<int>(unit >> 6) * kDirThreads + tid, cnt - 1);
             const int bucket = static_cast<int>(r0.w & 0xffffu), flags = static_cast<int>(r0.w >> 16);
             // ---- beams with rays in this sector for some lane of the warp (lanes are bucket-sorted)
-            const int bmin = __reduce_min_sync(kFullMask, valid ? bucket : 0x7fffffff);
-            const int bmax = __reduce_max_sync(kFullMask, valid ? bucket : -1);
-            if (bmax < 0) continue;         // the whole warp is beyond the last particle
+            const int bmin = __reduce_min_sync(kFullMask, bucket);
+            const int bmax = __reduce_max_sync(kFullMask, bucket);
             RayStart st;
             st.p0x = r0.x;
             st.p0y = r0.y;
             st.bx = static_cast<int>(static_cast<int16_t>(r0.z & 0xffffu));
             st.by = static_cast<int>(static_cast<int16_t>(r0.z >> 16));
-            const WindowV8S wacc{static_cast<uint32_t>(pin_reg(static_cast<int>(win_saddr) + (st.by - wg.wy0) * wg.pitch + (st.bx - wg.wx0))), wg.pitch};
+            const WindowV8S wacc{static_cast<uint32_t>(pin_reg(static_cast<int>(win_saddr) + (st.by - wg.wy0) * spitch + (st.bx - wg.wx0))), spitch};
             const GlobalV8 gacc = make_global_v8(smap, mp.PW, st.bx, st.by);
+            // A particle outside the map: the first sample of every beam is already out of bounds (:632-636), step index
+            // 0.  Its march starts beyond M (no lookup is made) and the result is masked to 0.
+            const int inmap = (flags & 1) ? 0xff : 0;
+            int k0 = (flags & 1) ? 1 : M + 1;
             // the start cell's code lets all of this particle's rays in the sector begin at sample k0 (march.cuh)
             // (particles outside the window box are rare and simply start at sample 1)
-            int k0 = 1;
-            if (valid && (flags & 3) == 3) k0 = dir_first_sample(wacc, st);
+            if ((flags & 3) == 3) k0 = dir_first_sample(wacc, st);
+            const RayStartOfs so = offset_ray_start(st);   // the march works on positions offset by kEta (march.cuh)
             uint8_t* const out = a.steps_sorted + pos;
-            // one ray: beam j of this lane's particle, if it lies in sector s (`inside`: it does for every lane of the warp)
-            auto cast = [&](int j, bool inside) {
-                if (!valid) return;
-                if (!inside && dir_sector_of(bucket, a.io[j], Bmask, a.shift) != s) return;   // another unit's ray
-                int r = 0;   // outside the map: the first sample is already out of bounds (:632-636)
-                if (flags & 1) {
-                    int dxf, dyf;
-                    beam_direction_prescaled(cs.x, cs.y, a.beams.cosa[j], a.beams.sina[j], &dxf, &dyf);
-                    const ReplayLazy rep{a.replay, pos, j};
-                    if (flags & 2)
-                        r = march_ray_dir(wacc, st, dxf, dyf, M, rep, &replays, k0);
-                    else
-                        r = march_ray_dir(gacc, st, dxf, dyf, M, rep, &replays, k0);
-                }
-                out[static_cast<uint64_t>(static_cast<uint32_t>(j)) * static_cast<uint32_t>(a.stride)] = static_cast<uint8_t>(r);
+            // one ray: beam j of this lane's particle
+            auto cast = [&](int j) {
+                int dxf, dyf;
+                beam_direction_prescaled(cs.x, cs.y, a.beams.cosa[j], a.beams.sina[j], &dxf, &dyf);
+                const ReplayLazy rep{a.replay, pos, j};
+                int r;
+                if (flags & 2)
+                    r = march_ray_dir(wacc, so, dxf, dyf, M, rep, &replays, k0);
+                else
+                    r = march_ray_dir(gacc, so, dxf, dyf, M, rep, &replays, k0);
+                out[static_cast<uint64_t>(static_cast<uint32_t>(j)) * static_cast<uint32_t>(a.stride)] = static_cast<uint8_t>(r & inmap);
             };
             const int span = bmax - bmin;
-            if (a.beam_ranges) {
-                // Beam j has rays in sector s for some bucket of [bmin, bmax] iff io_j lies in the cyclic interval
-                // [s K - bmax, s K - bmin + K) of length K + span.  The offsets are sorted from beam 0 on, so that is
-                // one index range of the table, or two when the interval wraps past beam 0's offset.
-                const int L = K + span;
-                int j0 = 0, j1 = R, j2 = 0, j3 = 0;
-                if (L < a.B) {
-                    const int aU = (s * K - bmax - s_io[0]) & Bmask;
-                    j0 = s_cnt[aU];
-                    if (aU + L <= a.B) {
-                        j1 = s_cnt[aU + L];
-                    } else {
-                        j3 = s_cnt[aU + L - a.B];
-                    }
-                }
-                for (int j = j0; j < j1; ++j) cast(j, ((bmin + s_io[j] - s * K) & Bmask) + span < K);
-                for (int j = j2; j < j3; ++j) cast(j, ((bmin + s_io[j] - s * K) & Bmask) + span < K);
+            if (!a.beam_ranges) {
+                // beam offsets in no particular order (no real scan): every beam, every lane tests its own sector
+                for (int j = 0; j < R; ++j)
+                    if (dir_sector_of(bucket, s_io[j], Bmask, a.shift) == s) cast(j);
                 continue;
             }
-            for (int jb = 0; jb < R; jb += 32) {
-                const int jl = jb + lane;
-                // the warp's buckets shifted by the beam's offset: [start, start + len) cyclically; sector s = [0, K)
-                uint32_t io_l;   // io[jl]: beams 0..63 live in two registers per lane, the rest in shared memory
-                if (jb == 0)
-                    io_l = io_r0;
-                else if (jb == 32)
-                    io_l = io_r1;
-                else
-                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(io_l) : "r"(io_saddr + static_cast<uint32_t>(jb * 4)));
-                const int start = (bmin + static_cast<int>(io_l) - s * K) & Bmask;
-                unsigned mask = __ballot_sync(kFullMask, jl < R && (start < K || start + span >= a.B));
-                // beams for which EVERY lane's ray lies in the sector (the usual case: a warp spans a few buckets of the
-                // sector's K): no per-lane sector test
-                const unsigned full = __ballot_sync(kFullMask, jl < R && start + span < K);
-                while (mask) {
-                    const int jbit = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    cast(jb + jbit, ((full >> jbit) & 1u) != 0);
+            // Beam j has rays in sector s for some bucket of [bmin, bmax] iff io_j lies in the cyclic interval
+            // [s K - bmax, s K - bmin + K) of length K + span.  The offsets are sorted from beam 0 on, so that is
+            // one index range of the table, [j0, j1), plus [0, j3) when the interval wraps past beam 0's offset.
+            int j0 = 0, j1 = R, j3 = 0;
+            if (K + span < a.B) {
+                const int aU = (s * K - bmax - s_io[0]) & Bmask;
+                j0 = s_cnt[aU];
+                if (aU + K + span <= a.B) {
+                    j1 = s_cnt[aU + K + span];
+                } else {
+                    j3 = s_cnt[aU + K + span - a.B];
+                }
+            }
+            const int n1 = j1 - j0, nb = n1 + j3;      // the (warp, sector)'s beams: list index q -> beam
+            const int base_u = bmin - s * K;
+            for (int qb = 0; qb < nb; qb += 32) {
+                // lane l looks at list entry qb + l: is EVERY lane's ray of that beam in the sector (the usual case: a warp
+                // spans a few buckets of the sector's K)?  Then no per-lane sector test is needed for it.
+                const int ql = qb + lane;
+                const int jl = ql < n1 ? j0 + ql : ql - n1;            // < R + 32: s_io is padded
+                uint32_t io_l;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(io_l) : "r"(io_base + static_cast<uint32_t>(jl) * 4u));
+                const unsigned whole = __ballot_sync(kFullMask, ((base_u + static_cast<int>(io_l)) & Bmask) + span < K);
+                const int qe = min(nb, qb + 32);
+                for (int q = qb; q < qe; ++q) {
+                    const int j = q < n1 ? j0 + q : q - n1;
+                    if (!((whole >> (q - qb)) & 1u)) {
+                        const int io_j = __shfl_sync(kFullMask, static_cast<int>(io_l), q - qb);
+                        if (dir_sector_of(bucket, io_j, Bmask, a.shift) != s) continue;   // another unit's ray
+                    }
+                    cast(j);
                 }
             }
         }
     }
     if (a.replay_count && replays) atomicAdd(reinterpret_cast<unsigned long long*>(a.replay_count), static_cast<unsigned long long>(replays));
+#if MCL_DIR_DIAG
+    if (tid == 0) {
+        unsigned long long dg_g1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dg_g1));
+        unsigned long long* d = g_dir_diag[blockIdx.x];
+        d[0] = clock64() - dg_t0;
+        d[1] = dg_units;
+        d[2] = dg_pieces;
+        d[3] = dg_wins;
+        d[4] = dg_sched;
+        d[5] = dg_stage;
+        d[6] = dg_g0;
+        d[7] = dg_g1;
+    }
+#endif
 }
 
 struct WeightStepsArgs {

@@ -162,6 +162,12 @@ MCL_HD DirWindow dir_window(const DirSector& sc, int box_x0, int box_y0, int box
     return w;
 }
 
+// Row pitch of a window in shared memory: the copied width padded to an ODD multiple of 16 bytes.  A warp's lanes
+// are heading-neighbours casting the same beam, a few cells apart in x and y: with 4 (mod 8) words per row eight
+// consecutive rows start in eight different bank groups, whereas a width that is a multiple of 128 bytes puts every
+// row on the same banks.  (16-byte granularity: the rows are the destinations of bulk copies.)
+MCL_HD int dir_smem_pitch(int pitch) { return pitch | 16; }
+
 // Largest particle box (multiple of 16 cells, <= 192) whose windows fit `capacity` bytes for
 // every sector; 0 if none does.
 inline int dir_choose_box(const DirSector* sectors, size_t capacity) {
@@ -169,7 +175,7 @@ inline int dir_choose_box(const DirSector* sectors, size_t capacity) {
         bool ok = true;
         for (int s = 0; s < kDirSectors && ok; ++s) {
             const DirSector& sc = sectors[s];
-            const size_t pitch = static_cast<size_t>((box + sc.exh - sc.exl + 30) & ~15);
+            const size_t pitch = static_cast<size_t>(dir_smem_pitch((box + sc.exh - sc.exl + 30) & ~15));
             const size_t rows = static_cast<size_t>(box + sc.eyh - sc.eyl);
             ok = pitch * rows <= capacity;
         }

@@ -79,15 +79,25 @@ void edt_squared(const std::vector<uint8_t>& mask, int W, int H, std::vector<int
     }
 }
 
-bool build_skip_map(const int8_t* data, int W, int H, SkipMap& out) {
+bool skip_map_layout(const int8_t* data, int W, int H, SkipMap& out) {
     if (W <= 0 || H <= 0) return false;
     if (static_cast<int64_t>(W) * H > (int64_t{1} << 30)) return false;
     out.W = W;
     out.H = H;
-    const int PW = ((W + kPadL + kPadR) + 31) / 32 * 32;
-    const int PH = H + kPadL + kPadR;
-    out.PW = PW;
-    out.PH = PH;
+    out.PW = ((W + kPadL + kPadR) + 31) / 32 * 32;
+    out.PH = H + kPadL + kPadR;
+    out.v8.clear();
+    out.v4.clear();
+    out.free_cells.clear();
+    for (int r = 0; r < H; ++r)
+        for (int c = 0; c < W; ++c)
+            if (data[static_cast<size_t>(r) * W + c] == 0) out.free_cells.push_back(r * W + c);
+    return true;
+}
+
+bool build_skip_map(const int8_t* data, int W, int H, SkipMap& out) {
+    if (!skip_map_layout(data, W, H, out)) return false;
+    const int PW = out.PW, PH = out.PH;
     const size_t n = static_cast<size_t>(PW) * PH;
 
     // blocked mask on the P-grid
@@ -146,10 +156,6 @@ bool build_skip_map(const int8_t* data, int W, int H, SkipMap& out) {
         const uint8_t lo = std::min<uint8_t>(out.v8[i], 15), hi = std::min<uint8_t>(out.v8[i + 1], 15);
         out.v4[i / 2] = static_cast<uint8_t>(lo | (hi << 4));
     }
-    out.free_cells.clear();
-    for (int r = 0; r < H; ++r)
-        for (int c = 0; c < W; ++c)
-            if (data[static_cast<size_t>(r) * W + c] == 0) out.free_cells.push_back(r * W + c);
     return true;
 }
 

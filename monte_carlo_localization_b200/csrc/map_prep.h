@@ -41,7 +41,12 @@ struct SkipMap {
 };
 
 // Build the skip map.  Returns false if the grid is too large for the fixed-point march.
+// (CPU twin of the device build in map_kernels.cuh: the product calls skip_map_layout() and builds the
+// codes on the GPU; tests/emu builds them here.)
 bool build_skip_map(const int8_t* data, int W, int H, SkipMap& out);
+
+// Dimensions of the P-grid and the free-cell list only (v8 / v4 stay empty).
+bool skip_map_layout(const int8_t* data, int W, int H, SkipMap& out);
 
 // Exact squared Euclidean distance transform to the set {mask != 0} (Felzenszwalb-
 // Huttenlocher lower envelopes); out[i] = squared distance in cells, big if no seed.

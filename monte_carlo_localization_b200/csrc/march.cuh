@@ -303,33 +303,53 @@ MCL_HD int dir_first_sample(const Acc& acc, const RayStart& st) {
 }
 
 // k0: first sample to look at (1, or dir_first_sample's answer)
+//
+// The hot loop is branch-free (15 instructions per lookup, no divergence inside a trip).  Positions carry a constant
+// +kEta offset, so ONE mask test per axis tells whether a sample lies within kEta of a cell edge (the band
+// [-kEta, 2^-14 - kEta) around the edge, a superset of the +-kEta band the resolver applies).  The looked-up cell is
+// the cell of the OFFSET position: for a sample clear of edges that is the sample's own cell; for a sample inside
+// the band it may be the neighbour across the edge, which is harmless --
+//   * a free-space code (< 0x80) is only used to skip: the true position is then within 2 kEta < kDirEta of the
+//     looked-up cell, which the cone tracing of dirmap.cuh covers (its boxes and balls carry kDirEta of slack), and
+//     the sample cannot be a hit (a blocked cell's neighbours all carry the near flag);
+//   * a near or blocked code (>= 0x80) inside the band stops the loop, and the resolver below works on the
+//     un-offset position exactly as before.
+struct RayStartOfs {
+    uint32_t ox, oy;   // RayStart::p0x / p0y + kEtaFix
+};
+MCL_HD RayStartOfs offset_ray_start(const RayStart& st) { return RayStartOfs{st.p0x + kEtaFix, st.p0y + kEtaFix}; }
+
 template <class Acc, class Rep>
-MCL_HD int march_ray_dir(const Acc& acc, const RayStart& st, int dxf, int dyf, int M, const Rep& rep, int* replays, int k0 = 1) {
-    constexpr int kPark = 1 << 20;
+MCL_HD int march_ray_dir(const Acc& acc, const RayStartOfs& so, int dxf, int dyf, int M, const Rep& rep, int* replays, int k0 = 1) {
+    static_assert(2u * kEtaFix < (1u << 9), "the edge band of the hot loop must contain the kEta band after the offset");
+    const uint32_t ox = so.ox, oy = so.oy;
     int k = k0;
     if (k > M) return M;
     for (;;) {
-        int kstop = 0;   // sample at which the loop stopped: blocked cell, or a near-wall sample close to an edge
+        int adv;
+        unsigned stop;
+        uint32_t pxo, pyo;   // offset position of the sample just looked at
         do {
-            const uint32_t px = st.p0x + static_cast<uint32_t>(k * dxf);
-            const uint32_t py = st.p0y + static_cast<uint32_t>(k * dyf);
-            int v = acc.get_p(px, py);
-            if (v >= 0x80) {
-                // blocked, or next to a blocked cell: the class of this very sample matters
-                const bool clear = (((px + kEtaFix) & kEdgeMask) != 0u) & (((py + kEtaFix) & kEdgeMask) != 0u) & (v != 0x80);
-                if (!clear) {
-                    kstop = k;
-                    k = kPark;
-                }
-                v &= 0x7f;
-            }
-            k += v;
-        } while (k <= M);
-        if (kstop == 0) return M;
-        k = kstop;
-        const uint32_t px = st.p0x + static_cast<uint32_t>(k * dxf);
-        const uint32_t py = st.p0y + static_cast<uint32_t>(k * dyf);
-        if ((((px + kEtaFix) & kEdgeMask) != 0u) & (((py + kEtaFix) & kEdgeMask) != 0u)) return k - 1;   // blocked, clear of edges
+            pxo = ox + static_cast<uint32_t>(k * dxf);
+            pyo = oy + static_cast<uint32_t>(k * dyf);
+            const int v = acc.get_p(pxo, pyo);
+            const unsigned edge = static_cast<unsigned>((pxo & kEdgeMask) == 0u) | static_cast<unsigned>((pyo & kEdgeMask) == 0u);
+            // blocked, or next to a blocked cell and close to an edge: the class of this very sample must be settled
+            stop = static_cast<unsigned>(v == 0x80) | (static_cast<unsigned>(v > 0x80) & edge);
+            adv = v & 0x7f;
+            k += adv;
+        } while ((stop == 0u) & (k <= M));
+        if (stop == 0u) return M;
+        // the sample that stopped the loop (opaque to the compiler, which would otherwise carry a copy of k and the
+        // products k * d through every trip to have them ready here)
+#if defined(__CUDA_ARCH__)
+        asm volatile("sub.s32 %0, %0, %1;" : "+r"(k) : "r"(adv));
+        asm volatile("" : "+r"(pxo), "+r"(pyo));
+#else
+        k -= adv;
+#endif
+        if (((pxo & kEdgeMask) != 0u) & ((pyo & kEdgeMask) != 0u)) return k - 1;   // blocked, clear of edges
+        const uint32_t px = pxo - kEtaFix, py = pyo - kEtaFix;
         const int res = resolve_uncertain_dir(acc, px, py, acc.get_p(px, py), rep, k);
         *replays += res >> 1;
         if (res & 1) return k - 1;

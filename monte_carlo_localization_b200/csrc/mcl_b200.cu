@@ -20,6 +20,7 @@
 
 #include "../../include/mcl_b200.h"
 #include "kernels.cuh"
+#include "map_kernels.cuh"
 
 using namespace mclb200;
 
@@ -111,6 +112,7 @@ struct mcl_ctx {
     int8_t* d_grid = nullptr;
     uint8_t* d_v8 = nullptr;
     uint8_t* d_v4 = nullptr;
+    float* d_gap = nullptr;          // Euclidean gap map: lives from mcl_set_map until the sector maps are built
     int32_t* d_free = nullptr;
     double* d_tabT = nullptr;
     int32_t* d_step2idx = nullptr;
@@ -568,6 +570,44 @@ int upload_replay_ctx(mcl_ctx* c) {
     return MCL_OK;
 }
 
+// Skip codes (v8, v4) and the Euclidean gap map from the int8 grid, on the device (map_kernels.cuh).  `codes` false:
+// only the gap map is wanted again (d_v8 / d_v4 are written with the same bytes).
+int device_build_maps(mcl_ctx* c, bool codes) {
+    const int PW = c->skip.PW, PH = c->skip.PH;
+    const size_t n = static_cast<size_t>(PW) * PH;
+    if (codes) {
+        CK(dalloc(&c->d_v8, n));
+        CK(dalloc(&c->d_v4, n / 2));
+    }
+    if (!c->d_gap) CK(dalloc(&c->d_gap, n));
+    // scratch: blocked | dil (bytes), column distances + envelope stack (ints), envelope bounds (doubles), squared distances
+    struct Scratch {
+        void* p = nullptr;
+        ~Scratch() {
+            if (p) cudaFree(p);
+        }
+    } scr;
+    const size_t nz = n + static_cast<size_t>(PH);
+    const size_t bytes = 2 * n + 2 * n * sizeof(int) + nz * sizeof(double) + n * sizeof(long long) + 64;
+    CK(cudaMalloc(&scr.p, bytes));
+    char* b = static_cast<char*>(scr.p);
+    long long* d2T = reinterpret_cast<long long*>(b);
+    double* z = reinterpret_cast<double*>(b + n * sizeof(long long));
+    int* gT = reinterpret_cast<int*>(b + n * sizeof(long long) + nz * sizeof(double));
+    int* v = gT + n;
+    uint8_t* blocked = reinterpret_cast<uint8_t*>(v + n);
+    uint8_t* dil = blocked + n;
+    cudaStream_t s = c->stream;
+    k_map_masks<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(c->d_grid, c->skip.W, c->skip.H, PW, PH, blocked, dil);
+    k_edt_cols<<<static_cast<unsigned>((PW + 127) / 128), 128, 0, s>>>(dil, PW, PH, gT);
+    k_edt_rows<<<static_cast<unsigned>((PH + 127) / 128), 128, 0, s>>>(gT, PW, PH, v, z, d2T);
+    k_map_codes<<<static_cast<unsigned>((n / 2 + 255) / 256), 256, 0, s>>>(blocked, dil, d2T, PW, PH, c->d_v8, c->d_v4, c->d_gap);
+    c->launches += 4;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(s));
+    return MCL_OK;
+}
+
 // Directional ray stage: eligible for ONE large filter whose heading sort has at least
 // kDirMinBuckets buckets.  Builds the sector maps on the device (k_build_dir_maps) and the
 // per-update work buffers.  Called whenever the map or the beam table changes.
@@ -595,29 +635,24 @@ int ensure_dir(mcl_ctx* c, bool map_changed) {
         size_t smem = 0;
         for (int s = 0; s < kDirSectors; ++s) {
             const DirSector& sc = c->sectors[s];
-            smem = std::max(smem, static_cast<size_t>((c->dir_box + sc.exh - sc.exl + 30) & ~15) *
+            smem = std::max(smem, static_cast<size_t>(dir_smem_pitch((c->dir_box + sc.exh - sc.exl + 30) & ~15)) *
                                       static_cast<size_t>(c->dir_box + sc.eyh - sc.eyl));
         }
         c->dir_smem = pool ? ncell : smem;
-        std::vector<float> gap;
-        build_gap_map(c->skip, gap);
-        float* d_gap = nullptr;
-        struct GapGuard {
-            float*& p;
-            ~GapGuard() {
-                if (p) cudaFree(p);
-            }
-        } gap_guard{d_gap};
-        CK(dalloc(&d_gap, ncell));
-        CK(cudaMemcpy(d_gap, gap.data(), ncell * sizeof(float), cudaMemcpyHostToDevice));
+        if (!c->d_gap) {   // the map's gap field was released after an earlier build: transform again
+            const int rc = device_build_maps(c, false);
+            if (rc) return rc;
+        }
         CK(dalloc(&c->d_sectors, static_cast<size_t>(kDirSectors)));
         CK(cudaMemcpy(c->d_sectors, c->sectors, sizeof(c->sectors), cudaMemcpyHostToDevice));
         CK(dalloc(&c->d_dirmaps, ncell * kDirSectors));
-        DirBuildArgs ba{c->d_v8, d_gap, c->d_sectors, c->d_dirmaps, c->skip.PW, c->skip.PH};
+        DirBuildArgs ba{c->d_v8, c->d_gap, c->d_sectors, c->d_dirmaps, c->skip.PW, c->skip.PH};
         k_build_dir_maps<<<dim3(static_cast<unsigned>((ncell + 255) / 256), kDirSectors), 256, 0, c->stream>>>(ba);
         c->launches++;
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_gap);
+        c->d_gap = nullptr;
         CK(dalloc(&c->d_plan, static_cast<size_t>(kPlanInts)));
         CK(cudaMemset(c->d_plan, 0, sizeof(int) * kPlanInts));
         CK(dalloc(&c->d_rec, static_cast<size_t>(2 * pool_n)));
@@ -1419,7 +1454,7 @@ int mcl_destroy(mcl_ctx* c) {
     cudaDeviceSynchronize();
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     void* ptrs[] = {c->d_pose4[0], c->d_pose4[1],
-                    c->d_grid, c->d_v8, c->d_v4, c->d_free, c->d_tabT, c->d_step2idx, c->d_px[0], c->d_px[1], c->d_py[0],
+                    c->d_grid, c->d_v8, c->d_v4, c->d_gap, c->d_free, c->d_tabT, c->d_step2idx, c->d_px[0], c->d_px[1], c->d_py[0],
                     c->d_py[1], c->d_pt[0], c->d_pt[1], c->d_wraw, c->d_wn, c->d_cdf2[0], c->d_cdf2[1], c->d_mid2[0], c->d_mid2[1], c->d_idx, c->d_steps, c->d_u, c->d_z,
                     c->d_action, c->d_slice, c->d_tile_sum, c->d_chunk_fn, c->d_opq_pre, c->d_opq_idx, c->d_opq_add,
                     c->d_tile_opq, c->d_tile_elem, c->d_list_chunk, c->arena ? nullptr : c->d_list_fn, c->arena ? nullptr : c->d_list_add,
@@ -1455,7 +1490,7 @@ int mcl_set_map(mcl_ctx* c, const int8_t* data, int width, int height, float res
     if (M < 1 || M > 65534)
         return fail(MCL_ERR_UNSUPPORTED, "MAX_RANGE_PX = %d outside [1,65534] (max_range %.3f / resolution %.6f)", M,
                     c->prm.max_range, res);
-    if (!build_skip_map(data, width, height, c->skip)) return fail(MCL_ERR_UNSUPPORTED, "grid %dx%d too large", width, height);
+    if (!skip_map_layout(data, width, height, c->skip)) return fail(MCL_ERR_UNSUPPORTED, "grid %dx%d too large", width, height);
     CK(cudaStreamSynchronize(c->stream));
     c->res = res;
     c->ox = ox;
@@ -1463,19 +1498,20 @@ int mcl_set_map(mcl_ctx* c, const int8_t* data, int width, int height, float res
     c->oyaw = oyaw;   // read by the reference (:192-193) but never used by the march (:628-629)
     c->M = M;
     for (void* p : {static_cast<void*>(c->d_grid), static_cast<void*>(c->d_v8), static_cast<void*>(c->d_v4),
-                    static_cast<void*>(c->d_free), static_cast<void*>(c->d_step2idx)})
+                    static_cast<void*>(c->d_gap), static_cast<void*>(c->d_free), static_cast<void*>(c->d_step2idx)})
         if (p) cudaFree(p);
     c->d_grid = nullptr;
     c->d_v8 = c->d_v4 = nullptr;
+    c->d_gap = nullptr;
     c->d_free = nullptr;
     c->d_step2idx = nullptr;
     const size_t cells = static_cast<size_t>(width) * height;
     CK(dalloc(&c->d_grid, cells));
     CK(cudaMemcpy(c->d_grid, data, cells, cudaMemcpyHostToDevice));
-    CK(dalloc(&c->d_v8, c->skip.v8.size()));
-    CK(cudaMemcpy(c->d_v8, c->skip.v8.data(), c->skip.v8.size(), cudaMemcpyHostToDevice));
-    CK(dalloc(&c->d_v4, c->skip.v4.size()));
-    CK(cudaMemcpy(c->d_v4, c->skip.v4.data(), c->skip.v4.size(), cudaMemcpyHostToDevice));
+    {   // skip codes and gap map: one exact Euclidean distance transform on the device (host twin: map_prep.cpp)
+        const int rc = device_build_maps(c, true);
+        if (rc) return rc;
+    }
     CK(dalloc(&c->d_free, c->skip.free_cells.size()));
     if (!c->skip.free_cells.empty())
         CK(cudaMemcpy(c->d_free, c->skip.free_cells.data(), c->skip.free_cells.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
@@ -2121,6 +2157,17 @@ int mcl_ray_stage_info(mcl_ctx* c, int* directional_ready, int* last_mode, int* 
 
 int mcl_get_dir_map(mcl_ctx* c, int sector, uint8_t* out, int* pw, int* ph) {
     if (!c) return fail(MCL_ERR_INVALID, "null context");
+    if (sector == -1) {   // the isotropic skip codes
+        if (!c->have_map) return fail(MCL_ERR_NO_MAP, "map not set");
+        if (pw) *pw = c->skip.PW;
+        if (ph) *ph = c->skip.PH;
+        if (out) {
+            CK(cudaSetDevice(c->device));
+            CK(cudaStreamSynchronize(c->stream));
+            CK(cudaMemcpy(out, c->d_v8, static_cast<size_t>(c->skip.PW) * c->skip.PH, cudaMemcpyDeviceToHost));
+        }
+        return MCL_OK;
+    }
     if (!c->dir_ready) return fail(MCL_ERR_UNSUPPORTED, "the directional ray stage is not active for this context");
     if (sector < 0 || sector >= kDirSectors) return fail(MCL_ERR_INVALID, "sector %d not in [0,%d)", sector, kDirSectors);
     if (pw) *pw = c->skip.PW;
@@ -2133,6 +2180,16 @@ int mcl_get_dir_map(mcl_ctx* c, int sector, uint8_t* out, int* pw, int* ph) {
     }
     return MCL_OK;
 }
+
+#if MCL_DIR_DIAG
+extern "C" int mcl_debug_dir_diag(mcl_ctx* c, unsigned long long* out) {   // development builds only
+    if (!c || !out) return fail(MCL_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpyFromSymbol(out, g_dir_diag, sizeof(unsigned long long) * kDirMaxRanges * 8));
+    return MCL_OK;
+}
+#endif
 
 int mcl_set_stream(mcl_ctx* c, void* stream) {
     if (!c) return fail(MCL_ERR_INVALID, "null context");

@@ -271,14 +271,14 @@ long long emu_range_steps_dir(emu_map* m, const double* px, const double* py, co
                     k0 = dir_first_sample(acc, st);
                     k0_sector = s;
                 }
-                r = march_ray_dir(acc, st, dxf, dyf, M, rep, &replays, k0);
+                r = march_ray_dir(acc, offset_ray_start(st), dxf, dyf, M, rep, &replays, k0);
             } else {
                 const DirGlobal acc{d.data() + static_cast<int64_t>(st.by) * sk.PW + st.bx, sk.PW, &lk};
                 if (s != k0_sector) {
                     k0 = dir_first_sample(acc, st);
                     k0_sector = s;
                 }
-                r = march_ray_dir(acc, st, dxf, dyf, M, rep, &replays, k0);
+                r = march_ray_dir(acc, offset_ray_start(st), dxf, dyf, M, rep, &replays, k0);
             }
             out[j] = static_cast<uint8_t>(r);
             if (lookups_out) lookups_out[i * R + j] = static_cast<int32_t>(lk);

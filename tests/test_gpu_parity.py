@@ -429,6 +429,28 @@ def test_directional_maps_equal_cpu_build():
     c.close()
 
 
+@pytest.mark.parametrize("name", ["sibal1", "basement_fixed", "Spielberg_map"])
+def test_device_distance_transform_equals_host_build(name):
+    """mcl_set_map builds the isotropic skip codes (and the gap map behind the sector maps) with an exact Euclidean
+    distance transform on the device (map_kernels.cuh): same bytes as the host build (map_prep.cpp)."""
+    import sys, os, time
+    sys.path.insert(0, os.path.dirname(__file__))
+    from emu_bindings import EmuMap
+    from monte_carlo_localization_b200 import maps, synth
+    g = maps.load_named_map(name)
+    t0 = time.perf_counter()
+    c = _ctx(g, synth.beam_angles(), 20000)
+    t_set = time.perf_counter() - t0
+    em = EmuMap(g)
+    v8 = c.dir_map(-1)
+    assert v8.shape == em.v8().shape
+    assert np.array_equal(v8, em.v8()), "%d codes differ" % int((v8 != em.v8()).sum())
+    for s in (3, 12, 29):   # the sector maps are traced against the device-built gap map
+        assert np.array_equal(c.dir_map(s), em.dir_map(s)), "sector %d differs" % s
+    print("context + mcl_set_map(%s) incl. sector maps: %.1f ms" % (name, 1e3 * t_set))
+    c.close()
+
+
 def test_scattered_cloud_falls_back_to_isotropic_kernel():
     """After initialize_global the cloud is not compact: the plan keeps the isotropic kernel;
     forcing the directional stage (all particles on the global-memory path) gives the same."""
