@@ -54,7 +54,7 @@ WORKLOADS = {
 }
 
 
-def workload_config(workload: str, n_gpus: int, n_particles: int, R: int, exchange: str = "fused") -> dict:
+def workload_config(workload: str, n_gpus: int, n_particles: int, R: int, exchange: str = "fused", route: str = "two-hop") -> dict:
     wl = WORKLOADS[workload]
     if workload == "batch":
         F = wl["filters"]
@@ -69,7 +69,8 @@ def workload_config(workload: str, n_gpus: int, n_particles: int, R: int, exchan
             "map": wl["map"], "particles_per_gpu": n_particles, "particles_global": n_particles * n_gpus,
             "beams": R, "max_range_px": wl["max_range_px"],
             "sharding": "single GPU" if n_gpus == 1 else
-            "particle-sharded x%d, exact global multinomial resampling, slice-local state, %s exchange" % (n_gpus, exchange),
+            "particle-sharded x%d, exact global multinomial resampling, slice-local state, %s routing, %s exchange" % (
+                n_gpus, route, exchange),
             "l2": "flushed between timed steps (256 MiB write)", "rng": "device Philox (no injected noise)"}
 
 
@@ -243,6 +244,8 @@ def kernel_table(kernel_samples, N: int, R: int, cbar: float | None, peak_gbs: f
         "k_resample_motion": lambda: (104 + 8 * log2n) * N,
         "k_resample_motion(routed)": lambda: (32 + 24 + 32 + 32 + 4) * N,
         "k_route": lambda: (32 + 32 + 8 * log2n) * N,
+        "k_route_request": lambda: 4 * N,
+        "k_route_serve": lambda: (4 + 32 + 32 + 8 * log2n) * N,
         "k_sort_hist": lambda: 8 * N,
         "k_sort_scatter": lambda: 20 * N,
         "k_dir_gather": lambda: 68 * N,
@@ -314,7 +317,7 @@ def run_gpu(args):
         elif world > 1:
             from monte_carlo_localization_b200.sharded import ShardedFilter
             flt = ShardedFilter(grid, angles, n_local=N, rank=rank, world=world, device=local_rank, seed=20250 + 3,
-                                exchange=args.shard_exchange)
+                                exchange=args.shard_exchange, route=args.shard_route)
             ctx = flt.ctx
         else:
             ctx = MclContext(device=local_rank, max_particles=N, seed=20250 + 3)
@@ -528,7 +531,7 @@ def run_gpu(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "updates_per_s": 1e3 / ms_per_step * (F * world if batch else 1),
-                "config": workload_config(args.workload, world, N, R, args.shard_exchange), "clocks": clocks, "e2e": e2e,
+                "config": workload_config(args.workload, world, N, R, args.shard_exchange, args.shard_route), "clocks": clocks, "e2e": e2e,
                 "gpu_launches": launches, "roofline": roof, "cpu_baseline": cb, "stage_ms": stage, "kernels": kernels,
                 "ray_stage": ray_stage, "wall_ms_per_step_incl_flush": 1e3 * wall / K, "pose_error_m": pose_err}
         print(json.dumps(line))
@@ -553,6 +556,8 @@ def main():
                     help="0 auto (default), 1 isotropic skip-map kernel only, 2 directional stage always")
     ap.add_argument("--shard-exchange", default="fused", choices=["fused", "nccl"],
                     help="multi-GPU: how ranks meet at an exchange (in-kernel NVLink flags, or a one-word ncclAllGather)")
+    ap.add_argument("--shard-route", default="two-hop", choices=["two-hop", "one-hop"],
+                    help="multi-GPU: request routing of the resampling draws (default) or every rank testing all draws")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

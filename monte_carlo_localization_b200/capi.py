@@ -101,6 +101,7 @@ SIGNATURES = {
     "mcl_shard_connect_local": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "mcl_shard_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "mcl_shard_set_exchange": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "mcl_shard_set_route": (C.c_int, [C.c_void_p, C.c_int]),
     "mcl_nccl_unique_id": (C.c_int, [C.c_void_p, C.c_size_t]),
     "mcl_create_sharded": (C.c_int, [C.POINTER(MclParams), C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
     "mcl_sharded_gather": (C.c_int, [C.c_void_p, c_double_p, c_double_p]),
@@ -453,6 +454,10 @@ class MclContext:
         self._hook = cb   # keep the trampoline alive
         self._check(self._L.mcl_shard_set_exchange(self._h, int(fused), C.cast(cb, C.c_void_p) if cb else None, None),
                     "mcl_shard_set_exchange")
+
+    def shard_set_route(self, two_hop: bool):
+        """Two-hop request routing (default) or every rank testing all draws; same result bit for bit."""
+        self._check(self._L.mcl_shard_set_route(self._h, int(bool(two_hop))), "mcl_shard_set_route")
 
     def sharded_gather(self):
         """(particles [3, NG], weights [NG]) of the whole filter, on every rank (NCCL, collective)."""

@@ -522,6 +522,215 @@ __global__ void __launch_bounds__(32) k_route_check(ShardDev sh) {
     route_finish(sh, epoch);
 }
 
+// ------------------------------------------------------------------------------------------
+// sharded filter: sender-driven resampling in two hops (the default from 3 ranks on)
+// ------------------------------------------------------------------------------------------
+// k_route makes every rank evaluate ALL world * N draws to find the 1 / world it has to serve: work per rank
+// grows with the number of ranks.  Here the owner of a SLOT evaluates its own N draws, finds the rank whose
+// CDF range holds each draw (world - 1 comparisons against the replicated rank_end table) and appends the
+// slot's local index to that rank's inbox (k_route_request; 4 bytes per slot over NVLink, written as
+// contiguous runs).  After one exchange of the per-destination counts the source ranks serve their inboxes
+// with full warps (k_route_serve): draw recomputed from the global slot, search in the local CDF slice, 32-byte
+// push of the source pose into the slot owner's `routed` array.  Per rank: N classifications + (on balanced
+// weights) N searches, independent of the world size.  Results are identical to k_route's by construction:
+// the same draw, the same claim rule (rank_end[q-1] < u <= rank_end[q]), the same local lower_bound.
+struct RouteReqArgs {
+    int64_t N;                      // slots of this rank
+    const double* rank_end;         // [world]
+    uint32_t* inbox[kMaxWorld];     // every rank's inbox [world senders][N] (own included)
+    unsigned int* req_count;        // [kMaxWorld] own: requests appended per destination (zeroed by the serve kernel)
+    const double* u;                // [NG] injected uniforms or nullptr
+    uint64_t seed;
+    const unsigned long long* update_no;
+    unsigned int* done;
+    ShardDev sh;
+};
+constexpr int kReqThreads = 1024;
+constexpr int kReqPer = 8;          // slots per thread (four Philox calls)
+constexpr int kReqBlock = kReqThreads * kReqPer;
+
+__global__ void __launch_bounds__(kReqThreads) k_route_request(RouteReqArgs a) {
+    __shared__ uint32_t stage[kReqBlock];           // the block's slots grouped by destination
+    __shared__ unsigned int s_cnt[kMaxWorld], s_off[kMaxWorld + 1], s_base[kMaxWorld];
+    __shared__ double s_end[kMaxWorld];
+    __shared__ unsigned long long s_pay[kMaxWorld];
+    __shared__ bool is_last;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int me = a.sh.rank, world = a.sh.world;
+    if (tid < kMaxWorld) {
+        s_cnt[tid] = 0;
+        s_end[tid] = tid < world - 1 ? a.rank_end[tid] : 2.0;
+    }
+    __syncthreads();
+    const uint64_t update_no = *a.update_no;
+    const int64_t glo = static_cast<int64_t>(me) * a.N;
+    const int64_t b0 = static_cast<int64_t>(blockIdx.x) * kReqBlock;
+    // pass 1: destination of every slot and its position among the block's slots for that destination
+    int dest[kReqPer];
+    unsigned int posn[kReqPer];
+#pragma unroll
+    for (int e = 0; e < kReqPer; e += 2) {
+        // a thread's pair of slots shares one Philox call; consecutive threads take consecutive pairs
+        const int64_t li = b0 + static_cast<int64_t>(e / 2) * (2 * kReqThreads) + 2 * tid;
+        double u0 = 3.0, u1 = 3.0;
+        if (li < a.N) {
+            const int64_t i = glo + li;          // glo and li are even or N is odd: pair by GLOBAL slot parity below
+            if (a.u) {
+                u0 = a.u[i];
+                if (li + 1 < a.N) u1 = a.u[i + 1];
+            } else if ((i & 1) == 0) {
+                const Philox4 r = noise_words(static_cast<uint64_t>(i) >> 1, 0, 0u, a.seed, update_no);
+                u0 = canonical_from_words(r.v[0], r.v[1]);
+                if (li + 1 < a.N) u1 = canonical_from_words(r.v[2], r.v[3]);
+            } else {
+                u0 = resample_uniform(i, 0, a.seed, update_no);
+                if (li + 1 < a.N) u1 = resample_uniform(i + 1, 0, a.seed, update_no);
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const double u = h ? u1 : u0;
+            int q = -1;
+            if (u < 2.5) {
+                q = 0;
+                for (int k = 0; k < world - 1; ++k) q += s_end[k] < u;   // the rank with rank_end[q-1] < u <= rank_end[q]
+            }
+            dest[e + h] = q;
+            // warp-aggregated count: one shared-memory atomic per (warp, destination)
+            const unsigned same = __match_any_sync(kFullMask, q);
+            const int leader = __ffs(same) - 1;
+            unsigned int base = 0;
+            if (lane == leader && q >= 0) base = atomicAdd(&s_cnt[q], static_cast<unsigned int>(__popc(same)));
+            base = __shfl_sync(kFullMask, base, leader);
+            posn[e + h] = base + static_cast<unsigned int>(__popc(same & ((1u << lane) - 1u)));
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        unsigned int o = 0;
+        for (int q = 0; q < world; ++q) {
+            s_off[q] = o;
+            o += s_cnt[q];
+        }
+        s_off[world] = o;
+    }
+    if (tid < world) s_base[tid] = s_cnt[tid] ? atomicAdd(a.req_count + tid, s_cnt[tid]) : 0u;
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < kReqPer; ++e) {
+        if (dest[e] >= 0) {
+            const int64_t li = b0 + static_cast<int64_t>(e / 2) * (2 * kReqThreads) + 2 * tid + (e & 1);
+            stage[s_off[dest[e]] + posn[e]] = static_cast<uint32_t>(li);
+        }
+    }
+    __syncthreads();
+    // pass 2: every destination's run goes out as consecutive 4-byte stores (whole sectors over NVLink)
+    for (int q = 0; q < world; ++q) {
+        uint32_t* dst = a.inbox[q] + static_cast<size_t>(me) * static_cast<size_t>(a.N) + s_base[q];
+        const unsigned int n = s_cnt[q], o = s_off[q];
+        for (unsigned int t = tid; t < n; t += kReqThreads) dst[t] = stage[o + t];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        is_last = atomicAdd(a.done, 1u) == gridDim.x - 1u;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (tid == 0) *a.done = 0;
+    // payload: this rank's request count for every destination
+    if (tid < kMaxWorld) s_pay[tid] = tid < world ? static_cast<unsigned long long>(ld_sys_u32(a.req_count + tid)) : 0ull;
+    __syncthreads();
+    const unsigned long long epoch = *a.sh.xseq + 1ull;
+    shard_publish(a.sh, epoch, s_pay, world);
+    if (!a.sh.fused) return;
+    if (!shard_wait(a.sh, epoch)) return;
+    route_finish(a.sh, epoch);
+}
+
+struct RouteServeArgs {
+    int64_t N;
+    const double* cdf;
+    const double* coarse;
+    int nc, cshift;
+    const double* mid;
+    const double4* spose4;
+    const double* sx;
+    const double* sy;
+    const double* st;
+    const uint32_t* inbox;          // own inbox [world][N]
+    double4* routed[kMaxWorld];
+    unsigned int* req_count;        // own request counters: cleared here for the next update
+    const double* u;
+    uint64_t seed;
+    const unsigned long long* update_no;
+    unsigned int* done;
+    ShardDev sh;
+};
+
+__global__ void __launch_bounds__(kRouteThreads) k_route_serve(RouteServeArgs a) {
+    extern __shared__ __align__(8) uint32_t ts[];   // nc keys of the coarse level
+    __shared__ unsigned int s_pre[kMaxWorld + 1];
+    __shared__ bool is_last;
+    const int tid = threadIdx.x;
+    const int me = a.sh.rank, world = a.sh.world;
+    for (int t = tid; t < a.nc; t += kRouteThreads) ts[t] = static_cast<uint32_t>(__double2hiint(a.coarse[t]));
+    // the counts travelled in the exchange the request kernel (or its check kernel) completed: epoch == *xseq
+    const unsigned long long req_epoch = *a.sh.xseq;
+    if (tid == 0) {
+        unsigned int o = 0;
+        for (int r = 0; r < world; ++r) {
+            s_pre[r] = o;
+            o += static_cast<unsigned int>(ld_sys_u64(mbox_slot(a.sh, me, req_epoch, r) + me));
+        }
+        s_pre[world] = o;
+    }
+    if (blockIdx.x == 0 && tid < kMaxWorld) a.req_count[tid] = 0;   // (own counters: only this rank's request kernel adds to them)
+    __syncthreads();
+    const unsigned int total = s_pre[world];
+    const uint64_t update_no = *a.update_no;
+    const int64_t glo = static_cast<int64_t>(me) * a.N;
+    for (unsigned int t = blockIdx.x * kRouteThreads + tid; t < total; t += gridDim.x * kRouteThreads) {
+        int r = 0;
+        while (r + 1 < world && s_pre[r + 1] <= t) ++r;
+        const uint32_t li = ld_sys_u32(a.inbox + static_cast<size_t>(r) * static_cast<size_t>(a.N) + (t - s_pre[r]));
+        const int64_t i = static_cast<int64_t>(r) * a.N + li;
+        const double u = a.u ? a.u[i] : resample_uniform(i, 0, a.seed, update_no);
+        const int64_t j = cdf_lower_bound(a.cdf, a.mid, a.N, ts, a.coarse, a.nc, a.cshift, u);
+        double x, y, th;
+        if (a.spose4) {
+            double pad;
+            ldg256(reinterpret_cast<const double*>(a.spose4 + j), x, y, th, pad);
+        } else {
+            x = a.sx[j];
+            y = a.sy[j];
+            th = a.st[j];
+        }
+        double* dst = reinterpret_cast<double*>(a.routed[r] + li);
+        asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "d"(x), "d"(y), "d"(th),
+                     "d"(__longlong_as_double(glo + j))
+                     : "memory");
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        is_last = atomicAdd(a.done, 1u) == gridDim.x - 1u;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (tid == 0) *a.done = 0;
+    __syncthreads();
+    const unsigned long long epoch = req_epoch + 1ull;
+    shard_publish(a.sh, epoch, nullptr, 0);
+    if (!a.sh.fused) return;
+    if (!shard_wait(a.sh, epoch)) return;
+    route_finish(a.sh, epoch);
+}
+
 // Counting sort of the particles by heading bucket, in two kernels of fat blocks so that the
 // only global atomics are one per (block, non-empty bucket):
 //   k_sort_hist     block-private shared-memory histogram of a contiguous chunk, flushed once

@@ -210,6 +210,10 @@ struct mcl_ctx {
     int* d_err = nullptr;
     ShardDev sh{};                    // device view (peer pointers), by value in kernel arguments
     double4* routed_peers[kMaxWorld] = {};
+    uint32_t* inbox_peers[kMaxWorld] = {};   // every rank's request inbox [world senders][N] (two-hop routing)
+    uint32_t* d_inbox = nullptr;
+    unsigned int* d_req_count = nullptr;     // [kMaxWorld] requests appended per destination in the current update
+    int route_mode = -1;                     // -1 auto (two-hop from 3 ranks on), 0 two-hop requests, 1 every rank tests all draws
     const StepFn* peer_list_fn[kMaxWorld] = {};
     const double* peer_list_add[kMaxWorld] = {};
     std::vector<void*> ipc_opened;
@@ -778,9 +782,64 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
     const bool sort = c->sort_enabled && !c->wide;   // (the heading order only serves the skip-map ray kernels)
     static const bool no_packed = std::getenv("MCL_NO_PACKED") != nullptr;   // debugging knob
     const bool packed = !no_packed && c->pose4_ok[src];   // the packed source copy was written by the last update (no set_particles / init since)
-    if (sharded(c)) {
-        // sender-driven resampling: every rank tests all NG draws, serves those that fall into its
-        // CDF range and pushes the source poses to the slots' owners (k_route)
+    if (sharded(c) && c->route_mode != 1) {
+        // sender-driven resampling in two hops: the slot owners classify their own draws and append
+        // requests to the source ranks' inboxes (k_route_request), one exchange of the counts, then the
+        // source ranks search and push the source poses to the slots' owners (k_route_serve)
+        RouteReqArgs qa{};
+        qa.N = c->N;
+        qa.rank_end = c->d_rank_end2[src];
+        for (int q = 0; q < kMaxWorld; ++q) qa.inbox[q] = c->inbox_peers[q];
+        qa.req_count = c->d_req_count;
+        qa.u = u_dev;
+        qa.seed = c->prm.seed;
+        qa.update_no = c->d_update_no;
+        qa.done = c->d_route_done;
+        qa.sh = c->sh;
+        qa.sh.fused = c->xmode;
+        k_route_request<<<static_cast<unsigned>((c->N + kReqBlock - 1) / kReqBlock), kReqThreads, 0, s>>>(qa);
+        mark(c, "k_route_request");
+        ShardDev sd = c->sh;
+        sd.fused = 0;
+        if (!c->xmode) {
+            rc = exchange_barrier(c);
+            if (rc) return rc;
+            k_route_check<<<1, 32, 0, s>>>(sd);
+            mark(c, "k_route_check");
+        }
+        RouteServeArgs va{};
+        va.N = c->N;
+        va.cdf = c->d_cdf2[src];
+        va.coarse = c->coarse_n > 0 ? c->d_coarse2[src] : nullptr;
+        va.nc = c->coarse_n;
+        va.cshift = c->coarse_shift;
+        va.mid = c->d_mid2[src];
+        va.spose4 = packed ? c->d_pose4[src] : nullptr;
+        va.sx = c->d_px[src];
+        va.sy = c->d_py[src];
+        va.st = c->d_pt[src];
+        va.inbox = c->d_inbox;
+        for (int q = 0; q < kMaxWorld; ++q) va.routed[q] = c->routed_peers[q];
+        va.req_count = c->d_req_count;
+        va.u = u_dev;
+        va.seed = c->prm.seed;
+        va.update_no = c->d_update_no;
+        va.done = c->d_route_done;
+        va.sh = c->sh;
+        va.sh.fused = c->xmode;
+        const size_t vsmem = sizeof(uint32_t) * static_cast<size_t>((c->coarse_n + 1) & ~1);
+        const int vblocks = static_cast<int>(std::min<int64_t>(c->num_sms, (c->N + kRouteThreads - 1) / kRouteThreads));
+        k_route_serve<<<vblocks, kRouteThreads, vsmem, s>>>(va);
+        mark(c, "k_route_serve");
+        if (!c->xmode) {
+            rc = exchange_barrier(c);
+            if (rc) return rc;
+            k_route_check<<<1, 32, 0, s>>>(sd);
+            mark(c, "k_route_check");
+        }
+    } else if (sharded(c)) {
+        // one hop: every rank tests all NG draws, serves those that fall into its CDF range and pushes
+        // the source poses to the slots' owners (k_route); work per rank grows with the number of ranks
         RouteArgs ra{};
         ra.NG = c->NG;
         ra.N = c->N;
@@ -1227,7 +1286,7 @@ int mcl_destroy(mcl_ctx* c);
 namespace {
 
 struct ArenaLayout {
-    size_t mbox, flag, routed, list_fn, list_add, bytes;
+    size_t mbox, flag, routed, list_fn, list_add, inbox, bytes;
 };
 ArenaLayout arena_layout(int world, int64_t n_local) {
     const size_t C = static_cast<size_t>((n_local + kTile - 1) / kTile) * kTileChunks;
@@ -1244,6 +1303,8 @@ ArenaLayout arena_layout(int world, int64_t n_local) {
     o = up(o + sizeof(StepFn) * 2 * C);
     L.list_add = o;
     o = up(o + sizeof(double) * 2 * C * kChunk);
+    L.inbox = o;
+    o = up(o + sizeof(uint32_t) * static_cast<size_t>(world) * static_cast<size_t>(n_local));
     L.bytes = o;
     return L;
 }
@@ -1387,6 +1448,9 @@ static int create_buffers(mcl_ctx* c, const mcl_params* p, int device, int world
         c->d_routed = reinterpret_cast<double4*>(c->arena + L.routed);
         c->d_list_fn = reinterpret_cast<StepFn*>(c->arena + L.list_fn);
         c->d_list_add = reinterpret_cast<double*>(c->arena + L.list_add);
+        c->d_inbox = reinterpret_cast<uint32_t*>(c->arena + L.inbox);
+        CK(dalloc(&c->d_req_count, static_cast<size_t>(kMaxWorld)));
+        CK(cudaMemset(c->d_req_count, 0, sizeof(unsigned int) * kMaxWorld));
         CK(dalloc(&c->d_xseq, size_t{1}));
         CK(cudaMemset(c->d_xseq, 0, sizeof(unsigned long long)));
         CK(dalloc(&c->d_nccl_tok, static_cast<size_t>(kMaxWorld)));
@@ -1405,6 +1469,7 @@ static int create_buffers(mcl_ctx* c, const mcl_params* p, int device, int world
     MCL_RAY_SMEM(4, 239);
 #undef MCL_RAY_SMEM
     CK(cudaFuncSetAttribute(k_resample_motion, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * static_cast<int>(sizeof(double))));
+    CK(cudaFuncSetAttribute(k_route_serve, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
     CK(cudaFuncSetAttribute(k_route, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             16384 * static_cast<int>(sizeof(double)) + (kRouteThreads / 32) * kRouteQueue * 12));
     CK(cudaFuncSetAttribute(k_weight_steps_sm<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
@@ -2212,6 +2277,7 @@ int install_arenas(mcl_ctx* c, void* const* bases) {
         c->sh.mbox[q] = reinterpret_cast<uint8_t*>(b + L.mbox);
         c->sh.flag[q] = reinterpret_cast<unsigned long long*>(b + L.flag);
         c->routed_peers[q] = reinterpret_cast<double4*>(b + L.routed);
+        c->inbox_peers[q] = reinterpret_cast<uint32_t*>(b + L.inbox);
         c->peer_list_fn[q] = reinterpret_cast<const StepFn*>(b + L.list_fn);
         c->peer_list_add[q] = reinterpret_cast<const double*>(b + L.list_add);
     }
@@ -2300,6 +2366,16 @@ int mcl_shard_set_exchange(mcl_ctx* c, int fused, mcl_barrier_fn hook, void* use
     c->xmode = fused ? 1 : 0;
     c->hook = fused ? nullptr : hook;
     c->hook_user = user;
+    drop_graphs(c);
+    return MCL_OK;
+}
+
+int mcl_shard_set_route(mcl_ctx* c, int two_hop) {
+    if (!c) return fail(MCL_ERR_INVALID, "null context");
+    if (!c->arena) return fail(MCL_ERR_INVALID, "not a sharded context");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    c->route_mode = two_hop ? 0 : 1;
     drop_graphs(c);
     return MCL_OK;
 }

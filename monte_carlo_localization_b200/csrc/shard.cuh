@@ -55,6 +55,11 @@ __device__ __forceinline__ unsigned long long ld_sys_u64(const void* p) {
     asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ uint32_t ld_sys_u32(const void* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ double ld_sys_f64(const double* p) { return __longlong_as_double(static_cast<long long>(ld_sys_u64(p))); }
 __device__ __forceinline__ void st_sys_u64(void* p, unsigned long long v) {
     asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");

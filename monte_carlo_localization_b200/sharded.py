@@ -5,8 +5,8 @@ places -- the weight sum (src/particle_filter.cpp:679), the CDF + source gather 
 resampling (:658-665) and the expected-pose sums (:702-710).  The sharding lives in the C library
 (`mcl_create_sharded`, include/mcl_b200.h): every rank holds only its own slot range of every
 per-particle array, the three sequentially rounded reductions exchange a < 2 KB summary per rank,
-resampling is sender-driven (the rank that owns a source particle pushes its pose to the slot's
-owner over NVLink), and the kernels perform the exchanges themselves -- an update has no host call
+resampling is sender-driven (the slot's owner sends a 4-byte request to the rank whose CDF range holds
+the draw, that rank pushes the source pose back over NVLink), and the kernels perform the exchanges themselves -- an update has no host call
 between its launches.  With the same noise the ranks' slices equal the single-GPU filter bit for
 bit (scripts/check_sharded_equals_single.py, tests/test_multi_gpu.py).
 
@@ -74,10 +74,12 @@ class ShardedFilter:
     """One rank's share of a particle-sharded global filter (torch.distributed carries the NCCL id)."""
 
     def __init__(self, grid, angles, n_local: int, rank: int, world: int, device: int = 0, seed: int = 0,
-                 exchange: str = "fused", **params):
+                 exchange: str = "fused", route: str = "two-hop", **params):
         """exchange "fused": the kernels publish and wait on their own (NVLink stores + system-scope
         flags).  "nccl": the same stores, but the ranks meet in a one-word ncclAllGather enqueued
-        between the publishing and the consuming kernel (for comparison)."""
+        between the publishing and the consuming kernel (for comparison).
+        route "two-hop" (default): request routing, work per rank independent of the world size;
+        "one-hop": every rank tests all draws (mcl_shard_set_route)."""
         from . import capi
         if exchange not in ("fused", "nccl"):
             raise ValueError("exchange must be 'fused' or 'nccl'")
@@ -90,6 +92,10 @@ class ShardedFilter:
         self.ctx.set_beam_angles(angles)
         if exchange == "nccl":
             self.ctx.shard_set_exchange(False)
+        if route not in ("two-hop", "one-hop"):
+            raise ValueError("route must be 'two-hop' or 'one-hop'")
+        if route == "one-hop":
+            self.ctx.shard_set_route(False)
 
     def init_pose(self, pose, normals_3n=None):
         """initialize_particles_pose of the WHOLE filter; the device RNG is keyed by the global slot.

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--particles-per-gpu", type=int, default=262144)
     ap.add_argument("--updates", type=int, default=12)
     ap.add_argument("--exchange", default="fused")
+    ap.add_argument("--route", default="two-hop")
     ap.add_argument("--degenerate", action="store_true",
                     help="also one update from weights that put all the mass on one particle (overflow path of the exchange)")
     a = ap.parse_args()
@@ -43,7 +44,7 @@ def main():
         angles_full = synth.laser_angles()
         angles = synth.downsample(angles_full)
         flt = ShardedFilter(g, angles, n_local=a.particles_per_gpu, rank=rank, world=world, device=local_rank, seed=99,
-                            exchange=a.exchange)
+                            exchange=a.exchange, route=a.route)
     finally:
         sys.stdout.flush()
         os.dup2(saved, 1)
@@ -79,7 +80,7 @@ def main():
         single.init_pose(gt[0])
         sposes = [single.update(actions[t], obs[t]).copy() for t in range(a.updates)]
         sp, sw = single.get_particles(), single.get_weights()
-        res = {"world": world, "exchange": a.exchange, "particles": NG, "updates": a.updates,
+        res = {"world": world, "exchange": a.exchange, "route": a.route, "particles": NG, "updates": a.updates,
                "indices_bit_identical": bool(np.array_equal(idx_all, single.resample_indices())),
                "weights_bit_identical": bool(np.array_equal(w, sw)), "particles_bit_identical": bool(np.array_equal(p, sp)),
                "max_pose_diff": float(np.abs(np.stack(poses) - np.stack(sposes)).max()),

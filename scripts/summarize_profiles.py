@@ -147,20 +147,27 @@ def dir_summary(rep, launches_csv, tag):
             src.append(x)
     tot = sum(int(x[5]) for x in src)
     rays = 1048576 * 60 / 32.0
-    b = collections.OrderedDict([("march loop, skip path", 0), ("march loop, near-wall path", 0),
-                                 ("per ray and per 32-beam round (direction, sector test, store)", 0),
-                                 ("per unit (record prefetch, window base, beam mask)", 0),
-                                 ("rare (window staging, scheduling, exact replay)", 0)])
+    b = collections.OrderedDict([("march loop (branch-free body, one trip per lookup)", 0),
+                                 ("per warp-ray (beam direction, sector test, result store, loop entry/exit)", 0),
+                                 ("per warp-unit (record load + prefetch, window base, first-sample lookup, beam range)", 0),
+                                 ("rare (window staging, unit counter, exact replay)", 0)])
+    samples = collections.OrderedDict((k, 0) for k in b)
+    lanes_loop = [0, 0]
     for x in src:
         ie = int(x[5])
         q = ie / rays
-        key = (list(b)[0] if q >= 5.2 else list(b)[1] if q >= 3 else list(b)[2] if q >= 0.7 else list(b)[3] if q >= 0.2 else list(b)[4])
+        key = (list(b)[0] if q >= 3 else list(b)[1] if q >= 0.7 else list(b)[2] if q >= 0.2 else list(b)[3])
         b[key] += ie
+        samples[key] += int(x[4])
+        if q >= 3:
+            lanes_loop[0] += int(x[6])
+            lanes_loop[1] += ie
+    nsamp = max(1, sum(samples.values()))
     dram = to_bytes(*vals["dram__bytes_read.sum"]) + to_bytes(*vals["dram__bytes_write.sum"])
     sass = " ".join(x[1] for x in src)
     md = ["# %s -- ncu --set full (directional ray stage)" % kname, "",
           "Command (under gpurun, after the same command exited 0 without ncu):", "",
-          "    ncu --set full --clock-control none --import-source on -k regex:k_raycast_dir -s 6 -c 1 \\",
+          "    ncu --set full --clock-control none --import-source on -k regex:k_raycast_dir -s 6 -c 1 -f \\",
           "        -o gpurun_out/prof_%s python bench.py --steps 3 --warmup 3 --no-cpu" % tag, "",
           "Workload: Spielberg_map, 1,048,576 particles x 60 beams (62.9 M rays), tracking cloud.",
           "Times under ncu are cold-cache and serialised: compare shares, not absolutes.", "",
@@ -174,17 +181,29 @@ def dir_summary(rep, launches_csv, tag):
            "no HMMA/UTC*MMA (no dense contraction on this path)." % tuple(
                "present" if t in sass else "absent" for t in ("UBLKCP", "SYNCS", "LDGSTS", "LDS.U8")),
            "", "Executed warp instructions by region (source page, `Instructions Executed`):", "",
-           "| region | warp instructions | share | per warp-ray |", "|---|---|---|---|"]
-    md += ["| %s | %.3e | %.1f %% | %.0f |" % (k, v, 100 * v / tot, v / rays) for k, v in b.items()]
-    md += ["| total | %.3e | | %.0f |" % (tot, tot / rays), "",
-           "Reading: warp-issue bound (issue active %s %% of peak; tensor, FP64 and LSU pipes far from saturated), SIMT lane efficiency %s of 32."
-           % (vals["smsp__issue_active.avg.pct_of_peak_sustained_active"][0][:4], vals["smsp__thread_inst_executed_per_inst_executed.ratio"][0])]
+           "| region | warp instructions | share | per warp-ray | share of the stall samples |", "|---|---|---|---|---|"]
+    md += ["| %s | %.3e | %.1f %% | %.0f | %.1f %% |" % (k, v, 100 * v / tot, v / rays, 100.0 * samples[k] / nsamp) for k, v in b.items()]
+    md += ["| total | %.3e | | %.0f | |" % (tot, tot / rays), "",
+           "Active lanes per instruction inside the march loop: %.1f of 32 (whole kernel: %s)." % (
+               lanes_loop[0] / max(1, lanes_loop[1]), vals["smsp__thread_inst_executed_per_inst_executed.ratio"][0]),
+           "", "Reading: warp-issue bound (issue active %s %% of peak over the whole launch, i.e. including window staging, barrier waits and the tail; "
+           "tensor, FP64 and LSU pipes far from saturated)." % vals["smsp__issue_active.avg.pct_of_peak_sustained_active"][0][:4]]
+    stalls = [(k.split("issue_stalled_")[1].split("_per_issue")[0], float(r[hdr.index(k)])) for k in hdr
+              if "average_warps_issue_stalled" in k and k.endswith("per_issue_active.ratio")]
+    stalls.sort(key=lambda kv: -kv[1])
+    md += ["", "Warp states per issued instruction (ncu `smsp__average_warps_issue_stalled_*_per_issue_active`): " +
+           ", ".join("%s %.2f" % kv for kv in stalls[:8]) + "."]
     open(os.path.join(ROOT, "profiles", tag + "_ray_ncu.md"), "w").write("\n".join(md) + "\n")
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     t = json.load(open(tp)) if os.path.exists(tp) else {}
     t["k_raycast_dir_dram_bytes_per_launch"] = dram
     t["k_raycast_dir_warp_instructions_per_launch"] = float(vals["smsp__inst_executed.sum"][0].replace(",", ""))
     t["k_raycast_dir_source"] = "profiles/%s_ray_ncu.md (ncu --set full, one launch, 1M x 60 Spielberg)" % tag
+    t["k_raycast_dir_threads_per_instruction"] = float(vals["smsp__thread_inst_executed_per_inst_executed.ratio"][0])
+    wf = float(vals["l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"][0].replace(",", ""))
+    t["k_raycast_dir_shared_conflict_share"] = float(vals["l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"][0].replace(",", "")) / max(1.0, wf)
+    # the configuration the capture belongs to: bench.py only quotes it for a run of the same workload
+    t.update({"map": "Spielberg_map", "particles": 1048576, "beams": 60, "capture": tag})
     json.dump(t, open(tp, "w"))
     # launch list
     import shutil
@@ -202,7 +221,7 @@ def dir_summary(rep, launches_csv, tag):
         except ValueError:
             continue
         agg.setdefault(rr[kn].split("(")[0][:60], []).append(v)
-    skip = ("k_range_queries", "k_init_pose", "k_fill", "k_build_dir_maps", "k_gather_bench")
+    skip = ("k_range_queries", "k_init_pose", "k_fill", "k_build_dir_maps", "k_gather_bench", "k_map_masks", "k_edt_cols", "k_edt_rows", "k_map_codes")
     upd = {k: v for k, v in agg.items() if "mclb200" in k and not any(x in k for x in skip)}
     n_upd = len(upd[[k for k in upd if "k_raycast_dir" in k][0]])
     # the diagnostics pass of bench.py (per-ray steps kept) inflates k_weight_steps: use the median
@@ -220,16 +239,63 @@ def dir_summary(rep, launches_csv, tag):
                                                         med[k] / 1e3, 100 * med[k] * len(v) / n_upd / tot_med))
     out.append("| total per update | %d | %.1f | |" % (round(sum(len(v) for v in upd.values()) / n_upd), tot_med / 1e3))
     bd = agg.get("mclb200::k_build_dir_maps", [0])
-    out += ["", "Outside the update: `k_build_dir_maps` once per map (%.1f ms for the 32 sector maps of Spielberg_map), `k_range_queries` "
-            "(synthetic scan generation), `k_init_pose`, `k_fill`, the gather micro-benchmark and the L2-flush fill of bench.py." % (bd[0] / 1e6)]
+    edt = sum(agg.get("mclb200::" + k, [0])[0] for k in ("k_map_masks", "k_edt_cols", "k_edt_rows", "k_map_codes"))
+    out += ["", "Outside the update: `k_build_dir_maps` once per map (%.1f ms for the 32 sector maps of Spielberg_map), the isotropic skip map "
+            "(`k_map_masks`, `k_edt_cols`, `k_edt_rows`, `k_map_codes`: %.1f ms, exact Euclidean transform on the device), `k_range_queries` "
+            "(synthetic scan generation), `k_init_pose`, `k_fill`, the gather micro-benchmark and the L2-flush fill of bench.py." % (bd[0] / 1e6, edt / 1e6)]
     open(os.path.join(ROOT, "profiles", tag + "_launches.md"), "w").write("\n".join(out) + "\n")
     print("wrote profiles/%s_ray_ncu.md, profiles/%s_launches.md, profiles/ncu_traffic.json" % (tag, tag))
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and not (len(sys.argv) >= 3 and sys.argv[1] == "--small"):
     if len(sys.argv) >= 4 and sys.argv[1] == "--dir":
         dir_summary(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else "r1_dir")
     else:
         ray_summary(sys.argv[1])
         launch_summary(sys.argv[2])
         print("wrote profiles/r1_final_ray_ncu.md, profiles/r1_final_launches.md, profiles/ncu_traffic.json")
+
+
+def small_summary(rep, tag):
+    """profiles/<tag>_small_ncu.md: one row per captured launch of the streaming kernels (ncu --set full)."""
+    raw = page(rep, "raw")
+    hdr, units = raw[0], raw[1]
+    cols = [("gpu__time_duration.sum", "us"), ("launch__grid_size", "grid"), ("launch__block_size", "block"),
+            ("launch__registers_per_thread", "regs"), ("dram__bytes_read.sum", "DRAM rd"), ("dram__bytes_write.sum", "DRAM wr"),
+            ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM %"),
+            ("l1tex__throughput.avg.pct_of_peak_sustained_active", "L1TEX %"),
+            ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2 %"),
+            ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue %"),
+            ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps active %"),
+            ("smsp__thread_inst_executed_per_inst_executed.ratio", "lanes")]
+    cols = [(k, n) for k, n in cols if k in hdr]
+    kn = hdr.index("Kernel Name")
+    seen, rows = {}, []
+    for r in raw[2:]:
+        name = r[kn].replace("void ", "").replace("mclb200::", "").split("(")[0]
+        seen[name] = seen.get(name, 0) + 1
+        if seen[name] > 2:
+            continue
+        cells = []
+        for k, _ in cols:
+            v, u = r[hdr.index(k)], units[hdr.index(k)]
+            if "byte" in u:
+                cells.append("%.1f MB" % (to_bytes(v, u) / 1e6))
+            else:
+                try:
+                    cells.append("%.1f" % float(v.replace(",", "")) if "." in v else v)
+                except ValueError:
+                    cells.append(v)
+        rows.append("| `%s` | %s |" % (name, " | ".join(cells)))
+    md = ["# Streaming kernels of the update -- ncu --set full", "",
+          "    ncu --set full --clock-control none --import-source on -k regex:'k_resample_motion|k_weight_steps|k_exact_pass|k_exact_emit|k_tile_sums|k_dir_gather|k_sort' \\",
+          "        -s 40 -c 12 -f -o gpurun_out/prof_%s_small python bench.py --steps 3 --warmup 3 --no-cpu" % tag, "",
+          "Workload: Spielberg_map, 1,048,576 particles x 60 beams.  Cold-cache, serialised launches (ncu): the CUDA-event times of the",
+          "bench line (`kernels`) are the timings; this table says what each kernel is bound by.", "",
+          "| kernel | " + " | ".join(n for _, n in cols) + " |", "|---|" + "---|" * len(cols)] + rows
+    open(os.path.join(ROOT, "profiles", tag + "_small_ncu.md"), "w").write("\n".join(md) + "\n")
+    print("wrote profiles/%s_small_ncu.md" % tag)
+
+
+if __name__ == "__main__" and len(sys.argv) >= 3 and sys.argv[1] == "--small":
+    small_summary(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else "r2")

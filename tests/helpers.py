@@ -51,7 +51,7 @@ class EmuRanks:
     same mailboxes, the same routed pushes (into the other context's memory on the same device).
     """
 
-    def __init__(self, grid, angles, n_global, world, keep_ranges=True, **params):
+    def __init__(self, grid, angles, n_global, world, keep_ranges=True, two_hop=None, **params):
         import threading
 
         from monte_carlo_localization_b200 import MclContext
@@ -67,6 +67,8 @@ class EmuRanks:
         self._barrier = threading.Barrier(world)
         for c in self.ctxs:
             c.shard_set_exchange(False, hook=self._hook)
+            if two_hop is not None:      # None: the library's default (two-hop request routing)
+                c.shard_set_route(two_hop)
 
     def _hook(self):
         self._barrier.wait(timeout=120)

@@ -641,17 +641,20 @@ def test_sharded_ranks_reproduce_golden_updates(world):
     ranks.close()
 
 
-@pytest.mark.parametrize("world,N", [(2, 4000), (2, 40000), (4, 65536)])
-def test_sharded_ranks_free_running_equal_single_filter(world, N):
+@pytest.mark.parametrize("world,N,two_hop", [(2, 4000, True), (2, 40000, True), (4, 65536, True), (3, 30000, True), (2, 4002, True),
+                                             (2, 40000, False), (4, 65536, False)])
+def test_sharded_ranks_free_running_equal_single_filter(world, N, two_hop):
     """No teacher forcing, device RNG: the sharded filter must stay BIT-identical to the same filter on
-    one GPU over several updates (noise is keyed by the global slot; sums are sequentially rounded)."""
+    one GPU over several updates (noise is keyed by the global slot; sums are sequentially rounded), with
+    the draws routed in two hops (requests to the source ranks; odd slice sizes and a world of 3 included)
+    and in one hop (every rank tests all draws)."""
     from helpers import EmuRanks
     g, angles, orc, ns, action, obs = _tracking_case("sibal1", N, 3.0, 11)
     p0, w0 = orc.get_state()
     single = _ctx(g, angles, N, seed=4242)
     single.set_graphs(False)
     single.set_particles(p0, w0)
-    ranks = EmuRanks(g, angles, N, world, seed=4242)
+    ranks = EmuRanks(g, angles, N, world, seed=4242, two_hop=two_hop)
     ranks.set_state(p0, w0)
     for t in range(4):
         pose_s = single.update(action, obs)
@@ -696,16 +699,17 @@ def test_sharded_ranks_degenerate_weights_match_oracle():
     cases["uniform"] = np.full(N, 1.0 / N)
     w = rng.random(N) ** 8 + 1e-300
     cases["heavy-tailed"] = w / w.sum()
-    ranks = EmuRanks(g, angles, N, world, keep_ranges=False)
-    for name, w in cases.items():
-        ns = ob.NoiseStream(5)
-        u, z = ns.update_noise(N)
-        ranks.set_state(p, w)
-        ranks.update([0.05, 0, 0.01], obs, u, z)
-        idx_ref, cdf_ref = ob.resample_indices(w, u, want_cdf=True)
-        assert np.array_equal(ranks.gather(lambda c: c.cdf()), cdf_ref), name
-        assert np.array_equal(ranks.gather(lambda c: c.resample_indices()), idx_ref), name
-    ranks.close()
+    for two_hop in (True, False):
+        ranks = EmuRanks(g, angles, N, world, keep_ranges=False, two_hop=two_hop)
+        for name, w in cases.items():
+            ns = ob.NoiseStream(5)
+            u, z = ns.update_noise(N)
+            ranks.set_state(p, w)
+            ranks.update([0.05, 0, 0.01], obs, u, z)
+            idx_ref, cdf_ref = ob.resample_indices(w, u, want_cdf=True)
+            assert np.array_equal(ranks.gather(lambda c: c.cdf()), cdf_ref), name
+            assert np.array_equal(ranks.gather(lambda c: c.resample_indices()), idx_ref), name
+        ranks.close()
 
 
 def test_viz_weighted_subsample_matches_reference_draws():
