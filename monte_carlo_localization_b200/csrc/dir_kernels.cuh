@@ -235,15 +235,18 @@ __global__ void __launch_bounds__(kPlanThreads) k_dir_plan(DirPlanArgs a) {
     }
     __syncthreads();
     if (warp == 0) {
-        const int n = cmax[lane] > cmin[lane] ? cmax[lane] - cmin[lane] : 0;   // kDirSectors == 32 lanes
+        const int ls = lane < kDirSectors ? lane : kDirSectors - 1;            // one lane per sector (kDirSectors <= 32)
+        const int n = (lane < kDirSectors && cmax[ls] > cmin[ls]) ? cmax[ls] - cmin[ls] : 0;
         int w = n;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const int o = __shfl_up_sync(kFullMask, w, d);
             if (lane >= d) w += o;
         }
-        a.sec_tab[lane] = w - n;
-        a.sec_tab[kDirSectors + 1 + lane] = n ? cmin[lane] : 0;
+        if (lane < kDirSectors) {
+            a.sec_tab[lane] = w - n;
+            a.sec_tab[kDirSectors + 1 + lane] = n ? cmin[ls] : 0;
+        }
         if (lane == 31) {
             a.sec_tab[kDirSectors] = w;
             const int in_box = a.plan[kPlanInBox];
@@ -256,7 +259,7 @@ __global__ void __launch_bounds__(kPlanThreads) k_dir_plan(DirPlanArgs a) {
         }
     }
 }
-static_assert(kDirSectors == 32, "k_dir_plan scans the sectors with one warp");
+static_assert(kDirSectors <= 32 && (kDirSectors & (kDirSectors - 1)) == 0, "k_dir_plan scans the sectors with one warp");
 
 // Everything the rare exact-replay path needs, kept in device memory so that the hot path
 // carries one pointer: the reference grid and the pose arrays of the update's destination buffer.
@@ -358,7 +361,7 @@ __global__ void __launch_bounds__(kDirThreads, 1) k_raycast_dir(DirRayArgs a) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     const int64_t ncell = static_cast<int64_t>(mp.PW) * mp.PH;
-    const int K = a.B >> 5, Bmask = a.B - 1;
+    const int K = a.B / kDirSectors, Bmask = a.B - 1;
     uint32_t phase = 0;
     unsigned seen = 0;
     int cur_s = -1, replays = 0;
@@ -396,7 +399,7 @@ __global__ void __launch_bounds__(kDirThreads, 1) k_raycast_dir(DirRayArgs a) {
             const int u = static_cast<int>(u0) + tid;
             int s = 0;
 #pragma unroll
-            for (int d = 16; d > 0; d >>= 1)
+            for (int d = kDirSectors / 2; d > 0; d >>= 1)
                 if (s_sec[s + d] <= u) s += d;
             s_units[tid] = (static_cast<uint32_t>(s_sec[kDirSectors + 1 + s] + (u - s_sec[s])) << 6) | static_cast<uint32_t>(s);
         }

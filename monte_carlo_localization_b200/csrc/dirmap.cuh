@@ -32,7 +32,13 @@
 
 namespace mclb200 {
 
-constexpr int kDirSectors = 32;          // heading sectors over [0, 2 pi)
+// Sectors trade march trips against per-(particle, sector) work: 64 / 32 / 16 / 8 sectors need 4.6 / 4.8 / 5.4 / 7.3
+// lookups per warp-ray on the bench cloud, but a lane marches 1.2 / 2.5 / 4.9 / 9.8 beams per unit whose fixed cost
+// (record, window base, beam range) is ~150 warp instructions: k_raycast_dir 0.481 ms at 32, 0.454 at 16, 0.538 at 8.
+#ifndef MCL_DIR_SECTORS
+#define MCL_DIR_SECTORS 16
+#endif
+constexpr int kDirSectors = MCL_DIR_SECTORS;   // heading sectors over [0, 2 pi)
 constexpr double kDirMargin = 0.002;     // validity margin on both sides of a sector (rad)
 constexpr int kDirTex = 16;              // steps tested with the exact bounding box
 constexpr int kDirMaxAdv = 127;

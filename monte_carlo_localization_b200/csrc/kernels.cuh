@@ -121,6 +121,7 @@ struct MotionArgs {
     // sharded filter: the source pose (and index) of every own slot, pushed here by the rank that
     // owns the source (k_route); nullptr = search and gather locally (k_resample_motion)
     const double4* routed;
+    const uint32_t* where;       // [N] two-hop routing: where in `routed` the answer of each slot lies (nullptr: at the slot)
     // coarse level of the CDF search, staged in shared memory: coarse[f][k] = cdf[(k+1) << cshift) - 1]
     const double* coarse;     // [F][nc] or nullptr
     int nc, cshift;
@@ -320,6 +321,7 @@ __device__ __forceinline__ void motion_store(const MotionArgs& a, const MotionSc
 }
 
 constexpr int kMotionThreads = 1024;
+constexpr int kWhereShift = 28;     // two-hop routing: slots per rank < 2^28, ranks <= 16 (MotionArgs::where)
 
 // One thread per output slot, persistent blocks when the coarse CDF level is large (one staging of
 // the table per SM).  a.routed == nullptr: search the CDF and gather the source pose here (whole
@@ -360,7 +362,12 @@ __global__ void __launch_bounds__(kMotionThreads) k_resample_motion(MotionArgs a
             }
         } else {
             // written by other GPUs over NVLink during k_route: system-scope loads (never a line of this SM's L1)
-            const double* r = reinterpret_cast<const double*>(a.routed + li);
+            int64_t at = li;
+            if (a.where) {   // two-hop routing: the answer lies at [server][position of the request]
+                const uint32_t w = a.where[li];
+                at = static_cast<int64_t>(w >> kWhereShift) * N + (w & ((1u << kWhereShift) - 1u));
+            }
+            const double* r = reinterpret_cast<const double*>(a.routed + at);
             x = ld_sys_f64(r);
             y = ld_sys_f64(r + 1);
             th = ld_sys_f64(r + 2);
@@ -523,7 +530,7 @@ __global__ void __launch_bounds__(32) k_route_check(ShardDev sh) {
 }
 
 // ------------------------------------------------------------------------------------------
-// sharded filter: sender-driven resampling in two hops (the default from 3 ranks on)
+// sharded filter: sender-driven resampling in two hops (the default)
 // ------------------------------------------------------------------------------------------
 // k_route makes every rank evaluate ALL world * N draws to find the 1 / world it has to serve: work per rank
 // grows with the number of ranks.  Here the owner of a SLOT evaluates its own N draws, finds the rank whose
@@ -531,7 +538,10 @@ __global__ void __launch_bounds__(32) k_route_check(ShardDev sh) {
 // slot's local index to that rank's inbox (k_route_request; 4 bytes per slot over NVLink, written as
 // contiguous runs).  After one exchange of the per-destination counts the source ranks serve their inboxes
 // with full warps (k_route_serve): draw recomputed from the global slot, search in the local CDF slice, 32-byte
-// push of the source pose into the slot owner's `routed` array.  Per rank: N classifications + (on balanced
+// push of the source pose into the slot owner's `routed` array -- at position [server][k], k being the request's
+// position in the inbox, so that the pushes of a warp are CONSECUTIVE 32-byte records (whole NVLink packets
+// instead of one packet per particle); the owner noted (server, k) of each of its slots in `where` when it
+// made the request and gathers the record from its own memory.  Per rank: N classifications + (on balanced
 // weights) N searches, independent of the world size.  Results are identical to k_route's by construction:
 // the same draw, the same claim rule (rank_end[q-1] < u <= rank_end[q]), the same local lower_bound.
 struct RouteReqArgs {
@@ -539,10 +549,12 @@ struct RouteReqArgs {
     const double* rank_end;         // [world]
     uint32_t* inbox[kMaxWorld];     // every rank's inbox [world senders][N] (own included)
     unsigned int* req_count;        // [kMaxWorld] own: requests appended per destination (zeroed by the serve kernel)
+    uint32_t* where;                // [N] own: server << kWhereShift | position of the slot's request (and of its answer)
     const double* u;                // [NG] injected uniforms or nullptr
     uint64_t seed;
     const unsigned long long* update_no;
     unsigned int* done;
+    unsigned long long* dbg;        // diagnostics (nullable): [8] slowest CTA until its stores are issued, [9] incl. the system fence, [10] last CTA's wait
     ShardDev sh;
 };
 constexpr int kReqThreads = 1024;
@@ -557,6 +569,7 @@ __global__ void __launch_bounds__(kReqThreads) k_route_request(RouteReqArgs a) {
     __shared__ bool is_last;
     const int tid = threadIdx.x, lane = tid & 31;
     const int me = a.sh.rank, world = a.sh.world;
+    const long long c_begin = clock64();
     if (tid < kMaxWorld) {
         s_cnt[tid] = 0;
         s_end[tid] = tid < world - 1 ? a.rank_end[tid] : 2.0;
@@ -621,6 +634,7 @@ __global__ void __launch_bounds__(kReqThreads) k_route_request(RouteReqArgs a) {
         if (dest[e] >= 0) {
             const int64_t li = b0 + static_cast<int64_t>(e / 2) * (2 * kReqThreads) + 2 * tid + (e & 1);
             stage[s_off[dest[e]] + posn[e]] = static_cast<uint32_t>(li);
+            a.where[li] = (static_cast<uint32_t>(dest[e]) << kWhereShift) | (s_base[dest[e]] + posn[e]);
         }
     }
     __syncthreads();
@@ -630,9 +644,14 @@ __global__ void __launch_bounds__(kReqThreads) k_route_request(RouteReqArgs a) {
         const unsigned int n = s_cnt[q], o = s_off[q];
         for (unsigned int t = tid; t < n; t += kReqThreads) dst[t] = stage[o + t];
     }
+    const long long c_loop = clock64();
     __threadfence_system();
     __syncthreads();
     if (tid == 0) {
+        if (a.dbg) {
+            atomicMax(a.dbg + 8, static_cast<unsigned long long>(c_loop - c_begin));
+            atomicMax(a.dbg + 9, static_cast<unsigned long long>(clock64() - c_begin));
+        }
         __threadfence();
         is_last = atomicAdd(a.done, 1u) == gridDim.x - 1u;
     }
@@ -644,9 +663,11 @@ __global__ void __launch_bounds__(kReqThreads) k_route_request(RouteReqArgs a) {
     if (tid < kMaxWorld) s_pay[tid] = tid < world ? static_cast<unsigned long long>(ld_sys_u32(a.req_count + tid)) : 0ull;
     __syncthreads();
     const unsigned long long epoch = *a.sh.xseq + 1ull;
+    const long long c_pub = clock64();
     shard_publish(a.sh, epoch, s_pay, world);
     if (!a.sh.fused) return;
     if (!shard_wait(a.sh, epoch)) return;
+    if (a.dbg && tid == 0) a.dbg[10] = static_cast<unsigned long long>(clock64() - c_pub);
     route_finish(a.sh, epoch);
 }
 
@@ -661,21 +682,23 @@ struct RouteServeArgs {
     const double* sy;
     const double* st;
     const uint32_t* inbox;          // own inbox [world][N]
-    double4* routed[kMaxWorld];
+    double4* routed[kMaxWorld];     // every rank's answer array [world servers][N]
     unsigned int* req_count;        // own request counters: cleared here for the next update
     const double* u;
     uint64_t seed;
     const unsigned long long* update_no;
     unsigned int* done;
+    unsigned long long* dbg;        // diagnostics (nullable): as RouteReqArgs
     ShardDev sh;
 };
 
-__global__ void __launch_bounds__(kRouteThreads) k_route_serve(RouteServeArgs a) {
+__global__ void __launch_bounds__(kRouteThreads, 1) k_route_serve(RouteServeArgs a) {
     extern __shared__ __align__(8) uint32_t ts[];   // nc keys of the coarse level
     __shared__ unsigned int s_pre[kMaxWorld + 1];
     __shared__ bool is_last;
     const int tid = threadIdx.x;
     const int me = a.sh.rank, world = a.sh.world;
+    const long long c_begin = clock64();
     for (int t = tid; t < a.nc; t += kRouteThreads) ts[t] = static_cast<uint32_t>(__double2hiint(a.coarse[t]));
     // the counts travelled in the exchange the request kernel (or its check kernel) completed: epoch == *xseq
     const unsigned long long req_epoch = *a.sh.xseq;
@@ -708,14 +731,20 @@ __global__ void __launch_bounds__(kRouteThreads) k_route_serve(RouteServeArgs a)
             y = a.sy[j];
             th = a.st[j];
         }
-        double* dst = reinterpret_cast<double*>(a.routed[r] + li);
+        // answer k of this rank for rank r: consecutive lanes write consecutive records
+        double* dst = reinterpret_cast<double*>(a.routed[r] + static_cast<size_t>(me) * static_cast<size_t>(a.N) + (t - s_pre[r]));
         asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "d"(x), "d"(y), "d"(th),
                      "d"(__longlong_as_double(glo + j))
                      : "memory");
     }
+    const long long c_loop = clock64();
     __threadfence_system();
     __syncthreads();
     if (tid == 0) {
+        if (a.dbg) {
+            atomicMax(a.dbg + 8, static_cast<unsigned long long>(c_loop - c_begin));
+            atomicMax(a.dbg + 9, static_cast<unsigned long long>(clock64() - c_begin));
+        }
         __threadfence();
         is_last = atomicAdd(a.done, 1u) == gridDim.x - 1u;
     }
@@ -725,9 +754,11 @@ __global__ void __launch_bounds__(kRouteThreads) k_route_serve(RouteServeArgs a)
     if (tid == 0) *a.done = 0;
     __syncthreads();
     const unsigned long long epoch = req_epoch + 1ull;
+    const long long c_pub = clock64();
     shard_publish(a.sh, epoch, nullptr, 0);
     if (!a.sh.fused) return;
     if (!shard_wait(a.sh, epoch)) return;
+    if (a.dbg && tid == 0) a.dbg[10] = static_cast<unsigned long long>(clock64() - c_pub);
     route_finish(a.sh, epoch);
 }
 

@@ -212,6 +212,7 @@ struct mcl_ctx {
     double4* routed_peers[kMaxWorld] = {};
     uint32_t* inbox_peers[kMaxWorld] = {};   // every rank's request inbox [world senders][N] (two-hop routing)
     uint32_t* d_inbox = nullptr;
+    uint32_t* d_where = nullptr;             // [N] (server, position) of every own slot's request
     unsigned int* d_req_count = nullptr;     // [kMaxWorld] requests appended per destination in the current update
     int route_mode = -1;                     // -1 auto (two-hop from 3 ranks on), 0 two-hop requests, 1 every rank tests all draws
     const StepFn* peer_list_fn[kMaxWorld] = {};
@@ -538,7 +539,8 @@ int ensure_slice(mcl_ctx* c) {
     return MCL_OK;
 }
 
-constexpr size_t kDirWindowBudget = 112 * 1024;   // one sector window (half of shared memory: room to double-buffer)
+// one sector window in shared memory (the ray-start prefetch buffers take another 64 KB): wider sectors reach further sideways
+constexpr size_t kDirWindowBudget = (kDirSectors >= 32 ? 112 : 120) * 1024;
 
 void free_dir(mcl_ctx* c) {
     drop_graphs(c);
@@ -791,10 +793,12 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
         qa.rank_end = c->d_rank_end2[src];
         for (int q = 0; q < kMaxWorld; ++q) qa.inbox[q] = c->inbox_peers[q];
         qa.req_count = c->d_req_count;
+        qa.where = c->d_where;
         qa.u = u_dev;
         qa.seed = c->prm.seed;
         qa.update_no = c->d_update_no;
         qa.done = c->d_route_done;
+        qa.dbg = (c->d_dbg && c->dbg_pass == 9) ? c->d_dbg : nullptr;
         qa.sh = c->sh;
         qa.sh.fused = c->xmode;
         k_route_request<<<static_cast<unsigned>((c->N + kReqBlock - 1) / kReqBlock), kReqThreads, 0, s>>>(qa);
@@ -825,6 +829,7 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
         va.seed = c->prm.seed;
         va.update_no = c->d_update_no;
         va.done = c->d_route_done;
+        va.dbg = (c->d_dbg && c->dbg_pass == 8) ? c->d_dbg : nullptr;
         va.sh = c->sh;
         va.sh.fused = c->xmode;
         const size_t vsmem = sizeof(uint32_t) * static_cast<size_t>((c->coarse_n + 1) & ~1);
@@ -893,6 +898,7 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
     ma.spose4 = packed ? c->d_pose4[src] : nullptr;
     ma.dpose4 = c->d_pose4[dst];
     ma.routed = sharded(c) ? c->d_routed : nullptr;
+    ma.where = (sharded(c) && c->route_mode != 1) ? c->d_where : nullptr;
     ma.coarse = c->coarse_n > 0 ? c->d_coarse2[src] : nullptr;
     ma.nc = c->coarse_n;
     ma.cshift = c->coarse_shift;
@@ -1298,7 +1304,7 @@ ArenaLayout arena_layout(int world, int64_t n_local) {
     L.flag = o;
     o = up(o + sizeof(unsigned long long) * kMaxWorld);
     L.routed = o;
-    o = up(o + sizeof(double4) * static_cast<size_t>(n_local));
+    o = up(o + sizeof(double4) * static_cast<size_t>(n_local) * static_cast<size_t>(world));   // [world servers][N] answers
     L.list_fn = o;
     o = up(o + sizeof(StepFn) * 2 * C);
     L.list_add = o;
@@ -1449,6 +1455,7 @@ static int create_buffers(mcl_ctx* c, const mcl_params* p, int device, int world
         c->d_list_fn = reinterpret_cast<StepFn*>(c->arena + L.list_fn);
         c->d_list_add = reinterpret_cast<double*>(c->arena + L.list_add);
         c->d_inbox = reinterpret_cast<uint32_t*>(c->arena + L.inbox);
+        CK(dalloc(&c->d_where, static_cast<size_t>(c->N)));
         CK(dalloc(&c->d_req_count, static_cast<size_t>(kMaxWorld)));
         CK(cudaMemset(c->d_req_count, 0, sizeof(unsigned int) * kMaxWorld));
         CK(dalloc(&c->d_xseq, size_t{1}));
@@ -1492,6 +1499,8 @@ static int create_any(const mcl_params* p, int device, int world, int rank, mcl_
     if (world > 1 && p->num_filters != 1) return fail(MCL_ERR_INVALID, "particle sharding applies to a single filter, not a batch");
     if (world > 1 && (p->max_particles % world) != 0)
         return fail(MCL_ERR_INVALID, "max_particles (%d) must be a multiple of the number of ranks (%d)", p->max_particles, world);
+    if (world > 1 && static_cast<int64_t>(p->max_particles) / world >= (int64_t{1} << kWhereShift))
+        return fail(MCL_ERR_INVALID, "a rank of a sharded filter holds fewer than 2^%d particles", kWhereShift);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();
@@ -1527,7 +1536,7 @@ int mcl_destroy(mcl_ctx* c) {
                     c->d_tile_start, c->d_coarse2[0], c->d_coarse2[1], c->d_S1, c->d_S2, c->d_scratch_total, c->d_slice_sum, c->d_rank_end2[0],
                     c->d_rank_end2[1],
                     c->d_partial, c->d_pose, c->d_centre, c->d_replays, c->d_hist, c->d_perm, c->d_done, c->d_route_done,
-                    c->d_xseq, c->d_nccl_tok, c->d_tmp, c->d_update_no, c->d_dbg, c->d_beam, c->d_steps16};
+                    c->d_xseq, c->d_nccl_tok, c->d_tmp, c->d_update_no, c->d_dbg, c->d_beam, c->d_steps16, c->d_where, c->d_req_count};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     free_dir(c);
@@ -2116,7 +2125,7 @@ int mcl_debug_pass_cycles(mcl_ctx* c, int pass_kind, unsigned long long* out) {
         CK(cudaMemset(c->d_dbg, 0, 16 * sizeof(unsigned long long)));
     }
     if (out) {
-        CK(cudaMemcpy(out, c->d_dbg + (pass_kind == 8 ? 8 : 0), 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(out, c->d_dbg + (pass_kind >= 8 ? 8 : 0), 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
         CK(cudaMemset(c->d_dbg, 0, 16 * sizeof(unsigned long long)));
     }
     c->dbg_pass = pass_kind;

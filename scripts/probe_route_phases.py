@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""k_route on real GPUs (torchrun, one rank per GPU): SM-cycle stamps of its phases on every rank
+"""The routing kernels (k_route_request / k_route_serve, or k_route with MCL_ROUTE=one-hop) on real GPUs (torchrun, one rank per GPU): SM-cycle stamps of its phases on every rank
 (mcl_debug_pass_cycles kind 8) and rank 0's per-kernel CUDA-event times."""
 import json
 import os
@@ -24,7 +24,8 @@ os.dup2(2, 1)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 g = maps.load_named_map("Spielberg_map")
 angles = synth.beam_angles()
-flt = ShardedFilter(g, angles, n_local=1 << 20, rank=rank, world=world, device=lr, seed=5)
+flt = ShardedFilter(g, angles, n_local=1 << 20, rank=rank, world=world, device=lr, seed=5,
+                    route=os.environ.get("MCL_ROUTE", "two-hop"))
 dist.barrier()
 sys.stdout.flush()
 os.dup2(saved, 1)
@@ -36,20 +37,22 @@ flt.init_pose(gt[0])
 ctx.set_graphs(False)
 for t in range(4):
     flt.update(actions[t], obs[t])
-ctx.debug_pass_cycles(8)
-rows = []
-for t in range(4, 10):
-    flt.update(actions[t], obs[t])
-    rows.append(ctx.debug_pass_cycles(8, read=True)[:3])
-ctx.debug_pass_cycles(-1)
-med = np.median(np.asarray(rows, dtype=np.float64), axis=0) / 1965.0
+phases = {}
+for kind, name in ((8, "serve"), (9, "request")):
+    ctx.debug_pass_cycles(kind)
+    rows = []
+    for t in range(4, 10):
+        flt.update(actions[t], obs[t])
+        rows.append(ctx.debug_pass_cycles(kind, read=True)[:3])
+    ctx.debug_pass_cycles(-1)
+    phases[name] = (np.median(np.asarray(rows, dtype=np.float64), axis=0) / 1965.0).tolist()
 ctx.set_profiling(True)
 flt.update(actions[10], obs[10])
 flt.update(actions[11], obs[11])
 km = ctx.kernel_ms()
 out = [None] * world
-dist.all_gather_object(out, {"rank": rank, "scan_serve_us": med[0], "with_fence_us": med[1], "last_cta_wait_us": med[2],
-                             "k_route_ms": dict(km).get("k_route")})
+dist.all_gather_object(out, {"rank": rank, "us [slowest CTA's work, with the system fence, last CTA's wait for the peers]": phases,
+                             "kernel_ms": {k: v for k, v in km if "route" in k}})
 if rank == 0:
     print(json.dumps({"world": world, "k_route_phases": out, "kernel_ms_rank0": km}))
 dist.destroy_process_group()

@@ -122,9 +122,9 @@ def dir_sector(theta, alpha, buckets):
 
 
 def dir_windows(em, bx0, by0, capacity):
-    out = np.zeros(4 * 32, dtype=np.int32)
+    out = np.zeros(4 * dir_constants()[0], dtype=np.int32)
     box = lib().emu_dir_windows(em._h, int(bx0), int(by0), int(capacity), out.ctypes.data_as(C.POINTER(C.c_int)))
-    return box, out.reshape(32, 4)
+    return box, out.reshape(-1, 4)
 
 
 def exact_scan(src, div=None, want_prefix=True, force_last_one=False):

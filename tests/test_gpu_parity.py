@@ -424,7 +424,7 @@ def test_directional_maps_equal_cpu_build():
     g = maps.load_named_map("sibal1")
     c = _ctx(g, synth.beam_angles(), 20000)
     em = EmuMap(g)
-    for s in (0, 5, 8, 17, 31):
+    for s in (0, 5, 8, 11, 15):
         assert np.array_equal(c.dir_map(s), em.dir_map(s)), "sector %d differs" % s
     c.close()
 
@@ -445,7 +445,7 @@ def test_device_distance_transform_equals_host_build(name):
     v8 = c.dir_map(-1)
     assert v8.shape == em.v8().shape
     assert np.array_equal(v8, em.v8()), "%d codes differ" % int((v8 != em.v8()).sum())
-    for s in (3, 12, 29):   # the sector maps are traced against the device-built gap map
+    for s in (3, 12, 14):   # the sector maps are traced against the device-built gap map
         assert np.array_equal(c.dir_map(s), em.dir_map(s)), "sector %d differs" % s
     print("context + mcl_set_map(%s) incl. sector maps: %.1f ms" % (name, 1e3 * t_set))
     c.close()
