@@ -246,7 +246,6 @@ def kernel_table(kernel_samples, N: int, R: int, cbar: float | None, peak_gbs: f
         "k_route": lambda: (32 + 32 + 8 * log2n) * N,
         "k_route_request": lambda: 4 * N,
         "k_route_serve": lambda: (4 + 32 + 32 + 8 * log2n) * N,
-        "k_sort_hist": lambda: 8 * N,
         "k_sort_scatter": lambda: 20 * N,
         "k_dir_gather": lambda: 68 * N,
         "k_dir_plan": lambda: 4 * 4096,
@@ -330,6 +329,8 @@ def run_gpu(args):
             os.close(saved_fd)
     if args.ray_mode:
         ctx.set_ray_mode(args.ray_mode)
+    if args.no_pdl:
+        ctx.set_pdl(False)
     # the library launches on this (non-default) torch stream so torch CUDA events time its kernels
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
@@ -556,6 +557,7 @@ def main():
                     help="0 auto (default), 1 isotropic skip-map kernel only, 2 directional stage always")
     ap.add_argument("--shard-exchange", default="fused", choices=["fused", "nccl"],
                     help="multi-GPU: how ranks meet at an exchange (in-kernel NVLink flags, or a one-word ncclAllGather)")
+    ap.add_argument("--no-pdl", action="store_true", help="plain stream order between the kernels of an update (comparison)")
     ap.add_argument("--shard-route", default="two-hop", choices=["two-hop", "one-hop"],
                     help="multi-GPU: request routing of the resampling draws (default) or every rank testing all draws")
     args = ap.parse_args()

@@ -176,6 +176,11 @@ int mcl_set_stream(mcl_ctx* ctx, void* cuda_stream);
  * graphs are dropped and re-captured whenever a setter changes a buffer, the stream or a mode. */
 int mcl_set_graphs(mcl_ctx* ctx, int enabled);
 
+/* Programmatic dependent launches between the kernels of an update (on by default): a kernel's blocks are
+ * scheduled while its predecessor drains and wait on griddepcontrol.wait, which hides launch latency at every
+ * kernel boundary; results are identical.  Off: plain stream order (for comparison). */
+int mcl_set_pdl(mcl_ctx* ctx, int enabled);
+
 /* Ray stage selection.  One filter of at least 1024 particles gets, besides the isotropic
  * skip-map kernel, the DIRECTIONAL stage: per-heading-sector skip maps built at mcl_set_map, rays
  * grouped by sector, each sector's window staged in shared memory.  Both compute the reference's

@@ -102,6 +102,7 @@ SIGNATURES = {
     "mcl_shard_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "mcl_shard_set_exchange": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "mcl_shard_set_route": (C.c_int, [C.c_void_p, C.c_int]),
+    "mcl_set_pdl": (C.c_int, [C.c_void_p, C.c_int]),
     "mcl_nccl_unique_id": (C.c_int, [C.c_void_p, C.c_size_t]),
     "mcl_create_sharded": (C.c_int, [C.POINTER(MclParams), C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
     "mcl_sharded_gather": (C.c_int, [C.c_void_p, c_double_p, c_double_p]),
@@ -404,6 +405,10 @@ class MclContext:
     def set_graphs(self, on: bool):
         """CUDA-graph replay of the steady-state host-facing update (default on)."""
         self._check(self._L.mcl_set_graphs(self._h, int(on)), "mcl_set_graphs")
+
+    def set_pdl(self, on: bool):
+        """Programmatic dependent launches between the kernels of an update (default on)."""
+        self._check(self._L.mcl_set_pdl(self._h, int(on)), "mcl_set_pdl")
 
     def set_ray_mode(self, mode: int):
         """0 auto, 1 isotropic skip-map kernel only, 2 directional stage always."""

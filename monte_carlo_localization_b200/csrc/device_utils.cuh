@@ -8,6 +8,16 @@ namespace mclb200 {
 
 constexpr unsigned kFullMask = 0xffffffffu;
 
+// First statement of every kernel of the update.  Launched with programmatic stream serialization (launch_dep in
+// mcl_b200.cu) the kernel's blocks may already be resident while the preceding kernel drains: griddepcontrol.wait
+// returns when that kernel has COMPLETED and its memory operations are visible (so completion is transitive along
+// the chain), launch_dependents lets the next kernel's blocks be scheduled as soon as every block of this one has
+// started.  Both are no-ops for a normal launch.
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // ---- shuffles for arbitrary trivially-copyable structs (multiples of 4 bytes) ----------
 template <class T>
 __device__ __forceinline__ T shfl_up_any(const T& v, int delta) {

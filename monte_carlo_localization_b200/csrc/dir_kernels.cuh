@@ -119,6 +119,7 @@ __device__ __forceinline__ void dir_write_record(const MapDev& mp, DirRec* rec, 
 // sorted slot, one 32-byte gather per particle, and sets the window-box flag -- the box needs the
 // cloud centre, which is complete only after the motion kernel.
 __global__ void __launch_bounds__(256) k_dir_gather(DirPrepArgs a) {
+    pdl_enter();
     __shared__ int s_cnt[8];
     const int64_t pos = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
     int bx0, by0;
@@ -164,6 +165,7 @@ constexpr int kPlanThreads = 1024;
 // chunks (1024 slots) touched by any beam's run form the sector's chunk range; a UNIT is one
 // (sector, chunk) pair, numbered sector by sector so that consecutive units share a window.
 __global__ void __launch_bounds__(kPlanThreads) k_dir_plan(DirPlanArgs a) {
+    pdl_enter();
     __shared__ int off[kMaxBuckets + 1];
     __shared__ int wsum[kPlanThreads / 32];
     __shared__ int cmin[kDirSectors], cmax[kDirSectors];
@@ -311,6 +313,7 @@ __host__ __device__ inline size_t dir_ray_smem(int win_bytes) {
 
 template <int MC>
 __global__ void __launch_bounds__(kDirThreads, 1) k_raycast_dir(DirRayArgs a) {
+    pdl_enter();
     extern __shared__ __align__(16) uint8_t smem_win[];
     __shared__ __align__(8) unsigned long long win_bar;
     __shared__ unsigned s_u0;
@@ -566,6 +569,7 @@ struct WeightStepsArgs {
 constexpr int kWeightThreads = 256;
 template <bool POOL>   // POOL: slots of several filters (slot / nfil is the filter, each with its own table slice)
 __global__ void __launch_bounds__(kWeightThreads) k_weight_steps(WeightStepsArgs a) {
+    pdl_enter();
     if (a.plan[kPlanMode] != 1) return;
     const int64_t pos = (static_cast<int64_t>(blockIdx.x) * kWeightThreads + threadIdx.x) * 4;
     if (pos >= a.cnt) return;
@@ -623,6 +627,7 @@ __global__ void __launch_bounds__(kWeightThreads) k_weight_steps(WeightStepsArgs
 // NT threads each, as many per SM as the table allows.  Results are bit-identical to k_weight_steps<false>.
 template <int NT>
 __global__ void __launch_bounds__(NT) k_weight_steps_sm(WeightStepsArgs a) {
+    pdl_enter();
     extern __shared__ __align__(16) double tab[];   // [R][tw]
     if (a.plan[kPlanMode] != 1) return;
     {

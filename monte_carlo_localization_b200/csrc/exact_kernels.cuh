@@ -165,6 +165,7 @@ __device__ __forceinline__ void slice_sums_consume(const ExactArgs& a, unsigned 
 }
 
 __global__ void __launch_bounds__(kTileChunks) k_tile_sums(ExactArgs a) {
+    pdl_enter();
     __shared__ double sm[kTileChunks / 32];
     __shared__ unsigned long long pay[kHdrWords];
     __shared__ bool is_last;
@@ -206,6 +207,7 @@ __global__ void __launch_bounds__(kTileChunks) k_tile_sums(ExactArgs a) {
 
 // host-ordered ranks: the consume half of k_tile_sums' exchange
 __global__ void __launch_bounds__(kTileChunks) k_slice_sums_collect(ExactArgs a) {
+    pdl_enter();
     const unsigned long long epoch = *a.sh.xseq + 1ull;
     if (!shard_wait(a.sh, epoch)) return;
     slice_sums_consume(a, epoch);
@@ -647,6 +649,7 @@ __device__ __forceinline__ bool pass_finish(const ExactArgs& a, FinishShared& S,
 
 template <bool POSE>
 __global__ void __launch_bounds__(kTileChunks) k_exact_pass(ExactArgs a) {
+    pdl_enter();
     __shared__ FinishShared S;
     __shared__ int wcnt[kTileChunks / 32];
     __shared__ bool is_last;
@@ -668,6 +671,7 @@ __global__ void __launch_bounds__(kTileChunks) k_exact_pass(ExactArgs a) {
 // host-ordered ranks: the consume half of an exact pass (one CTA)
 template <bool POSE>
 __global__ void __launch_bounds__(kTileChunks) k_exact_finish(ExactArgs a) {
+    pdl_enter();
     __shared__ FinishShared S;
     const unsigned long long epoch = *a.sh.xseq + 1ull;
     if (!shard_wait(a.sh, epoch)) return;
@@ -741,6 +745,7 @@ __device__ __forceinline__ void emit_tile(const ExactArgs& a, ScanElem* sms, Sca
 }
 
 __global__ void __launch_bounds__(kTileChunks) k_exact_emit(ExactArgs a) {
+    pdl_enter();
     __shared__ ScanElem sms[kTileChunks / 32];
     __shared__ ScanElem sm_inc[kTileChunks];
     emit_tile(a, sms, sm_inc, blockIdx.y, blockIdx.x);
@@ -752,6 +757,7 @@ __global__ void __launch_bounds__(kTileChunks) k_exact_emit(ExactArgs a) {
 // at 0: chunk step maps, the ordered serial pass over the opaque chunks (their addends re-read from
 // global memory by thread 0: they are rare), the total, and the prefix sums.
 __global__ void __launch_bounds__(kTileChunks) k_exact_single(ExactArgs a) {
+    pdl_enter();
     __shared__ double smd[kTileChunks / 32];
     __shared__ RFn smr[kTileChunks / 32];
     __shared__ RFn sm_inc[kTileChunks];

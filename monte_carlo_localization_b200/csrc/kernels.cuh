@@ -4,7 +4,7 @@
 //   exact sums / CDF   k_tile_sums, k_exact_chunks, k_exact_walk, k_exact_emit   (:658, :679)
 //                      (k_exact_single: all of a pass in one CTA for a filter of one tile)
 //   resample + motion  k_resample_motion                                         (:661-665, :449-503)
-//   heading sort       k_sort_hist, k_sort_scatter (processing order only)
+//   heading sort       histogram inside k_resample_motion, k_sort_scatter (processing order only)
 //   ray cast + weight  k_prepare_obs, then either k_raycast_weight (isotropic skip map, weights in
 //                      its epilogue) or the directional stage of dir_kernels.cuh: k_dir_gather,
 //                      k_dir_plan, k_raycast_dir, k_weight_steps                   (:506-650)
@@ -132,6 +132,10 @@ struct MotionArgs {
     uint64_t seed;
     const unsigned long long* update_no;   // device counter of completed updates (keys the Philox stream)
     double* centre;           // [F][2] accumulators (sum x, sum y)
+    // heading histogram of the counting sort (k_sort_scatter), accumulated here instead of in a pass of its own:
+    // block-private counts in shared memory, one global atomic per (block, non-empty bucket); nullptr = no sort
+    int* hist;                // [F][hist_B], zeroed by k_prepare_obs
+    int hist_B;
     // directional ray stage (dir_kernels.cuh): ray-start records in slot order, or nullptr;
     // k_dir_gather moves them to their heading-sorted slots
     DirRec* rec;
@@ -272,7 +276,7 @@ __device__ __forceinline__ int64_t cdf_lower_bound(const double* __restrict__ cp
 // motion_model for one particle (:474-502) + the stores of the proposal: SoA state, packed copy,
 // ray-start record; returns the (finite) position for the cloud-centre sums
 __device__ __forceinline__ void motion_store(const MotionArgs& a, const MotionScalars& m, uint64_t update_no, int f, int64_t li,
-                                             double x, double y, double th, double* sum_x, double* sum_y) {
+                                             double x, double y, double th, double* sum_x, double* sum_y, int* sort_cnt) {
     const int64_t fo = static_cast<int64_t>(f) * a.N;
     const int64_t i = a.glo + li;
     double z0, z1, z2;
@@ -314,7 +318,12 @@ __device__ __forceinline__ void motion_store(const MotionArgs& a, const MotionSc
         d4[0] = make_double2(nx, ny);
         d4[1] = make_double2(nt, 0.0);
     }
-    if (a.rec) dir_write_record(a.map, a.rec, fo + li, nx, ny, nt, theta_bucket(nt, a.B));
+    int bucket = -1;
+    if (a.rec) {
+        bucket = theta_bucket(nt, a.B);
+        dir_write_record(a.map, a.rec, fo + li, nx, ny, nt, bucket);
+    }
+    if (sort_cnt) atomicAdd(&sort_cnt[(bucket >= 0 && a.hist_B == a.B) ? bucket : theta_bucket(nt, a.hist_B)], 1);
     if (!(fabs(nx) < 1e12) || !(fabs(ny) < 1e12)) nx = ny = 0.0;  // keep the window centre finite
     *sum_x += nx;
     *sum_y += ny;
@@ -328,9 +337,15 @@ constexpr int kWhereShift = 28;     // two-hop routing: slots per rank < 2^28, r
 // filter on this GPU).  a.routed != nullptr (sharded filter): the source pose of every slot was
 // pushed into `routed` by k_route on the rank that owns the source; only the motion runs here.
 __global__ void __launch_bounds__(kMotionThreads) k_resample_motion(MotionArgs a) {
+    pdl_enter();
     __shared__ double sm[kMotionThreads / 32];
+    __shared__ int sort_cnt[kMaxBuckets];
     extern __shared__ uint32_t ts[];   // a.nc keys (high words of the coarse level) when it is used
     const int f = blockIdx.y;
+    if (a.hist) {
+        for (int b = threadIdx.x; b < a.hist_B; b += kMotionThreads) sort_cnt[b] = 0;
+        __syncthreads();
+    }
     const bool search = a.routed == nullptr;
     const int nc = (search && a.coarse != nullptr) ? a.nc : 0;
     const double* coarse = nc > 0 ? a.coarse + static_cast<int64_t>(f) * a.nc : nullptr;
@@ -373,7 +388,7 @@ __global__ void __launch_bounds__(kMotionThreads) k_resample_motion(MotionArgs a
             th = ld_sys_f64(r + 2);
             a.idx_out[li] = static_cast<int32_t>(__double_as_longlong(ld_sys_f64(r + 3)));
         }
-        motion_store(a, m, update_no, f, li, x, y, th, &sum_x, &sum_y);
+        motion_store(a, m, update_no, f, li, x, y, th, &sum_x, &sum_y, a.hist ? sort_cnt : nullptr);
     }
     // cloud centre for the shared-memory window of the ray kernel
     const double bx = block_sum<kMotionThreads>(sum_x, sm);
@@ -381,6 +396,13 @@ __global__ void __launch_bounds__(kMotionThreads) k_resample_motion(MotionArgs a
     if (threadIdx.x == 0) {
         atomicAdd(a.centre + 2 * f + 0, bx);
         atomicAdd(a.centre + 2 * f + 1, by);
+    }
+    if (a.hist) {   // (block_sum ended with a barrier: every thread's count is in)
+        int* hist = a.hist + static_cast<int64_t>(f) * a.hist_B;
+        for (int b = threadIdx.x; b < a.hist_B; b += kMotionThreads) {
+            const int c = sort_cnt[b];
+            if (c) atomicAdd(hist + b, c);
+        }
     }
 }
 
@@ -422,6 +444,7 @@ __device__ __forceinline__ void route_finish(const ShardDev& sh, unsigned long l
 }
 
 __global__ void __launch_bounds__(kRouteThreads) k_route(RouteArgs a) {
+    pdl_enter();
     extern __shared__ __align__(8) uint32_t ts[];   // nc keys of the coarse level (padded to even), then the warps' queues
     __shared__ bool is_last;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -498,14 +521,15 @@ __global__ void __launch_bounds__(kRouteThreads) k_route(RouteArgs a) {
     if (lane < qn) serve(lane);
     const long long c_loop = clock64();
     // every store of this CTA is performed at system scope before the CTA counts itself done
-    __threadfence_system();
+    // ONE system-scope fence per CTA: the barrier orders every thread's stores before thread 0's fence, which is
+    // cumulative over them (a fence by each of the 1024 threads cost 8-19 us per kernel)
     __syncthreads();
     if (tid == 0) {
+        __threadfence_system();
         if (a.dbg) {
             atomicMax(a.dbg + 8, static_cast<unsigned long long>(c_loop - c_begin));
             atomicMax(a.dbg + 9, static_cast<unsigned long long>(clock64() - c_begin));
         }
-        __threadfence();
         is_last = atomicAdd(a.done, 1u) == gridDim.x - 1u;
     }
     __syncthreads();
@@ -524,6 +548,7 @@ __global__ void __launch_bounds__(kRouteThreads) k_route(RouteArgs a) {
 
 // host-ordered ranks: checks that every rank's k_route has published
 __global__ void __launch_bounds__(32) k_route_check(ShardDev sh) {
+    pdl_enter();
     const unsigned long long epoch = *sh.xseq + 1ull;
     if (!shard_wait(sh, epoch)) return;
     route_finish(sh, epoch);
@@ -562,6 +587,7 @@ constexpr int kReqPer = 8;          // slots per thread (four Philox calls)
 constexpr int kReqBlock = kReqThreads * kReqPer;
 
 __global__ void __launch_bounds__(kReqThreads) k_route_request(RouteReqArgs a) {
+    pdl_enter();
     __shared__ uint32_t stage[kReqBlock];           // the block's slots grouped by destination
     __shared__ unsigned int s_cnt[kMaxWorld], s_off[kMaxWorld + 1], s_base[kMaxWorld];
     __shared__ double s_end[kMaxWorld];
@@ -645,14 +671,15 @@ __global__ void __launch_bounds__(kReqThreads) k_route_request(RouteReqArgs a) {
         for (unsigned int t = tid; t < n; t += kReqThreads) dst[t] = stage[o + t];
     }
     const long long c_loop = clock64();
-    __threadfence_system();
+    // ONE system-scope fence per CTA: the barrier orders every thread's stores before thread 0's fence, which is
+    // cumulative over them (a fence by each of the 1024 threads cost 8-19 us per kernel)
     __syncthreads();
     if (tid == 0) {
+        __threadfence_system();
         if (a.dbg) {
             atomicMax(a.dbg + 8, static_cast<unsigned long long>(c_loop - c_begin));
             atomicMax(a.dbg + 9, static_cast<unsigned long long>(clock64() - c_begin));
         }
-        __threadfence();
         is_last = atomicAdd(a.done, 1u) == gridDim.x - 1u;
     }
     __syncthreads();
@@ -693,6 +720,7 @@ struct RouteServeArgs {
 };
 
 __global__ void __launch_bounds__(kRouteThreads, 1) k_route_serve(RouteServeArgs a) {
+    pdl_enter();
     extern __shared__ __align__(8) uint32_t ts[];   // nc keys of the coarse level
     __shared__ unsigned int s_pre[kMaxWorld + 1];
     __shared__ bool is_last;
@@ -738,14 +766,15 @@ __global__ void __launch_bounds__(kRouteThreads, 1) k_route_serve(RouteServeArgs
                      : "memory");
     }
     const long long c_loop = clock64();
-    __threadfence_system();
+    // ONE system-scope fence per CTA: the barrier orders every thread's stores before thread 0's fence, which is
+    // cumulative over them (a fence by each of the 1024 threads cost 8-19 us per kernel)
     __syncthreads();
     if (tid == 0) {
+        __threadfence_system();
         if (a.dbg) {
             atomicMax(a.dbg + 8, static_cast<unsigned long long>(c_loop - c_begin));
             atomicMax(a.dbg + 9, static_cast<unsigned long long>(clock64() - c_begin));
         }
-        __threadfence();
         is_last = atomicAdd(a.done, 1u) == gridDim.x - 1u;
     }
     __syncthreads();
@@ -764,7 +793,7 @@ __global__ void __launch_bounds__(kRouteThreads, 1) k_route_serve(RouteServeArgs
 
 // Counting sort of the particles by heading bucket, in two kernels of fat blocks so that the
 // only global atomics are one per (block, non-empty bucket):
-//   k_sort_hist     block-private shared-memory histogram of a contiguous chunk, flushed once
+//   histogram       block-private shared-memory counts inside k_resample_motion, flushed once per block
 //   k_sort_scatter  bucket bases (scan of the global histogram), a block-private count to
 //                   reserve the block's range in each bucket, then shared-memory ranks
 // perm[f][pos] = particle index.  The order inside a bucket is arbitrary; it only decides
@@ -773,7 +802,7 @@ struct SortArgs {
     int64_t N;            // particles per filter (array stride)
     int64_t lo, cnt;      // the slots [lo, lo+cnt) being sorted; perm holds indices relative to lo
     const double* pt;     // [F][N]
-    int* hist;            // [F][B] zeroed before k_sort_hist
+    int* hist;            // [F][B] filled by k_resample_motion
     int* cursor;          // [F][B] zeroed
     int32_t* perm;        // [F][N]
     int B;
@@ -781,24 +810,8 @@ struct SortArgs {
 };
 constexpr int kSortThreads = 1024;
 
-__global__ void __launch_bounds__(kSortThreads) k_sort_hist(SortArgs a) {
-    __shared__ int cnt[kMaxBuckets];
-    const int f = blockIdx.y, tid = threadIdx.x;
-    for (int b = tid; b < a.B; b += kSortThreads) cnt[b] = 0;
-    __syncthreads();
-    const int64_t fo = static_cast<int64_t>(f) * a.N + a.lo;
-    const int64_t lo = static_cast<int64_t>(blockIdx.x) * a.chunk;
-    const int64_t hi = min(a.cnt, lo + a.chunk);
-    for (int64_t i = lo + tid; i < hi; i += kSortThreads) atomicAdd(&cnt[theta_bucket(a.pt[fo + i], a.B)], 1);
-    __syncthreads();
-    int* hist = a.hist + static_cast<int64_t>(f) * a.B;
-    for (int b = tid; b < a.B; b += kSortThreads) {
-        const int c = cnt[b];
-        if (c) atomicAdd(hist + b, c);
-    }
-}
-
 __global__ void __launch_bounds__(kSortThreads) k_sort_scatter(SortArgs a) {
+    pdl_enter();
     __shared__ int base[kMaxBuckets];
     __shared__ int cnt[kMaxBuckets];
     __shared__ int wsum[kSortThreads / 32];
@@ -878,6 +891,7 @@ struct ObsArgs {
 };
 
 __global__ void k_prepare_obs(ObsArgs a) {
+    pdl_enter();
     const int j = blockIdx.x, f = blockIdx.y;
     {   // per-update accumulators: cleared by the whole grid, ahead of the kernels that add to them
         const int nthreads = gridDim.x * gridDim.y * blockDim.x;
@@ -922,6 +936,7 @@ constexpr int kRayThreads = 1024;
 // MC > 0: MAX_RANGE_PX known at compile time (the loop bound becomes an immediate); 0: run time
 template <int WBITS, int MC>
 __global__ void __launch_bounds__(kRayThreads, 1) k_raycast_weight(RayArgs a) {
+    pdl_enter();
     extern __shared__ __align__(16) uint8_t smem_win[];
     if (a.plan && a.plan[0] == 1) return;   // k_raycast_dir + k_weight_steps take this update (dir_kernels.cuh)
     const int f = blockIdx.y;
@@ -1067,6 +1082,7 @@ struct NormArgs {
 constexpr int kNormThreads = 256;
 
 __global__ void __launch_bounds__(kNormThreads) k_normalize_pose(NormArgs a) {
+    pdl_enter();
     __shared__ double sm[kNormThreads / 32];
     const int f = blockIdx.y;
     const int64_t fo = static_cast<int64_t>(f) * a.N;

@@ -214,6 +214,7 @@ struct mcl_ctx {
     uint32_t* d_inbox = nullptr;
     uint32_t* d_where = nullptr;             // [N] (server, position) of every own slot's request
     unsigned int* d_req_count = nullptr;     // [kMaxWorld] requests appended per destination in the current update
+    bool pdl = true;                         // programmatic dependent launches inside an update (mcl_set_pdl)
     int route_mode = -1;                     // -1 auto (two-hop from 3 ranks on), 0 two-hop requests, 1 every rank tests all draws
     const StepFn* peer_list_fn[kMaxWorld] = {};
     const double* peer_list_add[kMaxWorld] = {};
@@ -281,6 +282,25 @@ int ensure_tmp(mcl_ctx* c, size_t bytes) {
 }
 
 // profiling: one event after every kernel of the update (mcl_get_kernel_ms)
+// Kernels of the update are launched with programmatic stream serialization (PDL): a kernel's blocks may be scheduled
+// while its predecessor drains; every kernel starts with griddepcontrol.wait (pdl_enter, device_utils.cuh), which
+// returns once the predecessor has completed and its writes are visible, so only launch latency and block
+// scheduling overlap.  Stream capture turns these launches into programmatic graph edges.
+template <class... P, class... A>
+inline cudaError_t launch_dep(bool pdl, void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, A&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, P(std::forward<A>(args))...);
+}
+
 void mark(mcl_ctx* c, const char* name) {
     c->launches++;
     if (!c->profiling || c->nmarks >= kMaxMarks) return;
@@ -351,12 +371,12 @@ int exchange_barrier(mcl_ctx* c) {
 int launch_tile_sums(mcl_ctx* c, const double* src) {
     ExactArgs a = exact_base(c);
     a.src = src;
-    k_tile_sums<<<dim3(c->T, c->F), kTileChunks, 0, c->stream>>>(a);
+    launch_dep(c->pdl, k_tile_sums, dim3(dim3(c->T, c->F)), dim3(kTileChunks), 0, c->stream, a);
     mark(c, "k_tile_sums");
     if (sharded(c) && !c->xmode) {
         const int rc = exchange_barrier(c);
         if (rc) return rc;
-        k_slice_sums_collect<<<1, kTileChunks, 0, c->stream>>>(a);
+        launch_dep(c->pdl, k_slice_sums_collect, dim3(1), dim3(kTileChunks), 0, c->stream, a);
         mark(c, "k_slice_sums_collect");
     }
     CK(cudaGetLastError());
@@ -407,9 +427,9 @@ int launch_pass(mcl_ctx* c, PassKind kind, int pose_buf, int cdf_idx) {
     a.dbg = (c->d_dbg && c->dbg_pass == static_cast<int>(kind)) ? c->d_dbg : nullptr;
     const dim3 g(c->T, c->F);
     if (pose)
-        k_exact_pass<true><<<g, kTileChunks, 0, c->stream>>>(a);
+        launch_dep(c->pdl, k_exact_pass<true>, dim3(g), dim3(kTileChunks), 0, c->stream, a);
     else
-        k_exact_pass<false><<<g, kTileChunks, 0, c->stream>>>(a);
+        launch_dep(c->pdl, k_exact_pass<false>, dim3(g), dim3(kTileChunks), 0, c->stream, a);
     mark(c, kind == kPassRaw ? "k_exact_pass(S1)" : kind == kPassNormalise ? "k_exact_pass(normalise+pose+S2)"
                                                 : kind == kPassStored      ? "k_exact_pass(S2)"
                                                                            : "k_exact_pass(cdf)");
@@ -417,9 +437,9 @@ int launch_pass(mcl_ctx* c, PassKind kind, int pose_buf, int cdf_idx) {
         const int rc = exchange_barrier(c);
         if (rc) return rc;
         if (pose)
-            k_exact_finish<true><<<1, kTileChunks, 0, c->stream>>>(a);
+            launch_dep(c->pdl, k_exact_finish<true>, dim3(1), dim3(kTileChunks), 0, c->stream, a);
         else
-            k_exact_finish<false><<<1, kTileChunks, 0, c->stream>>>(a);
+            launch_dep(c->pdl, k_exact_finish<false>, dim3(1), dim3(kTileChunks), 0, c->stream, a);
         mark(c, "k_exact_finish");
     }
     CK(cudaGetLastError());
@@ -436,7 +456,7 @@ int launch_emit(mcl_ctx* c, int cdf_idx) {
     a.coarse_m = a.coarse ? (1 << c->coarse_shift) / kChunk : 0;
     a.coarse_n = c->coarse_n;
     a.mid = c->d_mid2[cdf_idx];
-    k_exact_emit<<<dim3(c->T, c->F), kTileChunks, 0, c->stream>>>(a);
+    launch_dep(c->pdl, k_exact_emit, dim3(dim3(c->T, c->F)), dim3(kTileChunks), 0, c->stream, a);
     mark(c, "k_exact_emit");
     CK(cudaGetLastError());
     return MCL_OK;
@@ -454,7 +474,7 @@ int launch_single(mcl_ctx* c, const double* src, const double* div, double* tota
     a.coarse_m = a.coarse ? (1 << c->coarse_shift) / kChunk : 0;
     a.coarse_n = c->coarse_n;
     a.mid = out ? c->d_mid2[cdf_idx] : nullptr;
-    k_exact_single<<<dim3(1, c->F), kTileChunks, 0, c->stream>>>(a);
+    launch_dep(c->pdl, k_exact_single, dim3(dim3(1, c->F)), dim3(kTileChunks), 0, c->stream, a);
     mark(c, "k_exact_single");
     CK(cudaGetLastError());
     return MCL_OK;
@@ -708,7 +728,7 @@ int launch_pose(mcl_ctx* c, const double* w, const double* total, double* wn_out
     na.pose_out = c->d_pose;
     na.pose_host = c->d_pose_mapped;
     na.update_no = count_update ? c->d_update_no : nullptr;
-    k_normalize_pose<<<dim3(c->norm_blocks, c->F), kNormThreads, 0, c->stream>>>(na);
+    launch_dep(c->pdl, k_normalize_pose, dim3(dim3(c->norm_blocks, c->F)), dim3(kNormThreads), 0, c->stream, na);
     c->launches += 1;
     CK(cudaGetLastError());
     return MCL_OK;
@@ -772,7 +792,7 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
     oa.centre = c->d_centre;
     oa.hist = (c->sort_enabled && !c->wide) ? c->d_hist : nullptr;
     oa.nhist = 2 * c->B * c->F;
-    k_prepare_obs<<<dim3(c->R, c->F), 256, 0, s>>>(oa);
+    launch_dep(c->pdl, k_prepare_obs, dim3(dim3(c->R, c->F)), dim3(256), 0, s, oa);
     mark(c, "k_prepare_obs");
 
     int rc = ensure_cdf(c);
@@ -801,14 +821,14 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
         qa.dbg = (c->d_dbg && c->dbg_pass == 9) ? c->d_dbg : nullptr;
         qa.sh = c->sh;
         qa.sh.fused = c->xmode;
-        k_route_request<<<static_cast<unsigned>((c->N + kReqBlock - 1) / kReqBlock), kReqThreads, 0, s>>>(qa);
+        launch_dep(c->pdl, k_route_request, dim3(static_cast<unsigned>((c->N + kReqBlock - 1) / kReqBlock)), dim3(kReqThreads), 0, s, qa);
         mark(c, "k_route_request");
         ShardDev sd = c->sh;
         sd.fused = 0;
         if (!c->xmode) {
             rc = exchange_barrier(c);
             if (rc) return rc;
-            k_route_check<<<1, 32, 0, s>>>(sd);
+            launch_dep(c->pdl, k_route_check, dim3(1), dim3(32), 0, s, sd);
             mark(c, "k_route_check");
         }
         RouteServeArgs va{};
@@ -834,12 +854,12 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
         va.sh.fused = c->xmode;
         const size_t vsmem = sizeof(uint32_t) * static_cast<size_t>((c->coarse_n + 1) & ~1);
         const int vblocks = static_cast<int>(std::min<int64_t>(c->num_sms, (c->N + kRouteThreads - 1) / kRouteThreads));
-        k_route_serve<<<vblocks, kRouteThreads, vsmem, s>>>(va);
+        launch_dep(c->pdl, k_route_serve, dim3(vblocks), dim3(kRouteThreads), vsmem, s, va);
         mark(c, "k_route_serve");
         if (!c->xmode) {
             rc = exchange_barrier(c);
             if (rc) return rc;
-            k_route_check<<<1, 32, 0, s>>>(sd);
+            launch_dep(c->pdl, k_route_check, dim3(1), dim3(32), 0, s, sd);
             mark(c, "k_route_check");
         }
     } else if (sharded(c)) {
@@ -868,14 +888,14 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
         ra.sh.fused = c->xmode;
         const size_t rsmem = sizeof(uint32_t) * static_cast<size_t>((c->coarse_n + 1) & ~1) + (kRouteThreads / 32) * kRouteQueue * (sizeof(double) + sizeof(int));
         const int rblocks = static_cast<int>(std::min<int64_t>(c->num_sms, (c->NG + 2 * kRouteThreads - 1) / (2 * kRouteThreads)));
-        k_route<<<rblocks, kRouteThreads, rsmem, s>>>(ra);
+        launch_dep(c->pdl, k_route, dim3(rblocks), dim3(kRouteThreads), rsmem, s, ra);
         mark(c, "k_route");
         if (!c->xmode) {
             rc = exchange_barrier(c);
             if (rc) return rc;
             ShardDev sd = c->sh;
             sd.fused = 0;
-            k_route_check<<<1, 32, 0, s>>>(sd);
+            launch_dep(c->pdl, k_route_check, dim3(1), dim3(32), 0, s, sd);
             mark(c, "k_route_check");
         }
     }
@@ -911,11 +931,13 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
     ma.seed = c->prm.seed;
     ma.update_no = c->d_update_no;
     ma.centre = c->d_centre;
+    ma.hist = sort ? c->d_hist : nullptr;   // the counting sort's histogram is accumulated by the motion kernel
+    ma.hist_B = c->B;
     int mblocks = static_cast<int>((c->N + kMotionThreads - 1) / kMotionThreads);
     const size_t msmem = sharded(c) ? 0 : sizeof(uint32_t) * static_cast<size_t>(c->coarse_n);
     // a large table is staged once per SM by persistent blocks; a small one by every block
     if (msmem > 8 * 1024) mblocks = std::min(mblocks, std::max(1, c->num_sms / std::min(c->F, c->num_sms)));
-    k_resample_motion<<<dim3(mblocks, c->F), kMotionThreads, msmem, s>>>(ma);
+    launch_dep(c->pdl, k_resample_motion, dim3(dim3(mblocks, c->F)), dim3(kMotionThreads), msmem, s, ma);
     mark(c, sharded(c) ? "k_resample_motion(routed)" : "k_resample_motion");
     c->pose4_ok[dst] = true;
     if (sort) {
@@ -934,9 +956,7 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
         chunk = std::max<int64_t>(kSortThreads, (chunk + kSortThreads - 1) / kSortThreads * kSortThreads);
         sa.chunk = chunk;
         const dim3 gs(static_cast<unsigned>((c->N + chunk - 1) / chunk), c->F);
-        k_sort_hist<<<gs, kSortThreads, 0, s>>>(sa);
-        mark(c, "k_sort_hist");
-        k_sort_scatter<<<gs, kSortThreads, 0, s>>>(sa);
+        launch_dep(c->pdl, k_sort_scatter, dim3(gs), dim3(kSortThreads), 0, s, sa);
         mark(c, "k_sort_scatter");
     }
     const int64_t slots = static_cast<int64_t>(c->F) * c->N;   // slots of the directional stage (== N for one filter)
@@ -952,7 +972,7 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
         pa.nfil = c->dir_pool ? c->N : (int64_t{1} << 40);
         pa.box = c->dir_box;
         pa.whole = c->dir_pool ? 1 : 0;
-        k_dir_gather<<<static_cast<unsigned>((slots + 255) / 256), 256, 0, s>>>(pa);
+        launch_dep(c->pdl, k_dir_gather, dim3(static_cast<unsigned>((slots + 255) / 256)), dim3(256), 0, s, pa);
         mark(c, "k_dir_gather");
         DirPlanArgs la{};
         la.hist = c->d_hist;
@@ -964,7 +984,7 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
         la.R = c->R;
         la.force = c->dir_pool ? 2 : c->ray_mode;   // the pool has no cloud box to be outside of
         la.all_chunks = c->dir_pool ? 1 : 0;
-        k_dir_plan<<<1, kPlanThreads, 0, s>>>(la);
+        launch_dep(c->pdl, k_dir_plan, dim3(1), dim3(kPlanThreads), 0, s, la);
         mark(c, "k_dir_plan");
     }
     if (c->profiling) CK(cudaEventRecord(c->ev[2], s));
@@ -1022,7 +1042,7 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
         // MAX_RANGE_PX of the usual map resolutions is baked into specialised instances
         // (0.05 m -> 239, 0.0504 m -> 238, 0.05796 m -> 207); anything else takes the generic one
         const dim3 rgrid(rblocks, c->F);
-#define MCL_LAUNCH_RAY(WB, MCV) k_raycast_weight<WB, MCV><<<rgrid, kRayThreads, smem, s>>>(ra)
+#define MCL_LAUNCH_RAY(WB, MCV) launch_dep(c->pdl, (k_raycast_weight<WB, MCV>), dim3(rgrid), dim3(kRayThreads), smem, s, ra)
         if (c->map.wbits == 8) {
             switch (c->M) {
                 case 207: MCL_LAUNCH_RAY(8, 207); break;
@@ -1067,10 +1087,10 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
         const size_t dsmem = dir_ray_smem(da.win_bytes);
         const int dblocks = static_cast<int>(std::min<int64_t>(c->num_sms, (slots * c->R + kDirThreads - 1) / kDirThreads));
         switch (c->M) {
-            case 207: k_raycast_dir<207><<<dblocks, kDirThreads, dsmem, s>>>(da); break;
-            case 238: k_raycast_dir<238><<<dblocks, kDirThreads, dsmem, s>>>(da); break;
-            case 239: k_raycast_dir<239><<<dblocks, kDirThreads, dsmem, s>>>(da); break;
-            default: k_raycast_dir<0><<<dblocks, kDirThreads, dsmem, s>>>(da); break;
+            case 207: launch_dep(c->pdl, k_raycast_dir<207>, dim3(dblocks), dim3(kDirThreads), dsmem, s, da); break;
+            case 238: launch_dep(c->pdl, k_raycast_dir<238>, dim3(dblocks), dim3(kDirThreads), dsmem, s, da); break;
+            case 239: launch_dep(c->pdl, k_raycast_dir<239>, dim3(dblocks), dim3(kDirThreads), dsmem, s, da); break;
+            default: launch_dep(c->pdl, k_raycast_dir<0>, dim3(dblocks), dim3(kDirThreads), dsmem, s, da); break;
         }
         mark(c, "k_raycast_dir");
         if (c->profiling) CK(cudaEventRecord(c->ev[5], s));
@@ -1092,15 +1112,15 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
         const size_t tab_bytes = sizeof(double) * static_cast<size_t>(c->R) * (c->M + 1);
         static const bool no_sm_table = std::getenv("MCL_NO_SMEM_TABLE") != nullptr;   // debugging knob
         if (c->dir_pool) {
-            k_weight_steps<true><<<wblocks, kWeightThreads, 0, s>>>(wa);
+            launch_dep(c->pdl, k_weight_steps<true>, dim3(wblocks), dim3(kWeightThreads), 0, s, wa);
         } else if (!no_sm_table && tab_bytes <= 110 * 1024) {   // two persistent 512-thread CTAs per SM share the SM's shared memory
             const unsigned g = static_cast<unsigned>(std::min<int64_t>(2 * c->num_sms, (slots + 4 * 512 - 1) / (4 * 512)));
-            k_weight_steps_sm<512><<<g, 512, tab_bytes, s>>>(wa);
+            launch_dep(c->pdl, k_weight_steps_sm<512>, dim3(g), dim3(512), tab_bytes, s, wa);
         } else if (!no_sm_table && tab_bytes <= 220 * 1024) {
             const unsigned g = static_cast<unsigned>(std::min<int64_t>(c->num_sms, (slots + 4 * 1024 - 1) / (4 * 1024)));
-            k_weight_steps_sm<1024><<<g, 1024, tab_bytes, s>>>(wa);
+            launch_dep(c->pdl, k_weight_steps_sm<1024>, dim3(g), dim3(1024), tab_bytes, s, wa);
         } else {
-            k_weight_steps<false><<<wblocks, kWeightThreads, 0, s>>>(wa);
+            launch_dep(c->pdl, k_weight_steps<false>, dim3(wblocks), dim3(kWeightThreads), 0, s, wa);
         }
         mark(c, "k_weight_steps");
     }
@@ -2199,6 +2219,15 @@ int mcl_set_graphs(mcl_ctx* c, int enabled) {
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
     c->graphs_enabled = enabled != 0;
+    drop_graphs(c);
+    return MCL_OK;
+}
+
+int mcl_set_pdl(mcl_ctx* c, int enabled) {
+    if (!c) return fail(MCL_ERR_INVALID, "null context");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    c->pdl = enabled != 0;
     drop_graphs(c);
     return MCL_OK;
 }

@@ -80,9 +80,13 @@ __device__ __forceinline__ void shard_publish(const ShardDev& s, unsigned long l
         unsigned long long* dst = mbox_slot(s, q, epoch, s.rank);
         for (int w = threadIdx.x; w < nwords; w += blockDim.x) st_sys_u64(dst + w, payload[w]);
     }
-    __threadfence_system();
+    // the barrier orders the block's payload stores before the releasing threads; their fence + release store are
+    // cumulative over them at system scope
     __syncthreads();
-    if (static_cast<int>(threadIdx.x) < s.world) st_release_sys(s.flag[threadIdx.x] + s.rank, epoch);
+    if (static_cast<int>(threadIdx.x) < s.world) {
+        __threadfence_system();
+        st_release_sys(s.flag[threadIdx.x] + s.rank, epoch);
+    }
 }
 
 // Called by ALL threads of one block.  Returns false (and records the error) if a peer's payload
