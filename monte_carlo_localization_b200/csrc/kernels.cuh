@@ -214,6 +214,13 @@ __device__ __forceinline__ int count_below(const double* __restrict__ p, double 
     ldg256(p + 4, v4, v5, v6, v7);
     return (v0 < u) + (v1 < u) + (v2 < u) + (v3 < u) + (v4 < u) + (v5 < u) + (v6 < u) + (v7 < u);
 }
+// Position of coarse key k in shared memory.  A binary search over a power-of-two table probes multiples of large
+// powers of two first -- ALL in bank 0: with the keys stored at their index the 2^s candidates of step s <= 8 were
+// 2^s-way bank conflicts (ncu: 216 wavefronts per warp and search, 88 % of them replays).  One pad word per 32 keys
+// and another per 1024 spread every step's candidates over the banks (~36 wavefronts per warp and search).
+__host__ __device__ __forceinline__ int coarse_slot(int k) { return k + (k >> 5) + (k >> 10); }
+__host__ __device__ __forceinline__ int coarse_slots(int nc) { return nc > 0 ? coarse_slot(nc - 1) + 1 : 0; }
+
 // The coarse level is searched on 32-bit keys: for non-negative doubles the order of the values is the order of
 // their bit patterns, so the high word decides unless it ties (then the exact double from global memory does).
 // Random 4-byte shared-memory reads cost a third of the bank-conflict replays of 8-byte ones, and the table is
@@ -226,7 +233,7 @@ __device__ __forceinline__ int64_t cdf_lower_bound(const double* __restrict__ cp
         int kl = 0, kh = nc;
         while (kl < kh) {
             const int km = (kl + kh) >> 1;
-            const uint32_t t = ts[km];
+            const uint32_t t = ts[coarse_slot(km)];
             bool below = t < uh;
             if (t == uh) below = __ldg(coarse + km) < u;   // rare: same 32 leading bits
             if (below)
@@ -273,20 +280,21 @@ __device__ __forceinline__ int64_t cdf_lower_bound(const double* __restrict__ cp
     return lo;
 }
 
-// motion_model for one particle (:474-502) + the stores of the proposal: SoA state, packed copy,
-// ray-start record; returns the (finite) position for the cloud-centre sums
-__device__ __forceinline__ void motion_store(const MotionArgs& a, const MotionScalars& m, uint64_t update_no, int f, int64_t li,
-                                             double x, double y, double th, double* sum_x, double* sum_y, int* sort_cnt) {
-    const int64_t fo = static_cast<int64_t>(f) * a.N;
-    const int64_t i = a.glo + li;
+// motion_model for one particle (:474-502): kinematics + noise + wrap.  zp: the slot's three injected normals or
+// nullptr (device Philox keyed by the GLOBAL slot i, so the result does not depend on which GPU evaluates it)
+struct MotionNoise {
+    double disp_x, disp_y, disp_t;
+    uint64_t seed;
+};
+__device__ __forceinline__ void motion_apply(const MotionScalars& m, const MotionNoise& q, const double* zp, uint64_t update_no, int f,
+                                             int64_t i, double x, double y, double th, double* ox, double* oy, double* ot) {
     double z0, z1, z2;
-    if (a.z) {
-        const double* zp = a.z + 3 * (fo + i);   // [F][3 N]; a sharded filter is one filter (fo == 0), indexed by the global slot
+    if (zp) {
         z0 = zp[0];
         z1 = zp[1];
         z2 = zp[2];
     } else {
-        const Philox4 r = noise_words(static_cast<uint64_t>(i), f, 1u, a.seed, update_no);
+        const Philox4 r = noise_words(static_cast<uint64_t>(i), f, 1u, q.seed, update_no);
         double t;
         normal_pair(r.v[0], r.v[1], &z0, &z1);
         normal_pair(r.v[2], r.v[3], &z2, &t);
@@ -306,10 +314,25 @@ __device__ __forceinline__ void motion_store(const MotionArgs& a, const MotionSc
         ny = __dsub_rn(y, __dmul_rn(m.radius, __dsub_rn(c1, c0)));
         nt = __dadd_rn(th, m.dtheta);
     }
-    nx = __dadd_rn(nx, __dmul_rn(z0, a.disp_x));
-    ny = __dadd_rn(ny, __dmul_rn(z1, a.disp_y));
-    nt = __dadd_rn(nt, __dmul_rn(z2, a.disp_t));
-    nt = wrap_angle_dev(nt);
+    nx = __dadd_rn(nx, __dmul_rn(z0, q.disp_x));
+    ny = __dadd_rn(ny, __dmul_rn(z1, q.disp_y));
+    nt = __dadd_rn(nt, __dmul_rn(z2, q.disp_t));
+    *ox = nx;
+    *oy = ny;
+    *ot = wrap_angle_dev(nt);
+}
+
+// the stores of the proposal: SoA state, packed copy, ray-start record, heading count; adds the (finite) position to
+// the cloud-centre sums.  moved: (x, y, th) is already the moved pose (two-hop routing: the serving rank applied
+// the motion model), otherwise the source pose.
+__device__ __forceinline__ void motion_store(const MotionArgs& a, const MotionScalars& m, uint64_t update_no, int f, int64_t li,
+                                             double x, double y, double th, bool moved, double* sum_x, double* sum_y, int* sort_cnt) {
+    const int64_t fo = static_cast<int64_t>(f) * a.N;
+    const int64_t i = a.glo + li;
+    double nx = x, ny = y, nt = th;
+    if (!moved)
+        motion_apply(m, MotionNoise{a.disp_x, a.disp_y, a.disp_t, a.seed}, a.z ? a.z + 3 * (fo + i) : nullptr, update_no, f, i, x, y, th,
+                     &nx, &ny, &nt);
     a.dx[fo + li] = nx;
     a.dy[fo + li] = ny;
     a.dt[fo + li] = nt;
@@ -350,7 +373,7 @@ __global__ void __launch_bounds__(kMotionThreads) k_resample_motion(MotionArgs a
     const int nc = (search && a.coarse != nullptr) ? a.nc : 0;
     const double* coarse = nc > 0 ? a.coarse + static_cast<int64_t>(f) * a.nc : nullptr;
     if (nc > 0) {
-        for (int t = threadIdx.x; t < nc; t += kMotionThreads) ts[t] = static_cast<uint32_t>(__double2hiint(coarse[t]));
+        for (int t = threadIdx.x; t < nc; t += kMotionThreads) ts[coarse_slot(t)] = static_cast<uint32_t>(__double2hiint(coarse[t]));
         __syncthreads();
     }
     const int64_t N = a.N;
@@ -382,13 +405,15 @@ __global__ void __launch_bounds__(kMotionThreads) k_resample_motion(MotionArgs a
                 const uint32_t w = a.where[li];
                 at = static_cast<int64_t>(w >> kWhereShift) * N + (w & ((1u << kWhereShift) - 1u));
             }
-            const double* r = reinterpret_cast<const double*>(a.routed + at);
-            x = ld_sys_f64(r);
-            y = ld_sys_f64(r + 1);
-            th = ld_sys_f64(r + 2);
-            a.idx_out[li] = static_cast<int32_t>(__double_as_longlong(ld_sys_f64(r + 3)));
+            // one 32-byte request per slot (the answers are gathered in request order, i.e. at random)
+            double w3;
+            asm volatile("ld.relaxed.sys.global.v4.f64 {%0, %1, %2, %3}, [%4];"
+                         : "=d"(x), "=d"(y), "=d"(th), "=d"(w3)
+                         : "l"(a.routed + at)
+                         : "memory");
+            a.idx_out[li] = static_cast<int32_t>(__double_as_longlong(w3));
         }
-        motion_store(a, m, update_no, f, li, x, y, th, &sum_x, &sum_y, a.hist ? sort_cnt : nullptr);
+        motion_store(a, m, update_no, f, li, x, y, th, !search && a.where != nullptr, &sum_x, &sum_y, a.hist ? sort_cnt : nullptr);
     }
     // cloud centre for the shared-memory window of the ray kernel
     const double bx = block_sum<kMotionThreads>(sum_x, sm);
@@ -449,8 +474,8 @@ __global__ void __launch_bounds__(kRouteThreads) k_route(RouteArgs a) {
     __shared__ bool is_last;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long c_begin = clock64();
-    for (int t = tid; t < a.nc; t += kRouteThreads) ts[t] = static_cast<uint32_t>(__double2hiint(a.coarse[t]));
-    double* qbase = reinterpret_cast<double*>(ts + ((a.nc + 1) & ~1));
+    for (int t = tid; t < a.nc; t += kRouteThreads) ts[coarse_slot(t)] = static_cast<uint32_t>(__double2hiint(a.coarse[t]));
+    double* qbase = reinterpret_cast<double*>(ts + ((coarse_slots(a.nc) + 1) & ~1));
     double* qu = qbase + warp * kRouteQueue;                                               // queued draws
     int* qi = reinterpret_cast<int*>(qbase + (kRouteThreads / 32) * kRouteQueue) + warp * kRouteQueue;   // queued slots
     __syncthreads();
@@ -710,6 +735,11 @@ struct RouteServeArgs {
     const double* st;
     const uint32_t* inbox;          // own inbox [world][N]
     double4* routed[kMaxWorld];     // every rank's answer array [world servers][N]
+    // the serving rank also applies the motion model (the noise is keyed by the global slot, so any GPU computes the same
+    // bits): the search is L1TEX-bound with idle issue slots, and the owner's kernel becomes a pure scatter of the answers
+    const double* action;           // [3] device
+    const double* z;                // [3 NG] injected normals or nullptr
+    MotionNoise noise;
     unsigned int* req_count;        // own request counters: cleared here for the next update
     const double* u;
     uint64_t seed;
@@ -727,7 +757,7 @@ __global__ void __launch_bounds__(kRouteThreads, 1) k_route_serve(RouteServeArgs
     const int tid = threadIdx.x;
     const int me = a.sh.rank, world = a.sh.world;
     const long long c_begin = clock64();
-    for (int t = tid; t < a.nc; t += kRouteThreads) ts[t] = static_cast<uint32_t>(__double2hiint(a.coarse[t]));
+    for (int t = tid; t < a.nc; t += kRouteThreads) ts[coarse_slot(t)] = static_cast<uint32_t>(__double2hiint(a.coarse[t]));
     // the counts travelled in the exchange the request kernel (or its check kernel) completed: epoch == *xseq
     const unsigned long long req_epoch = *a.sh.xseq;
     if (tid == 0) {
@@ -743,6 +773,7 @@ __global__ void __launch_bounds__(kRouteThreads, 1) k_route_serve(RouteServeArgs
     const unsigned int total = s_pre[world];
     const uint64_t update_no = *a.update_no;
     const int64_t glo = static_cast<int64_t>(me) * a.N;
+    const MotionScalars m = motion_scalars(a.action[0], a.action[2]);
     for (unsigned int t = blockIdx.x * kRouteThreads + tid; t < total; t += gridDim.x * kRouteThreads) {
         int r = 0;
         while (r + 1 < world && s_pre[r + 1] <= t) ++r;
@@ -759,6 +790,7 @@ __global__ void __launch_bounds__(kRouteThreads, 1) k_route_serve(RouteServeArgs
             y = a.sy[j];
             th = a.st[j];
         }
+        motion_apply(m, a.noise, a.z ? a.z + 3 * i : nullptr, update_no, 0, i, x, y, th, &x, &y, &th);
         // answer k of this rank for rank r: consecutive lanes write consecutive records
         double* dst = reinterpret_cast<double*>(a.routed[r] + static_cast<size_t>(me) * static_cast<size_t>(a.N) + (t - s_pre[r]));
         asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "d"(x), "d"(y), "d"(th),

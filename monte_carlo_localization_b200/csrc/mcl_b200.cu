@@ -845,6 +845,9 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
         va.inbox = c->d_inbox;
         for (int q = 0; q < kMaxWorld; ++q) va.routed[q] = c->routed_peers[q];
         va.req_count = c->d_req_count;
+        va.action = action_dev;
+        va.z = z_dev;
+        va.noise = MotionNoise{c->prm.motion_dispersion_x, c->prm.motion_dispersion_y, c->prm.motion_dispersion_theta, c->prm.seed};
         va.u = u_dev;
         va.seed = c->prm.seed;
         va.update_no = c->d_update_no;
@@ -852,7 +855,7 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
         va.dbg = (c->d_dbg && c->dbg_pass == 8) ? c->d_dbg : nullptr;
         va.sh = c->sh;
         va.sh.fused = c->xmode;
-        const size_t vsmem = sizeof(uint32_t) * static_cast<size_t>((c->coarse_n + 1) & ~1);
+        const size_t vsmem = sizeof(uint32_t) * static_cast<size_t>((coarse_slots(c->coarse_n) + 1) & ~1);
         const int vblocks = static_cast<int>(std::min<int64_t>(c->num_sms, (c->N + kRouteThreads - 1) / kRouteThreads));
         launch_dep(c->pdl, k_route_serve, dim3(vblocks), dim3(kRouteThreads), vsmem, s, va);
         mark(c, "k_route_serve");
@@ -886,7 +889,7 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
         ra.dbg = (c->d_dbg && c->dbg_pass == 8) ? c->d_dbg : nullptr;
         ra.sh = c->sh;
         ra.sh.fused = c->xmode;
-        const size_t rsmem = sizeof(uint32_t) * static_cast<size_t>((c->coarse_n + 1) & ~1) + (kRouteThreads / 32) * kRouteQueue * (sizeof(double) + sizeof(int));
+        const size_t rsmem = sizeof(uint32_t) * static_cast<size_t>((coarse_slots(c->coarse_n) + 1) & ~1) + (kRouteThreads / 32) * kRouteQueue * (sizeof(double) + sizeof(int));
         const int rblocks = static_cast<int>(std::min<int64_t>(c->num_sms, (c->NG + 2 * kRouteThreads - 1) / (2 * kRouteThreads)));
         launch_dep(c->pdl, k_route, dim3(rblocks), dim3(kRouteThreads), rsmem, s, ra);
         mark(c, "k_route");
@@ -934,7 +937,7 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
     ma.hist = sort ? c->d_hist : nullptr;   // the counting sort's histogram is accumulated by the motion kernel
     ma.hist_B = c->B;
     int mblocks = static_cast<int>((c->N + kMotionThreads - 1) / kMotionThreads);
-    const size_t msmem = sharded(c) ? 0 : sizeof(uint32_t) * static_cast<size_t>(c->coarse_n);
+    const size_t msmem = sharded(c) ? 0 : sizeof(uint32_t) * static_cast<size_t>(coarse_slots(c->coarse_n));
     // a large table is staged once per SM by persistent blocks; a small one by every block
     if (msmem > 8 * 1024) mblocks = std::min(mblocks, std::max(1, c->num_sms / std::min(c->F, c->num_sms)));
     launch_dep(c->pdl, k_resample_motion, dim3(dim3(mblocks, c->F)), dim3(kMotionThreads), msmem, s, ma);
