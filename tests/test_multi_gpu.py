@@ -32,14 +32,15 @@ def _torchrun(world, script, *args, timeout=600):
     return subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout, cwd=ROOT)
 
 
-@pytest.mark.parametrize("exchange", ["fused", "nccl"])
-def test_sharded_filter_equals_single_gpu_bit_for_bit(exchange):
+@pytest.mark.parametrize("exchange,route", [("fused", "two-hop"), ("nccl", "two-hop"), ("fused", "one-hop")])
+def test_sharded_filter_equals_single_gpu_bit_for_bit(exchange, route):
     """2 ranks x 131072 particles, 8 device-RNG updates + one update from degenerate weights (the overflow
-    path of the exchange): indices, particles and weights bit-identical to the same filter on one GPU."""
+    path of the exchange, every request going to one rank): indices, particles and weights bit-identical to
+    the same filter on one GPU, for both routings of the resampling draws."""
     if _device_count() < 2:
         pytest.skip("needs 2 GPUs")
     res = _torchrun(2, "scripts/check_sharded_equals_single.py", "--particles-per-gpu", "131072", "--updates", "8",
-                    "--exchange", exchange, "--degenerate")
+                    "--exchange", exchange, "--route", route, "--degenerate")
     lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
     assert res.returncode == 0 and lines, res.stdout[-2000:] + res.stderr[-4000:]
     r = json.loads(lines[-1])
