@@ -185,9 +185,10 @@ int mcl_set_pdl(mcl_ctx* ctx, int enabled);
  * skip-map kernel, the DIRECTIONAL stage: per-heading-sector skip maps built at mcl_set_map, rays
  * grouped by sector, each sector's window staged in shared memory.  Both compute the reference's
  * cast_ray (src/particle_filter.cpp:611-650) exactly; they differ only in how many samples they
- * can prove irrelevant.  mode 0 (default): directional when at least 90 % of the particles lie in
- * the window box around the cloud centre, decided on the device every update; 1: isotropic
- * kernel only; 2: directional always (MCL_ERR_UNSUPPORTED if the context is not eligible).  A BATCH of
+ * can prove irrelevant.  mode 0 (default): directional whenever the context is eligible -- particles
+ * inside the window box around the cloud centre march shared memory, the others (all of them right
+ * after mcl_init_global) the same sector maps in L2; 1: isotropic kernel only; 2: directional
+ * always (MCL_ERR_UNSUPPORTED if the context is not eligible).  A BATCH of
  * filters whose whole padded map fits one window can run the directional stage over the pool of all
  * filters' particles; that is opt-in (mode 2): on such small maps the isotropic kernel measured faster. */
 int mcl_set_ray_mode(mcl_ctx* ctx, int mode);

@@ -182,6 +182,7 @@ struct mcl_ctx {
     bool dir_pool = false;            // batch of filters on a map that fits one window: the stage runs over the pool
     int dir_B = 0;                    // heading buckets of the sector arithmetic (the sort's B for one filter)
     int ray_mode = 0;                 // 0 auto, 1 isotropic kernel only, 2 directional forced
+    bool last_dir = false;            // the last update ran the directional stage (decided on the host since round 2)
     DirSector sectors[kDirSectors];
     uint8_t* d_dirmaps = nullptr;     // [S][PH*PW]
     DirSector* d_sectors = nullptr;
@@ -802,6 +803,7 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
     // a batch's pool mode is opt-in (ray mode 2): measured slower than the isotropic kernel on small maps
     const bool dir = !c->wide && c->dir_ready && c->sort_enabled && c->ray_mode != 1 && (!c->dir_pool || c->ray_mode == 2);
     const bool sort = c->sort_enabled && !c->wide;   // (the heading order only serves the skip-map ray kernels)
+    c->last_dir = dir;
     static const bool no_packed = std::getenv("MCL_NO_PACKED") != nullptr;   // debugging knob
     const bool packed = !no_packed && c->pose4_ok[src];   // the packed source copy was written by the last update (no set_particles / init since)
     if (sharded(c) && c->route_mode != 1) {
@@ -1019,7 +1021,7 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
         ww.inv_squash = 1.0 / c->prm.squash_factor;
         k_weight_wide<<<dim3(static_cast<unsigned>((c->N + 255) / 256), c->F), 256, 0, s>>>(ww);
         mark(c, "k_weight_wide");
-    } else if (!(dir && c->dir_pool)) {   // the pool mode of the directional stage has no fallback to hand the update to
+    } else if (!dir) {   // (the directional stage handles compact and scattered clouds alike: no fallback launch)
         RayArgs ra{};
         ra.map = c->map;
         ra.beams = c->beams;
@@ -2255,7 +2257,7 @@ int mcl_ray_stage_info(mcl_ctx* c, int* directional_ready, int* last_mode, int* 
         CK(cudaMemcpy(plan, c->d_plan, sizeof(plan), cudaMemcpyDeviceToHost));
     }
     if (directional_ready) *directional_ready = c->dir_ready ? 1 : 0;
-    if (last_mode) *last_mode = plan[kPlanMode];
+    if (last_mode) *last_mode = c->last_dir ? 1 : 0;
     if (box_cells) *box_cells = c->dir_ready ? c->dir_box : 0;
     if (units) *units = plan[kPlanUnits];
     return MCL_OK;

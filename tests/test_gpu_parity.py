@@ -451,9 +451,10 @@ def test_device_distance_transform_equals_host_build(name):
     c.close()
 
 
-def test_scattered_cloud_falls_back_to_isotropic_kernel():
-    """After initialize_global the cloud is not compact: the plan keeps the isotropic kernel;
-    forcing the directional stage (all particles on the global-memory path) gives the same."""
+def test_scattered_cloud_stays_on_the_directional_stage():
+    """After initialize_global no particle lies in the window box: the directional stage marches the sector maps in
+    global memory (all particles on the global-memory path); the isotropic kernel gives the same steps and weights,
+    and both equal the oracle's."""
     from monte_carlo_localization_b200 import maps, synth
     from oracle import bindings as ob
     g = maps.load_named_map("sibal1")
@@ -474,7 +475,12 @@ def test_scattered_cloud_falls_back_to_isotropic_kernel():
         c.set_particles(p0, w0)
         c.update(action, obs, u, z)
         res[mode] = (c.range_steps().copy(), c.raw_weights().copy())
-        assert c.ray_stage_info()["last_mode"] == (1 if mode == 2 else 0)
+        assert c.ray_stage_info()["last_mode"] == 1   # scattered clouds stay on the directional stage (sector maps from L2)
+    c.set_ray_mode(1)
+    c.set_particles(p0, w0)
+    c.update(action, obs, u, z)
+    assert c.ray_stage_info()["last_mode"] == 0
+    res[0] = (c.range_steps().copy(), c.raw_weights().copy())            # the isotropic kernel on the same cloud
     assert np.array_equal(res[0][0], res[2][0]) and np.array_equal(res[0][1], res[2][1])
     orc.update(action, obs, u, z)
     want = steps_from_ranges(orc.ranges(), g.resolution_f64, orc.M)
