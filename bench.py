@@ -219,7 +219,9 @@ def run_reference(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_update"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "updates_per_s": cb["updates_per_s"],
-            "config": dict(workload_config(args.workload, args.gpus, args.particles, cb["beams"]), reference_sample=note),
+            "config": dict(workload_config(args.workload, args.gpus, args.particles, cb["beams"], args.shard_exchange,
+                                           args.shard_route if args.shard_route != "auto" else ("two-hop" if args.gpus >= 3 else "one-hop")),
+                           reference_sample=note),
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "buckets_ms_per_update")},
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -532,7 +534,7 @@ def run_gpu(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "updates_per_s": 1e3 / ms_per_step * (F * world if batch else 1),
-                "config": workload_config(args.workload, world, N, R, args.shard_exchange, args.shard_route), "clocks": clocks, "e2e": e2e,
+                "config": workload_config(args.workload, world, N, R, args.shard_exchange, flt.route if flt is not None else "none"), "clocks": clocks, "e2e": e2e,
                 "gpu_launches": launches, "roofline": roof, "cpu_baseline": cb, "stage_ms": stage, "kernels": kernels,
                 "ray_stage": ray_stage, "wall_ms_per_step_incl_flush": 1e3 * wall / K, "pose_error_m": pose_err}
         print(json.dumps(line))
@@ -558,8 +560,9 @@ def main():
     ap.add_argument("--shard-exchange", default="fused", choices=["fused", "nccl"],
                     help="multi-GPU: how ranks meet at an exchange (in-kernel NVLink flags, or a one-word ncclAllGather)")
     ap.add_argument("--no-pdl", action="store_true", help="plain stream order between the kernels of an update (comparison)")
-    ap.add_argument("--shard-route", default="two-hop", choices=["two-hop", "one-hop"],
-                    help="multi-GPU: request routing of the resampling draws (default) or every rank testing all draws")
+    ap.add_argument("--shard-route", default="auto", choices=["auto", "two-hop", "one-hop"],
+                    help="multi-GPU: request routing of the resampling draws, every rank testing all draws, or the library's "
+                         "choice by world size (default: two hops from 3 ranks on)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

@@ -247,12 +247,12 @@ typedef int (*mcl_barrier_fn)(void* user);
 int mcl_shard_set_exchange(mcl_ctx* ctx, int fused, mcl_barrier_fn hook, void* user);
 
 /* How the draws of the global multinomial resampling (src/particle_filter.cpp:658-665) reach the rank that
- * owns their source particle.  two_hop = 1 (default): the owner of a slot classifies its own N draws against
+ * owns their source particle.  two_hop = 1 (the default from 3 ranks on): the owner of a slot classifies its own N draws against
  * the ranks' CDF ranges and appends a 4-byte request to the source rank's inbox; after one exchange of the
  * counts the source ranks search and push the poses (work per rank independent of the number of ranks).
- * two_hop = 0: every rank evaluates all world * N draws and serves the ones in its own range (one exchange
- * less, work per rank grows with the world size).  Both draw the same particles bit for bit; every rank of
- * a filter must use the same setting. */
+ * two_hop = 0 (the default for 2 ranks): every rank evaluates all world * N draws and serves the ones in its own
+ * range (one exchange less, work per rank grows with the world size).  two_hop < 0 restores the default.  Both
+ * draw the same particles bit for bit; every rank of a filter must use the same setting. */
 int mcl_shard_set_route(mcl_ctx* ctx, int two_hop);
 
 /* The same with the library owning the NCCL communicator (bound at run time from libnccl.so.2):

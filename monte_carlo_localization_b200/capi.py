@@ -460,9 +460,10 @@ class MclContext:
         self._check(self._L.mcl_shard_set_exchange(self._h, int(fused), C.cast(cb, C.c_void_p) if cb else None, None),
                     "mcl_shard_set_exchange")
 
-    def shard_set_route(self, two_hop: bool):
-        """Two-hop request routing (default) or every rank testing all draws; same result bit for bit."""
-        self._check(self._L.mcl_shard_set_route(self._h, int(bool(two_hop))), "mcl_shard_set_route")
+    def shard_set_route(self, two_hop):
+        """Two-hop request routing (True), every rank testing all draws (False) or the library's choice by world
+        size (None); same result bit for bit."""
+        self._check(self._L.mcl_shard_set_route(self._h, -1 if two_hop is None else int(bool(two_hop))), "mcl_shard_set_route")
 
     def sharded_gather(self):
         """(particles [3, NG], weights [NG]) of the whole filter, on every rank (NCCL, collective)."""

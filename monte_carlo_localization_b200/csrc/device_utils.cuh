@@ -57,6 +57,19 @@ __device__ __forceinline__ T block_scan_inclusive(T v, Op op, T* sm, const T& id
     return v;
 }
 
+// w = p^(1/squash) of the sensor model (src/particle_filter.cpp:577-579, std::pow).  MCL_FAST_POW: exp(y * log p), about half
+// the instructions of pow(); its error (~6e-14 relative for p >= 1e-230) is nine orders below the weight tolerance.
+#ifndef MCL_FAST_POW
+#define MCL_FAST_POW 0
+#endif
+__device__ __forceinline__ double squash_pow(double p, double inv_squash) {
+#if MCL_FAST_POW
+    return exp(inv_squash * log(p));
+#else
+    return pow(p, inv_squash);
+#endif
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(kFullMask, v, d);

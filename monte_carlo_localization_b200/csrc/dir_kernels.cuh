@@ -612,7 +612,7 @@ __global__ void __launch_bounds__(kWeightThreads) k_weight_steps(WeightStepsArgs
     for (int e = 0; e < 4; ++e) {
         if (pos + e < a.cnt) {
             const int64_t i = a.lo + (POOL ? fil[e] * a.nfil : int64_t{0}) + a.perm[a.lo + pos + e];
-            a.w_raw[i] = pow(acc[e], a.inv_squash);
+            a.w_raw[i] = squash_pow(acc[e], a.inv_squash);
             if (a.steps)   // diagnostics (mcl_get_ranges): particle-major copy of the step indices
                 for (int jj = 0; jj < a.R; ++jj) a.steps[i * a.R + jj] = a.steps_sorted[static_cast<int64_t>(jj) * a.stride + pos + e];
         }
@@ -693,7 +693,7 @@ __global__ void __launch_bounds__(NT) k_weight_steps_sm(WeightStepsArgs a) {
         for (int e = 0; e < 4; ++e) {
             if (pos + e < a.cnt) {
                 const int64_t i = a.lo + a.perm[a.lo + pos + e];
-                a.w_raw[i] = pow(acc[e], a.inv_squash);
+                a.w_raw[i] = squash_pow(acc[e], a.inv_squash);
                 if (a.steps)   // diagnostics (mcl_get_ranges): particle-major copy of the step indices
                     for (int jj = 0; jj < a.R; ++jj) a.steps[i * a.R + jj] = a.steps_sorted[static_cast<int64_t>(jj) * a.stride + pos + e];
             }

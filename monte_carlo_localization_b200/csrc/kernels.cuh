@@ -1088,7 +1088,7 @@ __global__ void __launch_bounds__(kRayThreads, 1) k_raycast_weight(RayArgs a) {
                 if (steps) steps[j] = static_cast<uint8_t>(r);
             }
         }
-        a.w_raw[fo + i] = pow(acc, a.inv_squash);
+        a.w_raw[fo + i] = squash_pow(acc, a.inv_squash);
     }
     if (a.replay_count && replays) atomicAdd(reinterpret_cast<unsigned long long*>(a.replay_count), static_cast<unsigned long long>(replays));
 }
@@ -1434,7 +1434,7 @@ __global__ void __launch_bounds__(256) k_weight_wide(WideWeightArgs a) {
     const double* row = a.slice + static_cast<int64_t>(f) * a.R * tw;
     double acc = 1.0;
     for (int j = 0; j < a.R; ++j) acc = __dmul_rn(acc, __ldg(row + static_cast<int64_t>(j) * tw + st[j]));
-    a.w_raw[static_cast<int64_t>(f) * a.N + i] = pow(acc, a.inv_squash);
+    a.w_raw[static_cast<int64_t>(f) * a.N + i] = squash_pow(acc, a.inv_squash);
 }
 
 struct WideQueryArgs {

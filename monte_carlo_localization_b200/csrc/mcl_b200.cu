@@ -216,7 +216,7 @@ struct mcl_ctx {
     uint32_t* d_where = nullptr;             // [N] (server, position) of every own slot's request
     unsigned int* d_req_count = nullptr;     // [kMaxWorld] requests appended per destination in the current update
     bool pdl = true;                         // programmatic dependent launches inside an update (mcl_set_pdl)
-    int route_mode = -1;                     // -1 auto (two-hop from 3 ranks on), 0 two-hop requests, 1 every rank tests all draws
+    int route_mode = -1;                     // -1 auto (two hops from 3 ranks on), 0 two-hop requests, 1 every rank tests all draws
     const StepFn* peer_list_fn[kMaxWorld] = {};
     const double* peer_list_add[kMaxWorld] = {};
     std::vector<void*> ipc_opened;
@@ -806,7 +806,10 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
     c->last_dir = dir;
     static const bool no_packed = std::getenv("MCL_NO_PACKED") != nullptr;   // debugging knob
     const bool packed = !no_packed && c->pose4_ok[src];   // the packed source copy was written by the last update (no set_particles / init since)
-    if (sharded(c) && c->route_mode != 1) {
+    // routing of the resampling draws: two hops from 3 ranks on (work per rank independent of the world size), one hop for
+    // 2 ranks (one exchange less; measured 0.757 against 0.765 ms at 2 GPUs, 0.891 against 0.838 ms at 8)
+    const bool two_hop = sharded(c) && (c->route_mode == 0 || (c->route_mode < 0 && c->world >= 3));
+    if (two_hop) {
         // sender-driven resampling in two hops: the slot owners classify their own draws and append
         // requests to the source ranks' inboxes (k_route_request), one exchange of the counts, then the
         // source ranks search and push the source poses to the slots' owners (k_route_serve)
@@ -923,7 +926,7 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
     ma.spose4 = packed ? c->d_pose4[src] : nullptr;
     ma.dpose4 = c->d_pose4[dst];
     ma.routed = sharded(c) ? c->d_routed : nullptr;
-    ma.where = (sharded(c) && c->route_mode != 1) ? c->d_where : nullptr;
+    ma.where = two_hop ? c->d_where : nullptr;
     ma.coarse = c->coarse_n > 0 ? c->d_coarse2[src] : nullptr;
     ma.nc = c->coarse_n;
     ma.cshift = c->coarse_shift;
@@ -2418,7 +2421,7 @@ int mcl_shard_set_route(mcl_ctx* c, int two_hop) {
     if (!c->arena) return fail(MCL_ERR_INVALID, "not a sharded context");
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
-    c->route_mode = two_hop ? 0 : 1;
+    c->route_mode = two_hop < 0 ? -1 : (two_hop ? 0 : 1);
     drop_graphs(c);
     return MCL_OK;
 }

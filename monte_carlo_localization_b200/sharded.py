@@ -74,12 +74,13 @@ class ShardedFilter:
     """One rank's share of a particle-sharded global filter (torch.distributed carries the NCCL id)."""
 
     def __init__(self, grid, angles, n_local: int, rank: int, world: int, device: int = 0, seed: int = 0,
-                 exchange: str = "fused", route: str = "two-hop", **params):
+                 exchange: str = "fused", route: str = "auto", **params):
         """exchange "fused": the kernels publish and wait on their own (NVLink stores + system-scope
         flags).  "nccl": the same stores, but the ranks meet in a one-word ncclAllGather enqueued
         between the publishing and the consuming kernel (for comparison).
-        route "two-hop" (default): request routing, work per rank independent of the world size;
-        "one-hop": every rank tests all draws (mcl_shard_set_route)."""
+        route "two-hop": request routing, work per rank independent of the world size; "one-hop": every
+        rank tests all draws; "auto" (default): the library's choice, two hops from 3 ranks on
+        (mcl_shard_set_route)."""
         from . import capi
         if exchange not in ("fused", "nccl"):
             raise ValueError("exchange must be 'fused' or 'nccl'")
@@ -92,10 +93,11 @@ class ShardedFilter:
         self.ctx.set_beam_angles(angles)
         if exchange == "nccl":
             self.ctx.shard_set_exchange(False)
-        if route not in ("two-hop", "one-hop"):
-            raise ValueError("route must be 'two-hop' or 'one-hop'")
-        if route == "one-hop":
-            self.ctx.shard_set_route(False)
+        if route not in ("auto", "two-hop", "one-hop"):
+            raise ValueError("route must be 'auto', 'two-hop' or 'one-hop'")
+        self.route = route if route != "auto" else ("two-hop" if world >= 3 else "one-hop")
+        if route != "auto":
+            self.ctx.shard_set_route(route == "two-hop")
 
     def init_pose(self, pose, normals_3n=None):
         """initialize_particles_pose of the WHOLE filter; the device RNG is keyed by the global slot.

@@ -24,7 +24,7 @@ def main():
     ap.add_argument("--particles-per-gpu", type=int, default=262144)
     ap.add_argument("--updates", type=int, default=12)
     ap.add_argument("--exchange", default="fused")
-    ap.add_argument("--route", default="two-hop")
+    ap.add_argument("--route", default="auto")
     ap.add_argument("--degenerate", action="store_true",
                     help="also one update from weights that put all the mass on one particle (overflow path of the exchange)")
     a = ap.parse_args()
