@@ -240,7 +240,7 @@ def dir_summary(rep, launches_csv, tag):
     out.append("| total per update | %d | %.1f | |" % (round(sum(len(v) for v in upd.values()) / n_upd), tot_med / 1e3))
     bd = agg.get("mclb200::k_build_dir_maps", [0])
     edt = sum(agg.get("mclb200::" + k, [0])[0] for k in ("k_map_masks", "k_edt_cols", "k_edt_rows", "k_map_codes"))
-    out += ["", "Outside the update: `k_build_dir_maps` once per map (%.1f ms for the 32 sector maps of Spielberg_map), the isotropic skip map "
+    out += ["", "Outside the update: `k_build_dir_maps` once per map (%.1f ms for the 16 sector maps of Spielberg_map), the isotropic skip map "
             "(`k_map_masks`, `k_edt_cols`, `k_edt_rows`, `k_map_codes`: %.1f ms, exact Euclidean transform on the device), `k_range_queries` "
             "(synthetic scan generation), `k_init_pose`, `k_fill`, the gather micro-benchmark and the L2-flush fill of bench.py." % (bd[0] / 1e6, edt / 1e6)]
     open(os.path.join(ROOT, "profiles", tag + "_launches.md"), "w").write("\n".join(out) + "\n")
