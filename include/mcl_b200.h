@@ -189,8 +189,9 @@ int mcl_set_pdl(mcl_ctx* ctx, int enabled);
  * inside the window box around the cloud centre march shared memory, the others (all of them right
  * after mcl_init_global) the same sector maps in L2; 1: isotropic kernel only; 2: directional
  * always (MCL_ERR_UNSUPPORTED if the context is not eligible).  A BATCH of
- * filters whose whole padded map fits one window can run the directional stage over the pool of all
- * filters' particles; that is opt-in (mode 2): on such small maps the isotropic kernel measured faster. */
+ * filters whose whole padded map fits one window runs the directional stage over the pool of all
+ * filters' particles (2.67 against 3.28 ms per step of 1024 x 4000 particles on sibal1); other batches and
+ * filters of fewer than 1024 particles use the isotropic kernel. */
 int mcl_set_ray_mode(mcl_ctx* ctx, int mode);
 /* directional_ready: the context is eligible and its sector maps are built; last_mode: 1 if the
  * last update ran the directional stage; box_cells: side of the window box; units: work units of
