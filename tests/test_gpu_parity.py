@@ -620,6 +620,38 @@ def test_batch_pool_directional_stage_equals_isotropic_kernel():
     assert_weights_close(out[0][0][2], orcs[0].get_state()[1])
 
 
+def test_programmatic_dependent_launches_change_nothing():
+    """mcl_set_pdl: the kernels of an update are launched with programmatic stream serialization (a kernel's blocks
+    may be resident while its predecessor drains and wait in griddepcontrol.wait).  Graph replay and direct launches,
+    a big filter on the directional stage and a batch: bit-identical to plain stream order."""
+    from monte_carlo_localization_b200 import MclContext, maps, synth
+    g = maps.load_named_map("sibal1")
+    angles_full = synth.laser_angles()
+    angles = synth.downsample(angles_full)
+    gt, actions = synth.trajectory(g, 8, 3.0)
+    for N, F, graphs in ((30000, 1, True), (30000, 1, False), (2000, 3, True)):
+        out = []
+        for pdl in (True, False):
+            c = MclContext(max_particles=N, num_filters=F, seed=99)
+            c.set_map(g)
+            c.set_beam_angles(angles)
+            c.set_graphs(graphs)
+            c.set_pdl(pdl)
+            rng = np.random.default_rng(3)
+            obs = [synth.scan_from_pose(c.calc_range_many, gt[t + 1], angles_full, rng)[::18] for t in range(6)]
+            for f in range(F):
+                c.init_pose(gt[0], filter=f)
+            for t in range(6):
+                a_ = np.tile(actions[t], (F, 1)) if F > 1 else actions[t]
+                o_ = np.tile(obs[t], (F, 1)) if F > 1 else obs[t]
+                pose = c.update(a_, o_)
+            out.append((np.asarray(pose).copy(), [c.get_particles(f).copy() for f in range(F)], [c.get_weights(f).copy() for f in range(F)]))
+            c.close()
+        assert np.array_equal(out[0][0], out[1][0])
+        for f in range(F):
+            assert np.array_equal(out[0][1][f], out[1][1][f]) and np.array_equal(out[0][2][f], out[1][2][f])
+
+
 # ---- particle-sharded filter: ranks emulated on ONE GPU (helpers.EmuRanks) ------------------------
 @pytest.mark.parametrize("world", [2, 4])
 def test_sharded_ranks_reproduce_golden_updates(world):
