@@ -1,4 +1,4 @@
-// csrc/dir_kernels.cuh -- the directional ray stage (large single filters, tracking clouds).
+// csrc/dir_kernels.cuh -- the directional ray stage (single filters of >= 1024 particles, batches on small maps).
 //
 // Replaces sensor_model's ray cast for every particle x beam (src/particle_filter.cpp:524-540,
 // :586-650) and its table product (:564-579) when one filter is large enough for the heading
@@ -9,8 +9,8 @@
 //   k_dir_plan         per update: per sector, the range of 1024-slot chunks of the heading-sorted
 //                      particles that cast rays into it; a work unit = (sector, chunk)
 //   k_raycast_dir      persistent CTAs pull units; the sector's window of the map is staged in
-//                      shared memory with cp.async.bulk; one lane = one particle, marching the two
-//                      or three beams of it that fall into the sector; step indices out
+//                      shared memory with cp.async.bulk; one lane = one particle, marching the ~5 beams
+//                      of it that fall into the sector (16 sectors, 60 beams over 270 degrees); step indices out
 //   k_weight_steps     table product in the reference's beam order + pow -> raw weights
 // A BATCH of filters whose whole padded map fits one window (small maps) runs the same stage over
 // the pool of all filters' particles ("pool mode"): slots are (filter, heading-sorted) order, every

@@ -1,14 +1,17 @@
 // csrc/kernels.cuh -- the sm_100a kernels of the MCL update.
 //
 // One update of the reference (src/particle_filter.cpp:652-716) becomes, per filter:
-//   exact sums / CDF   k_tile_sums, k_exact_chunks, k_exact_walk, k_exact_emit   (:658, :679)
+//   exact sums / CDF   k_tile_sums, k_exact_pass (x3), k_exact_emit (exact_kernels.cuh) (:658, :679)
 //                      (k_exact_single: all of a pass in one CTA for a filter of one tile)
 //   resample + motion  k_resample_motion                                         (:661-665, :449-503)
 //   heading sort       histogram inside k_resample_motion, k_sort_scatter (processing order only)
 //   ray cast + weight  k_prepare_obs, then either k_raycast_weight (isotropic skip map, weights in
 //                      its epilogue) or the directional stage of dir_kernels.cuh: k_dir_gather,
 //                      k_dir_plan, k_raycast_dir, k_weight_steps                   (:506-650)
-//   normalise + pose   k_normalize_pose (the last block writes the pose)         (:679-686, :696-716)
+//   normalise + pose   inside the exact pass that sums w_raw / S1; k_normalize_pose for one-tile filters
+//                      and mcl_expected_pose                                     (:679-686, :696-716)
+//   sharded filter     k_route_request + k_route_serve (or k_route): the draws reach the rank that owns
+//                      their source particle, the poses come back over NVLink       (:658-665)
 // blockIdx.y is the filter of a batch; every per-filter array is [F][...] contiguous.
 #pragma once
 #include <cuda_runtime.h>
