@@ -626,76 +626,91 @@ __global__ void __launch_bounds__(kWeightThreads) k_weight_steps(WeightStepsArgs
 // lookups; the next batch of step words is in flight while the current one is multiplied.  Persistent CTAs,
 // NT threads each, as many per SM as the table allows.  Results are bit-identical to k_weight_steps<false>.
 template <int NT>
-__global__ void __launch_bounds__(NT) k_weight_steps_sm(WeightStepsArgs a) {
+__global__ void __launch_bounds__(NT, 1024 / NT) k_weight_steps_sm(WeightStepsArgs a) {
     pdl_enter();
     extern __shared__ __align__(16) double tab[];   // [R][tw]
     if (a.plan[kPlanMode] != 1) return;
-    {
-        const int n2 = (a.R * a.tw) / 2;            // (R * tw is even or the tail entry is copied alone)
-        const double2* src = reinterpret_cast<const double2*>(a.slice);
-        double2* dst = reinterpret_cast<double2*>(tab);
-        for (int i = threadIdx.x; i < n2; i += NT) dst[i] = __ldg(src + i);
-        if (threadIdx.x == 0 && ((a.R * a.tw) & 1)) tab[a.R * a.tw - 1] = a.slice[a.R * a.tw - 1];
-    }
-    __syncthreads();
+    // one filter: persistent CTAs stride over all slots with the filter's slice.  POOL of filters (a.nfil < a.cnt; nfil a
+    // multiple of 4): a CTA takes whole filters -- their sorted slots are contiguous --, staging each filter's own slice
+    const bool pool = a.nfil < a.cnt;
+    const int nf = pool ? static_cast<int>(a.cnt / a.nfil) : 1;
     uint32_t tab_s;
     asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(tab_s) : "l"(tab));
     constexpr int kBatch = 10;
     const size_t wstride = static_cast<size_t>(a.stride) / 4;
     const uint32_t row_bytes = static_cast<uint32_t>(a.tw) * 8u;
-    for (int64_t pos = (static_cast<int64_t>(blockIdx.x) * NT + threadIdx.x) * 4; pos < a.cnt;
-         pos += static_cast<int64_t>(gridDim.x) * NT * 4) {
-        const uint32_t* sp = reinterpret_cast<const uint32_t*>(a.steps_sorted + pos);   // stride and pos are multiples of 4
-        double acc[4] = {1.0, 1.0, 1.0, 1.0};
-        uint32_t row_s = tab_s;
-        uint32_t w[kBatch], wn[kBatch];
-        int j = 0;
-        if (kBatch <= a.R) {
-#pragma unroll
-            for (int q = 0; q < kBatch; ++q) w[q] = __ldcs(sp + q * wstride);
-        }
-        for (; j + kBatch <= a.R; j += kBatch) {
-            sp += kBatch * wstride;
-            const bool more = j + 2 * kBatch <= a.R;
-            if (more) {
-#pragma unroll
-                for (int q = 0; q < kBatch; ++q) wn[q] = __ldcs(sp + q * wstride);   // the next batch, in flight during the products
+    for (int f = pool ? blockIdx.x : 0; f < nf; f += pool ? gridDim.x : 1) {
+        if (pool && f != static_cast<int>(blockIdx.x)) __syncthreads();   // every thread has left the previous filter's table
+        {
+            const int n2 = (a.R * a.tw) / 2;            // (R * tw is even or the tail entry is copied alone)
+            const double* slice = a.slice + static_cast<size_t>(f) * a.R * a.tw;
+            const bool vec = (reinterpret_cast<uintptr_t>(slice) & 15u) == 0;
+            if (vec) {
+                const double2* src = reinterpret_cast<const double2*>(slice);
+                double2* dst = reinterpret_cast<double2*>(tab);
+                for (int i = threadIdx.x; i < n2; i += NT) dst[i] = __ldg(src + i);
+                if (threadIdx.x == 0 && ((a.R * a.tw) & 1)) tab[a.R * a.tw - 1] = slice[a.R * a.tw - 1];
+            } else {
+                for (int i = threadIdx.x; i < a.R * a.tw; i += NT) tab[i] = __ldg(slice + i);
             }
+        }
+        __syncthreads();
+        const int64_t p_begin = pool ? static_cast<int64_t>(f) * a.nfil : 0;
+        const int64_t p_end = pool ? p_begin + a.nfil : a.cnt;
+        const int64_t p_step = (pool ? int64_t{1} : static_cast<int64_t>(gridDim.x)) * NT * 4;
+        for (int64_t pos = p_begin + ((pool ? int64_t{0} : static_cast<int64_t>(blockIdx.x) * NT) + threadIdx.x) * 4; pos < p_end; pos += p_step) {
+            const uint32_t* sp = reinterpret_cast<const uint32_t*>(a.steps_sorted + pos);   // stride and pos are multiples of 4
+            double acc[4] = {1.0, 1.0, 1.0, 1.0};
+            uint32_t row_s = tab_s;
+            uint32_t w[kBatch], wn[kBatch];
+            int j = 0;
+            if (kBatch <= a.R) {
 #pragma unroll
-            for (int q = 0; q < kBatch; ++q) {
+                for (int q = 0; q < kBatch; ++q) w[q] = __ldcs(sp + q * wstride);
+            }
+            for (; j + kBatch <= a.R; j += kBatch) {
+                sp += kBatch * wstride;
+                const bool more = j + 2 * kBatch <= a.R;
+                if (more) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {   // slots beyond cnt hold zeros or stale (valid) steps
-                    const uint32_t off = e == 0 ? (w[q] << 3) & 0x7f8u : (w[q] >> (8 * e - 3)) & 0x7f8u;
-                    double v;
-                    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(row_s + static_cast<uint32_t>(q) * row_bytes + off));
-                    acc[e] = __dmul_rn(acc[e], v);
+                    for (int q = 0; q < kBatch; ++q) wn[q] = __ldcs(sp + q * wstride);   // the next batch, in flight during the products
+                }
+#pragma unroll
+                for (int q = 0; q < kBatch; ++q) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {   // slots beyond the end hold zeros or stale (valid) steps
+                        const uint32_t off = e == 0 ? (w[q] << 3) & 0x7f8u : (w[q] >> (8 * e - 3)) & 0x7f8u;
+                        double v;
+                        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(row_s + static_cast<uint32_t>(q) * row_bytes + off));
+                        acc[e] = __dmul_rn(acc[e], v);
+                    }
+                }
+                row_s += kBatch * row_bytes;
+                if (more) {
+#pragma unroll
+                    for (int q = 0; q < kBatch; ++q) w[q] = wn[q];
                 }
             }
-            row_s += kBatch * row_bytes;
-            if (more) {
+            for (; j < a.R; ++j) {
+                const uint32_t ww = __ldcs(sp);
 #pragma unroll
-                for (int q = 0; q < kBatch; ++q) w[q] = wn[q];
+                for (int e = 0; e < 4; ++e) {
+                    const uint32_t off = e == 0 ? (ww << 3) & 0x7f8u : (ww >> (8 * e - 3)) & 0x7f8u;
+                    double v;
+                    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(row_s + off));
+                    acc[e] = __dmul_rn(acc[e], v);
+                }
+                sp += wstride;
+                row_s += row_bytes;
             }
-        }
-        for (; j < a.R; ++j) {
-            const uint32_t ww = __ldcs(sp);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const uint32_t off = e == 0 ? (ww << 3) & 0x7f8u : (ww >> (8 * e - 3)) & 0x7f8u;
-                double v;
-                asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(row_s + off));
-                acc[e] = __dmul_rn(acc[e], v);
-            }
-            sp += wstride;
-            row_s += row_bytes;
-        }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            if (pos + e < a.cnt) {
-                const int64_t i = a.lo + a.perm[a.lo + pos + e];
-                a.w_raw[i] = squash_pow(acc[e], a.inv_squash);
-                if (a.steps)   // diagnostics (mcl_get_ranges): particle-major copy of the step indices
-                    for (int jj = 0; jj < a.R; ++jj) a.steps[i * a.R + jj] = a.steps_sorted[static_cast<int64_t>(jj) * a.stride + pos + e];
+                if (pos + e < p_end) {
+                    const int64_t i = a.lo + p_begin + a.perm[a.lo + pos + e];
+                    a.w_raw[i] = squash_pow(acc[e], a.inv_squash);
+                    if (a.steps)   // diagnostics (mcl_get_ranges): particle-major copy of the step indices
+                        for (int jj = 0; jj < a.R; ++jj) a.steps[i * a.R + jj] = a.steps_sorted[static_cast<int64_t>(jj) * a.stride + pos + e];
+                }
             }
         }
     }

@@ -1120,7 +1120,11 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
         const unsigned wblocks = static_cast<unsigned>((slots + 4 * kWeightThreads - 1) / (4 * kWeightThreads));
         const size_t tab_bytes = sizeof(double) * static_cast<size_t>(c->R) * (c->M + 1);
         static const bool no_sm_table = std::getenv("MCL_NO_SMEM_TABLE") != nullptr;   // debugging knob
-        if (c->dir_pool) {
+        if (c->dir_pool && !no_sm_table && (c->N % 4) == 0 && tab_bytes <= 220 * 1024) {
+            // a CTA per filter: the filter's own slice in shared memory, its (contiguous) sorted slots
+            const unsigned g = static_cast<unsigned>(std::min<int64_t>(c->num_sms, c->F));
+            launch_dep(c->pdl, k_weight_steps_sm<1024>, dim3(g), dim3(1024), tab_bytes, s, wa);
+        } else if (c->dir_pool) {
             launch_dep(c->pdl, k_weight_steps<true>, dim3(wblocks), dim3(kWeightThreads), 0, s, wa);
         } else if (!no_sm_table && tab_bytes <= 110 * 1024) {   // two persistent 512-thread CTAs per SM share the SM's shared memory
             const unsigned g = static_cast<unsigned>(std::min<int64_t>(2 * c->num_sms, (slots + 4 * 512 - 1) / (4 * 512)));
