@@ -833,7 +833,10 @@ int update_device(mcl_ctx* c, const double* action_dev, const float* obs_dev, co
         sd.fused = 0;
         if (!c->xmode) {
             rc = exchange_barrier(c);
-            if (rc) return rc;
+            if (rc) {   // the requests of this update will never be served: the next update must not count them again
+                cudaMemsetAsync(c->d_req_count, 0, sizeof(unsigned int) * kMaxWorld, s);
+                return rc;
+            }
             launch_dep(c->pdl, k_route_check, dim3(1), dim3(32), 0, s, sd);
             mark(c, "k_route_check");
         }
