@@ -129,4 +129,12 @@ MCL_HD double chunk_seq_eval(const double* a, int n, double s) {
     return s;
 }
 
+// Position of key k of the resampling search's coarse level in shared memory (kernels.cuh::cdf_lower_bound).  A binary
+// search over a power-of-two table probes multiples of large powers of two first -- ALL in bank 0: with the keys stored
+// at their index the 2^s candidates of step s <= 8 were 2^s-way bank conflicts (ncu: 216 wavefronts per warp and search,
+// 88 % of them replays).  One pad word per 32 keys and another per 1024 spread every step's candidates over the banks
+// (~36 wavefronts per warp and search).  tests/test_emu_logic.py checks the spread level by level.
+MCL_HD int coarse_slot(int k) { return k + (k >> 5) + (k >> 10); }
+MCL_HD int coarse_slots(int nc) { return nc > 0 ? coarse_slot(nc - 1) + 1 : 0; }
+
 }  // namespace mclb200

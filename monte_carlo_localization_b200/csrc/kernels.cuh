@@ -217,13 +217,6 @@ __device__ __forceinline__ int count_below(const double* __restrict__ p, double 
     ldg256(p + 4, v4, v5, v6, v7);
     return (v0 < u) + (v1 < u) + (v2 < u) + (v3 < u) + (v4 < u) + (v5 < u) + (v6 < u) + (v7 < u);
 }
-// Position of coarse key k in shared memory.  A binary search over a power-of-two table probes multiples of large
-// powers of two first -- ALL in bank 0: with the keys stored at their index the 2^s candidates of step s <= 8 were
-// 2^s-way bank conflicts (ncu: 216 wavefronts per warp and search, 88 % of them replays).  One pad word per 32 keys
-// and another per 1024 spread every step's candidates over the banks (~36 wavefronts per warp and search).
-__host__ __device__ __forceinline__ int coarse_slot(int k) { return k + (k >> 5) + (k >> 10); }
-__host__ __device__ __forceinline__ int coarse_slots(int nc) { return nc > 0 ? coarse_slot(nc - 1) + 1 : 0; }
-
 // The coarse level is searched on 32-bit keys: for non-negative doubles the order of the values is the order of
 // their bit patterns, so the high word decides unless it ties (then the exact double from global memory does).
 // Random 4-byte shared-memory reads cost a third of the bank-conflict replays of 8-byte ones, and the table is

@@ -288,6 +288,10 @@ long long emu_range_steps_dir(emu_map* m, const double* px, const double* py, co
     return replays;
 }
 
+// shared-memory slot of coarse key k (exact_sum.cuh::coarse_slot) and the table size for nc keys
+int emu_coarse_slot(int k) { return coarse_slot(k); }
+int emu_coarse_slots(int nc) { return coarse_slots(nc); }
+
 // Sequential-order sum / prefix sums of src[k] (/ div if use_div), following the kernels:
 // k_tile_sums -> k_exact_chunks -> k_exact_walk -> k_exact_emit.  prefix_out nullable.
 // Returns the number of opaque chunks (diagnostic).

@@ -40,6 +40,8 @@ def lib():
         L.emu_exact_scan.restype = C.c_longlong
         L.emu_exact_scan.argtypes = [C.POINTER(C.c_double), C.c_longlong, C.c_int, C.c_double,
                                      C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int]
+        L.emu_coarse_slot.argtypes = [C.c_int]
+        L.emu_coarse_slots.argtypes = [C.c_int]
         _lib = L
     return _lib
 
@@ -125,6 +127,14 @@ def dir_windows(em, bx0, by0, capacity):
     out = np.zeros(4 * dir_constants()[0], dtype=np.int32)
     box = lib().emu_dir_windows(em._h, int(bx0), int(by0), int(capacity), out.ctypes.data_as(C.POINTER(C.c_int)))
     return box, out.reshape(-1, 4)
+
+
+def coarse_slot(k):
+    return lib().emu_coarse_slot(int(k))
+
+
+def coarse_slots(nc):
+    return lib().emu_coarse_slots(int(nc))
 
 
 def exact_scan(src, div=None, want_prefix=True, force_last_one=False):

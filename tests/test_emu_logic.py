@@ -255,3 +255,31 @@ def test_directional_march_reproduces_the_golden_range_steps(fixture, name):
             got, replays = em.range_steps_dir(p[0], p[1], p[2], z["angles"], buckets=2048, window_box=box)
             assert replays >= 0, "%d reads fell outside a sector window" % -replays
             assert np.array_equal(got, z["steps"][t]), "update %d box %d: %d rays differ" % (t, box, int((got != z["steps"][t]).sum()))
+
+
+def test_coarse_key_layout_spreads_every_search_step_over_the_banks():
+    """The coarse level of the resampling search is a binary search over a power-of-two table in shared memory.  Stored
+    at their index, the candidates of the first steps are multiples of large powers of two -- all in bank 0 (ncu found
+    216 wavefronts per warp and search, 88 % replays).  coarse_slot pads one word per 32 keys and one per 1024: the
+    layout stays injective and monotone, the table grows by ~3 %, and the candidates of EVERY step fall into as many
+    banks as a random access pattern would reach."""
+    from emu_bindings import coarse_slot, coarse_slots
+    for nc in (16384, 8192, 4096, 1000):
+        slots = np.array([coarse_slot(k) for k in range(nc)])
+        assert (np.diff(slots) >= 1).all() and slots[0] == 0                 # injective, monotone
+        assert coarse_slots(nc) == slots[-1] + 1 <= nc + nc // 32 + nc // 1024 + 1
+        if nc & (nc - 1):
+            continue
+        # the probes of a lower_bound over [0, nc): step s looks at the midpoints of the 2^s intervals
+        lo, hi = np.zeros(1, dtype=np.int64), np.full(1, nc, dtype=np.int64)
+        step = 0
+        while len(lo) <= 4096 and (hi - lo).min() >= 1:
+            mid = (lo + hi) // 2
+            cand = np.unique(mid)
+            per_bank = np.bincount(slots[cand] % 32, minlength=32)
+            assert (per_bank > 0).sum() == min(len(cand), 32)                # as many banks as candidates (up to all 32)
+            assert per_bank.max() == -(-len(cand) // 32)                     # and evenly filled
+            if nc == 16384 and 1 <= step <= 9:
+                assert len(np.unique(cand % 32)) == 1                        # unpadded: all of them in ONE bank
+            lo, hi = np.concatenate([lo, mid + 1]), np.concatenate([mid, hi])
+            step += 1
